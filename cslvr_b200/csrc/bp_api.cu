@@ -1,0 +1,484 @@
+// bp_api.cu -- the extern "C" boundary (include/cslvr_b200.h) and the host side of
+// the Newton-Krylov loop.
+//
+// bp_newton_solve is the drop-in for `dolfin.solve(F == 0, u, J=J, ...)` at
+// cslvr/physics.py:673-678 with dolfin NewtonSolver semantics:
+//     b = F(u); r0 = |b|
+//     while not (|b|/r0 < rtol or |b| < atol) and it < maxit:
+//         assemble J(u); solve J dx = b; u <- u - relax dx; b = F(u)
+// and PETSc KSPCG semantics for the inner solve (zero initial guess, preconditioned
+// residual norm, rtol 1e-5 by default).
+#include "bp_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+std::string g_bp_create_error;
+void bp_upload_quadrature(bp_ctx* c);
+void bp_launch_pcg_p_impl(bp_ctx* c, int first);
+
+// ------------------------------------------------------------------ helpers
+static int check_params(bp_ctx* c, const bp_params* p)
+{
+	if (!p) return bp_fail(c, BP_ERR_ARG, "bp_params is NULL");
+	if (!(p->n > 0) || !(p->eps_reg >= 0) || !(p->rho_i > 0) || !(p->g > 0))
+		return bp_fail(c, BP_ERR_ARG, "bp_params: n, rho_i, g must be positive and eps_reg non-negative");
+	if (p->n_quad < 1 || p->n_quad > BP_MAX_QUAD || !p->quad_points || !p->quad_weights)
+		return bp_fail(c, BP_ERR_ARG, "bp_params: n_quad must be in [1,%d] with points and weights", BP_MAX_QUAD);
+	double s = 0;
+	for (int q = 0; q < p->n_quad; ++q) s += p->quad_weights[q];
+	if (std::fabs(s - 1.0) > 1e-12) return bp_fail(c, BP_ERR_ARG, "bp_params: quadrature weights sum to %.17g, not 1", s);
+	if (p->pc < BP_PC_NONE || p->pc > BP_PC_COLUMN) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown preconditioner %d", p->pc);
+	return BP_OK;
+}
+
+static void store_params(bp_ctx* c, const bp_params* p)
+{
+	c->prm = *p;
+	c->quad_pts.assign(p->quad_points, p->quad_points + 4 * p->n_quad);
+	c->quad_wts.assign(p->quad_weights, p->quad_weights + p->n_quad);
+	c->prm.quad_points = c->quad_pts.data();
+	c->prm.quad_weights = c->quad_wts.data();
+}
+
+struct GroupStream {   // an in-process group runs on the first context's stream
+	bp_ctx** cs; int n; std::vector<cudaStream_t> saved;
+	GroupStream(bp_ctx** cs_, int n_) : cs(cs_), n(n_) { for (int r = 0; r < n; ++r) { saved.push_back(cs[r]->stream); cs[r]->stream = cs[0]->stream; } }
+	~GroupStream() { for (int r = 0; r < n; ++r) cs[r]->stream = saved[r]; }
+};
+
+static int ready(bp_ctx* c)
+{
+	if (!c->have_S || !c->have_A || !c->have_beta)
+		return bp_fail(c, BP_ERR_STATE, "fields not set: S=%d A=%d beta=%d (bp_set_field)", (int)c->have_S, (int)c->have_A, (int)c->have_beta);
+	return BP_OK;
+}
+
+// caller vector (host or device, caller numbering) -> internal vector
+static int vec_in(bp_ctx* c, const double* src, int on_device, double* dst)
+{
+	const double* dev = src;
+	if (!on_device) {
+		BP_CUDA(c, cudaMemcpyAsync(c->d_io, src, (size_t)c->nd_ext * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		dev = c->d_io;
+	}
+	bp_launch_gather_in(c, dev, dst);
+	return BP_OK;
+}
+static int vec_out(bp_ctx* c, const double* src, double* dst, int on_device)
+{
+	if (on_device) { bp_launch_scatter_out(c, src, dst); return BP_OK; }
+	bp_launch_scatter_out(c, src, c->d_io2);
+	BP_CUDA(c, cudaMemcpyAsync(dst, c->d_io2, (size_t)c->nd_ext * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return BP_OK;
+}
+
+static int read_scalars(bp_ctx* c)
+{
+	BP_CUDA(c, cudaMemcpyAsync(c->h_sc, c->d_sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	return BP_OK;
+}
+
+// ------------------------------------------------------------------ group core
+static int group_assemble(bp_ctx** cs, int n, int what)
+{
+	int rc = bp_comm_halo(cs, n, 0);
+	if (rc) return rc;
+	for (int r = 0; r < n; ++r) bp_launch_assemble(cs[r], what);
+	return BP_OK;
+}
+
+static int group_norm_F(bp_ctx** cs, int n, double* out)
+{
+	for (int r = 0; r < n; ++r) bp_launch_dot_owned(cs[r], cs[r]->d_F, cs[r]->d_F, SC_FF);
+	int rc = bp_comm_allreduce(cs, n, SC_FF, 1);
+	if (rc) return rc;
+	rc = read_scalars(cs[0]);
+	if (rc) return rc;
+	*out = std::sqrt(cs[0]->h_sc[SC_FF]);
+	return BP_OK;
+}
+
+// PCG on J dx = F (rhs in d_F, solution in d_dx)
+static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
+{
+	int rc;
+	for (int r = 0; r < n; ++r) { bp_launch_pc_setup(cs[r]); bp_launch_pcg_init(cs[r]); }
+	if ((rc = bp_comm_allreduce(cs, n, SC_RZ_NEXT, 3))) return rc;
+	for (int r = 0; r < n; ++r) bp_launch_pcg_p_impl(cs[r], 1);
+	const int maxit = cs[0]->prm.krylov_maxit > 0 ? cs[0]->prm.krylov_maxit : 10000;
+	int k = 0;
+	bool done = false;
+	while (k < maxit && !done) {
+		const int batch = std::min(32, maxit - k);
+		for (int i = 0; i < batch; ++i) {
+			if ((rc = bp_comm_halo(cs, n, 1))) return rc;
+			for (int r = 0; r < n; ++r) bp_launch_spmv(cs[r], cs[r]->d_p, cs[r]->d_Ap, 1);
+			if ((rc = bp_comm_allreduce(cs, n, SC_PAP, 1))) return rc;
+			for (int r = 0; r < n; ++r) bp_launch_pcg_update(cs[r]);
+			if ((rc = bp_comm_allreduce(cs, n, SC_RZ_NEXT, 3))) return rc;
+			for (int r = 0; r < n; ++r) bp_launch_pcg_p_impl(cs[r], 0);
+		}
+		k += batch;
+		if ((rc = read_scalars(cs[0]))) return rc;
+		done = cs[0]->h_sc[SC_DONE] != 0.0;
+	}
+	if (iters) *iters = (int)cs[0]->h_sc[SC_ITERS];
+	if (relres) *relres = cs[0]->h_sc[SC_NORM0] > 0 ? cs[0]->h_sc[SC_NORM] / cs[0]->h_sc[SC_NORM0] : 0.0;
+	if (cs[0]->h_sc[SC_BREAKDOWN] != 0.0)
+		return bp_fail(cs[0], BP_ERR_STATE, "CG breakdown: p.Ap <= 0 (Jacobian not positive definite or NaN)");
+	return BP_OK;
+}
+
+static int group_newton(bp_ctx** cs, int n, bp_stats* st)
+{
+	bp_ctx* c0 = cs[0];
+	const bp_params& P = c0->prm;
+	bp_stats s;
+	memset(&s, 0, sizeof(s));
+	int rc;
+	int64_t l0 = 0;
+	for (int r = 0; r < n; ++r) { if ((rc = ready(cs[r]))) { if (r) c0->err = cs[r]->err; return rc; } l0 += cs[r]->launches; }
+	cudaEvent_t eA, eB, eT0, eT1;
+	cudaEventCreate(&eA); cudaEventCreate(&eB); cudaEventCreate(&eT0); cudaEventCreate(&eT1);
+	float ms;
+	cudaEventRecord(eT0, c0->stream);
+	auto timed_assemble = [&](int what) -> int {
+		cudaEventRecord(eA, c0->stream);
+		int r_ = group_assemble(cs, n, what);
+		cudaEventRecord(eB, c0->stream);
+		if (r_) return r_;
+		cudaEventSynchronize(eB); cudaEventElapsedTime(&ms, eA, eB); s.t_assemble_ms += ms; s.n_assemblies++;
+		return BP_OK;
+	};
+	double rn = 0.0;
+	rc = timed_assemble(BP_ASSEMBLE_F | BP_ASSEMBLE_J);
+	if (!rc) rc = group_norm_F(cs, n, &rn);
+	if (rc) goto out;
+	s.residual_norm0 = rn;
+	s.residual_history[0] = rn;
+	if (!std::isfinite(rn)) { rc = bp_fail(c0, BP_ERR_STATE, "initial residual is not finite"); goto out; }
+	s.converged = (rn < P.newton_atol);
+	while (!s.converged && s.newton_iterations < P.newton_maxit) {
+		int kit = 0;
+		cudaEventRecord(eA, c0->stream);
+		rc = group_pcg(cs, n, &kit, nullptr);
+		cudaEventRecord(eB, c0->stream);
+		cudaEventSynchronize(eB); cudaEventElapsedTime(&ms, eA, eB); s.t_krylov_ms += ms;
+		if (rc) goto out;
+		s.krylov_iterations += kit;
+		for (int r = 0; r < n; ++r) bp_launch_axpy(cs[r], -P.newton_relax, cs[r]->d_dx, cs[r]->d_u);
+		s.newton_iterations++;
+		if ((rc = timed_assemble(BP_ASSEMBLE_F | BP_ASSEMBLE_J))) goto out;
+		if ((rc = group_norm_F(cs, n, &rn))) goto out;
+		if (s.newton_iterations < 64) s.residual_history[s.newton_iterations] = rn;
+		if (P.verbose)
+			printf("Newton iteration %d: r (abs) = %.3e (tol = %.3e) r (rel) = %.3e (tol = %.3e)  [krylov %d]\n",
+			       s.newton_iterations, rn, P.newton_atol, rn / s.residual_norm0, P.newton_rtol, kit);
+		if (!std::isfinite(rn)) { rc = bp_fail(c0, BP_ERR_STATE, "residual became non-finite at Newton iteration %d", s.newton_iterations); goto out; }
+		s.converged = (rn / s.residual_norm0 < P.newton_rtol) || (rn < P.newton_atol);
+	}
+	s.residual_norm = rn;
+	if (!s.converged && P.error_on_nonconvergence)
+		rc = bp_fail(c0, BP_ERR_NONCONV, "Newton solver did not converge in %d iterations (|F| = %.3e)", s.newton_iterations, rn);
+out:
+	cudaEventRecord(eT1, c0->stream);
+	cudaEventSynchronize(eT1);
+	cudaEventElapsedTime(&ms, eT0, eT1);
+	s.t_total_ms = ms;
+	cudaEventDestroy(eA); cudaEventDestroy(eB); cudaEventDestroy(eT0); cudaEventDestroy(eT1);
+	int64_t l1 = 0;
+	for (int r = 0; r < n; ++r) l1 += cs[r]->launches;
+	s.gpu_launches = (int32_t)(l1 - l0);
+	if (st) *st = s;
+	return rc;
+}
+
+// ------------------------------------------------------------------ C-ABI
+extern "C" {
+
+const char* bp_last_error(const bp_ctx* c) { return c ? c->err.c_str() : g_bp_create_error.c_str(); }
+
+int bp_create(bp_ctx** out, const bp_mesh* mesh, const bp_params* params, int device)
+{
+	if (!out || !mesh) return bp_fail(nullptr, BP_ERR_ARG, "bp_create: NULL argument");
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+		return bp_fail(nullptr, BP_ERR_CUDA, "bp_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+	if (device < 0 || device >= ndev) return bp_fail(nullptr, BP_ERR_ARG, "bp_create: device %d of %d", device, ndev);
+	bp_ctx* c = new bp_ctx();
+	c->device = device;
+	int rc = check_params(c, params);
+	if (!rc) {
+		store_params(c, params);
+		e = cudaSetDevice(device);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+		if (e != cudaSuccess) rc = bp_fail(c, BP_ERR_CUDA, "bp_create: %s", cudaGetErrorString(e));
+		c->own_stream = true;
+	}
+	if (!rc) rc = bp_setup_topology(c, mesh);
+	if (!rc) { cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); bp_upload_quadrature(c); }
+	if (rc) { g_bp_create_error = c->err; bp_destroy(c); return rc; }
+	*out = c;
+	return BP_OK;
+}
+
+void bp_destroy(bp_ctx* c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	bp_comm_free(c);
+	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
+		c->d_rowptr, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
+		c->d_io, c->d_io2, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
+	for (void* p : ptrs) if (p) cudaFree(p);
+	if (c->h_sc) cudaFreeHost(c->h_sc);
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int bp_set_params(bp_ctx* c, const bp_params* p)
+{
+	if (!c) return BP_ERR_ARG;
+	int rc = check_params(c, p);
+	if (rc) return rc;
+	if ((p->periodic != c->prm.periodic) || (p->use_pressure_bc != c->prm.use_pressure_bc))
+		return bp_fail(c, BP_ERR_ARG, "bp_set_params: periodic / use_pressure_bc select the facet sets at bp_create and cannot change");
+	store_params(c, p);
+	cudaSetDevice(c->device);
+	bp_upload_quadrature(c);
+	return BP_OK;
+}
+
+int bp_set_stream(bp_ctx* c, void* s)
+{
+	if (!c) return BP_ERR_ARG;
+	if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+	c->stream = (cudaStream_t)s;
+	c->own_stream = false;
+	return BP_OK;
+}
+
+int bp_set_field(bp_ctx* c, int field, const double* values, int64_t nvals, int on_device)
+{
+	if (!c || !values) return BP_ERR_ARG;
+	if (nvals != c->nv) return bp_fail(c, BP_ERR_ARG, "bp_set_field: expected %lld vertex values, got %lld", (long long)c->nv, (long long)nvals);
+	BP_CUDA(c, cudaSetDevice(c->device));
+	const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	switch (field) {
+	case BP_FIELD_S:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_io, values, nvals * sizeof(double), kind, c->stream));
+		bp_launch_set_S(c, c->d_io);
+		c->have_S = true; break;
+	case BP_FIELD_A:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_A, values, nvals * sizeof(double), kind, c->stream));
+		c->have_A = true; break;
+	case BP_FIELD_BETA:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_beta, values, nvals * sizeof(double), kind, c->stream));
+		c->have_beta = true; break;
+	default:
+		return bp_fail(c, BP_ERR_ARG, "bp_set_field: unknown field %d", field);
+	}
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->have_J = false;
+	return BP_OK;
+}
+
+int bp_get_sizes(const bp_ctx* c, int64_t* n_nodes, int64_t* n_dofs, int64_t* nnz_csr, int64_t* nnz_blocks, int64_t* n_cells, int64_t* n_basal)
+{
+	if (!c) return BP_ERR_ARG;
+	if (n_nodes) *n_nodes = c->nn;
+	if (n_dofs) *n_dofs = c->nd_ext;
+	if (nnz_csr) *nnz_csr = 4 * c->nnzb;
+	if (nnz_blocks) *nnz_blocks = c->nnzb;
+	if (n_cells) *n_cells = c->nt;
+	if (n_basal) *n_basal = c->n_basal;
+	return BP_OK;
+}
+
+int bp_csr_pattern(bp_ctx* c, int64_t* nnz, const int64_t** indptr, const int32_t** indices)
+{
+	if (!c) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = bp_build_csr_export(c);
+	if (rc) return rc;
+	if (nnz) *nnz = c->csr_indptr.back();
+	if (indptr) *indptr = c->csr_indptr.data();
+	if (indices) *indices = c->csr_indices.data();
+	return BP_OK;
+}
+
+int bp_assemble(bp_ctx* c, int what, const double* u, double* F, double* Jv, int on_device)
+{
+	if (!c || !u) return BP_ERR_ARG;
+	if (!(what & (BP_ASSEMBLE_F | BP_ASSEMBLE_J))) return bp_fail(c, BP_ERR_ARG, "bp_assemble: nothing to assemble");
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = ready(c);
+	if (rc) return rc;
+	if (Jv && (rc = bp_build_csr_export(c))) return rc;
+	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
+	bp_ctx* cs[1] = { c };
+	if ((rc = group_assemble(cs, 1, what))) return rc;
+	if (F && (what & BP_ASSEMBLE_F)) { if ((rc = vec_out(c, c->d_F, F, on_device))) return rc; }
+	if (Jv && (what & BP_ASSEMBLE_J)) {
+		const int64_t nnz = c->csr_indptr.back();
+		if (on_device) bp_launch_csr_export(c, Jv);
+		else {
+			double* tmp = nullptr;
+			BP_CUDA(c, cudaMalloc((void**)&tmp, std::max<int64_t>(nnz, 1) * sizeof(double)));
+			bp_launch_csr_export(c, tmp);
+			cudaError_t e = cudaMemcpyAsync(Jv, tmp, nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+			cudaFree(tmp);
+			BP_CUDA(c, e);
+		}
+	}
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return BP_OK;
+}
+
+int bp_spmv(bp_ctx* c, const double* x, double* y, int on_device)
+{
+	if (!c || !x || !y) return BP_ERR_ARG;
+	if (!c->have_J) return bp_fail(c, BP_ERR_STATE, "bp_spmv: no resident Jacobian (bp_assemble with BP_ASSEMBLE_J first)");
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc;
+	if ((rc = vec_in(c, x, on_device, c->d_p))) return rc;
+	bp_ctx* cs[1] = { c };
+	if ((rc = bp_comm_halo(cs, 1, 1))) return rc;
+	bp_launch_spmv(c, c->d_p, c->d_Ap, 0);
+	if ((rc = vec_out(c, c->d_Ap, y, on_device))) return rc;
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return BP_OK;
+}
+
+int bp_krylov_solve(bp_ctx* c, const double* b, double* dx, int on_device, int32_t* iterations, double* rel_residual)
+{
+	if (!c || !b || !dx) return BP_ERR_ARG;
+	if (!c->have_J) return bp_fail(c, BP_ERR_STATE, "bp_krylov_solve: no resident Jacobian");
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc;
+	if ((rc = vec_in(c, b, on_device, c->d_F))) return rc;
+	bp_ctx* cs[1] = { c };
+	int it = 0;
+	if ((rc = group_pcg(cs, 1, &it, rel_residual))) return rc;
+	if (iterations) *iterations = it;
+	if ((rc = vec_out(c, c->d_dx, dx, on_device))) return rc;
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return BP_OK;
+}
+
+int bp_newton_solve(bp_ctx* c, double* u, int on_device, bp_stats* st)
+{
+	if (!c || !u) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc;
+	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
+	bp_ctx* cs[1] = { c };
+	rc = group_newton(cs, 1, st);
+	if (rc && rc != BP_ERR_NONCONV) return rc;
+	int rc2 = vec_out(c, c->d_u, u, on_device);
+	if (rc2) return rc2;
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return rc;
+}
+
+int bp_newton_solve_group(bp_ctx** cs, int n, double** u, int on_device, bp_stats* st)
+{
+	if (!cs || n < 1 || n > 16 || !u) return BP_ERR_ARG;
+	for (int r = 0; r < n; ++r) if (!cs[r] || cs[r]->device != cs[0]->device)
+		return bp_fail(cs[0], BP_ERR_ARG, "bp_newton_solve_group: contexts must live on one device");
+	BP_CUDA(cs[0], cudaSetDevice(cs[0]->device));
+	GroupStream gs(cs, n);
+	int rc;
+	for (int r = 0; r < n; ++r) if ((rc = vec_in(cs[r], u[r], on_device, cs[r]->d_u))) return rc;
+	rc = group_newton(cs, n, st);
+	if (rc && rc != BP_ERR_NONCONV) return rc;
+	for (int r = 0; r < n; ++r) { int rc2 = vec_out(cs[r], cs[r]->d_u, u[r], on_device); if (rc2) return rc2; }
+	BP_CUDA(cs[0], cudaStreamSynchronize(cs[0]->stream));
+	BP_CUDA(cs[0], cudaGetLastError());
+	return rc;
+}
+
+int bp_assemble_group(bp_ctx** cs, int n, int what, const double** u, double** F, int on_device)
+{
+	if (!cs || n < 1 || n > 16 || !u) return BP_ERR_ARG;
+	for (int r = 0; r < n; ++r) if (!cs[r] || cs[r]->device != cs[0]->device)
+		return bp_fail(cs[0], BP_ERR_ARG, "bp_assemble_group: contexts must live on one device");
+	BP_CUDA(cs[0], cudaSetDevice(cs[0]->device));
+	GroupStream gs(cs, n);
+	int rc;
+	for (int r = 0; r < n; ++r) { if ((rc = ready(cs[r]))) return rc; if ((rc = vec_in(cs[r], u[r], on_device, cs[r]->d_u))) return rc; }
+	if ((rc = group_assemble(cs, n, what))) return rc;
+	if (F) for (int r = 0; r < n; ++r) if (F[r] && (rc = vec_out(cs[r], cs[r]->d_F, F[r], on_device))) return rc;
+	BP_CUDA(cs[0], cudaStreamSynchronize(cs[0]->stream));
+	BP_CUDA(cs[0], cudaGetLastError());
+	return BP_OK;
+}
+
+// ---- timing on the context's stream with CUDA events -------------------------
+static int flush_l2(bp_ctx* c, int enable)
+{
+	static void* buf = nullptr;
+	static size_t bytes = 0;
+	if (!enable) return BP_OK;
+	if (!buf) { bytes = (size_t)512 << 20; BP_CUDA(c, cudaMalloc(&buf, bytes)); }
+	BP_CUDA(c, cudaMemsetAsync(buf, 0, bytes, c->stream));
+	return BP_OK;
+}
+
+int bp_time_assemble(bp_ctx* c, int what, int repeats, int flush, double* ms_per_launch)
+{
+	if (!c || repeats < 1 || !ms_per_launch) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = ready(c);
+	if (rc) return rc;
+	double total = 0;
+	for (int i = 0; i < repeats; ++i) {
+		if ((rc = flush_l2(c, flush))) return rc;
+		BP_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+		bp_launch_assemble(c, what);
+		BP_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+		BP_CUDA(c, cudaEventSynchronize(c->ev1));
+		float ms; BP_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+		total += ms;
+	}
+	BP_CUDA(c, cudaGetLastError());
+	*ms_per_launch = total / repeats;
+	return BP_OK;
+}
+
+int bp_time_spmv(bp_ctx* c, int repeats, int flush, double* ms_per_launch)
+{
+	if (!c || repeats < 1 || !ms_per_launch) return BP_ERR_ARG;
+	if (!c->have_J) return bp_fail(c, BP_ERR_STATE, "bp_time_spmv: no resident Jacobian");
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc;
+	double total = 0;
+	for (int i = 0; i < repeats; ++i) {
+		if ((rc = flush_l2(c, flush))) return rc;
+		BP_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+		bp_launch_spmv(c, c->d_u, c->d_Ap, 0);
+		BP_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+		BP_CUDA(c, cudaEventSynchronize(c->ev1));
+		float ms; BP_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+		total += ms;
+	}
+	BP_CUDA(c, cudaGetLastError());
+	*ms_per_launch = total / repeats;
+	return BP_OK;
+}
+
+int64_t bp_launch_count(const bp_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,123 @@
+// bp_internal.h -- context layout shared by the translation units of libcslvr_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "cslvr_b200.h"
+
+#define BP_MAX_QUAD 128
+
+// ---- device scalar block used by the Krylov loop (doubles) ------------------
+enum {
+	SC_RZ = 0,      // r.z of the current iteration
+	SC_RZ_NEXT,     // r.z after the update        } contiguous: one all-reduce
+	SC_ZZ,          // z.z                         }
+	SC_RR,          // r.r                         }
+	SC_PAP,         // p.Ap
+	SC_NORM0,       // reference norm for the relative test
+	SC_NORM,        // current norm
+	SC_DONE,        // 1.0 once converged / broken down
+	SC_ITERS,       // iterations performed
+	SC_BREAKDOWN,   // 1.0 if p.Ap <= 0 or NaN
+	SC_FF,          // F.F (Newton residual norm squared)
+	SC_TMP,
+	SC_COUNT = 16
+};
+
+struct bp_comm_state;   // NCCL binding (bp_comm.cu)
+
+struct bp_ctx {
+	int          device = 0;
+	cudaStream_t stream = nullptr;
+	bool         own_stream = false;
+	std::string  err;
+	bp_params    prm{};
+	std::vector<double> quad_pts, quad_wts;
+
+	// sizes
+	int64_t nv = 0, nt = 0, nd_ext = 0;
+	int64_t nn = 0;          // local nodes (owned + ghost)
+	int64_t nn_owned = 0;
+	int64_t nnzb = 0;        // 2x2 blocks in the resident Jacobian (owned rows)
+	int64_t nf = 0;          // facets that integrate something (basal and/or pressure)
+	int64_t n_basal = 0;
+	bool    identity_dofs = true;    // caller's dof == 2*node + c
+	bool    identity_v2n = true;
+
+	// host topology kept for the lazy CSR export
+	std::vector<int32_t> h_ext_dof;      // [2*nn] caller's dof of (node, c): [2*i+c]
+	std::vector<int32_t> h_rowptr, h_col;
+	std::vector<int64_t> csr_indptr;
+	std::vector<int32_t> csr_indices;
+	bool    have_csr = false;
+
+	// device: mesh + coefficients
+	double4* d_geo = nullptr;            // per vertex {x, y, z, S}
+	double*  d_A = nullptr;              // per vertex
+	double*  d_beta = nullptr;           // per vertex
+	int4*    d_tets = nullptr;
+	int32_t* d_v2n = nullptr;            // nullptr when identity
+	int32_t* d_tet_blk = nullptr;        // [16][nt] block slot of (a,b), -1 = row not owned
+	int32_t* d_fac_cell = nullptr;       // [nf]
+	int32_t* d_fac_info = nullptr;       // [nf] local facet | basal<<8 | pressure<<9
+	int32_t* d_ext_dof = nullptr;        // nullptr when identity
+	// device: resident Jacobian, BSR 2x2, owned rows
+	int32_t* d_rowptr = nullptr;
+	int32_t* d_col = nullptr;
+	int32_t* d_diag = nullptr;           // slot of the diagonal block of each owned row
+	double*  d_val = nullptr;            // [nnzb*4] row-major 2x2
+	int32_t* d_csr_src = nullptr;        // CSR export gather map
+	// device: vectors in internal layout [2*node + c], length 2*nn
+	double *d_u = nullptr, *d_F = nullptr, *d_dx = nullptr, *d_r = nullptr, *d_z = nullptr,
+	       *d_p = nullptr, *d_Ap = nullptr, *d_io = nullptr, *d_io2 = nullptr;
+	double*  d_dinv = nullptr;           // [nn_owned*4] preconditioner blocks
+	double*  d_sc = nullptr;             // SC_COUNT scalars
+	double*  d_part = nullptr;           // block partials [4][max_blocks]
+	unsigned* d_counter = nullptr;       // last-block tickets
+	double*  h_sc = nullptr;             // pinned mirror of d_sc
+	// halo
+	int32_t n_nbr = 0;
+	std::vector<int32_t> nbr_rank;
+	std::vector<int64_t> send_ptr, recv_ptr;
+	int32_t* d_send_nodes = nullptr;
+	double*  d_sendbuf = nullptr;
+	int64_t  n_send = 0;
+	bp_comm_state* comm = nullptr;
+
+	bool have_S = false, have_A = false, have_beta = false, have_J = false;
+	int64_t launches = 0;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ---- helpers -------------------------------------------------------------
+int bp_fail(bp_ctx* c, int code, const char* fmt, ...);
+#define BP_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return bp_fail(ctx, BP_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+// setup (bp_setup.cu)
+int bp_setup_topology(bp_ctx* c, const bp_mesh* m);
+int bp_build_csr_export(bp_ctx* c);
+
+// kernels (bp_kernels.cu)
+void bp_launch_assemble(bp_ctx* c, int what);                 // d_u -> d_F / d_val
+void bp_launch_spmv(bp_ctx* c, const double* x, double* y, int with_dot);
+void bp_launch_gather_in(bp_ctx* c, const double* ext, double* internal);   // caller -> internal
+void bp_launch_scatter_out(bp_ctx* c, const double* internal, double* ext); // internal -> caller
+void bp_launch_csr_export(bp_ctx* c, double* out);
+void bp_launch_pc_setup(bp_ctx* c);
+void bp_launch_set_S(bp_ctx* c, const double* S_dev);
+void bp_launch_pack_halo(bp_ctx* c, const double* vec);
+void bp_launch_dot_owned(bp_ctx* c, const double* a, const double* b, int sc_slot);
+void bp_launch_axpy(bp_ctx* c, double alpha, const double* x, double* y);   // y += alpha x
+void bp_launch_pcg_init(bp_ctx* c);
+void bp_launch_pcg_update(bp_ctx* c);
+void bp_launch_pcg_p(bp_ctx* c);
+void bp_launch_sum_scalars(bp_ctx** ctxs, int n, int slot, int count);
+
+// comm (bp_comm.cu)
+int  bp_comm_halo(bp_ctx** ctxs, int n, int which_vec);   // 0:u 1:p
+int  bp_comm_allreduce(bp_ctx** ctxs, int n, int slot, int count);
+void bp_comm_free(bp_ctx* c);
+double* bp_vec(bp_ctx* c, int which);

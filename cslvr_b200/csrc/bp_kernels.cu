@@ -1,0 +1,599 @@
+// bp_kernels.cu -- sm_100a FP64 kernels of the Blatter-Pattyn momentum path.
+//
+// Replaces the FFC-generated tabulate_tensor + dolfin Assembler (residual:
+// cslvr/momentumbp.py:481-500 / 372-375, Jacobian: cslvr/physics.py:75-77) and the
+// PETSc MatMult / VecDot / VecAXPY inside KSPCG (cslvr/momentumbp.py:183-184).
+//
+// Element math is the closed form of SURVEY.md §8a: for P1 the strain rate is
+// cell-constant, so the only quadrature is  wbar = |T| sum_q w_q A(x_q)^(-1/n).
+#include "bp_internal.h"
+
+__constant__ double c_qw[BP_MAX_QUAD];
+__constant__ double c_ql[BP_MAX_QUAD * 4];
+
+struct AsmParams {
+	double n, eps_reg, rho_g, rho_sw_g;
+	int    n_quad;
+	int    n_is_3;
+};
+
+#define TPB 128
+
+// ---------------------------------------------------------------- math helpers
+__device__ __forceinline__ double pow_m1n(double a, const AsmParams& P)
+{	// a^(-1/n)
+	return P.n_is_3 ? rcbrt(a) : pow(a, -1.0 / P.n);
+}
+
+// ---------------------------------------------------------------- cell kernel
+// One thread per tetrahedron.  Loads: int4 connectivity, 4 x {x,y,z,S} (32 B each),
+// 4 x {u_x,u_y} (16 B), 4 x A.  Builds F_cell (8) and J_cell (8x8, symmetric) in
+// registers and scatter-adds into F / the resident BSR Jacobian.
+template <bool WANT_F, bool WANT_J>
+__global__ void __launch_bounds__(TPB)
+k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
+       const int32_t* __restrict__ v2n, const double2* __restrict__ u,
+       const double* __restrict__ Av, const int32_t* __restrict__ tet_blk,
+       int nn_owned, double* __restrict__ F, double* __restrict__ val, AsmParams P)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nt) return;
+	const int4 tv = tets[t];
+	const int vid[4] = { tv.x, tv.y, tv.z, tv.w };
+	double4 p[4];
+	int nd[4];
+	double2 uu[4];
+	double A[4];
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		p[a] = geo[vid[a]];
+		nd[a] = v2n ? v2n[vid[a]] : vid[a];
+		A[a] = Av[vid[a]];
+	}
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) uu[a] = u[nd[a]];
+
+	// gradients of the barycentric coordinates
+	const double e1x = p[1].x - p[0].x, e1y = p[1].y - p[0].y, e1z = p[1].z - p[0].z;
+	const double e2x = p[2].x - p[0].x, e2y = p[2].y - p[0].y, e2z = p[2].z - p[0].z;
+	const double e3x = p[3].x - p[0].x, e3y = p[3].y - p[0].y, e3z = p[3].z - p[0].z;
+	double X[4], Y[4], Z[4];
+	X[1] = e2y * e3z - e2z * e3y; Y[1] = e2z * e3x - e2x * e3z; Z[1] = e2x * e3y - e2y * e3x;
+	X[2] = e3y * e1z - e3z * e1y; Y[2] = e3z * e1x - e3x * e1z; Z[2] = e3x * e1y - e3y * e1x;
+	X[3] = e1y * e2z - e1z * e2y; Y[3] = e1z * e2x - e1x * e2z; Z[3] = e1x * e2y - e1y * e2x;
+	const double det = e1x * X[1] + e1y * Y[1] + e1z * Z[1];
+	const double idet = 1.0 / det;
+	#pragma unroll
+	for (int a = 1; a < 4; ++a) { X[a] *= idet; Y[a] *= idet; Z[a] *= idet; }
+	X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
+	const double vol = fabs(det) * (1.0 / 6.0);
+
+	// wbar = |T| * sum_q w_q A_q^(-1/n); one evaluation when A is constant on the cell
+	double wbar;
+	if (A[0] == A[1] && A[0] == A[2] && A[0] == A[3]) {
+		wbar = vol * pow_m1n(A[0], P);
+	} else {
+		double s = 0.0;
+		for (int q = 0; q < P.n_quad; ++q) {
+			const double aq = c_ql[4 * q] * A[0] + c_ql[4 * q + 1] * A[1] + c_ql[4 * q + 2] * A[2] + c_ql[4 * q + 3] * A[3];
+			s += c_qw[q] * pow_m1n(aq, P);
+		}
+		wbar = vol * s;
+	}
+
+	// velocity gradient g[c][j] and surface gradient
+	double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, sx = 0, sy = 0;
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		g00 += uu[a].x * X[a]; g01 += uu[a].x * Y[a]; g02 += uu[a].x * Z[a];
+		g10 += uu[a].y * X[a]; g11 += uu[a].y * Y[a]; g12 += uu[a].y * Z[a];
+		sx += p[a].w * X[a]; sy += p[a].w * Y[a];
+	}
+	const double sh = 0.5 * (g01 + g10);
+	const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
+	// 2 eta = ed^((1-n)/(2n)),  2 eta' = (1-n)/(2n) ed^((1-n)/(2n) - 1)
+	double two_eta, two_eta_p;
+	if (P.n_is_3) {
+		two_eta = rcbrt(ed);
+		two_eta_p = (-1.0 / 3.0) * two_eta / ed;
+	} else {
+		const double e = (1.0 - P.n) / (2.0 * P.n);
+		two_eta = pow(ed, e);
+		two_eta_p = e * two_eta / ed;
+	}
+	const double alpha = wbar * two_eta, gamma = wbar * two_eta_p;
+	const double cxx = 2.0 * g00 + g11, cyy = 2.0 * g11 + g00, hz0 = 0.5 * g02, hz1 = 0.5 * g12;
+	double dx[4], dy[4];
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		dx[a] = cxx * X[a] + sh * Y[a] + hz0 * Z[a];
+		dy[a] = cyy * Y[a] + sh * X[a] + hz1 * Z[a];
+	}
+
+	if (WANT_F) {
+		const double grav = P.rho_g * vol * 0.25;
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) {
+			if (nd[a] < nn_owned) {
+				atomicAdd(&F[2 * nd[a]], alpha * dx[a] + grav * sx);
+				atomicAdd(&F[2 * nd[a] + 1], alpha * dy[a] + grav * sy);
+			}
+		}
+	}
+	if (WANT_J) {
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) {
+			const double Pa = 2.0 * alpha * X[a], Qa = 0.5 * alpha * Y[a], Ra = 0.5 * alpha * Z[a];
+			const double Sa = 2.0 * alpha * Y[a], Ta = 0.5 * alpha * X[a];
+			const double Ua = alpha * X[a], Va = 0.5 * alpha * Y[a];
+			const double Ea = gamma * dx[a], Ga = gamma * dy[a];
+			#pragma unroll
+			for (int b = 0; b < 4; ++b) {
+				const int slot = tet_blk[(a * 4 + b) * nt + t];
+				if (slot < 0) continue;
+				const double jxx = Pa * X[b] + Qa * Y[b] + Ra * Z[b] + Ea * dx[b];
+				const double jyy = Sa * Y[b] + Ta * X[b] + Ra * Z[b] + Ga * dy[b];
+				const double jxy = Ua * Y[b] + Va * X[b] + Ea * dy[b];           // row (x,a), col (y,b)
+				const double jyx = alpha * Y[a] * X[b] + 0.5 * alpha * X[a] * Y[b] + Ga * dx[b];   // row (y,a), col (x,b)
+				double* v = val + 4 * (size_t)slot;
+				atomicAdd(v + 0, jxx); atomicAdd(v + 1, jxy);
+				atomicAdd(v + 2, jyx); atomicAdd(v + 3, jyy);
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------- facet kernel
+// Basal sliding  +1/2 beta u.u dGamma_b  and water pressure  -f_w u.n_h  on
+// dGamma_bw / dGamma_lt (cslvr/momentumbp.py:473-491), exact P1 mass integrals.
+template <bool WANT_F, bool WANT_J>
+__global__ void __launch_bounds__(TPB)
+k_facet(int nf, int nt, const int32_t* __restrict__ fcell, const int32_t* __restrict__ finfo,
+        const int4* __restrict__ tets, const double4* __restrict__ geo,
+        const int32_t* __restrict__ v2n, const double2* __restrict__ u,
+        const double* __restrict__ beta, const int32_t* __restrict__ tet_blk,
+        int nn_owned, double* __restrict__ F, double* __restrict__ val, AsmParams P)
+{
+	const int f = blockIdx.x * blockDim.x + threadIdx.x;
+	if (f >= nf) return;
+	const int cell = fcell[f], info = finfo[f];
+	const int lf = info & 0xff;
+	const bool basal = (info >> 8) & 1, press = (info >> 9) & 1;
+	const int4 tv = tets[cell];
+	const int vid[4] = { tv.x, tv.y, tv.z, tv.w };
+	int la[3], k = 0;
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) if (a != lf) la[k++] = a;
+	double4 p[3];
+	int nd[3];
+	double2 uu[3];
+	double bt[3];
+	#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		const int v = vid[la[a]];
+		p[a] = geo[v]; nd[a] = v2n ? v2n[v] : v; uu[a] = u[nd[a]]; bt[a] = beta[v];
+	}
+	const double4 po = geo[vid[lf]];
+	const double ax = p[1].x - p[0].x, ay = p[1].y - p[0].y, az = p[1].z - p[0].z;
+	const double bx = p[2].x - p[0].x, by = p[2].y - p[0].y, bz = p[2].z - p[0].z;
+	double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+	const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
+	const double area = 0.5 * nrm;
+	// outward: away from the opposite vertex
+	const double side = nx * (po.x - p[0].x) + ny * (po.y - p[0].y) + nz * (po.z - p[0].z);
+	const double sgn = (side > 0.0 ? -1.0 : 1.0) / nrm;
+	nx *= sgn; ny *= sgn;
+
+	double Fx[3] = { 0, 0, 0 }, Fy[3] = { 0, 0, 0 };
+	if (basal) {
+		// K[a][b] = |f| sum_d beta_d int(l_a l_b l_d),  int = {1/10, 1/30, 1/60}
+		const double bs = bt[0] + bt[1] + bt[2];
+		double K[3][3];
+		#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			#pragma unroll
+			for (int b = 0; b < 3; ++b)
+				K[a][b] = (a == b) ? area * (bt[a] * (1.0 / 10.0) + (bs - bt[a]) * (1.0 / 30.0))
+				                   : area * ((bt[a] + bt[b]) * (1.0 / 30.0) + (bs - bt[a] - bt[b]) * (1.0 / 60.0));
+		#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			#pragma unroll
+			for (int b = 0; b < 3; ++b) {
+				Fx[a] += K[a][b] * uu[b].x; Fy[a] += K[a][b] * uu[b].y;
+				if (WANT_J) {
+					const int slot = tet_blk[(la[a] * 4 + la[b]) * nt + cell];
+					if (slot >= 0) { atomicAdd(val + 4 * (size_t)slot, K[a][b]); atomicAdd(val + 4 * (size_t)slot + 3, K[a][b]); }
+				}
+			}
+	}
+	if (press && WANT_F) {
+		// f_w = rho g (S - z) - rho_sw g D,  D = -min(0, z)   (momentumbp.py:477, d3model.py:858-861)
+		double fw[3];
+		#pragma unroll
+		for (int a = 0; a < 3; ++a) fw[a] = P.rho_g * (p[a].w - p[a].z) - P.rho_sw_g * (-fmin(0.0, p[a].z));
+		const double fs = fw[0] + fw[1] + fw[2];
+		#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			const double m = area * (fs + fw[a]) * (1.0 / 12.0);
+			Fx[a] -= nx * m; Fy[a] -= ny * m;
+		}
+	}
+	if (WANT_F) {
+		#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			if (nd[a] < nn_owned) { atomicAdd(&F[2 * nd[a]], Fx[a]); atomicAdd(&F[2 * nd[a] + 1], Fy[a]); }
+	}
+}
+
+static AsmParams make_params(const bp_ctx* c)
+{
+	AsmParams P;
+	P.n = c->prm.n; P.eps_reg = c->prm.eps_reg;
+	P.rho_g = c->prm.rho_i * c->prm.g; P.rho_sw_g = c->prm.rho_sw * c->prm.g;
+	P.n_quad = (int)c->quad_wts.size();
+	P.n_is_3 = (c->prm.n == 3.0);
+	return P;
+}
+
+void bp_upload_quadrature(bp_ctx* c)
+{
+	cudaMemcpyToSymbol(c_qw, c->quad_wts.data(), c->quad_wts.size() * sizeof(double));
+	cudaMemcpyToSymbol(c_ql, c->quad_pts.data(), c->quad_pts.size() * sizeof(double));
+}
+
+void bp_launch_assemble(bp_ctx* c, int what)
+{
+	const AsmParams P = make_params(c);
+	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
+	if (wf) cudaMemsetAsync(c->d_F, 0, 2 * c->nn * sizeof(double), c->stream);
+	if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->nnzb * 4 * sizeof(double), c->stream);
+	const int gc = (int)((c->nt + TPB - 1) / TPB), gf = (int)((c->nf + TPB - 1) / TPB);
+	const double2* u2 = (const double2*)c->d_u;
+	#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
+	#define FACET(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
+	if (wf && wj) { CELL(true, true); if (c->nf) FACET(true, true); }
+	else if (wf)  { CELL(true, false); if (c->nf) FACET(true, false); }
+	else if (wj)  { CELL(false, true); if (c->nf) FACET(false, true); }
+	c->launches += 1 + (c->nf ? 1 : 0);
+	if (wj) c->have_J = true;
+}
+
+// ---------------------------------------------------------------- reductions
+// Block partials -> d_part[slot][block]; the last block to finish sums them in a
+// fixed order (deterministic) and writes d_sc[slot...].
+template <int NV>
+__device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], double* part, int pstride,
+                                                      unsigned* counter, double* out)
+{
+	__shared__ double sm[NV][32];
+	__shared__ bool last;
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+	#pragma unroll
+	for (int i = 0; i < NV; ++i) {
+		double x = v[i];
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+		if (lane == 0) sm[i][w] = x;
+	}
+	__syncthreads();
+	if (w == 0) {
+		#pragma unroll
+		for (int i = 0; i < NV; ++i) {
+			double x = (lane < nw) ? sm[i][lane] : 0.0;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+			if (lane == 0) part[i * pstride + blockIdx.x] = x;
+		}
+	}
+	if (threadIdx.x == 0) {
+		__threadfence();
+		const unsigned ticket = atomicAdd(counter, 1u);
+		last = (ticket == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (last) {
+		__threadfence();
+		#pragma unroll
+		for (int i = 0; i < NV; ++i) {
+			double x = 0.0;
+			for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) x += ((volatile double*)part)[i * pstride + b];
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+			__syncthreads();
+			if (lane == 0) sm[i][w] = x;
+			__syncthreads();
+			if (w == 0) {
+				x = (lane < nw) ? sm[i][lane] : 0.0;
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+				if (lane == 0) out[i] = x;
+			}
+		}
+		if (threadIdx.x == 0) *counter = 0u;
+	}
+}
+
+#define RED_BLOCKS_MAX 4096
+static inline int red_blocks(int64_t n_items, int per_block)
+{
+	int64_t b = (n_items + per_block - 1) / per_block;
+	if (b < 1) b = 1;
+	if (b > 148 * 8) b = 148 * 8;
+	return (int)b;
+}
+
+// ---------------------------------------------------------------- SpMV (BSR 2x2)
+// 16 lanes per block row: lane k reads block k of the row (32 B, contiguous across
+// the half-warp) and the {x,y} pair of its column node (16 B gather).
+template <bool WITH_DOT>
+__global__ void __launch_bounds__(256)
+k_spmv(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+       const double2* __restrict__ val, const double2* __restrict__ x, double2* __restrict__ y,
+       const double* __restrict__ sc, double* part, unsigned* counter, double* out)
+{
+	if (WITH_DOT && sc[SC_DONE] != 0.0) return;
+	double acc[1] = { 0.0 };
+	const int l16 = threadIdx.x & 15;
+	const int rows_per_block = blockDim.x >> 4;
+	for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 4); row < nrows; row += gridDim.x * rows_per_block) {
+		const int k0 = rowptr[row], k1 = rowptr[row + 1];
+		double s0 = 0.0, s1 = 0.0;
+		for (int k = k0 + l16; k < k1; k += 16) {
+			const double2 v01 = val[2 * (size_t)k], v23 = val[2 * (size_t)k + 1];
+			const double2 xv = x[col[k]];
+			s0 += v01.x * xv.x + v01.y * xv.y;
+			s1 += v23.x * xv.x + v23.y * xv.y;
+		}
+		#pragma unroll
+		for (int o = 8; o > 0; o >>= 1) {
+			s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+			s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+		}
+		if (l16 == 0) {
+			y[row] = make_double2(s0, s1);
+			if (WITH_DOT) { const double2 xr = x[row]; acc[0] += xr.x * s0 + xr.y * s1; }
+		}
+	}
+	if (WITH_DOT) block_reduce_finalize<1>(acc, part, RED_BLOCKS_MAX, counter, out);
+}
+
+void bp_launch_spmv(bp_ctx* c, const double* x, double* y, int with_dot)
+{
+	const int rows_per_block = 256 / 16;
+	const int grid = red_blocks(c->nn_owned, rows_per_block);
+	if (with_dot)
+		k_spmv<true><<<grid, 256, 0, c->stream>>>((int)c->nn_owned, c->d_rowptr, c->d_col, (const double2*)c->d_val,
+			(const double2*)x, (double2*)y, c->d_sc, c->d_part, c->d_counter, c->d_sc + SC_PAP);
+	else
+		k_spmv<false><<<grid, 256, 0, c->stream>>>((int)c->nn_owned, c->d_rowptr, c->d_col, (const double2*)c->d_val,
+			(const double2*)x, (double2*)y, c->d_sc, c->d_part, c->d_counter, c->d_sc + SC_PAP);
+	c->launches++;
+}
+
+// ---------------------------------------------------------------- vector glue
+__global__ void k_gather_in(int n2, const int32_t* __restrict__ ext_dof, const double* __restrict__ ext, double* __restrict__ in)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+		in[i] = ext[ext_dof ? ext_dof[i] : i];
+}
+__global__ void k_scatter_out(int n2, const int32_t* __restrict__ ext_dof, const double* __restrict__ in, double* __restrict__ ext)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+		ext[ext_dof ? ext_dof[i] : i] = in[i];
+}
+void bp_launch_gather_in(bp_ctx* c, const double* ext, double* internal)
+{
+	const int n2 = (int)(2 * c->nn);
+	k_gather_in<<<red_blocks(n2, 256), 256, 0, c->stream>>>(n2, c->d_ext_dof, ext, internal);
+	c->launches++;
+}
+void bp_launch_scatter_out(bp_ctx* c, const double* internal, double* ext)
+{
+	const int n2 = (int)(2 * c->nn);
+	k_scatter_out<<<red_blocks(n2, 256), 256, 0, c->stream>>>(n2, c->d_ext_dof, internal, ext);
+	c->launches++;
+}
+
+__global__ void k_csr_export(int64_t nnz, const int32_t* __restrict__ src, const double* __restrict__ val, double* __restrict__ out)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+		out[i] = val[src[i]];
+}
+void bp_launch_csr_export(bp_ctx* c, double* out)
+{
+	const int64_t nnz = c->csr_indptr.back();
+	k_csr_export<<<red_blocks(nnz, 256), 256, 0, c->stream>>>(nnz, c->d_csr_src, c->d_val, out);
+	c->launches++;
+}
+
+__global__ void k_set_S(int nv, const double* __restrict__ S, double4* geo)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) geo[i].w = S[i];
+}
+void bp_launch_set_S(bp_ctx* c, const double* S_dev)
+{
+	k_set_S<<<red_blocks(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, S_dev, c->d_geo);
+	c->launches++;
+}
+
+__global__ void k_pack_halo(int n, const int32_t* __restrict__ nodes, const double2* __restrict__ vec, double2* __restrict__ buf)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) buf[i] = vec[nodes[i]];
+}
+void bp_launch_pack_halo(bp_ctx* c, const double* vec)
+{
+	if (c->n_send == 0) return;
+	k_pack_halo<<<red_blocks(c->n_send, 256), 256, 0, c->stream>>>((int)c->n_send, c->d_send_nodes, (const double2*)vec, (double2*)c->d_sendbuf);
+	c->launches++;
+}
+
+// dot over the owned entries -> d_sc[slot]
+__global__ void __launch_bounds__(256)
+k_dot(int n, const double* __restrict__ a, const double* __restrict__ b, double* part, unsigned* counter, double* out)
+{
+	double acc[1] = { 0.0 };
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) acc[0] += a[i] * b[i];
+	block_reduce_finalize<1>(acc, part, RED_BLOCKS_MAX, counter, out);
+}
+void bp_launch_dot_owned(bp_ctx* c, const double* a, const double* b, int sc_slot)
+{
+	const int n = (int)(2 * c->nn_owned);
+	k_dot<<<red_blocks(n, 1024), 256, 0, c->stream>>>(n, a, b, c->d_part, c->d_counter, c->d_sc + sc_slot);
+	c->launches++;
+}
+
+__global__ void k_axpy(int n, double alpha, const double* __restrict__ x, double* __restrict__ y)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) y[i] += alpha * x[i];
+}
+void bp_launch_axpy(bp_ctx* c, double alpha, const double* x, double* y)
+{
+	const int n = (int)(2 * c->nn_owned);
+	k_axpy<<<red_blocks(n, 1024), 256, 0, c->stream>>>(n, alpha, x, y);
+	c->launches++;
+}
+
+// ---------------------------------------------------------------- preconditioner
+// dinv[row] = inverse of the 2x2 diagonal block (BLOCK_JACOBI), or diag(1/a00, 1/a11)
+// (JACOBI), or identity (NONE).
+__global__ void k_pc_setup(int nrows, int kind, const int32_t* __restrict__ diag, const double* __restrict__ val, double* __restrict__ dinv)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+		double a = 1.0, b = 0.0, cc = 0.0, d = 1.0;
+		if (kind != BP_PC_NONE && diag[i] >= 0) {
+			const double* v = val + 4 * (size_t)diag[i];
+			if (kind == BP_PC_JACOBI) { a = 1.0 / v[0]; d = 1.0 / v[3]; }
+			else {
+				const double idet = 1.0 / (v[0] * v[3] - v[1] * v[2]);
+				a = v[3] * idet; b = -v[1] * idet; cc = -v[2] * idet; d = v[0] * idet;
+			}
+		}
+		dinv[4 * (size_t)i] = a; dinv[4 * (size_t)i + 1] = b; dinv[4 * (size_t)i + 2] = cc; dinv[4 * (size_t)i + 3] = d;
+	}
+}
+void bp_launch_pc_setup(bp_ctx* c)
+{
+	int kind = c->prm.pc;
+	if (kind != BP_PC_NONE && kind != BP_PC_JACOBI) kind = BP_PC_BLOCK_JACOBI;
+	k_pc_setup<<<red_blocks(c->nn_owned, 256), 256, 0, c->stream>>>((int)c->nn_owned, kind, c->d_diag, c->d_val, c->d_dinv);
+	c->launches++;
+}
+
+// ---------------------------------------------------------------- PCG kernels
+// PETSc KSPCG semantics: zero initial guess, preconditioned residual norm ||z||_2,
+// converged when ||z|| <= max(rtol * ||z_0||, atol).
+__device__ __forceinline__ double2 apply_dinv(const double* __restrict__ dinv, int i, double2 r)
+{
+	const double2 d01 = ((const double2*)dinv)[2 * (size_t)i], d23 = ((const double2*)dinv)[2 * (size_t)i + 1];
+	return make_double2(d01.x * r.x + d01.y * r.y, d23.x * r.x + d23.y * r.y);
+}
+
+// x = 0, r = b, z = M^-1 r, p = z;  (rz, zz, rr)
+__global__ void __launch_bounds__(256)
+k_pcg_init(int nrows, const double2* __restrict__ b, const double* __restrict__ dinv,
+           double2* x, double2* r, double2* z, double2* p, double* part, unsigned* counter, double* sc)
+{
+	double acc[3] = { 0.0, 0.0, 0.0 };
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+		const double2 rv = b[i];
+		const double2 zv = apply_dinv(dinv, i, rv);
+		x[i] = make_double2(0.0, 0.0); r[i] = rv; z[i] = zv; p[i] = zv;
+		acc[0] += rv.x * zv.x + rv.y * zv.y; acc[1] += zv.x * zv.x + zv.y * zv.y; acc[2] += rv.x * rv.x + rv.y * rv.y;
+	}
+	block_reduce_finalize<3>(acc, part, RED_BLOCKS_MAX, counter, sc + SC_RZ_NEXT);
+}
+
+// alpha = rz / pAp;  x += alpha p;  r -= alpha Ap;  z = M^-1 r;  (rz_next, zz, rr)
+__global__ void __launch_bounds__(256)
+k_pcg_update(int nrows, const double* __restrict__ dinv, const double2* __restrict__ p, const double2* __restrict__ Ap,
+             double2* x, double2* r, double2* z, double* part, unsigned* counter, double* sc)
+{
+	if (sc[SC_DONE] != 0.0) return;
+	const double pAp = sc[SC_PAP];
+	const double alpha = sc[SC_RZ] / pAp;
+	double acc[3] = { 0.0, 0.0, 0.0 };
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+		const double2 pv = p[i], av = Ap[i];
+		double2 xv = x[i], rv = r[i];
+		xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+		rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+		const double2 zv = apply_dinv(dinv, i, rv);
+		x[i] = xv; r[i] = rv; z[i] = zv;
+		acc[0] += rv.x * zv.x + rv.y * zv.y; acc[1] += zv.x * zv.x + zv.y * zv.y; acc[2] += rv.x * rv.x + rv.y * rv.y;
+	}
+	block_reduce_finalize<3>(acc, part, RED_BLOCKS_MAX, counter, sc + SC_RZ_NEXT);
+}
+
+// convergence test + p = z + beta p.  One designated thread does the bookkeeping.
+__global__ void __launch_bounds__(256)
+k_pcg_p(int nrows, int first, double rtol, double atol, const double2* __restrict__ z, double2* p, double* sc)
+{
+	if (!first && sc[SC_DONE] != 0.0) return;
+	const double rz = sc[SC_RZ], rz_next = sc[SC_RZ_NEXT], zz = sc[SC_ZZ], pAp = sc[SC_PAP];
+	const double norm = sqrt(zz);
+	const double norm0 = first ? norm : sc[SC_NORM0];
+	const bool bad = !first && !(pAp > 0.0);
+	const bool conv = bad || !(norm > fmax(rtol * norm0, atol));     // also stops on NaN
+	const double beta = first ? 0.0 : rz_next / rz;
+	if (!conv && !first)
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+			const double2 zv = z[i], pv = p[i];
+			p[i] = make_double2(zv.x + beta * pv.x, zv.y + beta * pv.y);
+		}
+	// bookkeeping by the last thread of the last block: SC_RZ is read by every thread
+	// above, so it is rotated by the next kernel in the stream instead (k_pcg_rotate).
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
+		sc[SC_NORM] = norm;
+		if (first) { sc[SC_NORM0] = norm; sc[SC_ITERS] = 0.0; sc[SC_BREAKDOWN] = 0.0; }
+		else sc[SC_ITERS] += 1.0;
+		if (bad) sc[SC_BREAKDOWN] = 1.0;
+		sc[SC_TMP] = conv ? 1.0 : 0.0;
+	}
+}
+__global__ void k_pcg_rotate(double* sc)
+{
+	sc[SC_RZ] = sc[SC_RZ_NEXT];
+	if (sc[SC_TMP] != 0.0) sc[SC_DONE] = 1.0;
+}
+
+void bp_launch_pcg_init(bp_ctx* c)
+{
+	const int n = (int)c->nn_owned;
+	cudaMemsetAsync(c->d_sc + SC_DONE, 0, sizeof(double), c->stream);
+	k_pcg_init<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, (const double2*)c->d_F, c->d_dinv, (double2*)c->d_dx, (double2*)c->d_r,
+		(double2*)c->d_z, (double2*)c->d_p, c->d_part, c->d_counter, c->d_sc);
+	c->launches++;
+}
+void bp_launch_pcg_update(bp_ctx* c)
+{
+	const int n = (int)c->nn_owned;
+	k_pcg_update<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, c->d_dinv, (const double2*)c->d_p, (const double2*)c->d_Ap,
+		(double2*)c->d_dx, (double2*)c->d_r, (double2*)c->d_z, c->d_part, c->d_counter, c->d_sc);
+	c->launches++;
+}
+void bp_launch_pcg_p_impl(bp_ctx* c, int first)
+{
+	const int n = (int)c->nn_owned;
+	k_pcg_p<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, first, c->prm.krylov_rtol, c->prm.krylov_atol, (const double2*)c->d_z, (double2*)c->d_p, c->d_sc);
+	k_pcg_rotate<<<1, 1, 0, c->stream>>>(c->d_sc);
+	c->launches += 2;
+}
+void bp_launch_pcg_p(bp_ctx* c) { bp_launch_pcg_p_impl(c, 0); }
+
+// sum d_sc[slot..slot+count) across the contexts of an in-process group (same device)
+struct ScPtrs { double* p[16]; };
+__global__ void k_sum_scalars(ScPtrs P, int n, int slot, int count)
+{
+	const int i = threadIdx.x;
+	if (i >= count) return;
+	double s = 0.0;
+	for (int r = 0; r < n; ++r) s += P.p[r][slot + i];
+	for (int r = 0; r < n; ++r) P.p[r][slot + i] = s;
+}
+void bp_launch_sum_scalars(bp_ctx** ctxs, int n, int slot, int count)
+{
+	ScPtrs P;
+	for (int r = 0; r < n; ++r) P.p[r] = ctxs[r]->d_sc;
+	k_sum_scalars<<<1, 32, 0, ctxs[0]->stream>>>(P, n, slot, count);
+	ctxs[0]->launches++;
+}

@@ -1,0 +1,291 @@
+// bp_setup.cu -- one-off host-side digestion of the mesh and dof map.
+//
+// Replaces what dolfin does once per FunctionSpace in the reference: DofMapBuilder
+// for QM2 (cslvr/model.py:438-447), the periodic merge (cslvr/d3model.py:62-108) and
+// SparsityPatternBuilder (SURVEY A-S).  Output: node-blocked (2x2) BSR pattern of the
+// Jacobian for the owned rows, the per-tet block slots used by the assembly kernels,
+// and -- lazily -- the scalar CSR pattern in the caller's dof numbering.
+#include "bp_internal.h"
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <numeric>
+
+int bp_fail(bp_ctx* c, int code, const char* fmt, ...)
+{
+	static thread_local char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	extern std::string g_bp_create_error;
+	if (c) c->err = buf; else g_bp_create_error = buf;
+	return code;
+}
+
+template <class T>
+static int upload(bp_ctx* c, T** dst, const T* src, size_t n)
+{
+	*dst = nullptr;
+	if (n == 0) n = 1;
+	BP_CUDA(c, cudaMalloc((void**)dst, n * sizeof(T)));
+	if (src) BP_CUDA(c, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+	return BP_OK;
+}
+#define UP(dst, src, n) do { int rc_ = upload(c, &(dst), (src), (size_t)(n)); if (rc_) return rc_; } while (0)
+
+int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
+{
+	const int64_t nv = m->n_vertices, nt = m->n_cells;
+	if (nv <= 0 || nt <= 0 || !m->coords || !m->cells)
+		return bp_fail(c, BP_ERR_ARG, "bp_mesh: empty mesh or NULL coords/cells");
+	if (nv > INT32_MAX / 4 || nt > INT32_MAX / 32)
+		return bp_fail(c, BP_ERR_ARG, "bp_mesh: mesh too large for 32-bit slots on one rank");
+	c->nv = nv; c->nt = nt; c->nd_ext = m->n_dofs;
+	for (int64_t i = 0; i < nt * 4; ++i)
+		if (m->cells[i] < 0 || m->cells[i] >= nv)
+			return bp_fail(c, BP_ERR_ARG, "bp_mesh: cells[%lld] = %d out of range", (long long)i, m->cells[i]);
+
+	// ---- nodes --------------------------------------------------------------
+	std::vector<int32_t> v2n(nv, -1);
+	if (m->cell_dofs) {
+		if (m->n_owned_nodes >= 0)
+			return bp_fail(c, BP_ERR_ARG, "bp_mesh: a partitioned mesh requires the canonical numbering (cell_dofs == NULL)");
+		if (m->n_dofs <= 0 || (m->n_dofs & 1))
+			return bp_fail(c, BP_ERR_ARG, "bp_mesh: n_dofs must be positive and even with cell_dofs");
+		// a node is identified by its u_x dof; nodes are numbered by ascending u_x dof
+		std::vector<int32_t> dof_node(m->n_dofs, -1), ydof(m->n_dofs, -1);
+		for (int64_t t = 0; t < nt; ++t)
+			for (int a = 0; a < 4; ++a) {
+				int32_t dx = m->cell_dofs[t * 8 + a], dy = m->cell_dofs[t * 8 + 4 + a];
+				if (dx < 0 || dx >= m->n_dofs || dy < 0 || dy >= m->n_dofs || dx == dy)
+					return bp_fail(c, BP_ERR_ARG, "bp_mesh: cell_dofs of cell %lld out of range", (long long)t);
+				if (ydof[dx] >= 0 && ydof[dx] != dy)
+					return bp_fail(c, BP_ERR_ARG, "bp_mesh: cell_dofs is not a P1xP1 mixed dof map (u_x dof %d pairs with u_y dofs %d and %d)", dx, ydof[dx], dy);
+				ydof[dx] = dy;
+			}
+		int32_t nn = 0;
+		for (int64_t d = 0; d < m->n_dofs; ++d) if (ydof[d] >= 0) dof_node[d] = nn++;
+		if ((int64_t)nn * 2 != m->n_dofs)
+			return bp_fail(c, BP_ERR_ARG, "bp_mesh: cell_dofs references %d nodes but n_dofs = %lld", nn, (long long)m->n_dofs);
+		c->nn = nn;
+		c->h_ext_dof.resize((size_t)nn * 2);
+		c->identity_dofs = true;
+		for (int64_t d = 0; d < m->n_dofs; ++d) if (ydof[d] >= 0) {
+			int32_t i = dof_node[d];
+			c->h_ext_dof[2 * i] = (int32_t)d; c->h_ext_dof[2 * i + 1] = ydof[d];
+			if (d != 2 * i || ydof[d] != 2 * i + 1) c->identity_dofs = false;
+		}
+		for (int64_t t = 0; t < nt; ++t)
+			for (int a = 0; a < 4; ++a) {
+				int32_t v = m->cells[t * 4 + a], i = dof_node[m->cell_dofs[t * 8 + a]];
+				if (v2n[v] >= 0 && v2n[v] != i)
+					return bp_fail(c, BP_ERR_ARG, "bp_mesh: vertex %d maps to two different dofs", v);
+				v2n[v] = i;
+			}
+	} else {
+		int32_t mx = -1;
+		for (int64_t v = 0; v < nv; ++v) {
+			v2n[v] = m->vertex_to_node ? m->vertex_to_node[v] : (int32_t)v;
+			if (v2n[v] < 0) return bp_fail(c, BP_ERR_ARG, "bp_mesh: vertex_to_node[%lld] < 0", (long long)v);
+			mx = std::max(mx, v2n[v]);
+		}
+		c->nn = (int64_t)mx + 1;
+		if (m->n_dofs != 2 * c->nn)
+			return bp_fail(c, BP_ERR_ARG, "bp_mesh: n_dofs = %lld but the node map has %lld nodes", (long long)m->n_dofs, (long long)c->nn);
+		c->identity_dofs = true;
+		c->h_ext_dof.resize((size_t)c->nn * 2);
+		std::iota(c->h_ext_dof.begin(), c->h_ext_dof.end(), 0);
+	}
+	c->identity_v2n = true;
+	for (int64_t v = 0; v < nv; ++v) {
+		if (v2n[v] < 0) v2n[v] = 0;                 // vertex not used by any cell
+		if (v2n[v] != v) c->identity_v2n = false;
+	}
+	const int64_t nn = c->nn;
+	c->nn_owned = (m->n_owned_nodes >= 0) ? m->n_owned_nodes : nn;
+	if (c->nn_owned > nn) return bp_fail(c, BP_ERR_ARG, "bp_mesh: n_owned_nodes > number of nodes");
+	const int64_t no = c->nn_owned;
+
+	// ---- node -> incident cells ------------------------------------------------
+	std::vector<int32_t> cn((size_t)nt * 4);
+	for (int64_t i = 0; i < nt * 4; ++i) cn[i] = v2n[m->cells[i]];
+	std::vector<int64_t> nptr(nn + 1, 0);
+	for (int64_t i = 0; i < nt * 4; ++i) nptr[cn[i] + 1]++;
+	for (int64_t i = 0; i < nn; ++i) nptr[i + 1] += nptr[i];
+	std::vector<int32_t> ncell(nptr[nn]);
+	{
+		std::vector<int64_t> fill(nptr.begin(), nptr.end() - 1);
+		for (int64_t t = 0; t < nt; ++t)
+			for (int a = 0; a < 4; ++a) ncell[fill[cn[t * 4 + a]]++] = (int32_t)t;
+	}
+	// ---- BSR pattern of the owned rows: row i = sorted unique nodes sharing a cell ---
+	c->h_rowptr.assign(no + 1, 0);
+	#pragma omp parallel
+	{
+		std::vector<int32_t> tmp;
+		#pragma omp for schedule(static)
+		for (int64_t i = 0; i < no; ++i) {
+			tmp.clear();
+			for (int64_t k = nptr[i]; k < nptr[i + 1]; ++k)
+				for (int a = 0; a < 4; ++a) tmp.push_back(cn[(int64_t)ncell[k] * 4 + a]);
+			std::sort(tmp.begin(), tmp.end());
+			c->h_rowptr[i + 1] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+		}
+	}
+	for (int64_t i = 0; i < no; ++i) {
+		int64_t s = (int64_t)c->h_rowptr[i] + c->h_rowptr[i + 1];
+		if (s > INT32_MAX / 4) return bp_fail(c, BP_ERR_ARG, "bp_mesh: too many Jacobian blocks for one rank");
+		c->h_rowptr[i + 1] = (int32_t)s;
+	}
+	c->nnzb = c->h_rowptr[no];
+	c->h_col.resize(c->nnzb);
+	std::vector<int32_t> diag(no, -1);
+	#pragma omp parallel
+	{
+		std::vector<int32_t> tmp;
+		#pragma omp for schedule(static)
+		for (int64_t i = 0; i < no; ++i) {
+			tmp.clear();
+			for (int64_t k = nptr[i]; k < nptr[i + 1]; ++k)
+				for (int a = 0; a < 4; ++a) tmp.push_back(cn[(int64_t)ncell[k] * 4 + a]);
+			std::sort(tmp.begin(), tmp.end());
+			size_t nu = std::unique(tmp.begin(), tmp.end()) - tmp.begin();
+			int32_t* dst = c->h_col.data() + c->h_rowptr[i];
+			for (size_t k = 0; k < nu; ++k) { dst[k] = tmp[k]; if (tmp[k] == i) diag[i] = c->h_rowptr[i] + (int32_t)k; }
+		}
+	}
+	// rows of owned nodes that touch no cell get an empty row; give them a diagonal guard
+	for (int64_t i = 0; i < no; ++i)
+		if (diag[i] < 0 && nptr[i + 1] > nptr[i]) return bp_fail(c, BP_ERR_ARG, "internal: missing diagonal block");
+
+	// ---- per-tet block slots [16][nt] ------------------------------------------
+	std::vector<int32_t> tet_blk((size_t)nt * 16);
+	#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < nt; ++t)
+		for (int a = 0; a < 4; ++a) {
+			int32_t r = cn[t * 4 + a];
+			for (int b = 0; b < 4; ++b) {
+				int32_t slot = -1;
+				if (r < no) {
+					const int32_t* lo = c->h_col.data() + c->h_rowptr[r];
+					const int32_t* hi = c->h_col.data() + c->h_rowptr[r + 1];
+					slot = (int32_t)(std::lower_bound(lo, hi, cn[t * 4 + b]) - c->h_col.data());
+				}
+				tet_blk[(size_t)(a * 4 + b) * nt + t] = slot;
+			}
+		}
+
+	// ---- facets that integrate something ----------------------------------------
+	// dGamma_b = {3,5}, dGamma_bw = {5}, dGamma_lt = {4,10}: cslvr/d3model.py:576-598
+	std::vector<int32_t> fcell, finfo;
+	const bool lateral = (!c->prm.periodic) && c->prm.use_pressure_bc;    // momentumbp.py:488
+	c->n_basal = 0;
+	for (int64_t f = 0; f < m->n_facets; ++f) {
+		int32_t mk = m->facet_marker[f], cell = m->facet_cell[f], lf = m->facet_local[f];
+		if (cell < 0 || cell >= nt || lf < 0 || lf > 3)
+			return bp_fail(c, BP_ERR_ARG, "bp_mesh: facet %lld has cell %d / local facet %d", (long long)f, cell, lf);
+		int basal = (mk == 3 || mk == 5), press = (mk == 5) || (lateral && (mk == 4 || mk == 10));
+		if (!basal && !press) continue;
+		c->n_basal += basal;
+		fcell.push_back(cell);
+		finfo.push_back(lf | (basal << 8) | (press << 9));
+	}
+	c->nf = (int64_t)fcell.size();
+
+	// ---- halo -----------------------------------------------------------------
+	c->n_nbr = (m->n_owned_nodes >= 0) ? m->n_neighbors : 0;
+	if (c->n_nbr > 0) {
+		c->nbr_rank.assign(m->neighbor_rank, m->neighbor_rank + c->n_nbr);
+		c->send_ptr.assign(m->send_ptr, m->send_ptr + c->n_nbr + 1);
+		c->recv_ptr.assign(m->recv_ptr, m->recv_ptr + c->n_nbr + 1);
+		c->n_send = c->send_ptr[c->n_nbr];
+		if (c->recv_ptr[c->n_nbr] != nn - no)
+			return bp_fail(c, BP_ERR_ARG, "bp_mesh: recv_ptr covers %lld ghost nodes, mesh has %lld", (long long)c->recv_ptr[c->n_nbr], (long long)(nn - no));
+		for (int64_t k = 0; k < c->n_send; ++k)
+			if (m->send_nodes[k] < 0 || m->send_nodes[k] >= no)
+				return bp_fail(c, BP_ERR_ARG, "bp_mesh: send_nodes[%lld] is not an owned node", (long long)k);
+		UP(c->d_send_nodes, m->send_nodes, c->n_send);
+		UP(c->d_sendbuf, (const double*)nullptr, 2 * c->n_send);
+	} else if (nn != no) {
+		return bp_fail(c, BP_ERR_ARG, "bp_mesh: ghost nodes without neighbours");
+	}
+
+	// ---- upload ---------------------------------------------------------------
+	{
+		std::vector<double4> geo(nv);
+		for (int64_t v = 0; v < nv; ++v)
+			geo[v] = make_double4(m->coords[3 * v], m->coords[3 * v + 1], m->coords[3 * v + 2], 0.0);
+		UP(c->d_geo, geo.data(), nv);
+	}
+	UP(c->d_A, (const double*)nullptr, nv);
+	UP(c->d_beta, (const double*)nullptr, nv);
+	UP(c->d_tets, (const int4*)m->cells, nt);
+	if (!c->identity_v2n) UP(c->d_v2n, v2n.data(), nv);
+	UP(c->d_tet_blk, tet_blk.data(), (size_t)nt * 16);
+	UP(c->d_fac_cell, fcell.data(), c->nf);
+	UP(c->d_fac_info, finfo.data(), c->nf);
+	if (!c->identity_dofs) UP(c->d_ext_dof, c->h_ext_dof.data(), 2 * nn);
+	UP(c->d_rowptr, c->h_rowptr.data(), no + 1);
+	UP(c->d_col, c->h_col.data(), c->nnzb);
+	UP(c->d_diag, diag.data(), no);
+	UP(c->d_val, (const double*)nullptr, (size_t)c->nnzb * 4);
+	double** vecs[] = { &c->d_u, &c->d_F, &c->d_dx, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap, &c->d_io, &c->d_io2 };
+	for (double** v : vecs) {
+		size_t len = std::max<size_t>((size_t)2 * nn, (size_t)std::max<int64_t>(std::max<int64_t>(c->nd_ext, nv), 1));
+		UP(*v, (const double*)nullptr, len);
+		BP_CUDA(c, cudaMemset(*v, 0, len * sizeof(double)));
+	}
+	UP(c->d_dinv, (const double*)nullptr, (size_t)no * 4);
+	UP(c->d_sc, (const double*)nullptr, SC_COUNT);
+	BP_CUDA(c, cudaMemset(c->d_sc, 0, SC_COUNT * sizeof(double)));
+	UP(c->d_part, (const double*)nullptr, 4 * 4096);
+	UP(c->d_counter, (const unsigned*)nullptr, 16);
+	BP_CUDA(c, cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned)));
+	BP_CUDA(c, cudaMallocHost((void**)&c->h_sc, SC_COUNT * sizeof(double)));
+	BP_CUDA(c, cudaMemset(c->d_val, 0, (size_t)std::max<int64_t>(c->nnzb, 1) * 4 * sizeof(double)));
+	return BP_OK;
+}
+
+// Scalar CSR in the caller's numbering: row = caller's dof, columns ascending,
+// explicit zeros kept (dolfin SparsityPatternBuilder / PETSc AIJ, SURVEY A-S).
+int bp_build_csr_export(bp_ctx* c)
+{
+	if (c->have_csr) return BP_OK;
+	if (c->nn_owned != c->nn)
+		return bp_fail(c, BP_ERR_STATE, "CSR export is defined for an unpartitioned context only");
+	const int64_t nn = c->nn, nd = c->nd_ext;
+	// internal row (node, comp) of every caller dof
+	std::vector<int32_t> row_of(nd, -1);
+	for (int64_t i = 0; i < 2 * nn; ++i) row_of[c->h_ext_dof[i]] = (int32_t)i;
+	c->csr_indptr.assign(nd + 1, 0);
+	for (int64_t d = 0; d < nd; ++d) {
+		int32_t r = row_of[d];
+		int64_t len = (r < 0) ? 0 : 2 * (int64_t)(c->h_rowptr[r / 2 + 1] - c->h_rowptr[r / 2]);
+		c->csr_indptr[d + 1] = c->csr_indptr[d] + len;
+	}
+	const int64_t nnz = c->csr_indptr[nd];
+	c->csr_indices.resize(nnz);
+	std::vector<int32_t> src(nnz);
+	#pragma omp parallel
+	{
+		std::vector<std::pair<int32_t, int32_t>> tmp;
+		#pragma omp for schedule(static)
+		for (int64_t d = 0; d < nd; ++d) {
+			int32_t r = row_of[d];
+			if (r < 0) continue;
+			int32_t node = r / 2, comp = r % 2;
+			tmp.clear();
+			for (int32_t k = c->h_rowptr[node]; k < c->h_rowptr[node + 1]; ++k)
+				for (int cc = 0; cc < 2; ++cc)
+					tmp.push_back({ c->h_ext_dof[2 * c->h_col[k] + cc], k * 4 + comp * 2 + cc });
+			std::sort(tmp.begin(), tmp.end());
+			int64_t o = c->csr_indptr[d];
+			for (size_t k = 0; k < tmp.size(); ++k) { c->csr_indices[o + k] = tmp[k].first; src[o + k] = tmp[k].second; }
+		}
+	}
+	int rc = upload(c, &c->d_csr_src, src.data(), (size_t)nnz);
+	if (rc) return rc;
+	c->have_csr = true;
+	return BP_OK;
+}

@@ -1,0 +1,190 @@
+"""``MomentumBPBase`` / ``MomentumBP`` / ``MomentumDukowiczBP`` on the B200 path.
+
+Same class names, constructor arguments, ``solve_params`` dictionary, ``solve()``
+sequence and error behaviour as cslvr/momentumbp.py; the variational forms are not
+built symbolically -- the kernels implement them in closed form:
+
+* ``MomentumDukowiczBP`` (cslvr/momentumbp.py:406-506): action
+  ``A = (V_d - P_e) dOmega - S_l dGamma_b - P_b dGamma_bw [- P_b dGamma_lt]``,
+  residual = first variation (:500), Jacobian = second variation (physics.py:75-77);
+* ``MomentumBP`` (cslvr/momentumbp.py:289-399): ``inner(sigma, grad v) dOmega +
+  rho g grad_h S . v dOmega + beta u.v dGamma_b - p_e n_h.v dGamma_bw[,lt]`` (:372-381),
+  which is the same residual term by term (p_e = f_w, sigma:grad v = 2 eta d(epsdot));
+  both classes therefore drive the same kernels.
+"""
+import sys
+
+import numpy as np
+
+from . import capi
+from .d3model import D3Model, Function, DOLFIN_EPS
+from .inputoutput import print_text, print_min_max
+from .momentum import Momentum
+
+
+class MomentumBPBase(Momentum):
+
+	def __init__(self, model, solve_params=None, linear=False, use_lat_bcs=False,
+	             use_pressure_bc=True, device=0):
+		print_text("::: INITIALIZING BP VELOCITY BASE PHYSICS :::", cls=self)
+		if type(model) != D3Model:
+			s = ">>> MomentumBPBase REQUIRES A 'D3Model' INSTANCE, NOT %s <<<"
+			print_text(s % type(model), 'red', 1)
+			sys.exit(1)
+		if model.ff is None:
+			raise RuntimeError("model.calculate_boundaries() must be called before a momentum object is created")
+		if use_lat_bcs:
+			# cslvr/momentumbp.py:495 calls quasi_stress_tensor with three arguments (it
+			# takes two, :150): the reference raises here as well
+			raise TypeError("quasi_stress_tensor() takes 3 positional arguments but 4 were given "
+			                "(use_lat_bcs=True is broken in cslvr/momentumbp.py:495 too)")
+		self.Q = model.QM2
+		self.device = device
+		self.set_unknown(Function(self.Q, name='u_h'))
+		self.u_z = Function(model.Q, name='u_z')
+		self.set_boundary_conditions([])          # cslvr/momentumbp.py:101-112: none without mark_divide
+		self._ctx = None
+		self._ctx_key = None
+		super(MomentumBPBase, self).__init__(model=model, solve_params=solve_params, linear=linear,
+		                                     use_lat_bcs=use_lat_bcs, use_pressure_bc=use_pressure_bc)
+
+	def get_velocity(self):
+		"""(u_x, u_y, 0) from the unknown, cslvr/momentumbp.py:156-163."""
+		v = self.get_unknown().values
+		return v[0::2], v[1::2], np.zeros(v.size // 2)
+
+	def default_solve_params(self):
+		"""cslvr/momentumbp.py:165-203: Newton + CG + AMG, rtol 1e-9, 25 iterations,
+		relaxation 1.0 iff (isothermal or uniform T) and periodic, else 0.7."""
+		if (self.model.energy_dependent_rate_factor == False
+		    or (self.model.energy_dependent_rate_factor == True
+		        and np.unique(self.model.T.vector().get_local()).size == 1)) \
+		   and self.model.use_periodic:
+			relax = 1.0
+		else:
+			relax = 0.7
+		if self.linear:
+			params = {'linear_solver': 'cg', 'preconditioner': 'hypre_amg'}
+		else:
+			params = {'newton_solver': {
+				'linear_solver'           : 'cg',
+				'preconditioner'          : 'hypre_amg',
+				'relative_tolerance'      : 1e-9,
+				'relaxation_parameter'    : relax,
+				'maximum_iterations'      : 25,
+				'error_on_nonconvergence' : False,
+				'krylov_solver'           : {'monitor_convergence': False}}}
+		return {'solver'              : params,
+		        'solve_vert_velocity' : True,
+		        'solve_pressure'      : True,
+		        'vert_solve_method'   : 'mumps'}
+
+	# ---- the device context --------------------------------------------------
+	def _context(self):
+		m = self.model
+		X = m.mesh.coordinates()
+		key = (id(m.mesh), float(X[:, 2].sum()), float(np.abs(X[:, 2]).sum()), int(m.ff.sum()),
+		       bool(self.use_pressure_bc))
+		if self._ctx is None or key != self._ctx_key:
+			if self._ctx is not None:
+				self._ctx.close()
+			params = dict(n=m.n, eps_reg=m.eps_reg, rho_i=m.rho_i, rhosw=m.rhosw, g=m.g,
+			              periodic=m.use_periodic, use_pressure_bc=self.use_pressure_bc)
+			self._ctx = capi.BPContext(X, m.mesh.cells(), self.Q.dim(),
+			                           (m.facet_cell, m.facet_local, m.ff), params,
+			                           vertex_to_node=m.vertex_to_node if m.use_periodic else None,
+			                           device=self.device)
+			self._ctx_key = key
+		c = self._ctx
+		c.set_field(capi.FIELD_S, m.vertex_field(m.S))
+		c.set_field(capi.FIELD_A, m.vertex_field(m.A))
+		c.set_field(capi.FIELD_BETA, m.vertex_field(m.beta))
+		return c
+
+	_PC_MAP = {'hypre_amg': 'block_jacobi', 'amg': 'block_jacobi', 'default': 'block_jacobi',
+	           'none': 'none', 'jacobi': 'jacobi', 'block_jacobi': 'block_jacobi',
+	           'chebyshev': 'chebyshev', 'column': 'column'}
+
+	def _solver_kwargs(self, ns):
+		ks = ns.get('krylov_solver', {})
+		pc = ns.get('preconditioner', 'default')
+		if ns.get('linear_solver', 'cg') not in ('cg', 'default'):
+			print_text("    - linear_solver '%s' is served by the device PCG (the BP Hessian is SPD) -"
+			           % ns['linear_solver'], cls=self)
+		kw = dict(relative_tolerance=ns['relative_tolerance'],
+		          absolute_tolerance=ns.get('absolute_tolerance', 1e-10),
+		          maximum_iterations=ns['maximum_iterations'],
+		          relaxation_parameter=ns['relaxation_parameter'],
+		          error_on_nonconvergence=ns.get('error_on_nonconvergence', False),
+		          krylov_rtol=ks.get('relative_tolerance', 1e-5),
+		          krylov_atol=ks.get('absolute_tolerance', 1e-50),
+		          krylov_maxit=ks.get('maximum_iterations', 10000),
+		          preconditioner=self._PC_MAP.get(pc, 'block_jacobi'),
+		          verbose=ks.get('monitor_convergence', False) or ns.get('report', False),
+		          quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		return kw
+
+	def _newton_solve(self, ns):
+		c = self._context()
+		c.set_params(**self._solver_kwargs(ns))
+		u = self.get_unknown()
+		stats = c.newton_solve(u.values)
+		return stats
+
+	# ---- assemble(residual) / assemble(jacobian) ------------------------------
+	def assemble_residual(self, u=None):
+		c = self._context()
+		c.set_params(quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		F, _ = c.assemble(self.get_unknown().values if u is None else u, want_F=True, want_J=False)
+		return F
+
+	def assemble_jacobian(self, u=None):
+		"""(indptr, indices, values) of the CSR Jacobian in the QM2 dof numbering."""
+		c = self._context()
+		c.set_params(quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		_, J = c.assemble(self.get_unknown().values if u is None else u, want_F=False, want_J=True)
+		ip, ix = c.csr_pattern()
+		return ip, ix, J
+
+	# ---- cslvr/momentumbp.py:205-253 ------------------------
+	def solve_pressure(self, annotate=False):
+		print_text("::: solving BP pressure :::", cls=self)
+		print_text(">>> solve_pressure is not on the B200 path yet (SURVEY.md §8f rank 2); model.p unchanged <<<", 'red', 1)
+
+	def solve_vert_velocity(self, annotate=False):
+		print_text("::: solving BP vertical velocity :::", cls=self)
+		print_text(">>> solve_vert_velocity is not on the B200 path yet (SURVEY.md §8f rank 1); u_z unchanged <<<", 'red', 1)
+
+	def solve(self, annotate=False):
+		"""Newton solve of the first-order equations, cslvr/momentumbp.py:255-273:
+		cold start from DOLFIN_EPS, Physics.solve, then u_z and p if requested."""
+		model  = self.model
+		params = self.solve_params
+		model.assign_variable(self.get_unknown(), DOLFIN_EPS, annotate=annotate, cls=self)
+		super(MomentumBPBase, self).solve(annotate)
+		if params['solve_vert_velocity']: self.solve_vert_velocity(annotate)
+		if params['solve_pressure']:      self.solve_pressure(annotate)
+
+	def update_model_var(self, u, annotate=False):
+		"""copy (u_x, u_y) into model.u, cslvr/momentumbp.py:275-282."""
+		self.model.u.values[0::3] = u.values[0::2]
+		self.model.u.values[1::3] = u.values[1::2]
+		print_min_max(self.model.u, 'model.u', cls=self)
+
+
+class MomentumBP(MomentumBPBase):
+
+	def initialize(self, model, solve_params=None, linear=False, use_lat_bcs=False, use_pressure_bc=True):
+		print_text("::: INITIALIZING BP VELOCITY PHYSICS :::", cls=self)
+		if (not model.use_periodic and use_pressure_bc):
+			print_text("    - using water pressure lateral boundary condition -", cls=self)
+		self.set_residual('bp-classic')
+
+
+class MomentumDukowiczBP(MomentumBPBase):
+
+	def initialize(self, model, solve_params=None, linear=False, use_lat_bcs=False, use_pressure_bc=True):
+		print_text("::: INITIALIZING DUKOWICZ BP VELOCITY PHYSICS :::", cls=self)
+		if (not model.use_periodic and use_pressure_bc):
+			print_text("    - using water pressure lateral boundary condition -", cls=self)
+		self.set_residual('bp-dukowicz')

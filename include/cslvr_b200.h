@@ -1,0 +1,187 @@
+/* cslvr_b200.h -- C-ABI of the B200-native Blatter-Pattyn momentum path.
+ *
+ * The reference (pf4d/cslvr) has no FFI: its hot path leaves Python at ONE call,
+ *
+ *     dolfin.solve(F == 0, u, J=J, bcs=bcs, solver_parameters=params['solver'])
+ *                                                   cslvr/physics.py:673-678
+ *
+ * (equivalently assemble_system + solve(A,x,b,method,pc), cslvr/model.py:2679,2698).
+ * Everything below is what a ctypes binding at that seam needs: plain pointers
+ * and sizes, an opaque context, integer return codes (0 = ok) and a message via
+ * bp_last_error().  No torch types cross this boundary.  Host arrays are
+ * borrowed for the duration of the call; device arrays passed in are owned by
+ * the caller (PyTorch tensors in the Python glue) and never freed here.
+ */
+#ifndef CSLVR_B200_H
+#define CSLVR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BP_OK              0
+#define BP_ERR_ARG         1   /* bad argument / inconsistent mesh or dof map   */
+#define BP_ERR_CUDA        2   /* CUDA runtime error (no GPU, OOM, launch fail) */
+#define BP_ERR_STATE       3   /* call out of order (field not set, no J yet)   */
+#define BP_ERR_COMM        4   /* NCCL could not be loaded / collective failed  */
+#define BP_ERR_NONCONV     5   /* Newton did not converge and error_on_nonconvergence != 0 */
+
+/* field ids for bp_set_field.  All coefficient fields are VERTEX-indexed
+ * (n = n_vertices): a P1 Function f on a dolfin space with dofmap dm is passed
+ * as f_vertex[cells[c][a]] = f.vector()[dm.cell_dofs(c)[a]].                     */
+#define BP_FIELD_S      0   /* surface height S      cslvr/model.py:2511, momentumbp.py:467 */
+#define BP_FIELD_A      1   /* rate factor A         cslvr/model.py:2530, momentum.py:181   */
+#define BP_FIELD_BETA   2   /* basal traction beta   cslvr/model.py:2527, momentumbp.py:473 */
+
+/* what bp_assemble computes */
+#define BP_ASSEMBLE_F   1
+#define BP_ASSEMBLE_J   2
+
+/* preconditioners for the Krylov solve (reference: PETSc CG + hypre BoomerAMG,
+ * cslvr/momentumbp.py:183-184; here a device-resident PCG) */
+#define BP_PC_NONE          0
+#define BP_PC_JACOBI        1   /* point Jacobi                                   */
+#define BP_PC_BLOCK_JACOBI  2   /* 2x2 (u_x,u_y) node-block Jacobi                */
+#define BP_PC_CHEBYSHEV     3   /* Chebyshev polynomial smoother on block-Jacobi  */
+#define BP_PC_COLUMN        4   /* vertical-line (column block-tridiagonal) solve */
+
+typedef struct bp_ctx bp_ctx;
+
+/* The mesh and the P1xP1 dof map: what the adapter pulls out of dolfin
+ * (mesh.coordinates(), mesh.cells(), Q.dofmap().cell_dofs, model.ff) -- or what
+ * cslvr_b200.D3Model generates for BoxMesh.  Replaces D3Model's mesh/marker
+ * state consumed by the forms: cslvr/d3model.py:337-475, 477-626, 629-667.      */
+typedef struct {
+	int64_t        n_vertices;
+	int64_t        n_cells;
+	int64_t        n_dofs;          /* length of the caller's u vector                     */
+	const double*  coords;          /* [n_vertices*3] x,y,z per vertex (deformed mesh)      */
+	const int32_t* cells;           /* [n_cells*4] vertex ids                               */
+	const int32_t* cell_dofs;       /* [n_cells*8] component-major (UFC mixed P1xP1:
+	                                   0..3 = u_x, 4..7 = u_y), or NULL for the canonical
+	                                   numbering dof = 2*vertex_to_node[v] + c              */
+	const int32_t* vertex_to_node;  /* [n_vertices] periodic identification (d3model.py:
+	                                   62-108), or NULL = identity; used iff cell_dofs NULL */
+	int64_t        n_facets;        /* exterior facets carrying a marker                    */
+	const int32_t* facet_cell;      /* [n_facets] cell of the facet                         */
+	const int32_t* facet_local;     /* [n_facets] local facet = opposite local vertex       */
+	const int32_t* facet_marker;    /* [n_facets] D3Model marker ids (d3model.py:16-27):
+	                                   3/5 basal grounded/floating, 4/10 lateral; others
+	                                   are ignored                                          */
+	/* ---- partition (one context per GPU/rank); single rank: n_owned_nodes = -1 ---- */
+	int64_t        n_owned_nodes;   /* nodes [0,n_owned) are owned, the rest are ghosts;
+	                                   requires cell_dofs == NULL                           */
+	int32_t        n_neighbors;
+	const int32_t* neighbor_rank;   /* [n_neighbors]                                        */
+	const int64_t* send_ptr;        /* [n_neighbors+1] into send_nodes                      */
+	const int32_t* send_nodes;      /* owned local nodes whose values neighbour k needs     */
+	const int64_t* recv_ptr;        /* [n_neighbors+1] ghost nodes from neighbour k are
+	                                   n_owned + [recv_ptr[k], recv_ptr[k+1])               */
+} bp_mesh;
+
+/* Physical constants (cslvr/model.py:212-236) and solver parameters
+ * (cslvr/momentumbp.py:177-203; dolfin NewtonSolver / PETSc KSP defaults).       */
+typedef struct {
+	double  n;                 /* Glen exponent                      model.py:215 */
+	double  eps_reg;           /* strain-rate regularisation         model.py:212 */
+	double  rho_i;             /* ice density                        model.py:221 */
+	double  rho_sw;            /* sea-water density                  model.py:227 */
+	double  g;                 /* gravitational acceleration         model.py:236 */
+	int32_t periodic;          /* model.use_periodic                              */
+	int32_t use_pressure_bc;   /* momentumbp.py:488: lateral water pressure iff
+	                              !periodic && use_pressure_bc                    */
+	/* quadrature for the only non-polynomial factor, A(x)^(-1/n):
+	 * barycentric points [n_quad*4] and weights [n_quad] summing to 1            */
+	int32_t       n_quad;
+	const double* quad_points;
+	const double* quad_weights;
+	/* Newton (dolfin NewtonSolver semantics)                                    */
+	double  newton_rtol;       /* 'relative_tolerance'   momentumbp.py:185 (1e-9) */
+	double  newton_atol;       /* dolfin default 1e-10                            */
+	int32_t newton_maxit;      /* 'maximum_iterations'   momentumbp.py:187 (25)   */
+	double  newton_relax;      /* 'relaxation_parameter' momentumbp.py:186        */
+	int32_t error_on_nonconvergence;          /* momentumbp.py:188 (False)       */
+	/* Krylov (PETSc KSPCG defaults: rtol 1e-5, atol 1e-50, maxit 1e4)           */
+	double  krylov_rtol;
+	double  krylov_atol;
+	int32_t krylov_maxit;
+	int32_t pc;                /* BP_PC_*                                         */
+	int32_t pc_degree;         /* Chebyshev degree                                */
+	int32_t verbose;
+} bp_params;
+
+typedef struct {
+	int32_t converged;
+	int32_t newton_iterations;
+	int32_t krylov_iterations;       /* total over all Newton steps               */
+	double  residual_norm0;          /* ||F(u0)||_2                               */
+	double  residual_norm;           /* final ||F(u)||_2                          */
+	double  t_assemble_ms;           /* device time, CUDA events                  */
+	double  t_krylov_ms;
+	double  t_total_ms;
+	int32_t n_assemblies;
+	int32_t gpu_launches;            /* kernels launched by this call             */
+	double  residual_history[64];
+} bp_stats;
+
+/* ---- life cycle ---------------------------------------------------------- */
+int  bp_create(bp_ctx** out, const bp_mesh* mesh, const bp_params* params, int device);
+void bp_destroy(bp_ctx* ctx);
+const char* bp_last_error(const bp_ctx* ctx);      /* ctx may be NULL: last create error */
+int  bp_set_params(bp_ctx* ctx, const bp_params* params);
+int  bp_set_stream(bp_ctx* ctx, void* cuda_stream); /* run on the caller's stream        */
+
+/* coefficient Functions: model.init_beta / init_A / init_S,
+ * cslvr/model.py:486-497, 691-733 -> assign_variable model.py:2166-2221           */
+int  bp_set_field(bp_ctx* ctx, int field, const double* values, int64_t n, int on_device);
+
+/* sizes after the mesh has been digested */
+int  bp_get_sizes(const bp_ctx* ctx, int64_t* n_nodes, int64_t* n_dofs, int64_t* nnz_csr,
+                  int64_t* nnz_blocks, int64_t* n_cells, int64_t* n_basal_facets);
+
+/* ---- sparsity: dolfin SparsityPatternBuilder / PETSc AIJ layout -------------
+ * rows = caller's dofs, columns sorted ascending, explicit zeros kept.
+ * The arrays are host memory owned by the context.                                */
+int  bp_csr_pattern(bp_ctx* ctx, int64_t* nnz, const int64_t** indptr, const int32_t** indices);
+
+/* ---- assemble(F), assemble(J): replaces FFC tabulate_tensor + dolfin Assembler
+ * for cslvr/momentumbp.py:481-500 (action -> residual) and physics.py:75-77
+ * (Jacobian).  u, F: caller's dof numbering, length n_dofs.  J_values: aligned
+ * with bp_csr_pattern.  Any output may be NULL.  *_on_device: pointers are device
+ * pointers on the context's GPU.  The Jacobian also stays resident in the context
+ * (for bp_spmv / bp_krylov_solve).                                                 */
+int  bp_assemble(bp_ctx* ctx, int what, const double* u, double* F, double* J_values,
+                 int on_device);
+
+/* y = J x with the resident Jacobian (PETSc MatMult)                              */
+int  bp_spmv(bp_ctx* ctx, const double* x, double* y, int on_device);
+
+/* solve J dx = b with the resident Jacobian (PETSc KSPCG + PC)                    */
+int  bp_krylov_solve(bp_ctx* ctx, const double* b, double* dx, int on_device,
+                     int32_t* iterations, double* rel_residual);
+
+/* the whole dolfin.solve(F == 0, u, J=J) call: damped Newton from u_inout         */
+int  bp_newton_solve(bp_ctx* ctx, double* u_inout, int on_device, bp_stats* stats);
+
+/* ---- timing of the kernels themselves (CUDA events on the context's stream) --- */
+/* flush_l2 != 0: a 512 MiB buffer is written before every timed launch            */
+int  bp_time_assemble(bp_ctx* ctx, int what, int repeats, int flush_l2, double* ms_per_launch);
+int  bp_time_spmv(bp_ctx* ctx, int repeats, int flush_l2, double* ms_per_launch);
+int64_t bp_launch_count(const bp_ctx* ctx);        /* kernels launched so far      */
+
+/* ---- multi-GPU: one context per rank, NCCL only for halo + reductions --------- */
+int  bp_comm_unique_id(const char* nccl_library_path, char id_out[128]);
+int  bp_comm_init(bp_ctx* ctx, const char* nccl_library_path, const char id[128],
+                  int rank, int n_ranks);
+/* several contexts living in ONE process (one per device, or all on one device to
+ * exercise the partitioned path on a single GPU): solved in lock-step, halo and
+ * reductions by device copies.                                                     */
+int  bp_newton_solve_group(bp_ctx** ctxs, int n, double** u_inout, int on_device, bp_stats* stats);
+int  bp_assemble_group(bp_ctx** ctxs, int n, int what, const double** u, double** F, int on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,83 @@
+"""Problem cases shared by the CPU and GPU tests: each builds the SAME mesh through
+the product's host mirror (cslvr_b200.D3Model) and hands its arrays to the oracle."""
+import numpy as np
+
+from cslvr_b200 import BoxMesh, Point, D3Model
+from oracle import bp_oracle as bo
+
+
+def ismip_model(exp='A', L=80000.0, n=(15, 15, 5), periodic=True):
+	"""docs/get_started.rst:13-45 (A) / simulations/ismip_hom/ismip_hom_c.py:4-25 (C)."""
+	mesh = BoxMesh(Point(0, 0, 0), Point(L, L, 1), *n)
+	model = D3Model(mesh, use_periodic=periodic)
+	model.calculate_boundaries()
+	if exp == 'A':
+		a = 0.5 * np.pi / 180
+		S = lambda x, y, z: -x * np.tan(a)
+		B = lambda x, y, z: -x * np.tan(a) - 1000.0 + 500.0 * np.sin(2 * np.pi * x / L) * np.sin(2 * np.pi * y / L)
+		beta = 1000.0
+	else:
+		a = 0.1 * np.pi / 180
+		S = lambda x, y, z: -x * np.tan(a)
+		B = lambda x, y, z: -x * np.tan(a) - 1000.0
+		beta = lambda x, y, z: 1000.0 + 1000.0 * np.sin(2 * np.pi * x / L) * np.sin(2 * np.pi * y / L)
+	model.deform_mesh_to_geometry(S, B)
+	model.init_beta(beta)
+	model.init_A(1e-16)
+	return model
+
+
+def marine_model(n=(8, 7, 4), L=40000.0, variable_A=True):
+	"""non-periodic slab with a floating tongue below sea level: exercises
+	dGamma_bw (marker 5), dGamma_lt (4, 10), D > 0 and a P1 rate factor."""
+	mesh = BoxMesh(Point(0, 0, 0), Point(L, 0.8 * L, 1), *n)
+	model = D3Model(mesh, use_periodic=False)
+	S = lambda x, y, z: 600.0 - 500.0 * x / L + 30.0 * np.sin(3 * y / L)
+	B = lambda x, y, z: -200.0 - 300.0 * x / L + 80.0 * np.cos(5 * x / L) * np.sin(4 * y / L)
+	model.calculate_boundaries()
+	model.deform_mesh_to_geometry(S, B)
+	mask = lambda x, y, z: np.where(x > 0.6 * L, 2.0, 1.0)
+	model.calculate_boundaries(mask=mask)
+	model.init_beta(lambda x, y, z: 200.0 + 150.0 * np.sin(7 * x / L) * np.cos(3 * y / L))
+	if variable_A:
+		Tp = lambda x, y, z: 250.0 + 18.0 * (1.0 - (z + 500.0) / 1100.0) + 3.0 * np.sin(5 * x / L)
+		X = mesh.coordinates()
+		model.init_A(model.rate_factor(Tp(X[:, 0], X[:, 1], X[:, 2])))
+	else:
+		model.init_A(3e-17)
+	return model
+
+
+def oracle_problem(model, use_pressure_bc=True, quad_degree=None, cell_dofs=None, n_dofs=None):
+	return bo.BPProblem(model.mesh.coordinates(), model.mesh.cells(),
+	                    model.cell_dofs if cell_dofs is None else cell_dofs,
+	                    2 * model.n_nodes if n_dofs is None else n_dofs,
+	                    model.facet_cell, model.facet_local, model.ff,
+	                    model.vertex_field(model.S), model.vertex_field(model.A),
+	                    model.vertex_field(model.beta), periodic=model.use_periodic,
+	                    use_pressure_bc=use_pressure_bc, quad_degree=quad_degree,
+	                    consts=dict(n=model.n, eps_reg=model.eps_reg, rho_i=model.rho_i,
+	                                rhosw=model.rhosw, g=model.g))
+
+
+def product_context(model, use_pressure_bc=True, cell_dofs=None, **params):
+	from cslvr_b200 import capi
+	p = dict(n=model.n, eps_reg=model.eps_reg, rho_i=model.rho_i, rhosw=model.rhosw, g=model.g,
+	         periodic=model.use_periodic, use_pressure_bc=use_pressure_bc)
+	p.update(params)
+	c = capi.BPContext(model.mesh.coordinates(), model.mesh.cells(), 2 * model.n_nodes,
+	                   (model.facet_cell, model.facet_local, model.ff), p,
+	                   cell_dofs=cell_dofs,
+	                   vertex_to_node=(model.vertex_to_node if (model.use_periodic and cell_dofs is None) else None))
+	c.set_field(capi.FIELD_S, model.vertex_field(model.S))
+	c.set_field(capi.FIELD_A, model.vertex_field(model.A))
+	c.set_field(capi.FIELD_BETA, model.vertex_field(model.beta))
+	return c
+
+
+def state(n_dofs, seed=1234, scale=30.0):
+	return np.random.default_rng(seed).normal(size=n_dofs) * scale
+
+
+def relerr(a, b):
+	return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))

@@ -1,0 +1,153 @@
+"""GPU parity: the CUDA path through the C-ABI vs the oracle on the same inputs.
+
+Tolerances are BASELINE.json's: CSR sparsity / dof map bit-exact, assembled
+residual and Jacobian to a relative 1e-12, converged velocity to a relative 1e-8.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cases import (ismip_model, marine_model, oracle_problem, product_context, state, relerr)
+
+pytestmark = pytest.mark.gpu
+
+TOL_ASM = 1e-12
+TOL_U = 1e-8
+
+
+def _check_assembly(model, **kw):
+	P = oracle_problem(model, **{k: v for k, v in kw.items() if k in ('use_pressure_bc', 'quad_degree')})
+	pk = {}
+	if 'quad_degree' in kw and kw['quad_degree'] is not None:
+		pk['quadrature_degree'] = kw['quad_degree']
+	c = product_context(model, use_pressure_bc=kw.get('use_pressure_bc', True), **pk)
+	ip, ix = c.csr_pattern()
+	oip, oix = P.pattern()
+	assert np.array_equal(ip, oip) and np.array_equal(ix, oix)       # bit-exact sparsity
+	for seed, scale in ((1, 30.0), (2, 1e-3), (3, 0.0)):
+		u = state(P.n_dofs, seed, scale) + 3e-16
+		F, J = c.assemble(u, want_F=True, want_J=True)
+		Fo, Jo = P.residual(u), P.jacobian(u)
+		assert relerr(F, Fo) < TOL_ASM, (seed, relerr(F, Fo))
+		assert relerr(J, Jo) < TOL_ASM, (seed, relerr(J, Jo))
+		# F-only and J-only launches give the same numbers as the fused one
+		F2, _ = c.assemble(u, want_F=True, want_J=False)
+		_, J2 = c.assemble(u, want_F=False, want_J=True)
+		assert relerr(F2, F) < 1e-14 and relerr(J2, J) < 1e-14
+	c.close()
+	return P
+
+
+def test_assembly_ismip_a_periodic():
+	_check_assembly(ismip_model('A'))
+
+
+def test_assembly_ismip_c_periodic():
+	_check_assembly(ismip_model('C', L=20000.0, n=(12, 9, 4)))
+
+
+def test_assembly_nonperiodic_marine_variable_A():
+	m = marine_model()
+	assert m.N_GAMMA_B_FLT > 0 and m.N_GAMMA_L_UDR > 0 and m.N_GAMMA_L_OVR > 0
+	_check_assembly(m)
+	_check_assembly(m, use_pressure_bc=False)
+
+
+@pytest.mark.parametrize('deg', [1, 2, 3, 4, 6, 9])
+def test_assembly_quadrature_degrees(deg):
+	_check_assembly(marine_model(n=(5, 4, 3)), quad_degree=deg)
+
+
+def test_assembly_glen_exponent_generic():
+	m = marine_model(n=(5, 4, 3))
+	m.n = 2.5
+	_check_assembly(m)
+
+
+def test_arbitrary_cell_dofs_numbering():
+	"""a dolfin-like reordered dof map: sparsity must follow the caller's numbering."""
+	m = ismip_model('A', n=(6, 5, 3))
+	nd = 2 * m.n_nodes
+	perm = np.random.default_rng(7).permutation(nd).astype(np.int32)
+	cd = perm[m.cell_dofs]
+	P = oracle_problem(m, cell_dofs=cd, n_dofs=nd)
+	c = product_context(m, cell_dofs=cd)
+	ip, ix = c.csr_pattern()
+	oip, oix = P.pattern()
+	assert np.array_equal(ip, oip) and np.array_equal(ix, oix)
+	u = state(nd, 5)
+	F, J = c.assemble(u, want_F=True, want_J=True)
+	assert relerr(F, P.residual(u)) < TOL_ASM and relerr(J, P.jacobian(u)) < TOL_ASM
+	c.close()
+
+
+def test_spmv_and_krylov_against_scipy():
+	m = marine_model()
+	c = product_context(m, krylov_rtol=1e-13)
+	u = state(2 * m.n_nodes, 11)
+	_, J = c.assemble(u, want_F=True, want_J=True)
+	ip, ix = c.csr_pattern()
+	A = sp.csr_matrix((J, ix, ip), shape=(2 * m.n_nodes,) * 2)
+	x = state(2 * m.n_nodes, 12, 1.0)
+	assert relerr(c.spmv(x), A @ x) < 1e-13
+	b = state(2 * m.n_nodes, 13, 1e6)
+	dx, its, rr = c.krylov_solve(b)
+	import scipy.sparse.linalg as spla
+	ref = spla.spsolve(A.tocsc(), b)
+	assert relerr(dx, ref) < 1e-8 and its > 0
+	c.close()
+
+
+@pytest.mark.parametrize('exp,L,n', [('A', 80000.0, (15, 15, 5)), ('C', 20000.0, (10, 10, 4))])
+def test_newton_velocity_matches_oracle(exp, L, n):
+	"""tightened tolerances on both sides (SURVEY §7 hard parts): Newton rtol 1e-13,
+	Krylov rtol 1e-13 vs sparse LU, relax 1.0."""
+	m = ismip_model(exp, L=L, n=n)
+	P = oracle_problem(m)
+	uo, io = P.newton(rtol=1e-13, maxit=40)
+	assert io['converged']
+	c = product_context(m, relative_tolerance=1e-13, maximum_iterations=40, krylov_rtol=1e-13)
+	u = np.full(P.n_dofs, 3e-16)
+	st = c.newton_solve(u)
+	assert st['converged']
+	assert relerr(u, uo) < TOL_U, relerr(u, uo)
+	assert abs(st['iterations'] - io['iterations']) <= 1
+	c.close()
+
+
+def test_newton_default_tolerances_and_marine():
+	"""reference defaults: rtol 1e-9, Krylov rtol 1e-5, relax 0.7 (non-periodic)."""
+	m = marine_model()
+	P = oracle_problem(m)
+	uo, io = P.newton(rtol=1e-9, relax=0.7, maxit=60)
+	c = product_context(m, relative_tolerance=1e-9, relaxation_parameter=0.7, maximum_iterations=60, krylov_rtol=1e-10)
+	u = np.full(P.n_dofs, 3e-16)
+	st = c.newton_solve(u)
+	assert st['converged'] == io['converged']
+	assert relerr(u, uo) < 1e-6
+	c.close()
+
+
+def test_reference_script_runs_unchanged():
+	"""docs/get_started.rst:13-50 line for line (Expressions -> callables)."""
+	from cslvr_b200 import BoxMesh, Point, D3Model, MomentumDukowiczBP, MomentumBP
+	L = 8000
+	mesh = BoxMesh(Point(0.0, 0.0, 0.0), Point(L, L, 1), 15, 15, 5)
+	model = D3Model(mesh, out_dir='./results/', use_periodic=True)
+	model.calculate_boundaries()
+	a = 0.5 * np.pi / 180
+	surface = lambda x, y, z: -x * np.tan(a)
+	bed = lambda x, y, z: -x * np.tan(a) - 1000.0 + 500.0 * np.sin(2 * np.pi * x / L) * np.sin(2 * np.pi * y / L)
+	model.deform_mesh_to_geometry(surface, bed)
+	model.init_beta(1000)
+	model.init_A(1e-16)
+	mom = MomentumDukowiczBP(model)
+	mom.solve()
+	assert mom.stats['converged']
+	ux = model.u.sub(0)
+	top = model.mesh.coordinates()[model.node_vertex, 2] >= model.S.values[model.node_vertex] - 1e-6
+	# docs/get_started.rst:102-104 contour levels for this set-up (full Stokes): 87-92 m/a
+	assert 60.0 < ux[top].min() and ux[top].max() < 120.0
+	mom2 = MomentumBP(model)
+	mom2.solve()
+	assert relerr(mom2.get_unknown().values, mom.get_unknown().values) < 1e-12
