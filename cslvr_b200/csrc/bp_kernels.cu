@@ -245,6 +245,13 @@ void bp_launch_assemble(bp_ctx* c, int what)
 {
 	const AsmParams P = make_params(c);
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
+	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
+		const int gc = (int)((c->nt + TPB - 1) / TPB);
+		k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P);
+		c->launches++;
+		c->have_J = false;
+		return;
+	}
 	if (wf) cudaMemsetAsync(c->d_F, 0, 2 * c->nn * sizeof(double), c->stream);
 	if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->nnzb * 4 * sizeof(double), c->stream);
 	const int gc = (int)((c->nt + TPB - 1) / TPB), gf = (int)((c->nf + TPB - 1) / TPB);

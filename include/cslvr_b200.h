@@ -38,6 +38,8 @@ extern "C" {
 /* what bp_assemble computes */
 #define BP_ASSEMBLE_F   1
 #define BP_ASSEMBLE_J   2
+#define BP_TIME_CELL_ONLY 4 /* bp_time_assemble only: launch the cell kernel alone (no zero-fill,
+                               no facet kernel); the resident Jacobian is invalid afterwards  */
 
 /* preconditioners for the Krylov solve (reference: PETSc CG + hypre BoomerAMG,
  * cslvr/momentumbp.py:183-184; here a device-resident PCG) */
