@@ -42,7 +42,7 @@ class bp_params(C.Structure):
 	            ('error_on_nonconvergence', C.c_int32),
 	            ('krylov_rtol', C.c_double), ('krylov_atol', C.c_double),
 	            ('krylov_maxit', C.c_int32), ('pc', C.c_int32), ('pc_degree', C.c_int32),
-	            ('verbose', C.c_int32)]
+	            ('verbose', C.c_int32), ('assembly', C.c_int32)]
 
 
 class bp_stats(C.Structure):
@@ -232,6 +232,7 @@ class BPContext(object):
 		p.pc = PC[pc] if isinstance(pc, str) else int(pc)
 		p.pc_degree = int(d.get('pc_degree', 3))
 		p.verbose = int(bool(d.get('verbose', False)))
+		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
 		return p
 
 	def _check(self, rc, allow=()):

@@ -28,6 +28,7 @@ static int check_params(bp_ctx* c, const bp_params* p)
 	double s = 0;
 	for (int q = 0; q < p->n_quad; ++q) s += p->quad_weights[q];
 	if (std::fabs(s - 1.0) > 1e-12) return bp_fail(c, BP_ERR_ARG, "bp_params: quadrature weights sum to %.17g, not 1", s);
+	if (p->assembly < BP_ASM_AUTO || p->assembly > BP_ASM_GATHER) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown assembly mode %d", p->assembly);
 	if (p->pc < BP_PC_NONE || p->pc > BP_PC_COLUMN) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown preconditioner %d", p->pc);
 	return BP_OK;
 }
@@ -232,7 +233,7 @@ void bp_destroy(bp_ctx* c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	bp_comm_free(c);
-	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
+	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
 		c->d_rowptr, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
 		c->d_io, c->d_io2, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);

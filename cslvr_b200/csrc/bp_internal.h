@@ -60,6 +60,13 @@ struct bp_ctx {
 	int4*    d_tets = nullptr;
 	int32_t* d_v2n = nullptr;            // nullptr when identity
 	int32_t* d_tet_blk = nullptr;        // [16][nt] block slot of (a,b), -1 = row not owned
+	int32_t* d_inc_slice = nullptr;      // row-gather incidences, SELL-32: slice offsets
+	int32_t* d_inc_code = nullptr;       //   tet*4 + local vertex, -1 = padding
+	uint32_t* d_inc_pos = nullptr;       //   4 x uint8 block positions inside the row
+	int32_t* d_inc_v = nullptr;          //   [4][slots] vertex ids, the row's own vertex first
+	int64_t  n_inc_slots = 0;
+	double*  d_soa = nullptr;            // [4][nv] x | y | z | S (struct-of-arrays copy of d_geo)
+	int32_t  max_row = 0;                // longest block row
 	int32_t* d_fac_cell = nullptr;       // [nf]
 	int32_t* d_fac_info = nullptr;       // [nf] local facet | basal<<8 | pressure<<9
 	int32_t* d_ext_dof = nullptr;        // nullptr when identity

@@ -143,6 +143,159 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 	}
 }
 
+// ---------------------------------------------------------------- row-gather kernel
+// One thread per Jacobian block row (= owned node i).  The thread walks the tets that
+// touch node i (SELL-32 incidence list), rebuilds each tet's cell-constant quantities
+// from the vertex data with node i rotated to local position 0, and adds the two rows
+// (u_x, u_y of node i) of that tet's element matrix into a private accumulator in
+// shared memory (layout [entry][thread]: bank = thread, conflict-free).  Every J entry
+// and every F entry is then written exactly once: no atomics, no zero-fill, bitwise
+// reproducible.  The price is that the cell-constant part of a tet is recomputed by
+// each of its four nodes.
+#define RTPB 128
+template <bool WANT_F, bool WANT_J>
+__global__ void __launch_bounds__(RTPB)
+k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restrict__ inc_code,
+       const uint32_t* __restrict__ inc_pos, const int32_t* __restrict__ inc_v, size_t nslot,
+       const double* __restrict__ soa, size_t nv, const int32_t* __restrict__ v2n,
+       const double2* __restrict__ u, const double* __restrict__ Av,
+       const int32_t* __restrict__ rowptr, double* __restrict__ F, double* __restrict__ val, AsmParams P)
+{
+	extern __shared__ double acc[];                  // [4*max_row][RTPB]
+	const int tid = threadIdx.x;
+	const int i = blockIdx.x * RTPB + tid;
+	const bool active = i < nrows;
+	const int r0 = active ? rowptr[i] : 0;
+	const int len = active ? rowptr[i + 1] - r0 : 0;
+	if (WANT_J) for (int k = 0; k < 4 * len; ++k) acc[k * RTPB + tid] = 0.0;
+	double Fx = 0.0, Fy = 0.0;
+	const int slice = i >> 5, lane = i & 31;
+	const int e0 = active ? inc_slice[slice] : 0, e1 = active ? inc_slice[slice + 1] : 0;
+	// software pipeline: the index words of incidence e+32 are requested before the
+	// arithmetic of incidence e, its vertex data as soon as the raw data of e is consumed
+	int e = e0 + lane;
+	int code = (e < e1) ? inc_code[e] : -1;
+	uint32_t pk = 0;
+	int vid[4] = { 0, 0, 0, 0 };
+	double4 p[4];
+	double2 uu[4];
+	double A[4];
+	if (code >= 0) {
+		pk = inc_pos[e];
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) vid[j] = inc_v[j * nslot + e];
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
+			A[j] = Av[vid[j]];
+			uu[j] = u[v2n ? v2n[vid[j]] : vid[j]];
+		}
+	}
+	while (code >= 0) {
+		const int a = code & 3;
+		const uint32_t pk_cur = pk;
+		e += 32;
+		const int code_n = (e < e1) ? inc_code[e] : -1;
+		if (code_n >= 0) {
+			pk = inc_pos[e];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) vid[j] = inc_v[j * nslot + e];
+		}
+		const double e1x = p[1].x - p[0].x, e1y = p[1].y - p[0].y, e1z = p[1].z - p[0].z;
+		const double e2x = p[2].x - p[0].x, e2y = p[2].y - p[0].y, e2z = p[2].z - p[0].z;
+		const double e3x = p[3].x - p[0].x, e3y = p[3].y - p[0].y, e3z = p[3].z - p[0].z;
+		double X[4], Y[4], Z[4];
+		X[1] = e2y * e3z - e2z * e3y; Y[1] = e2z * e3x - e2x * e3z; Z[1] = e2x * e3y - e2y * e3x;
+		X[2] = e3y * e1z - e3z * e1y; Y[2] = e3z * e1x - e3x * e1z; Z[2] = e3x * e1y - e3y * e1x;
+		X[3] = e1y * e2z - e1z * e2y; Y[3] = e1z * e2x - e1x * e2z; Z[3] = e1x * e2y - e1y * e2x;
+		const double det = e1x * X[1] + e1y * Y[1] + e1z * Z[1];
+		const double idet = 1.0 / det;
+		#pragma unroll
+		for (int j = 1; j < 4; ++j) { X[j] *= idet; Y[j] *= idet; Z[j] *= idet; }
+		X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
+		const double vol = fabs(det) * (1.0 / 6.0);
+		double wbar;
+		if (A[0] == A[1] && A[0] == A[2] && A[0] == A[3]) {
+			wbar = vol * pow_m1n(A[0], P);
+		} else {
+			// the quadrature points are stored for the tet's own vertex order: undo the rotation
+			double Ao[4];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) Ao[(a + j) & 3] = A[j];
+			double sacc = 0.0;
+			for (int q = 0; q < P.n_quad; ++q) {
+				const double aq = c_ql[4 * q] * Ao[0] + c_ql[4 * q + 1] * Ao[1] + c_ql[4 * q + 2] * Ao[2] + c_ql[4 * q + 3] * Ao[3];
+				sacc += c_qw[q] * pow_m1n(aq, P);
+			}
+			wbar = vol * sacc;
+		}
+		double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, sx = 0, sy = 0;
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			g00 += uu[j].x * X[j]; g01 += uu[j].x * Y[j]; g02 += uu[j].x * Z[j];
+			g10 += uu[j].y * X[j]; g11 += uu[j].y * Y[j]; g12 += uu[j].y * Z[j];
+			sx += p[j].w * X[j]; sy += p[j].w * Y[j];
+		}
+		// raw vertex data of this incidence is consumed: request the next incidence's
+		if (code_n >= 0) {
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
+				A[j] = Av[vid[j]];
+				uu[j] = u[v2n ? v2n[vid[j]] : vid[j]];
+			}
+		}
+		const double sh = 0.5 * (g01 + g10);
+		const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
+		double two_eta, two_eta_p;
+		if (P.n_is_3) {
+			two_eta = rcbrt(ed);
+			two_eta_p = (-1.0 / 3.0) * (two_eta * two_eta) * (two_eta * two_eta);    // ed^(-4/3)
+		} else {
+			const double ex = (1.0 - P.n) / (2.0 * P.n);
+			two_eta = pow(ed, ex);
+			two_eta_p = ex * two_eta / ed;
+		}
+		const double alpha = wbar * two_eta, gamma = wbar * two_eta_p;
+		const double cxx = 2.0 * g00 + g11, cyy = 2.0 * g11 + g00, hz0 = 0.5 * g02, hz1 = 0.5 * g12;
+		const double dx0 = cxx * X[0] + sh * Y[0] + hz0 * Z[0];
+		const double dy0 = cyy * Y[0] + sh * X[0] + hz1 * Z[0];
+		if (WANT_F) {
+			const double grav = P.rho_g * vol * 0.25;
+			Fx += alpha * dx0 + grav * sx;
+			Fy += alpha * dy0 + grav * sy;
+		}
+		if (WANT_J) {
+			const double Pa = 2.0 * alpha * X[0], Qa = 0.5 * alpha * Y[0], Ra = 0.5 * alpha * Z[0];
+			const double Sa = 2.0 * alpha * Y[0], Ta = 0.5 * alpha * X[0];
+			const double Ua = alpha * X[0], Wa = alpha * Y[0];
+			const double Ea = gamma * dx0, Ga = gamma * dy0;
+			#pragma unroll
+			for (int b = 0; b < 4; ++b) {
+				const double dxb = cxx * X[b] + sh * Y[b] + hz0 * Z[b];
+				const double dyb = cyy * Y[b] + sh * X[b] + hz1 * Z[b];
+				const int k = (pk_cur >> (8 * b)) & 255;
+				double* s4 = acc + (4 * k) * RTPB + tid;
+				s4[0]        += Pa * X[b] + Qa * Y[b] + Ra * Z[b] + Ea * dxb;
+				s4[RTPB]     += Ua * Y[b] + Qa * X[b] + Ea * dyb;
+				s4[2 * RTPB] += Wa * X[b] + Ta * Y[b] + Ga * dxb;
+				s4[3 * RTPB] += Sa * Y[b] + Ta * X[b] + Ra * Z[b] + Ga * dyb;
+			}
+		}
+		code = code_n;
+	}
+	if (!active) return;
+	if (WANT_F) { F[2 * i] = Fx; F[2 * i + 1] = Fy; }
+	if (WANT_J) {
+		double2* out = (double2*)(val + 4 * (size_t)r0);
+		for (int k = 0; k < len; ++k) {
+			const double* s4 = acc + (4 * k) * RTPB + tid;
+			out[2 * k]     = make_double2(s4[0], s4[RTPB]);
+			out[2 * k + 1] = make_double2(s4[2 * RTPB], s4[3 * RTPB]);
+		}
+	}
+}
+
 // ---------------------------------------------------------------- facet kernel
 // Basal sliding  +1/2 beta u.u dGamma_b  and water pressure  -f_w u.n_h  on
 // dGamma_bw / dGamma_lt (cslvr/momentumbp.py:473-491), exact P1 mass integrals.
@@ -246,21 +399,50 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	const AsmParams P = make_params(c);
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
-		const int gc = (int)((c->nt + TPB - 1) / TPB);
-		k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P);
+		const size_t rs = (size_t)4 * c->max_row * RTPB * sizeof(double);
+		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
+			cudaFuncSetAttribute(k_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			k_rows<true, true><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
+				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_rowptr, c->d_F, c->d_val, P);
+		} else {
+			const int gc = (int)((c->nt + TPB - 1) / TPB);
+			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P);
+		}
 		c->launches++;
 		c->have_J = false;
 		return;
 	}
-	if (wf) cudaMemsetAsync(c->d_F, 0, 2 * c->nn * sizeof(double), c->stream);
-	if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->nnzb * 4 * sizeof(double), c->stream);
-	const int gc = (int)((c->nt + TPB - 1) / TPB), gf = (int)((c->nf + TPB - 1) / TPB);
+	const int gf = (int)((c->nf + TPB - 1) / TPB);
 	const double2* u2 = (const double2*)c->d_u;
-	#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
+	const size_t row_smem = (size_t)4 * c->max_row * RTPB * sizeof(double);
+	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
 	#define FACET(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
-	if (wf && wj) { CELL(true, true); if (c->nf) FACET(true, true); }
-	else if (wf)  { CELL(true, false); if (c->nf) FACET(true, false); }
-	else if (wj)  { CELL(false, true); if (c->nf) FACET(false, true); }
+	if (gather) {
+		static bool attr_set = false;
+		if (!attr_set) {
+			cudaFuncSetAttribute(k_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			cudaFuncSetAttribute(k_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			attr_set = true;
+		}
+		const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
+		#define ROWS(WF, WJ, SM) k_rows<WF, WJ><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, c->d_v2n, u2, c->d_A, c->d_rowptr, c->d_F, c->d_val, P)
+		if (wf && wj) ROWS(true, true, row_smem);
+		else if (wf)  ROWS(true, false, 0);
+		else if (wj)  ROWS(false, true, row_smem);
+	} else {
+		if (wf) cudaMemsetAsync(c->d_F, 0, 2 * c->nn * sizeof(double), c->stream);
+		if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->nnzb * 4 * sizeof(double), c->stream);
+		const int gc = (int)((c->nt + TPB - 1) / TPB);
+		#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
+		if (wf && wj) CELL(true, true);
+		else if (wf)  CELL(true, false);
+		else if (wj)  CELL(false, true);
+	}
+	if (c->nf) {
+		if (wf && wj) FACET(true, true);
+		else if (wf)  FACET(true, false);
+		else if (wj)  FACET(false, true);
+	}
 	c->launches += 1 + (c->nf ? 1 : 0);
 	if (wj) c->have_J = true;
 }
@@ -413,13 +595,13 @@ void bp_launch_csr_export(bp_ctx* c, double* out)
 	c->launches++;
 }
 
-__global__ void k_set_S(int nv, const double* __restrict__ S, double4* geo)
+__global__ void k_set_S(int nv, const double* __restrict__ S, double4* geo, double* soa_S)
 {
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) geo[i].w = S[i];
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) { geo[i].w = S[i]; soa_S[i] = S[i]; }
 }
 void bp_launch_set_S(bp_ctx* c, const double* S_dev)
 {
-	k_set_S<<<red_blocks(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, S_dev, c->d_geo);
+	k_set_S<<<red_blocks(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, S_dev, c->d_geo, c->d_soa + 3 * (size_t)c->nv);
 	c->launches++;
 }
 

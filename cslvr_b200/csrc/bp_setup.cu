@@ -176,6 +176,54 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 			}
 		}
 
+	// ---- row-gather incidences: for every owned node the (tet, local vertex) pairs that
+	// touch it, SELL-32 layout (slice of 32 rows, entry e of lane l at base + 32 e + l),
+	// with the block positions of the tet's four nodes inside the node's block row.
+	{
+		const int64_t nsl = (no + 31) / 32;
+		std::vector<int32_t> cnt(no, 0);
+		for (int64_t i = 0; i < nt * 4; ++i) if (cn[i] < no) cnt[cn[i]]++;
+		std::vector<int32_t> sl_ptr(nsl + 1, 0);
+		c->max_row = 0;
+		for (int64_t s = 0; s < nsl; ++s) {
+			int32_t w = 0;
+			for (int64_t i = s * 32; i < std::min<int64_t>(no, s * 32 + 32); ++i) {
+				w = std::max(w, cnt[i]);
+				c->max_row = std::max(c->max_row, c->h_rowptr[i + 1] - c->h_rowptr[i]);
+			}
+			int64_t nxt = (int64_t)sl_ptr[s] + 32 * (int64_t)w;
+			if (nxt > INT32_MAX) return bp_fail(c, BP_ERR_ARG, "bp_mesh: too many incidences for one rank");
+			sl_ptr[s + 1] = (int32_t)nxt;
+		}
+		std::vector<int32_t> code(sl_ptr[nsl], -1);
+		std::vector<uint32_t> pos(sl_ptr[nsl], 0u);
+		const size_t nslot = (size_t)sl_ptr[nsl];
+		std::vector<int32_t> incv(4 * nslot, 0);
+		std::vector<int32_t> fill(no, 0);
+		for (int64_t t = 0; t < nt; ++t)
+			for (int a = 0; a < 4; ++a) {
+				const int32_t i = cn[t * 4 + a];
+				if (i >= no) continue;
+				const int64_t at = (int64_t)sl_ptr[i / 32] + 32 * (int64_t)(fill[i]++) + (i % 32);
+				code[at] = (int32_t)(t * 4 + a);
+				uint32_t pk = 0;
+				const int32_t* lo = c->h_col.data() + c->h_rowptr[i];
+				const int32_t* hi = c->h_col.data() + c->h_rowptr[i + 1];
+				for (int j = 0; j < 4; ++j) {
+					const uint32_t k = (uint32_t)(std::lower_bound(lo, hi, cn[t * 4 + ((a + j) & 3)]) - lo);
+					if (k > 255) return bp_fail(c, BP_ERR_ARG, "bp_mesh: a Jacobian row has more than 255 node blocks");
+					pk |= k << (8 * j);
+					incv[(size_t)j * nslot + at] = m->cells[t * 4 + ((a + j) & 3)];
+				}
+				pos[at] = pk;
+			}
+		UP(c->d_inc_slice, sl_ptr.data(), nsl + 1);
+		UP(c->d_inc_code, code.data(), code.size());
+		UP(c->d_inc_pos, pos.data(), pos.size());
+		UP(c->d_inc_v, incv.data(), incv.size());
+		c->n_inc_slots = (int64_t)nslot;
+	}
+
 	// ---- facets that integrate something ----------------------------------------
 	// dGamma_b = {3,5}, dGamma_bw = {5}, dGamma_lt = {4,10}: cslvr/d3model.py:576-598
 	std::vector<int32_t> fcell, finfo;
@@ -217,6 +265,9 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		for (int64_t v = 0; v < nv; ++v)
 			geo[v] = make_double4(m->coords[3 * v], m->coords[3 * v + 1], m->coords[3 * v + 2], 0.0);
 		UP(c->d_geo, geo.data(), nv);
+		std::vector<double> soa((size_t)4 * nv, 0.0);        // x | y | z | S, for the row-gather kernel
+		for (int64_t v = 0; v < nv; ++v) for (int d = 0; d < 3; ++d) soa[(size_t)d * nv + v] = m->coords[3 * v + d];
+		UP(c->d_soa, soa.data(), (size_t)4 * nv);
 	}
 	UP(c->d_A, (const double*)nullptr, nv);
 	UP(c->d_beta, (const double*)nullptr, nv);

@@ -49,6 +49,11 @@ extern "C" {
 #define BP_PC_CHEBYSHEV     3   /* Chebyshev polynomial smoother on block-Jacobi  */
 #define BP_PC_COLUMN        4   /* vertical-line (column block-tridiagonal) solve */
 
+/* how the element tensors reach the resident Jacobian */
+#define BP_ASM_AUTO     0   /* row gather unless a block row is too long for shared memory     */
+#define BP_ASM_SCATTER  1   /* one thread per tetrahedron, FP64 atomics into F and J           */
+#define BP_ASM_GATHER   2   /* one thread per Jacobian block row, no atomics, deterministic    */
+
 typedef struct bp_ctx bp_ctx;
 
 /* The mesh and the P1xP1 dof map: what the adapter pulls out of dolfin
@@ -112,6 +117,7 @@ typedef struct {
 	int32_t pc;                /* BP_PC_*                                         */
 	int32_t pc_degree;         /* Chebyshev degree                                */
 	int32_t verbose;
+	int32_t assembly;          /* BP_ASM_*                                        */
 } bp_params;
 
 typedef struct {
