@@ -115,9 +115,10 @@ def nccl_library_path():
 	"""the NCCL torch itself is linked against (so both agree on one libnccl)."""
 	try:
 		import nvidia.nccl
-		p = os.path.join(os.path.dirname(nvidia.nccl.__file__), 'lib', 'libnccl.so.2')
-		if os.path.exists(p):
-			return p
+		for d in list(getattr(nvidia.nccl, '__path__', [])):
+			p = os.path.join(d, 'lib', 'libnccl.so.2')
+			if os.path.exists(p):
+				return p
 	except ImportError:
 		pass
 	return 'libnccl.so.2'

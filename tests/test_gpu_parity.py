@@ -158,3 +158,46 @@ def test_reference_script_runs_unchanged():
 	mom2 = MomentumBP(model)
 	mom2.solve()
 	assert relerr(mom2.get_unknown().values, mom.get_unknown().values) < 1e-12
+
+
+@pytest.mark.parametrize('name', ['ismip_a_6x5x3', 'marine_6x5x3'])
+def test_against_committed_golden_vectors(name):
+	"""tests/golden/*.npz (oracle outputs, see make_golden.py) through the C-ABI."""
+	import os
+	from golden.make_golden import build
+	g = np.load(os.path.join(os.path.dirname(__file__), 'golden', name + '.npz'))
+	m = build(name)
+	c = product_context(m, relative_tolerance=1e-11, maximum_iterations=80, krylov_rtol=1e-13,
+	                    relaxation_parameter=float(g['relax']))
+	ip, ix = c.csr_pattern()
+	assert np.array_equal(ip, g['indptr']) and np.array_equal(ix, g['indices'])
+	F, J = c.assemble(g['u'], want_F=True, want_J=True)
+	assert relerr(F, g['F']) < TOL_ASM and relerr(J, g['J']) < TOL_ASM
+	u = np.full(2 * m.n_nodes, 3e-16)
+	st = c.newton_solve(u)
+	assert st['converged'] and relerr(u, g['u_newton']) < TOL_U
+	assert abs(st['iterations'] - int(g['newton_iterations'])) <= 1
+	c.close()
+
+
+def test_empty_and_ragged_inputs_are_rejected():
+	"""C-ABI misuse: integer return + message, no crash (SURVEY §8b errors)."""
+	from cslvr_b200 import capi
+	m = ismip_model('A', n=(3, 3, 2))
+	c = product_context(m)
+	with pytest.raises(capi.BPError):
+		c.set_field(capi.FIELD_A, np.ones(5))                       # ragged field
+	with pytest.raises(capi.BPError):
+		c.spmv(np.ones(2 * m.n_nodes)) if False else capi.BPContext(  # empty mesh
+			np.zeros((0, 3)), np.zeros((0, 4), dtype=np.int32), 0, ([], [], []), c.params)
+	bad = m.cell_dofs.copy()
+	bad[0, 4] = bad[0, 0]                                           # u_y dof equal to u_x dof
+	with pytest.raises(capi.BPError):
+		product_context(m, cell_dofs=bad)
+	c2 = capi.BPContext(m.mesh.coordinates(), m.mesh.cells(), 2 * m.n_nodes, (m.facet_cell, m.facet_local, m.ff),
+	                    c.params, vertex_to_node=m.vertex_to_node)
+	with pytest.raises(capi.BPError):                               # fields not set yet
+		c2.assemble(np.zeros(2 * m.n_nodes))
+	with pytest.raises(capi.BPError):                               # no resident Jacobian yet
+		c.spmv(np.ones(2 * m.n_nodes))
+	c.close(); c2.close()

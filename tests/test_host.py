@@ -1,0 +1,103 @@
+"""Host logic without a GPU: the D3Model mirror against the oracle's independent mesh
+code, the reference's parameter dictionary, and the C-ABI library (loads, exports every
+symbol of include/cslvr_b200.h, refuses to compute without a device)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cases import ismip_model, marine_model, oracle_problem
+from oracle import bp_oracle as bo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mirror_mesh_equals_oracle_mesh():
+	m = ismip_model('A')
+	P = bo.ismip_hom('A')
+	assert np.array_equal(P.cells, m.mesh.cells()) and np.array_equal(P.coords, m.mesh.coordinates())
+	assert np.array_equal(P.cell_dofs, m.cell_dofs)
+	assert np.array_equal(P.fc, m.facet_cell) and np.array_equal(P.fl, m.facet_local) and np.array_equal(P.ff, m.ff)
+	assert np.array_equal(P.beta, m.vertex_field(m.beta)) and np.array_equal(P.S, m.vertex_field(m.S))
+
+
+def test_markers_follow_d3model_rules():
+	m = marine_model()
+	# all six marker classes of cslvr/d3model.py:410-455 that the defaults can produce
+	assert m.N_GAMMA_U_GND > 0 and m.N_GAMMA_U_FLT > 0 and m.N_GAMMA_B_GND > 0 and m.N_GAMMA_B_FLT > 0
+	assert m.N_GAMMA_L_OVR > 0 and m.N_GAMMA_L_UDR > 0 and m.N_OMEGA_FLT > 0
+	nx, ny, nz = m.mesh.shape
+	assert m.N_GAMMA_B_GND + m.N_GAMMA_B_FLT == 2 * nx * ny == m.N_GAMMA_U_GND + m.N_GAMMA_U_FLT
+	assert m.N_GAMMA_L_OVR + m.N_GAMMA_L_UDR == 2 * nz * 2 * (nx + ny)
+	# deform_mesh_to_geometry re-marks with the default mask: everything grounded (d3model.py:667)
+	m.deform_mesh_to_geometry(m.S.values.copy(), m.B.values.copy())
+	assert m.N_GAMMA_B_FLT == 0
+
+
+def test_periodic_map_and_dof_counts():
+	m = ismip_model('A')
+	assert m.n_nodes == 15 * 15 * 6 and m.QM2.dim() == 2700
+	X = m.flat_coordinates
+	img = m.node_vertex[m.vertex_to_node]
+	d = np.abs(X - X[img])
+	assert np.all((d[:, 0] < 1e-9) | (np.abs(d[:, 0] - 80000.0) < 1e-6)) and np.all(d[:, 2] < 1e-12)
+
+
+def test_default_solve_params_match_reference():
+	"""cslvr/momentumbp.py:165-203."""
+	from cslvr_b200.momentumbp import MomentumBPBase
+
+	class Probe(MomentumBPBase):
+		def __init__(self, model):
+			self.model, self.linear = model, False
+	for per, relax in ((True, 1.0), (False, 0.7)):
+		p = Probe(ismip_model('A', n=(3, 3, 2), periodic=per)).default_solve_params()
+		ns = p['solver']['newton_solver']
+		assert ns['relative_tolerance'] == 1e-9 and ns['maximum_iterations'] == 25
+		assert ns['relaxation_parameter'] == relax and ns['error_on_nonconvergence'] is False
+		assert ns['linear_solver'] == 'cg' and ns['preconditioner'] == 'hypre_amg'
+		assert p['solve_vert_velocity'] and p['solve_pressure'] and p['vert_solve_method'] == 'mumps'
+
+
+def test_misuse_errors_like_the_reference():
+	from cslvr_b200 import MomentumDukowiczBP, D3Model, BoxMesh, Point
+	with pytest.raises(SystemExit):                      # cslvr/momentumbp.py:30-33
+		MomentumDukowiczBP(object())
+	with pytest.raises(NotImplementedError):             # P1 only
+		D3Model(BoxMesh(Point(0, 0, 0), Point(1, 1, 1), 2, 2, 2), order=2)
+	m = ismip_model('A', n=(3, 3, 2))
+	with pytest.raises(SystemExit):                      # cslvr/momentum.py:49-53
+		MomentumDukowiczBP(m, solve_params=3)
+	with pytest.raises(TypeError):                       # use_lat_bcs is broken upstream too
+		MomentumDukowiczBP(m, use_lat_bcs=True)
+
+
+def test_library_exports_every_declared_symbol(lib_built):
+	hdr = open(os.path.join(ROOT, 'include', 'cslvr_b200.h')).read()
+	declared = set(re.findall(r'\b(bp_[a-z_0-9]+)\s*\(', hdr))
+	from cslvr_b200 import capi
+	assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+	lib = ctypes.CDLL(lib_built)
+	for s in sorted(declared):
+		assert hasattr(lib, s), s
+
+
+def test_no_cpu_fallback(lib_built):
+	import torch
+	if torch.cuda.is_available():
+		pytest.skip("a GPU is visible")
+	from cases import product_context
+	from cslvr_b200.capi import BPError
+	with pytest.raises(BPError) as e:
+		product_context(ismip_model('A', n=(3, 3, 2)))
+	assert 'no CPU path' in str(e.value)
+
+
+def test_product_does_not_import_the_oracle():
+	import glob
+	for f in glob.glob(os.path.join(ROOT, 'cslvr_b200', '**', '*'), recursive=True):
+		if f.endswith(('.py', '.cu', '.h')):
+			src = open(f).read()
+			assert 'import oracle' not in src and 'from oracle' not in src and 'bp_oracle' not in src, f
