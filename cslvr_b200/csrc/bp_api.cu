@@ -15,7 +15,6 @@
 
 std::string g_bp_create_error;
 void bp_upload_quadrature(bp_ctx* c);
-void bp_launch_pcg_p_impl(bp_ctx* c, int first);
 
 // ------------------------------------------------------------------ helpers
 static int check_params(bp_ctx* c, const bp_params* p)
@@ -107,8 +106,8 @@ static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 {
 	int rc;
 	for (int r = 0; r < n; ++r) { bp_launch_pc_setup(cs[r]); bp_launch_pcg_init(cs[r]); }
-	if ((rc = bp_comm_allreduce(cs, n, SC_RZ_NEXT, 3))) return rc;
-	for (int r = 0; r < n; ++r) bp_launch_pcg_p_impl(cs[r], 1);
+	if ((rc = bp_comm_allreduce(cs, n, SC_T0, 3))) return rc;
+	for (int r = 0; r < n; ++r) bp_launch_pcg_p(cs[r], 1, 0);
 	const int maxit = cs[0]->prm.krylov_maxit > 0 ? cs[0]->prm.krylov_maxit : 10000;
 	int k = 0;
 	bool done = false;
@@ -118,9 +117,10 @@ static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 			if ((rc = bp_comm_halo(cs, n, 1))) return rc;
 			for (int r = 0; r < n; ++r) bp_launch_spmv(cs[r], cs[r]->d_p, cs[r]->d_Ap, 1);
 			if ((rc = bp_comm_allreduce(cs, n, SC_PAP, 1))) return rc;
-			for (int r = 0; r < n; ++r) bp_launch_pcg_update(cs[r]);
-			if ((rc = bp_comm_allreduce(cs, n, SC_RZ_NEXT, 3))) return rc;
-			for (int r = 0; r < n; ++r) bp_launch_pcg_p_impl(cs[r], 0);
+			const int par = (k + i) & 1;
+			for (int r = 0; r < n; ++r) bp_launch_pcg_update(cs[r], par);
+			if ((rc = bp_comm_allreduce(cs, n, par ? SC_T0 : SC_T1, 3))) return rc;
+			for (int r = 0; r < n; ++r) bp_launch_pcg_p(cs[r], 0, par);
 		}
 		k += batch;
 		if ((rc = read_scalars(cs[0]))) return rc;
@@ -233,8 +233,8 @@ void bp_destroy(bp_ctx* c)
 	if (!c) return;
 	cudaSetDevice(c->device);
 	bp_comm_free(c);
-	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
-		c->d_rowptr, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
+	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
+		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
 		c->d_io, c->d_io2, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -467,9 +467,9 @@ int bp_time_spmv(bp_ctx* c, int repeats, int flush, double* ms_per_launch)
 	int rc;
 	double total = 0;
 	for (int i = 0; i < repeats; ++i) {
-		if ((rc = flush_l2(c, flush))) return rc;
+		if ((rc = flush_l2(c, flush & 1))) return rc;
 		BP_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-		bp_launch_spmv(c, c->d_u, c->d_Ap, 0);
+		bp_launch_spmv(c, c->d_u, c->d_Ap, (flush >> 1) & 1);
 		BP_CUDA(c, cudaEventRecord(c->ev1, c->stream));
 		BP_CUDA(c, cudaEventSynchronize(c->ev1));
 		float ms; BP_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));

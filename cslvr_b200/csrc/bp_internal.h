@@ -11,11 +11,9 @@
 
 // ---- device scalar block used by the Krylov loop (doubles) ------------------
 enum {
-	SC_RZ = 0,      // r.z of the current iteration
-	SC_RZ_NEXT,     // r.z after the update        } contiguous: one all-reduce
-	SC_ZZ,          // z.z                         }
-	SC_RR,          // r.r                         }
-	SC_PAP,         // p.Ap
+	SC_T0 = 0,      // {r.z, z.z, r.r} written by even updates / the init   } one all-reduce each
+	SC_T1 = 3,      // {r.z, z.z, r.r} written by odd updates               }
+	SC_PAP = 6,     // p.Ap
 	SC_NORM0,       // reference norm for the relative test
 	SC_NORM,        // current norm
 	SC_DONE,        // 1.0 once converged / broken down
@@ -65,16 +63,20 @@ struct bp_ctx {
 	uint32_t* d_inc_pos = nullptr;       //   4 x uint8 block positions inside the row
 	int32_t* d_inc_v = nullptr;          //   [4][slots] vertex ids, the row's own vertex first
 	int64_t  n_inc_slots = 0;
+	double*  d_uvert = nullptr;          // [2*nv] u per vertex (only when vertices != nodes)
 	double*  d_soa = nullptr;            // [4][nv] x | y | z | S (struct-of-arrays copy of d_geo)
 	int32_t  max_row = 0;                // longest block row
 	int32_t* d_fac_cell = nullptr;       // [nf]
 	int32_t* d_fac_info = nullptr;       // [nf] local facet | basal<<8 | pressure<<9
 	int32_t* d_ext_dof = nullptr;        // nullptr when identity
 	// device: resident Jacobian, BSR 2x2, owned rows
-	int32_t* d_rowptr = nullptr;
+	int32_t* d_sell_ptr = nullptr;       // [slices+1] first slot of every 32-row slice
+	int32_t* d_rowlen = nullptr;         // [nn_owned] blocks in the row
+	int64_t  n_slots = 0;                // slots incl. padding
+	std::vector<int32_t> h_sell_ptr;
 	int32_t* d_col = nullptr;
 	int32_t* d_diag = nullptr;           // slot of the diagonal block of each owned row
-	double*  d_val = nullptr;            // [nnzb*4] row-major 2x2
+	double*  d_val = nullptr;            // [n_slots*4] 2x2 blocks {a00 a01 a10 a11}, SELL-32 slot order
 	int32_t* d_csr_src = nullptr;        // CSR export gather map
 	// device: vectors in internal layout [2*node + c], length 2*nn
 	double *d_u = nullptr, *d_F = nullptr, *d_dx = nullptr, *d_r = nullptr, *d_z = nullptr,
@@ -119,8 +121,8 @@ void bp_launch_pack_halo(bp_ctx* c, const double* vec);
 void bp_launch_dot_owned(bp_ctx* c, const double* a, const double* b, int sc_slot);
 void bp_launch_axpy(bp_ctx* c, double alpha, const double* x, double* y);   // y += alpha x
 void bp_launch_pcg_init(bp_ctx* c);
-void bp_launch_pcg_update(bp_ctx* c);
-void bp_launch_pcg_p(bp_ctx* c);
+void bp_launch_pcg_update(bp_ctx* c, int par);
+void bp_launch_pcg_p(bp_ctx* c, int first, int par);
 void bp_launch_sum_scalars(bp_ctx** ctxs, int n, int slot, int count);
 
 // comm (bp_comm.cu)

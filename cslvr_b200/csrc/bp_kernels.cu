@@ -7,10 +7,13 @@
 // Element math is the closed form of SURVEY.md §8a: for P1 the strain rate is
 // cell-constant, so the only quadrature is  wbar = |T| sum_q w_q A(x_q)^(-1/n).
 #include "bp_internal.h"
+#include <algorithm>
 
 __constant__ double c_qw[BP_MAX_QUAD];
 __constant__ double c_ql[BP_MAX_QUAD * 4];
 
+struct AsmParams;
+static AsmParams make_params_fwd(const bp_ctx* c);
 struct AsmParams {
 	double n, eps_reg, rho_g, rho_sw_g;
 	int    n_quad;
@@ -143,6 +146,92 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 	}
 }
 
+// ---------------------------------------------------------------- EXPERIMENT (timing only)
+// Thread-per-tet element computation with the 64 + 8 contributions accumulated by
+// shared-memory atomicAdd(double) (ATOMS.CAST.SPIN.64) at slot-derived addresses in a
+// 200 KB strip: measures what a tile kernel with shared-memory accumulation would cost.
+__global__ void __launch_bounds__(384, 1)
+k_proxy_smem(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
+             const int32_t* __restrict__ v2n, const double2* __restrict__ u,
+             const double* __restrict__ Av, const int32_t* __restrict__ tet_blk, AsmParams P, int nacc, double* sink)
+{
+	extern __shared__ double acc[];
+	for (int k = threadIdx.x; k < nacc; k += blockDim.x) acc[k] = 0.0;
+	__syncthreads();
+	const int per = (nt + gridDim.x - 1) / gridDim.x;
+	const int t0 = blockIdx.x * per, t1 = min(nt, t0 + per);
+	for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+		const int4 tv = tets[t];
+		const int vid[4] = { tv.x, tv.y, tv.z, tv.w };
+		double4 p[4]; int nd[4]; double2 uu[4]; double A[4];
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) { p[a] = geo[vid[a]]; nd[a] = v2n ? v2n[vid[a]] : vid[a]; A[a] = Av[vid[a]]; }
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) uu[a] = u[nd[a]];
+		const double e1x = p[1].x - p[0].x, e1y = p[1].y - p[0].y, e1z = p[1].z - p[0].z;
+		const double e2x = p[2].x - p[0].x, e2y = p[2].y - p[0].y, e2z = p[2].z - p[0].z;
+		const double e3x = p[3].x - p[0].x, e3y = p[3].y - p[0].y, e3z = p[3].z - p[0].z;
+		double X[4], Y[4], Z[4];
+		X[1] = e2y * e3z - e2z * e3y; Y[1] = e2z * e3x - e2x * e3z; Z[1] = e2x * e3y - e2y * e3x;
+		X[2] = e3y * e1z - e3z * e1y; Y[2] = e3z * e1x - e3x * e1z; Z[2] = e3x * e1y - e3y * e1x;
+		X[3] = e1y * e2z - e1z * e2y; Y[3] = e1z * e2x - e1x * e2z; Z[3] = e1x * e2y - e1y * e2x;
+		const double det = e1x * X[1] + e1y * Y[1] + e1z * Z[1];
+		const double idet = 1.0 / det;
+		#pragma unroll
+		for (int a = 1; a < 4; ++a) { X[a] *= idet; Y[a] *= idet; Z[a] *= idet; }
+		X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
+		const double vol = fabs(det) * (1.0 / 6.0);
+		const double wbar = vol * pow_m1n(A[0], P);
+		double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, sx = 0, sy = 0;
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) {
+			g00 += uu[a].x * X[a]; g01 += uu[a].x * Y[a]; g02 += uu[a].x * Z[a];
+			g10 += uu[a].y * X[a]; g11 += uu[a].y * Y[a]; g12 += uu[a].y * Z[a];
+			sx += p[a].w * X[a]; sy += p[a].w * Y[a];
+		}
+		const double sh = 0.5 * (g01 + g10);
+		const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
+		const double two_eta = rcbrt(ed), two_eta_p = (-1.0 / 3.0) * (two_eta * two_eta) * (two_eta * two_eta);
+		const double alpha = wbar * two_eta, gamma = wbar * two_eta_p;
+		const double cxx = 2.0 * g00 + g11, cyy = 2.0 * g11 + g00, hz0 = 0.5 * g02, hz1 = 0.5 * g12;
+		double dx[4], dy[4];
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) { dx[a] = cxx * X[a] + sh * Y[a] + hz0 * Z[a]; dy[a] = cyy * Y[a] + sh * X[a] + hz1 * Z[a]; }
+		const double grav = P.rho_g * vol * 0.25;
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) {
+			atomicAdd(&acc[(2 * nd[a]) % nacc], alpha * dx[a] + grav * sx);
+			atomicAdd(&acc[(2 * nd[a] + 1) % nacc], alpha * dy[a] + grav * sy);
+			const double Pa = 2.0 * alpha * X[a], Qa = 0.5 * alpha * Y[a], Ra = 0.5 * alpha * Z[a];
+			const double Sa = 2.0 * alpha * Y[a], Ta = 0.5 * alpha * X[a];
+			const double Ua = alpha * X[a], Wa = alpha * Y[a];
+			const double Ea = gamma * dx[a], Ga = gamma * dy[a];
+			#pragma unroll
+			for (int b = 0; b < 4; ++b) {
+				const int slot = tet_blk[(a * 4 + b) * nt + t];
+				double* v = acc + (4 * (size_t)slot) % (size_t)(nacc - 4);
+				atomicAdd(v + 0, Pa * X[b] + Qa * Y[b] + Ra * Z[b] + Ea * dx[b]);
+				atomicAdd(v + 1, Ua * Y[b] + Qa * X[b] + Ea * dy[b]);
+				atomicAdd(v + 2, Wa * X[b] + Ta * Y[b] + Ga * dx[b]);
+				atomicAdd(v + 3, Sa * Y[b] + Ta * X[b] + Ra * Z[b] + Ga * dy[b]);
+			}
+		}
+	}
+	__syncthreads();
+	double s = 0.0;
+	for (int k = threadIdx.x; k < nacc; k += blockDim.x) s += acc[k];
+	if (s == 1.2345e-300) sink[0] = s;
+}
+
+void bp_launch_proxy(bp_ctx* c)
+{
+	const AsmParams P = make_params_fwd(c);
+	const int nacc = 25000;
+	cudaFuncSetAttribute(k_proxy_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, nacc * 8);
+	k_proxy_smem<<<148, 384, nacc * 8, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_tet_blk, P, nacc, c->d_part);
+	c->launches++;
+}
+
 // ---------------------------------------------------------------- row-gather kernel
 // One thread per Jacobian block row (= owned node i).  The thread walks the tets that
 // touch node i (SELL-32 incidence list), rebuilds each tet's cell-constant quantities
@@ -157,16 +246,16 @@ template <bool WANT_F, bool WANT_J>
 __global__ void __launch_bounds__(RTPB)
 k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restrict__ inc_code,
        const uint32_t* __restrict__ inc_pos, const int32_t* __restrict__ inc_v, size_t nslot,
-       const double* __restrict__ soa, size_t nv, const int32_t* __restrict__ v2n,
-       const double2* __restrict__ u, const double* __restrict__ Av,
-       const int32_t* __restrict__ rowptr, double* __restrict__ F, double* __restrict__ val, AsmParams P)
+       const double* __restrict__ soa, size_t nv,
+       const double2* __restrict__ u /* per VERTEX */, const double* __restrict__ Av,
+       const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
+       double* __restrict__ F, double* __restrict__ val, AsmParams P)
 {
 	extern __shared__ double acc[];                  // [4*max_row][RTPB]
 	const int tid = threadIdx.x;
 	const int i = blockIdx.x * RTPB + tid;
 	const bool active = i < nrows;
-	const int r0 = active ? rowptr[i] : 0;
-	const int len = active ? rowptr[i + 1] - r0 : 0;
+	const int len = active ? rowlen[i] : 0;
 	if (WANT_J) for (int k = 0; k < 4 * len; ++k) acc[k * RTPB + tid] = 0.0;
 	double Fx = 0.0, Fy = 0.0;
 	const int slice = i >> 5, lane = i & 31;
@@ -188,15 +277,16 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		for (int j = 0; j < 4; ++j) {
 			p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
 			A[j] = Av[vid[j]];
-			uu[j] = u[v2n ? v2n[vid[j]] : vid[j]];
+			uu[j] = u[vid[j]];
 		}
 	}
 	while (code >= 0) {
 		const int a = code & 3;
 		const uint32_t pk_cur = pk;
 		e += 32;
-		const int code_n = (e < e1) ? inc_code[e] : -1;
-		if (code_n >= 0) {
+		int code_n = -1;
+		if (e < e1) {                                // padding slots hold code -1, vertex 0: safe to load
+			code_n = inc_code[e];
 			pk = inc_pos[e];
 			#pragma unroll
 			for (int j = 0; j < 4; ++j) vid[j] = inc_v[j * nslot + e];
@@ -242,7 +332,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 			for (int j = 0; j < 4; ++j) {
 				p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
 				A[j] = Av[vid[j]];
-				uu[j] = u[v2n ? v2n[vid[j]] : vid[j]];
+				uu[j] = u[vid[j]];
 			}
 		}
 		const double sh = 0.5 * (g01 + g10);
@@ -287,11 +377,12 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	if (!active) return;
 	if (WANT_F) { F[2 * i] = Fx; F[2 * i + 1] = Fy; }
 	if (WANT_J) {
-		double2* out = (double2*)(val + 4 * (size_t)r0);
+		// SELL-32: block k of the 32 rows of a slice is contiguous -> coalesced 1 KB stores
+		double2* out = (double2*)val + 2 * ((size_t)sell_ptr[slice] + lane);
 		for (int k = 0; k < len; ++k) {
 			const double* s4 = acc + (4 * k) * RTPB + tid;
-			out[2 * k]     = make_double2(s4[0], s4[RTPB]);
-			out[2 * k + 1] = make_double2(s4[2 * RTPB], s4[3 * RTPB]);
+			out[64 * (size_t)k]     = make_double2(s4[0], s4[RTPB]);
+			out[64 * (size_t)k + 1] = make_double2(s4[2 * RTPB], s4[3 * RTPB]);
 		}
 	}
 }
@@ -388,22 +479,40 @@ static AsmParams make_params(const bp_ctx* c)
 	return P;
 }
 
+static AsmParams make_params_fwd(const bp_ctx* c) { return make_params(c); }
+
 void bp_upload_quadrature(bp_ctx* c)
 {
 	cudaMemcpyToSymbol(c_qw, c->quad_wts.data(), c->quad_wts.size() * sizeof(double));
 	cudaMemcpyToSymbol(c_ql, c->quad_pts.data(), c->quad_pts.size() * sizeof(double));
 }
 
+// u per vertex for the row-gather kernel (periodic images read their master's value)
+__global__ void k_expand_u(int nv, const int32_t* __restrict__ v2n, const double2* __restrict__ u, double2* __restrict__ uv)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) uv[i] = u[v2n[i]];
+}
+static inline int red_blocks_fwd(int64_t n_items, int per_block);
+static const double2* bp_vertex_u(bp_ctx* c)
+{
+	if (!c->d_v2n) return (const double2*)c->d_u;
+	k_expand_u<<<red_blocks_fwd(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, c->d_v2n, (const double2*)c->d_u, (double2*)c->d_uvert);
+	c->launches++;
+	return (const double2*)c->d_uvert;
+}
+
+void bp_launch_proxy(bp_ctx* c);
 void bp_launch_assemble(bp_ctx* c, int what)
 {
 	const AsmParams P = make_params(c);
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
+	if (what & 8) { bp_launch_proxy(c); return; }
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
 		const size_t rs = (size_t)4 * c->max_row * RTPB * sizeof(double);
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
 			cudaFuncSetAttribute(k_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			k_rows<true, true><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
-				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_rowptr, c->d_F, c->d_val, P);
+				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P);
 		} else {
 			const int gc = (int)((c->nt + TPB - 1) / TPB);
 			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P);
@@ -425,13 +534,14 @@ void bp_launch_assemble(bp_ctx* c, int what)
 			attr_set = true;
 		}
 		const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
-		#define ROWS(WF, WJ, SM) k_rows<WF, WJ><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, c->d_v2n, u2, c->d_A, c->d_rowptr, c->d_F, c->d_val, P)
+		const double2* uvert = bp_vertex_u(c);
+		#define ROWS(WF, WJ, SM) k_rows<WF, WJ><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P)
 		if (wf && wj) ROWS(true, true, row_smem);
 		else if (wf)  ROWS(true, false, 0);
 		else if (wj)  ROWS(false, true, row_smem);
 	} else {
 		if (wf) cudaMemsetAsync(c->d_F, 0, 2 * c->nn * sizeof(double), c->stream);
-		if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->nnzb * 4 * sizeof(double), c->stream);
+		if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->n_slots * 4 * sizeof(double), c->stream);
 		const int gc = (int)((c->nt + TPB - 1) / TPB);
 		#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
 		if (wf && wj) CELL(true, true);
@@ -503,6 +613,8 @@ __device__ __forceinline__ void block_reduce_finalize(double (&v)[NV], double* p
 }
 
 #define RED_BLOCKS_MAX 4096
+static inline int red_blocks(int64_t n_items, int per_block);
+static inline int red_blocks_fwd(int64_t n_items, int per_block) { return red_blocks(n_items, per_block); }
 static inline int red_blocks(int64_t n_items, int per_block)
 {
 	int64_t b = (n_items + per_block - 1) / per_block;
@@ -511,34 +623,42 @@ static inline int red_blocks(int64_t n_items, int per_block)
 	return (int)b;
 }
 
-// ---------------------------------------------------------------- SpMV (BSR 2x2)
-// 16 lanes per block row: lane k reads block k of the row (32 B, contiguous across
-// the half-warp) and the {x,y} pair of its column node (16 B gather).
+// ---------------------------------------------------------------- SpMV (2x2 blocks, SELL-32)
+// One thread per block row; block k of the 32 rows of a slice is contiguous, so every
+// warp load of values (2 x 16 B per lane) and of column ids is a full-line access; the
+// {x,y} pair of the column node is a 16 B gather.  No shuffles, no row pointer chase.
 template <bool WITH_DOT>
 __global__ void __launch_bounds__(256)
-k_spmv(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+k_spmv(int nrows, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ col,
        const double2* __restrict__ val, const double2* __restrict__ x, double2* __restrict__ y,
        const double* __restrict__ sc, double* part, unsigned* counter, double* out)
 {
 	if (WITH_DOT && sc[SC_DONE] != 0.0) return;
 	double acc[1] = { 0.0 };
-	const int l16 = threadIdx.x & 15;
-	const int rows_per_block = blockDim.x >> 4;
-	for (int row = blockIdx.x * rows_per_block + (threadIdx.x >> 4); row < nrows; row += gridDim.x * rows_per_block) {
-		const int k0 = rowptr[row], k1 = rowptr[row + 1];
+	const int lane = threadIdx.x & 31;
+	const int nsl = (nrows + 31) >> 5;
+	for (int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slice < nsl; slice += (gridDim.x * blockDim.x) >> 5) {
+		const int b0 = sell_ptr[slice], w = (sell_ptr[slice + 1] - b0) >> 5;
+		const int row = (slice << 5) + lane;
+		const int32_t* cp = col + b0 + lane;
+		const double2* vp = val + 2 * ((size_t)b0 + lane);
 		double s0 = 0.0, s1 = 0.0;
-		for (int k = k0 + l16; k < k1; k += 16) {
-			const double2 v01 = val[2 * (size_t)k], v23 = val[2 * (size_t)k + 1];
-			const double2 xv = x[col[k]];
-			s0 += v01.x * xv.x + v01.y * xv.y;
-			s1 += v23.x * xv.x + v23.y * xv.y;
+		int k = 0;
+		for (; k + 4 <= w; k += 4) {
+			int cc[4]; double2 v01[4], v23[4], xv[4];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) { cc[j] = cp[32 * (k + j)]; v01[j] = vp[64 * (size_t)(k + j)]; v23[j] = vp[64 * (size_t)(k + j) + 1]; }
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) xv[j] = x[cc[j]];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) { s0 += v01[j].x * xv[j].x + v01[j].y * xv[j].y; s1 += v23[j].x * xv[j].x + v23[j].y * xv[j].y; }
 		}
-		#pragma unroll
-		for (int o = 8; o > 0; o >>= 1) {
-			s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-			s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+		for (; k < w; ++k) {
+			const double2 a01 = vp[64 * (size_t)k], a23 = vp[64 * (size_t)k + 1];
+			const double2 xv = x[cp[32 * k]];
+			s0 += a01.x * xv.x + a01.y * xv.y; s1 += a23.x * xv.x + a23.y * xv.y;
 		}
-		if (l16 == 0) {
+		if (row < nrows) {
 			y[row] = make_double2(s0, s1);
 			if (WITH_DOT) { const double2 xr = x[row]; acc[0] += xr.x * s0 + xr.y * s1; }
 		}
@@ -546,15 +666,36 @@ k_spmv(int nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 	if (WITH_DOT) block_reduce_finalize<1>(acc, part, RED_BLOCKS_MAX, counter, out);
 }
 
+// grid = one wave of resident blocks (a second, partial wave costs a full block time)
+template <class K>
+static int one_wave(K kernel, int block, int64_t n_items, int per_block)
+{
+	int per_sm = 0, dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, 0);
+	int64_t b = (n_items + per_block - 1) / per_block;
+	const int64_t cap = (int64_t)std::max(per_sm, 1) * sms;
+	if (b > cap) b = cap;
+	if (b > RED_BLOCKS_MAX) b = RED_BLOCKS_MAX;
+	return (int)std::max<int64_t>(b, 1);
+}
+
 void bp_launch_spmv(bp_ctx* c, const double* x, double* y, int with_dot)
 {
-	const int rows_per_block = 256 / 16;
-	const int grid = red_blocks(c->nn_owned, rows_per_block);
+	const int rows_per_block = 256;
+	static int g1 = 0, g0 = 0;
+	static int64_t n_cached = -1;
+	if (n_cached != c->nn_owned) {
+		g1 = one_wave(k_spmv<true>, 256, c->nn_owned, rows_per_block);
+		g0 = one_wave(k_spmv<false>, 256, c->nn_owned, rows_per_block);
+		n_cached = c->nn_owned;
+	}
 	if (with_dot)
-		k_spmv<true><<<grid, 256, 0, c->stream>>>((int)c->nn_owned, c->d_rowptr, c->d_col, (const double2*)c->d_val,
+		k_spmv<true><<<g1, 256, 0, c->stream>>>((int)c->nn_owned, c->d_sell_ptr, c->d_col, (const double2*)c->d_val,
 			(const double2*)x, (double2*)y, c->d_sc, c->d_part, c->d_counter, c->d_sc + SC_PAP);
 	else
-		k_spmv<false><<<grid, 256, 0, c->stream>>>((int)c->nn_owned, c->d_rowptr, c->d_col, (const double2*)c->d_val,
+		k_spmv<false><<<g0, 256, 0, c->stream>>>((int)c->nn_owned, c->d_sell_ptr, c->d_col, (const double2*)c->d_val,
 			(const double2*)x, (double2*)y, c->d_sc, c->d_part, c->d_counter, c->d_sc + SC_PAP);
 	c->launches++;
 }
@@ -677,7 +818,9 @@ __device__ __forceinline__ double2 apply_dinv(const double* __restrict__ dinv, i
 	return make_double2(d01.x * r.x + d01.y * r.y, d23.x * r.x + d23.y * r.y);
 }
 
-// x = 0, r = b, z = M^-1 r, p = z;  (rz, zz, rr)
+// Scalars: iteration k (parity par = k & 1) reads r.z from triple T[par] and writes the
+// new {r.z, z.z, r.r} into T[par ^ 1]; the init writes T[0].  No kernel rotates scalars.
+// x = 0, r = b, z = M^-1 r, p = z;  (rz, zz, rr) -> T[0]
 __global__ void __launch_bounds__(256)
 k_pcg_init(int nrows, const double2* __restrict__ b, const double* __restrict__ dinv,
            double2* x, double2* r, double2* z, double2* p, double* part, unsigned* counter, double* sc)
@@ -689,17 +832,18 @@ k_pcg_init(int nrows, const double2* __restrict__ b, const double* __restrict__ 
 		x[i] = make_double2(0.0, 0.0); r[i] = rv; z[i] = zv; p[i] = zv;
 		acc[0] += rv.x * zv.x + rv.y * zv.y; acc[1] += zv.x * zv.x + zv.y * zv.y; acc[2] += rv.x * rv.x + rv.y * rv.y;
 	}
-	block_reduce_finalize<3>(acc, part, RED_BLOCKS_MAX, counter, sc + SC_RZ_NEXT);
+	block_reduce_finalize<3>(acc, part, RED_BLOCKS_MAX, counter, sc + SC_T0);
 }
 
-// alpha = rz / pAp;  x += alpha p;  r -= alpha Ap;  z = M^-1 r;  (rz_next, zz, rr)
+// alpha = rz / pAp;  x += alpha p;  r -= alpha Ap;  z = M^-1 r;  (rz, zz, rr) -> T[par^1]
 __global__ void __launch_bounds__(256)
-k_pcg_update(int nrows, const double* __restrict__ dinv, const double2* __restrict__ p, const double2* __restrict__ Ap,
+k_pcg_update(int nrows, int par, const double* __restrict__ dinv, const double2* __restrict__ p, const double2* __restrict__ Ap,
              double2* x, double2* r, double2* z, double* part, unsigned* counter, double* sc)
 {
 	if (sc[SC_DONE] != 0.0) return;
 	const double pAp = sc[SC_PAP];
-	const double alpha = sc[SC_RZ] / pAp;
+	if (!(pAp > 0.0)) return;                        // breakdown: k_pcg_p flags it, x keeps the last good iterate
+	const double alpha = sc[par ? SC_T1 : SC_T0] / pAp;
 	double acc[3] = { 0.0, 0.0, 0.0 };
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
 		const double2 pv = p[i], av = Ap[i];
@@ -710,15 +854,19 @@ k_pcg_update(int nrows, const double* __restrict__ dinv, const double2* __restri
 		x[i] = xv; r[i] = rv; z[i] = zv;
 		acc[0] += rv.x * zv.x + rv.y * zv.y; acc[1] += zv.x * zv.x + zv.y * zv.y; acc[2] += rv.x * rv.x + rv.y * rv.y;
 	}
-	block_reduce_finalize<3>(acc, part, RED_BLOCKS_MAX, counter, sc + SC_RZ_NEXT);
+	block_reduce_finalize<3>(acc, part, RED_BLOCKS_MAX, counter, sc + (par ? SC_T0 : SC_T1));
 }
 
-// convergence test + p = z + beta p.  One designated thread does the bookkeeping.
+// convergence test + p = z + beta p.  One designated thread does the bookkeeping; it is
+// the only writer of SC_DONE, and blocks that already see it set skip the same work the
+// others skip because they evaluate the same predicate.
 __global__ void __launch_bounds__(256)
-k_pcg_p(int nrows, int first, double rtol, double atol, const double2* __restrict__ z, double2* p, double* sc)
+k_pcg_p(int nrows, int first, int par, double rtol, double atol, const double2* __restrict__ z, double2* p, double* sc)
 {
 	if (!first && sc[SC_DONE] != 0.0) return;
-	const double rz = sc[SC_RZ], rz_next = sc[SC_RZ_NEXT], zz = sc[SC_ZZ], pAp = sc[SC_PAP];
+	const double* Told = sc + (par ? SC_T1 : SC_T0);
+	const double* Tnew = first ? sc + SC_T0 : sc + (par ? SC_T0 : SC_T1);
+	const double rz = Told[0], rz_next = Tnew[0], zz = Tnew[1], pAp = sc[SC_PAP];
 	const double norm = sqrt(zz);
 	const double norm0 = first ? norm : sc[SC_NORM0];
 	const bool bad = !first && !(pAp > 0.0);
@@ -729,20 +877,13 @@ k_pcg_p(int nrows, int first, double rtol, double atol, const double2* __restric
 			const double2 zv = z[i], pv = p[i];
 			p[i] = make_double2(zv.x + beta * pv.x, zv.y + beta * pv.y);
 		}
-	// bookkeeping by the last thread of the last block: SC_RZ is read by every thread
-	// above, so it is rotated by the next kernel in the stream instead (k_pcg_rotate).
 	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == blockDim.x - 1) {
-		sc[SC_NORM] = norm;
+		sc[SC_NORM] = bad ? sc[SC_NORM] : norm;
 		if (first) { sc[SC_NORM0] = norm; sc[SC_ITERS] = 0.0; sc[SC_BREAKDOWN] = 0.0; }
-		else sc[SC_ITERS] += 1.0;
+		else if (!bad) sc[SC_ITERS] += 1.0;
 		if (bad) sc[SC_BREAKDOWN] = 1.0;
-		sc[SC_TMP] = conv ? 1.0 : 0.0;
+		if (conv) sc[SC_DONE] = 1.0;
 	}
-}
-__global__ void k_pcg_rotate(double* sc)
-{
-	sc[SC_RZ] = sc[SC_RZ_NEXT];
-	if (sc[SC_TMP] != 0.0) sc[SC_DONE] = 1.0;
 }
 
 void bp_launch_pcg_init(bp_ctx* c)
@@ -753,21 +894,19 @@ void bp_launch_pcg_init(bp_ctx* c)
 		(double2*)c->d_z, (double2*)c->d_p, c->d_part, c->d_counter, c->d_sc);
 	c->launches++;
 }
-void bp_launch_pcg_update(bp_ctx* c)
+void bp_launch_pcg_update(bp_ctx* c, int par)
 {
 	const int n = (int)c->nn_owned;
-	k_pcg_update<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, c->d_dinv, (const double2*)c->d_p, (const double2*)c->d_Ap,
+	k_pcg_update<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, par, c->d_dinv, (const double2*)c->d_p, (const double2*)c->d_Ap,
 		(double2*)c->d_dx, (double2*)c->d_r, (double2*)c->d_z, c->d_part, c->d_counter, c->d_sc);
 	c->launches++;
 }
-void bp_launch_pcg_p_impl(bp_ctx* c, int first)
+void bp_launch_pcg_p(bp_ctx* c, int first, int par)
 {
 	const int n = (int)c->nn_owned;
-	k_pcg_p<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, first, c->prm.krylov_rtol, c->prm.krylov_atol, (const double2*)c->d_z, (double2*)c->d_p, c->d_sc);
-	k_pcg_rotate<<<1, 1, 0, c->stream>>>(c->d_sc);
-	c->launches += 2;
+	k_pcg_p<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, first, par, c->prm.krylov_rtol, c->prm.krylov_atol, (const double2*)c->d_z, (double2*)c->d_p, c->d_sc);
+	c->launches++;
 }
-void bp_launch_pcg_p(bp_ctx* c) { bp_launch_pcg_p_impl(c, 0); }
 
 // sum d_sc[slot..slot+count) across the contexts of an in-process group (same device)
 struct ScPtrs { double* p[16]; };

@@ -159,6 +159,34 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	for (int64_t i = 0; i < no; ++i)
 		if (diag[i] < 0 && nptr[i + 1] > nptr[i]) return bp_fail(c, BP_ERR_ARG, "internal: missing diagonal block");
 
+	// ---- SELL-32 slots of the resident Jacobian: block k of row i lives at
+	// sell_ptr[i/32] + 32 k + (i%32); padding slots keep value 0 and point at the row itself
+	const int64_t nsl_j = (no + 31) / 32;
+	std::vector<int32_t> sell_ptr(nsl_j + 1, 0), row_len(no, 0);
+	for (int64_t sidx = 0; sidx < nsl_j; ++sidx) {
+		int32_t w = 0;
+		for (int64_t i = sidx * 32; i < std::min<int64_t>(no, sidx * 32 + 32); ++i) {
+			row_len[i] = c->h_rowptr[i + 1] - c->h_rowptr[i];
+			w = std::max(w, row_len[i]);
+		}
+		const int64_t nxt = (int64_t)sell_ptr[sidx] + 32 * (int64_t)w;
+		if (nxt > INT32_MAX / 4) return bp_fail(c, BP_ERR_ARG, "bp_mesh: too many Jacobian blocks for one rank");
+		sell_ptr[sidx + 1] = (int32_t)nxt;
+	}
+	c->n_slots = sell_ptr[nsl_j];
+	auto slot_of = [&](int64_t i, int32_t k) -> int32_t { return sell_ptr[i >> 5] + 32 * k + (int32_t)(i & 31); };
+	std::vector<int32_t> sell_col((size_t)std::max<int64_t>(c->n_slots, 1), 0);
+	for (int64_t i = 0; i < no; ++i) {
+		const int32_t w = (sell_ptr[(i >> 5) + 1] - sell_ptr[i >> 5]) >> 5;
+		for (int32_t k = 0; k < w; ++k)
+			sell_col[slot_of(i, k)] = (k < row_len[i]) ? c->h_col[c->h_rowptr[i] + k] : (int32_t)i;
+		if (diag[i] >= 0) diag[i] = slot_of(i, diag[i] - c->h_rowptr[i]);
+	}
+	for (int64_t i = no; i < nsl_j * 32; ++i) {          // lanes past the last row
+		const int32_t w = (sell_ptr[(i >> 5) + 1] - sell_ptr[i >> 5]) >> 5;
+		for (int32_t k = 0; k < w; ++k) sell_col[slot_of(i, k)] = 0;
+	}
+
 	// ---- per-tet block slots [16][nt] ------------------------------------------
 	std::vector<int32_t> tet_blk((size_t)nt * 16);
 	#pragma omp parallel for schedule(static)
@@ -170,7 +198,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 				if (r < no) {
 					const int32_t* lo = c->h_col.data() + c->h_rowptr[r];
 					const int32_t* hi = c->h_col.data() + c->h_rowptr[r + 1];
-					slot = (int32_t)(std::lower_bound(lo, hi, cn[t * 4 + b]) - c->h_col.data());
+					slot = slot_of(r, (int32_t)(std::lower_bound(lo, hi, cn[t * 4 + b]) - lo));
 				}
 				tet_blk[(size_t)(a * 4 + b) * nt + t] = slot;
 			}
@@ -272,15 +300,17 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	UP(c->d_A, (const double*)nullptr, nv);
 	UP(c->d_beta, (const double*)nullptr, nv);
 	UP(c->d_tets, (const int4*)m->cells, nt);
-	if (!c->identity_v2n) UP(c->d_v2n, v2n.data(), nv);
+	if (!c->identity_v2n) { UP(c->d_v2n, v2n.data(), nv); UP(c->d_uvert, (const double*)nullptr, (size_t)2 * nv); }
 	UP(c->d_tet_blk, tet_blk.data(), (size_t)nt * 16);
 	UP(c->d_fac_cell, fcell.data(), c->nf);
 	UP(c->d_fac_info, finfo.data(), c->nf);
 	if (!c->identity_dofs) UP(c->d_ext_dof, c->h_ext_dof.data(), 2 * nn);
-	UP(c->d_rowptr, c->h_rowptr.data(), no + 1);
-	UP(c->d_col, c->h_col.data(), c->nnzb);
+	UP(c->d_sell_ptr, sell_ptr.data(), nsl_j + 1);
+	UP(c->d_rowlen, row_len.data(), no);
+	UP(c->d_col, sell_col.data(), c->n_slots);
+	c->h_sell_ptr = sell_ptr;
 	UP(c->d_diag, diag.data(), no);
-	UP(c->d_val, (const double*)nullptr, (size_t)c->nnzb * 4);
+	UP(c->d_val, (const double*)nullptr, (size_t)c->n_slots * 4);
 	double** vecs[] = { &c->d_u, &c->d_F, &c->d_dx, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap, &c->d_io, &c->d_io2 };
 	for (double** v : vecs) {
 		size_t len = std::max<size_t>((size_t)2 * nn, (size_t)std::max<int64_t>(std::max<int64_t>(c->nd_ext, nv), 1));
@@ -294,7 +324,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	UP(c->d_counter, (const unsigned*)nullptr, 16);
 	BP_CUDA(c, cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned)));
 	BP_CUDA(c, cudaMallocHost((void**)&c->h_sc, SC_COUNT * sizeof(double)));
-	BP_CUDA(c, cudaMemset(c->d_val, 0, (size_t)std::max<int64_t>(c->nnzb, 1) * 4 * sizeof(double)));
+	BP_CUDA(c, cudaMemset(c->d_val, 0, (size_t)std::max<int64_t>(c->n_slots, 1) * 4 * sizeof(double)));
 	return BP_OK;
 }
 
@@ -329,7 +359,7 @@ int bp_build_csr_export(bp_ctx* c)
 			tmp.clear();
 			for (int32_t k = c->h_rowptr[node]; k < c->h_rowptr[node + 1]; ++k)
 				for (int cc = 0; cc < 2; ++cc)
-					tmp.push_back({ c->h_ext_dof[2 * c->h_col[k] + cc], k * 4 + comp * 2 + cc });
+					tmp.push_back({ c->h_ext_dof[2 * c->h_col[k] + cc], (c->h_sell_ptr[node >> 5] + 32 * (k - c->h_rowptr[node]) + (node & 31)) * 4 + comp * 2 + cc });
 			std::sort(tmp.begin(), tmp.end());
 			int64_t o = c->csr_indptr[d];
 			for (size_t k = 0; k < tmp.size(); ++k) { c->csr_indices[o + k] = tmp[k].first; src[o + k] = tmp[k].second; }
