@@ -221,7 +221,7 @@ def main():
 		t_e2e = time.perf_counter() - t0
 		newton = {"solve_s": t_dev, "e2e_s": t_e2e, "converged": st['converged'], "newton_iterations": st['iterations'],
 		          "krylov_iterations": st['krylov_iterations'], "assemble_ms": st['t_assemble_ms'], "krylov_ms": st['t_krylov_ms'],
-		          "preconditioner": ctx.params.get('preconditioner', 'block_jacobi'), "rtol": 1e-9, "krylov_rtol": 1e-5,
+		          "preconditioner": "%s(degree %d, ratio %g)" % (ctx.params.get('preconditioner', 'chebyshev'), ctx.params.get('pc_degree', 8), ctx.params.get('pc_eig_ratio', 100.0)), "rtol": 1e-9, "krylov_rtol": 1e-5,
 		          "gpu_launches": st['gpu_launches']}
 		if st['converged']:
 			u_host = uh * (1.0 + 1e-3 * np.random.default_rng(1234).normal(size=uh.size))

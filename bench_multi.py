@@ -54,7 +54,7 @@ def run_multi(args, rank, world, local):
 		t = torch.tensor([time.perf_counter() - t0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 		newton = {"solve_s": t.item(), "converged": st['converged'], "newton_iterations": st['iterations'],
 		          "krylov_iterations": st['krylov_iterations'], "assemble_ms": st['t_assemble_ms'], "krylov_ms": st['t_krylov_ms'],
-		          "preconditioner": ctx.params.get('preconditioner', 'block_jacobi'), "rtol": 1e-9, "krylov_rtol": 1e-5}
+		          "preconditioner": "%s(degree %d, ratio %g)" % (ctx.params.get('preconditioner', 'chebyshev'), ctx.params.get('pc_degree', 8), ctx.params.get('pc_eig_ratio', 100.0)), "rtol": 1e-9, "krylov_rtol": 1e-5}
 
 	u_dev = torch.from_numpy(u_host).to(dev)
 	F_dev = torch.empty_like(u_dev)

@@ -42,7 +42,7 @@ class bp_params(C.Structure):
 	            ('error_on_nonconvergence', C.c_int32),
 	            ('krylov_rtol', C.c_double), ('krylov_atol', C.c_double),
 	            ('krylov_maxit', C.c_int32), ('pc', C.c_int32), ('pc_degree', C.c_int32),
-	            ('verbose', C.c_int32), ('assembly', C.c_int32)]
+	            ('verbose', C.c_int32), ('assembly', C.c_int32), ('pc_eig_ratio', C.c_double)]
 
 
 class bp_stats(C.Structure):
@@ -229,9 +229,10 @@ class BPContext(object):
 		p.krylov_rtol = d.get('krylov_rtol', 1e-5)
 		p.krylov_atol = d.get('krylov_atol', 1e-50)
 		p.krylov_maxit = int(d.get('krylov_maxit', 10000))
-		pc = d.get('preconditioner', 'block_jacobi')
+		pc = d.get('preconditioner', 'chebyshev')
 		p.pc = PC[pc] if isinstance(pc, str) else int(pc)
-		p.pc_degree = int(d.get('pc_degree', 3))
+		p.pc_degree = int(d.get('pc_degree', 8))
+		p.pc_eig_ratio = float(d.get('pc_eig_ratio', 100.0))
 		p.verbose = int(bool(d.get('verbose', False)))
 		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
 		return p

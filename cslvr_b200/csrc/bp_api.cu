@@ -101,24 +101,84 @@ static int group_norm_F(bp_ctx** cs, int n, double* out)
 	return BP_OK;
 }
 
+// ---- preconditioner set-up, once per Jacobian ---------------------------------------
+static int group_pc_prepare(bp_ctx** cs, int n)
+{
+	int rc;
+	for (int r = 0; r < n; ++r) bp_launch_pc_setup(cs[r]);
+	if (cs[0]->prm.pc == BP_PC_CHEBYSHEV) {
+		// upper bound of lmax(D^-1 J): Gershgorin row bound, max over all ranks
+		double lmax = 0.0;
+		for (int r = 0; r < n; ++r) bp_launch_gershgorin(cs[r], SC_TMP);
+		if (n == 1 && (rc = bp_comm_allreduce_max(cs[0], SC_TMP, 1))) return rc;
+		for (int r = 0; r < n; ++r) { if ((rc = read_scalars(cs[r]))) return rc; lmax = std::max(lmax, cs[r]->h_sc[SC_TMP]); }
+		if (!(lmax > 0.0) || !std::isfinite(lmax)) return bp_fail(cs[0], BP_ERR_STATE, "Chebyshev: eigenvalue bound failed (%g)", lmax);
+		for (int r = 0; r < n; ++r) cs[r]->cheb_lmax = lmax;
+	}
+	if (cs[0]->prm.pc == BP_PC_COLUMN)
+		for (int r = 0; r < n; ++r) if (cs[r]->max_layers > 64)
+			return bp_fail(cs[0], BP_ERR_ARG, "column preconditioner supports at most 64 nodes per ice column (mesh has %d)", cs[r]->max_layers);
+	return BP_OK;
+}
+
+// z = M^-1 r for the preconditioners that are not fused into the CG update kernel
+static int group_pc_apply(bp_ctx** cs, int n)
+{
+	int rc;
+	if (cs[0]->prm.pc == BP_PC_COLUMN) {
+		for (int r = 0; r < n; ++r) bp_launch_col_solve(cs[r], cs[r]->d_r, cs[r]->d_z);
+		return BP_OK;
+	}
+	// Chebyshev on [b / ratio, b], b = 1.1 lmax
+	const int deg = std::max(cs[0]->prm.pc_degree, 1);
+	const double b = cs[0]->cheb_lmax, a = b / std::max(cs[0]->prm.pc_eig_ratio, 1.5);
+	const double theta = 0.5 * (b + a), delta = 0.5 * (b - a), sigma = theta / delta;
+	double rho = 1.0 / sigma;
+	for (int r = 0; r < n; ++r) bp_launch_cheb_first(cs[r], 1.0 / theta, cs[r]->d_r, cs[r]->d_z);
+	for (int k = 1; k < deg; ++k) {
+		const double rho_n = 1.0 / (2.0 * sigma - rho);
+		if ((rc = bp_comm_halo(cs, n, 2))) return rc;
+		for (int r = 0; r < n; ++r) { bp_launch_cheb_step(cs[r], rho_n * rho, 2.0 * rho_n / delta, cs[r]->d_r, cs[r]->d_z, cs[r]->d_z2); std::swap(cs[r]->d_z, cs[r]->d_z2); }
+		rho = rho_n;
+	}
+	return BP_OK;
+}
+
 // PCG on J dx = F (rhs in d_F, solution in d_dx)
 static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 {
 	int rc;
-	for (int r = 0; r < n; ++r) { bp_launch_pc_setup(cs[r]); bp_launch_pcg_init(cs[r]); }
+	const bool fused = cs[0]->prm.pc <= BP_PC_BLOCK_JACOBI;       // pointwise: applied inside the update kernel
+	if ((rc = group_pc_prepare(cs, n))) return rc;
+	if (fused) {
+		for (int r = 0; r < n; ++r) bp_launch_pcg_init(cs[r]);
+	} else {
+		for (int r = 0; r < n; ++r) bp_launch_pcg_init2(cs[r]);
+		if ((rc = group_pc_apply(cs, n))) return rc;
+		for (int r = 0; r < n; ++r) {
+			cudaMemcpyAsync(cs[r]->d_p, cs[r]->d_z, (size_t)2 * cs[r]->nn_owned * sizeof(double), cudaMemcpyDeviceToDevice, cs[r]->stream);
+			bp_launch_dots3(cs[r], SC_T0, 0);
+		}
+	}
 	if ((rc = bp_comm_allreduce(cs, n, SC_T0, 3))) return rc;
 	for (int r = 0; r < n; ++r) bp_launch_pcg_p(cs[r], 1, 0);
 	const int maxit = cs[0]->prm.krylov_maxit > 0 ? cs[0]->prm.krylov_maxit : 10000;
 	int k = 0;
 	bool done = false;
 	while (k < maxit && !done) {
-		const int batch = std::min(32, maxit - k);
+		const int batch = std::min(fused ? 32 : 8, maxit - k);
 		for (int i = 0; i < batch; ++i) {
 			if ((rc = bp_comm_halo(cs, n, 1))) return rc;
 			for (int r = 0; r < n; ++r) bp_launch_spmv(cs[r], cs[r]->d_p, cs[r]->d_Ap, 1);
 			if ((rc = bp_comm_allreduce(cs, n, SC_PAP, 1))) return rc;
 			const int par = (k + i) & 1;
-			for (int r = 0; r < n; ++r) bp_launch_pcg_update(cs[r], par);
+			if (fused) {
+				for (int r = 0; r < n; ++r) bp_launch_pcg_update(cs[r], par);
+			} else {
+				for (int r = 0; r < n; ++r) bp_launch_pcg_update2(cs[r], par);
+				if ((rc = group_pc_apply(cs, n))) return rc;
+				for (int r = 0; r < n; ++r) bp_launch_dots3(cs[r], par ? SC_T0 : SC_T1, 1);
+			}
 			if ((rc = bp_comm_allreduce(cs, n, par ? SC_T0 : SC_T1, 3))) return rc;
 			for (int r = 0; r < n; ++r) bp_launch_pcg_p(cs[r], 0, par);
 		}
@@ -235,7 +295,7 @@ void bp_destroy(bp_ctx* c)
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
-		c->d_io, c->d_io2, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
+		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
 	if (c->ev0) cudaEventDestroy(c->ev0);

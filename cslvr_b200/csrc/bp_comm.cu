@@ -18,7 +18,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess_ = 0 };
 enum { ncclFloat64_ = 8 };   // ncclDataType_t
-enum { ncclSum_ = 0 };       // ncclRedOp_t
+enum { ncclSum_ = 0, ncclMax_ = 2 };   // ncclRedOp_t
 
 struct nccl_api {
 	void* handle = nullptr;
@@ -91,7 +91,10 @@ void bp_comm_free(bp_ctx* c)
 	}
 }
 
-double* bp_vec(bp_ctx* c, int which) { return which == 0 ? c->d_u : c->d_p; }
+double* bp_vec(bp_ctx* c, int which)
+{
+	switch (which) { case 0: return c->d_u; case 1: return c->d_p; case 2: return c->d_z; case 3: return c->d_z2; default: return c->d_p; }
+}
 
 // ghost values of vector `which` (0: u, 1: p) from the owning ranks
 int bp_comm_halo(bp_ctx** ctxs, int n, int which)
@@ -141,5 +144,12 @@ int bp_comm_allreduce(bp_ctx** ctxs, int n, int slot, int count)
 		return BP_OK;
 	}
 	bp_launch_sum_scalars(ctxs, n, slot, count);
+	return BP_OK;
+}
+
+int bp_comm_allreduce_max(bp_ctx* c, int slot, int count)
+{
+	if (!c->comm || c->comm->n_ranks == 1) return BP_OK;
+	BP_NCCL(c, g_nccl.AllReduce(c->d_sc + slot, c->d_sc + slot, (size_t)count, ncclFloat64_, ncclMax_, c->comm->comm, c->stream));
 	return BP_OK;
 }

@@ -81,6 +81,12 @@ struct bp_ctx {
 	// device: vectors in internal layout [2*node + c], length 2*nn
 	double *d_u = nullptr, *d_F = nullptr, *d_dx = nullptr, *d_r = nullptr, *d_z = nullptr,
 	       *d_p = nullptr, *d_Ap = nullptr, *d_io = nullptr, *d_io2 = nullptr;
+	double  *d_z2 = nullptr, *d_cd = nullptr;   // Chebyshev ping-pong iterate and direction
+	// vertical-line preconditioner: owned nodes grouped by ice column, bottom to top
+	int64_t  n_cols = 0;
+	int32_t  max_layers = 0;
+	int32_t *d_colptr = nullptr, *d_colnode = nullptr, *d_tri_d = nullptr, *d_tri_u = nullptr, *d_tri_l = nullptr;
+	double   cheb_lmax = 0.0;
 	double*  d_dinv = nullptr;           // [nn_owned*4] preconditioner blocks
 	double*  d_sc = nullptr;             // SC_COUNT scalars
 	double*  d_part = nullptr;           // block partials [4][max_blocks]
@@ -124,9 +130,20 @@ void bp_launch_pcg_init(bp_ctx* c);
 void bp_launch_pcg_update(bp_ctx* c, int par);
 void bp_launch_pcg_p(bp_ctx* c, int first, int par);
 void bp_launch_sum_scalars(bp_ctx** ctxs, int n, int slot, int count);
+void bp_launch_pcg_init2(bp_ctx* c);                       // x = 0, r = b (preconditioner applied separately)
+void bp_launch_pcg_update2(bp_ctx* c, int par);            // x += alpha p, r -= alpha Ap
+void bp_launch_dots3(bp_ctx* c, int slot, int guard);      // {r.z, z.z, r.r} -> d_sc[slot..]
+void bp_launch_col_solve(bp_ctx* c, const double* r, double* z);
+void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z);
+void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew);
+void bp_launch_apply_dinv(bp_ctx* c, double* v);           // v <- D^-1 v
+void bp_launch_scale_inv_norm(bp_ctx* c, double* v, int sc_slot);   // v <- v / sqrt(d_sc[slot])
+void bp_launch_fill_probe(bp_ctx* c, double* v);
+void bp_launch_gershgorin(bp_ctx* c, int sc_slot);        // upper bound of lmax(D^-1 J) -> d_sc[slot]
 
 // comm (bp_comm.cu)
 int  bp_comm_halo(bp_ctx** ctxs, int n, int which_vec);   // 0:u 1:p
 int  bp_comm_allreduce(bp_ctx** ctxs, int n, int slot, int count);
+int  bp_comm_allreduce_max(bp_ctx* c, int slot, int count);
 void bp_comm_free(bp_ctx* c);
 double* bp_vec(bp_ctx* c, int which);

@@ -908,6 +908,252 @@ void bp_launch_pcg_p(bp_ctx* c, int first, int par)
 	c->launches++;
 }
 
+// ---------------------------------------------------------------- general preconditioners
+// CG steps with the preconditioner applied by separate kernels (Chebyshev, column solve)
+__global__ void __launch_bounds__(256)
+k_pcg_init2(int nrows, const double2* __restrict__ b, double2* x, double2* r)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) { x[i] = make_double2(0.0, 0.0); r[i] = b[i]; }
+}
+__global__ void __launch_bounds__(256)
+k_pcg_update2(int nrows, int par, const double2* __restrict__ p, const double2* __restrict__ Ap, double2* x, double2* r, const double* sc)
+{
+	if (sc[SC_DONE] != 0.0) return;
+	const double pAp = sc[SC_PAP];
+	if (!(pAp > 0.0)) return;
+	const double alpha = sc[par ? SC_T1 : SC_T0] / pAp;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+		const double2 pv = p[i], av = Ap[i];
+		double2 xv = x[i], rv = r[i];
+		xv.x += alpha * pv.x; xv.y += alpha * pv.y; rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+		x[i] = xv; r[i] = rv;
+	}
+}
+__global__ void __launch_bounds__(256)
+k_dots3(int nrows, const double2* __restrict__ r, const double2* __restrict__ z, double* part, unsigned* counter, double* out, const double* sc, int guard)
+{
+	if (guard && (sc[SC_DONE] != 0.0 || !(sc[SC_PAP] > 0.0))) return;
+	double acc[3] = { 0.0, 0.0, 0.0 };
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+		const double2 rv = r[i], zv = z[i];
+		acc[0] += rv.x * zv.x + rv.y * zv.y; acc[1] += zv.x * zv.x + zv.y * zv.y; acc[2] += rv.x * rv.x + rv.y * rv.y;
+	}
+	block_reduce_finalize<3>(acc, part, RED_BLOCKS_MAX, counter, out);
+}
+void bp_launch_pcg_init2(bp_ctx* c)
+{
+	const int n = (int)c->nn_owned;
+	cudaMemsetAsync(c->d_sc + SC_DONE, 0, sizeof(double), c->stream);
+	cudaMemsetAsync(c->d_sc + SC_PAP, 0, sizeof(double), c->stream);
+	k_pcg_init2<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, (const double2*)c->d_F, (double2*)c->d_dx, (double2*)c->d_r);
+	c->launches++;
+}
+void bp_launch_pcg_update2(bp_ctx* c, int par)
+{
+	const int n = (int)c->nn_owned;
+	k_pcg_update2<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, par, (const double2*)c->d_p, (const double2*)c->d_Ap, (double2*)c->d_dx, (double2*)c->d_r, c->d_sc);
+	c->launches++;
+}
+void bp_launch_dots3(bp_ctx* c, int slot, int guard)
+{
+	const int n = (int)c->nn_owned;
+	k_dots3<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, (const double2*)c->d_r, (const double2*)c->d_z, c->d_part, c->d_counter, c->d_sc + slot, c->d_sc, guard);
+	c->launches++;
+}
+
+// vertical-line solve z = T^-1 r: T = the block-tridiagonal coupling of the nodes of one
+// ice column (2x2 blocks), one thread per column, block Thomas algorithm.
+#define BP_MAX_LAYERS 64
+__device__ __forceinline__ void inv2(const double a, const double b, const double c, const double d, double& ia, double& ib, double& ic, double& id)
+{
+	const double idet = 1.0 / (a * d - b * c);
+	ia = d * idet; ib = -b * idet; ic = -c * idet; id = a * idet;
+}
+__global__ void __launch_bounds__(128)
+k_col_solve(int ncol, const int32_t* __restrict__ colptr, const int32_t* __restrict__ colnode,
+            const int32_t* __restrict__ tri_d, const int32_t* __restrict__ tri_u, const int32_t* __restrict__ tri_l,
+            const double* __restrict__ val, const double2* __restrict__ r, double2* __restrict__ z)
+{
+	const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cidx >= ncol) return;
+	const int j0 = colptr[cidx], n = colptr[cidx + 1] - j0;
+	double Di[BP_MAX_LAYERS][4];        // inverse of the eliminated diagonal blocks
+	double2 rr[BP_MAX_LAYERS];
+	for (int k = 0; k < n; ++k) {
+		const int j = j0 + k;
+		const double* D = val + 4 * (size_t)tri_d[j];
+		double a = D[0], b = D[1], cc = D[2], d = D[3];
+		double2 rv = r[colnode[j]];
+		if (k > 0 && tri_l[j] >= 0 && tri_u[j - 1] >= 0) {
+			const double* L = val + 4 * (size_t)tri_l[j];
+			const double* U = val + 4 * (size_t)tri_u[j - 1];
+			// M = L * Di[k-1]
+			const double m0 = L[0] * Di[k - 1][0] + L[1] * Di[k - 1][2], m1 = L[0] * Di[k - 1][1] + L[1] * Di[k - 1][3];
+			const double m2 = L[2] * Di[k - 1][0] + L[3] * Di[k - 1][2], m3 = L[2] * Di[k - 1][1] + L[3] * Di[k - 1][3];
+			a -= m0 * U[0] + m1 * U[2]; b -= m0 * U[1] + m1 * U[3];
+			cc -= m2 * U[0] + m3 * U[2]; d -= m2 * U[1] + m3 * U[3];
+			rv.x -= m0 * rr[k - 1].x + m1 * rr[k - 1].y; rv.y -= m2 * rr[k - 1].x + m3 * rr[k - 1].y;
+		}
+		inv2(a, b, cc, d, Di[k][0], Di[k][1], Di[k][2], Di[k][3]);
+		rr[k] = rv;
+	}
+	double2 zn = make_double2(0.0, 0.0);
+	for (int k = n - 1; k >= 0; --k) {
+		const int j = j0 + k;
+		double2 rv = rr[k];
+		if (k < n - 1 && tri_u[j] >= 0) {
+			const double* U = val + 4 * (size_t)tri_u[j];
+			rv.x -= U[0] * zn.x + U[1] * zn.y; rv.y -= U[2] * zn.x + U[3] * zn.y;
+		}
+		zn = make_double2(Di[k][0] * rv.x + Di[k][1] * rv.y, Di[k][2] * rv.x + Di[k][3] * rv.y);
+		z[colnode[j]] = zn;
+	}
+}
+void bp_launch_col_solve(bp_ctx* c, const double* r, double* z)
+{
+	k_col_solve<<<(int)((c->n_cols + 127) / 128), 128, 0, c->stream>>>((int)c->n_cols, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l,
+		c->d_val, (const double2*)r, (double2*)z);
+	c->launches++;
+}
+
+// Chebyshev polynomial in D^-1 J: first step d = c0 D^-1 r, z = d; further steps fused with
+// the SpMV: res = r - J z_old; d = c1 d + c2 D^-1 res; z_new = z_old + d.
+__global__ void __launch_bounds__(256)
+k_cheb_first(int nrows, double c0, const double* __restrict__ dinv, const double2* __restrict__ r, double2* z, double2* d)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
+		const double2 v = apply_dinv(dinv, i, r[i]);
+		const double2 dv = make_double2(c0 * v.x, c0 * v.y);
+		d[i] = dv; z[i] = dv;
+	}
+}
+__global__ void __launch_bounds__(256)
+k_cheb_step(int nrows, double c1, double c2, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ col,
+            const double2* __restrict__ val, const double* __restrict__ dinv, const double2* __restrict__ r,
+            const double2* __restrict__ zold, double2* __restrict__ znew, double2* __restrict__ d)
+{
+	const int lane = threadIdx.x & 31;
+	const int nsl = (nrows + 31) >> 5;
+	for (int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slice < nsl; slice += (gridDim.x * blockDim.x) >> 5) {
+		const int b0 = sell_ptr[slice], w = (sell_ptr[slice + 1] - b0) >> 5;
+		const int row = (slice << 5) + lane;
+		const int32_t* cp = col + b0 + lane;
+		const double2* vp = val + 2 * ((size_t)b0 + lane);
+		double s0 = 0.0, s1 = 0.0;
+		#pragma unroll 4
+		for (int k = 0; k < w; ++k) {
+			const double2 a01 = vp[64 * (size_t)k], a23 = vp[64 * (size_t)k + 1];
+			const double2 xv = zold[cp[32 * k]];
+			s0 += a01.x * xv.x + a01.y * xv.y; s1 += a23.x * xv.x + a23.y * xv.y;
+		}
+		if (row < nrows) {
+			const double2 rv = r[row], zo = zold[row], dv = d[row];
+			const double2 pr = apply_dinv(dinv, row, make_double2(rv.x - s0, rv.y - s1));
+			const double2 dn = make_double2(c1 * dv.x + c2 * pr.x, c1 * dv.y + c2 * pr.y);
+			d[row] = dn;
+			znew[row] = make_double2(zo.x + dn.x, zo.y + dn.y);
+		}
+	}
+}
+void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z)
+{
+	const int n = (int)c->nn_owned;
+	k_cheb_first<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, c0, c->d_dinv, (const double2*)r, (double2*)z, (double2*)c->d_cd);
+	c->launches++;
+}
+void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew)
+{
+	static int g = 0; static int64_t nc = -1;
+	if (nc != c->nn_owned) { g = one_wave(k_cheb_step, 256, c->nn_owned, 256); nc = c->nn_owned; }
+	k_cheb_step<<<g, 256, 0, c->stream>>>((int)c->nn_owned, c1, c2, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, c->d_dinv,
+		(const double2*)r, (const double2*)zold, (double2*)znew, (double2*)c->d_cd);
+	c->launches++;
+}
+
+// Gershgorin bound of lmax(D^-1 J): max over block rows of sum_j |D_i^-1 J_ij|_inf.
+// A guaranteed upper bound (power iteration converges from below and a Chebyshev interval
+// that misses the top of the spectrum makes the preconditioner indefinite).
+__global__ void __launch_bounds__(256)
+k_gershgorin(int nrows, const int32_t* __restrict__ sell_ptr, const double2* __restrict__ val,
+             const double* __restrict__ dinv, double* part, unsigned* counter, double* out)
+{
+	__shared__ double sm[32];
+	__shared__ bool last;
+	const int lane = threadIdx.x & 31, w_ = threadIdx.x >> 5;
+	const int nsl = (nrows + 31) >> 5;
+	double mx = 0.0;
+	for (int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slice < nsl; slice += (gridDim.x * blockDim.x) >> 5) {
+		const int b0 = sell_ptr[slice], w = (sell_ptr[slice + 1] - b0) >> 5;
+		const int row = (slice << 5) + lane;
+		if (row >= nrows) continue;
+		const double2 d01 = ((const double2*)dinv)[2 * (size_t)row], d23 = ((const double2*)dinv)[2 * (size_t)row + 1];
+		const double2* vp = val + 2 * ((size_t)b0 + lane);
+		double g0 = 0.0, g1 = 0.0;
+		for (int k = 0; k < w; ++k) {
+			const double2 a01 = vp[64 * (size_t)k], a23 = vp[64 * (size_t)k + 1];
+			g0 += fabs(d01.x * a01.x + d01.y * a23.x) + fabs(d01.x * a01.y + d01.y * a23.y);
+			g1 += fabs(d23.x * a01.x + d23.y * a23.x) + fabs(d23.x * a01.y + d23.y * a23.y);
+		}
+		mx = fmax(mx, fmax(g0, g1));
+	}
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	if (lane == 0) sm[w_] = mx;
+	__syncthreads();
+	if (w_ == 0) {
+		mx = (lane < (int)(blockDim.x >> 5)) ? sm[lane] : 0.0;
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		if (lane == 0) part[blockIdx.x] = mx;
+	}
+	if (threadIdx.x == 0) { __threadfence(); last = (atomicAdd(counter, 1u) == gridDim.x - 1); }
+	__syncthreads();
+	if (last && w_ == 0) {
+		__threadfence();
+		mx = 0.0;
+		for (int b = lane; b < (int)gridDim.x; b += 32) mx = fmax(mx, ((volatile double*)part)[b]);
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+		if (lane == 0) { *out = mx; *counter = 0u; }
+	}
+}
+void bp_launch_gershgorin(bp_ctx* c, int sc_slot)
+{
+	k_gershgorin<<<red_blocks(c->nn_owned, 256), 256, 0, c->stream>>>((int)c->nn_owned, c->d_sell_ptr, (const double2*)c->d_val, c->d_dinv,
+		c->d_part, c->d_counter, c->d_sc + sc_slot);
+	c->launches++;
+}
+
+// helpers for the power iteration that estimates lmax(D^-1 J)
+__global__ void k_apply_dinv(int nrows, const double* __restrict__ dinv, double2* v)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) v[i] = apply_dinv(dinv, i, v[i]);
+}
+__global__ void k_scale_inv_norm(int n, double* v, const double* sc, int slot)
+{
+	const double s = rsqrt(sc[slot]);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] *= s;
+}
+__global__ void k_fill_probe(int n, double* v)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = 1.0 + 0.5 * sin(0.7 * (double)i) + 0.25 * cos(0.013 * (double)i);
+}
+void bp_launch_apply_dinv(bp_ctx* c, double* v)
+{
+	k_apply_dinv<<<red_blocks(c->nn_owned, 512), 256, 0, c->stream>>>((int)c->nn_owned, c->d_dinv, (double2*)v);
+	c->launches++;
+}
+void bp_launch_scale_inv_norm(bp_ctx* c, double* v, int sc_slot)
+{
+	k_scale_inv_norm<<<red_blocks(2 * c->nn_owned, 1024), 256, 0, c->stream>>>((int)(2 * c->nn_owned), v, c->d_sc, sc_slot);
+	c->launches++;
+}
+void bp_launch_fill_probe(bp_ctx* c, double* v)
+{
+	k_fill_probe<<<red_blocks(2 * c->nn_owned, 1024), 256, 0, c->stream>>>((int)(2 * c->nn_owned), v);
+	c->launches++;
+}
+
 // sum d_sc[slot..slot+count) across the contexts of an in-process group (same device)
 struct ScPtrs { double* p[16]; };
 __global__ void k_sum_scalars(ScPtrs P, int n, int slot, int count)

@@ -269,6 +269,50 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	}
 	c->nf = (int64_t)fcell.size();
 
+	// ---- ice columns (vertical-line preconditioner): owned nodes with the same (x, y),
+	// ordered bottom to top; slots of the diagonal and of the up / down coupling blocks
+	{
+		std::vector<int32_t> rep(nn, -1);                       // lowest vertex id of every node
+		for (int64_t v = nv - 1; v >= 0; --v) rep[v2n[v]] = (int32_t)v;
+		double lo[2] = { 1e300, 1e300 }, hi[2] = { -1e300, -1e300 };
+		for (int64_t v = 0; v < nv; ++v) for (int d = 0; d < 2; ++d) { lo[d] = std::min(lo[d], m->coords[3 * v + d]); hi[d] = std::max(hi[d], m->coords[3 * v + d]); }
+		const double sx_ = (hi[0] > lo[0]) ? 1048576.0 / (hi[0] - lo[0]) : 0.0, sy_ = (hi[1] > lo[1]) ? 1048576.0 / (hi[1] - lo[1]) : 0.0;
+		std::vector<std::pair<int64_t, std::pair<double, int32_t>>> key(no);
+		for (int64_t i = 0; i < no; ++i) {
+			const int32_t v = rep[i] < 0 ? 0 : rep[i];
+			const int64_t kx = (int64_t)std::llround((m->coords[3 * v] - lo[0]) * sx_), ky = (int64_t)std::llround((m->coords[3 * v + 1] - lo[1]) * sy_);
+			key[i] = { (kx << 22) | ky, { m->coords[3 * v + 2], (int32_t)i } };
+		}
+		std::sort(key.begin(), key.end());
+		std::vector<int32_t> colptr, colnode(no), tri_d(no, -1), tri_u(no, -1), tri_l(no, -1);
+		c->max_layers = 0;
+		for (int64_t j = 0; j < no; ++j) {
+			if (j == 0 || key[j].first != key[j - 1].first) colptr.push_back((int32_t)j);
+			colnode[j] = key[j].second.second;
+		}
+		colptr.push_back((int32_t)no);
+		c->n_cols = (int64_t)colptr.size() - 1;
+		auto find_slot = [&](int32_t r, int32_t cnode) -> int32_t {
+			const int32_t* lo_ = c->h_col.data() + c->h_rowptr[r];
+			const int32_t* hi_ = c->h_col.data() + c->h_rowptr[r + 1];
+			const int32_t* it = std::lower_bound(lo_, hi_, cnode);
+			return (it != hi_ && *it == cnode) ? slot_of(r, (int32_t)(it - lo_)) : -1;
+		};
+		for (int64_t cc = 0; cc < c->n_cols; ++cc) {
+			c->max_layers = std::max(c->max_layers, colptr[cc + 1] - colptr[cc]);
+			for (int32_t j = colptr[cc]; j < colptr[cc + 1]; ++j) {
+				tri_d[j] = diag[colnode[j]];
+				if (j + 1 < colptr[cc + 1]) tri_u[j] = find_slot(colnode[j], colnode[j + 1]);
+				if (j > colptr[cc]) tri_l[j] = find_slot(colnode[j], colnode[j - 1]);
+			}
+		}
+		UP(c->d_colptr, colptr.data(), colptr.size());
+		UP(c->d_colnode, colnode.data(), no);
+		UP(c->d_tri_d, tri_d.data(), no);
+		UP(c->d_tri_u, tri_u.data(), no);
+		UP(c->d_tri_l, tri_l.data(), no);
+	}
+
 	// ---- halo -----------------------------------------------------------------
 	c->n_nbr = (m->n_owned_nodes >= 0) ? m->n_neighbors : 0;
 	if (c->n_nbr > 0) {
@@ -311,7 +355,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	c->h_sell_ptr = sell_ptr;
 	UP(c->d_diag, diag.data(), no);
 	UP(c->d_val, (const double*)nullptr, (size_t)c->n_slots * 4);
-	double** vecs[] = { &c->d_u, &c->d_F, &c->d_dx, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap, &c->d_io, &c->d_io2 };
+	double** vecs[] = { &c->d_u, &c->d_F, &c->d_dx, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap, &c->d_io, &c->d_io2, &c->d_z2, &c->d_cd };
 	for (double** v : vecs) {
 		size_t len = std::max<size_t>((size_t)2 * nn, (size_t)std::max<int64_t>(std::max<int64_t>(c->nd_ext, nv), 1));
 		UP(*v, (const double*)nullptr, len);

@@ -101,7 +101,9 @@ class MomentumBPBase(Momentum):
 		c.set_field(capi.FIELD_BETA, m.vertex_field(m.beta))
 		return c
 
-	_PC_MAP = {'hypre_amg': 'block_jacobi', 'amg': 'block_jacobi', 'default': 'block_jacobi',
+	# the reference asks PETSc for hypre BoomerAMG; the device PCG offers Jacobi-type,
+	# Chebyshev-polynomial and vertical-line preconditioners -- AMG requests get Chebyshev
+	_PC_MAP = {'hypre_amg': 'chebyshev', 'amg': 'chebyshev', 'default': 'chebyshev',
 	           'none': 'none', 'jacobi': 'jacobi', 'block_jacobi': 'block_jacobi',
 	           'chebyshev': 'chebyshev', 'column': 'column'}
 
@@ -119,7 +121,7 @@ class MomentumBPBase(Momentum):
 		          krylov_rtol=ks.get('relative_tolerance', 1e-5),
 		          krylov_atol=ks.get('absolute_tolerance', 1e-50),
 		          krylov_maxit=ks.get('maximum_iterations', 10000),
-		          preconditioner=self._PC_MAP.get(pc, 'block_jacobi'),
+		          preconditioner=self._PC_MAP.get(pc, 'chebyshev'),
 		          verbose=ks.get('monitor_convergence', False) or ns.get('report', False),
 		          quadrature_degree=self.solve_params.get('quadrature_degree', 5))
 		return kw

@@ -46,8 +46,10 @@ extern "C" {
 #define BP_PC_NONE          0
 #define BP_PC_JACOBI        1   /* point Jacobi                                   */
 #define BP_PC_BLOCK_JACOBI  2   /* 2x2 (u_x,u_y) node-block Jacobi                */
-#define BP_PC_CHEBYSHEV     3   /* Chebyshev polynomial smoother on block-Jacobi  */
-#define BP_PC_COLUMN        4   /* vertical-line (column block-tridiagonal) solve */
+#define BP_PC_CHEBYSHEV     3   /* Chebyshev polynomial in D^-1 J (D = 2x2 node blocks), degree
+                                   pc_degree, lmax by power iteration once per Newton step     */
+#define BP_PC_COLUMN        4   /* vertical-line solve: exact inverse of the block-tridiagonal
+                                   coupling inside every ice column (extruded meshes)          */
 
 /* how the element tensors reach the resident Jacobian */
 #define BP_ASM_AUTO     0   /* row gather unless a block row is too long for shared memory     */
@@ -118,6 +120,7 @@ typedef struct {
 	int32_t pc_degree;         /* Chebyshev degree                                */
 	int32_t verbose;
 	int32_t assembly;          /* BP_ASM_*                                        */
+	double  pc_eig_ratio;      /* Chebyshev: interval [lmax/ratio, 1.1 lmax] of D^-1 J (30)  */
 } bp_params;
 
 typedef struct {

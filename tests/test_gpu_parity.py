@@ -201,3 +201,48 @@ def test_empty_and_ragged_inputs_are_rejected():
 	with pytest.raises(capi.BPError):                               # no resident Jacobian yet
 		c.spmv(np.ones(2 * m.n_nodes))
 	c.close(); c2.close()
+
+
+@pytest.mark.parametrize('pc', ['none', 'jacobi', 'block_jacobi', 'chebyshev', 'column'])
+def test_every_preconditioner_solves_the_same_system(pc):
+	"""bp_krylov_solve with each BP_PC_* against a sparse direct solve of the exported J."""
+	import scipy.sparse.linalg as spla
+	m = ismip_model('A', n=(10, 8, 5))                     # dx = 8 km >> dz = 200 m: strongly anisotropic
+	c = product_context(m, krylov_rtol=1e-12, preconditioner=pc, pc_degree=4)
+	u = state(2 * m.n_nodes, 31)
+	F, J = c.assemble(u, want_F=True, want_J=True)
+	ip, ix = c.csr_pattern()
+	A = sp.csr_matrix((J, ix, ip), shape=(2 * m.n_nodes,) * 2)
+	ref = spla.spsolve(A.tocsc(), F)
+	dx, its, rr = c.krylov_solve(F)
+	assert relerr(dx, ref) < 1e-8, (pc, its, relerr(dx, ref))
+	test_every_preconditioner_solves_the_same_system.its = getattr(test_every_preconditioner_solves_the_same_system, 'its', {})
+	test_every_preconditioner_solves_the_same_system.its[pc] = its
+	c.close()
+
+
+def test_preconditioner_quality_ordering():
+	"""on an anisotropic ice mesh the vertical-line solve must beat block Jacobi by a wide
+	margin, and Chebyshev(4) must cut the CG iteration (= all-reduce) count."""
+	its = {}
+	m = ismip_model('A', n=(12, 12, 5))
+	u = state(2 * m.n_nodes, 32)
+	for pc in ('block_jacobi', 'chebyshev', 'column'):
+		c = product_context(m, krylov_rtol=1e-8, preconditioner=pc, pc_degree=4)
+		F, _ = c.assemble(u, want_F=True, want_J=True, J=False)
+		_, its[pc], _ = c.krylov_solve(F)
+		c.close()
+	assert its['column'] * 3 < its['block_jacobi'], its
+	assert its['chebyshev'] * 2 < its['block_jacobi'], its
+
+
+@pytest.mark.parametrize('pc', ['chebyshev', 'column'])
+def test_newton_with_other_preconditioners(pc):
+	m = ismip_model('C', L=20000.0, n=(10, 10, 4))
+	P = oracle_problem(m)
+	uo, io = P.newton(rtol=1e-11, maxit=40)
+	c = product_context(m, relative_tolerance=1e-11, maximum_iterations=40, krylov_rtol=1e-12, preconditioner=pc)
+	u = np.full(P.n_dofs, 3e-16)
+	st = c.newton_solve(u)
+	assert st['converged'] and relerr(u, uo) < TOL_U
+	c.close()
