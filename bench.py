@@ -69,7 +69,7 @@ class ClockSampler(object):
 	def __init__(self, index=0):
 		self.p = None
 		try:
-			self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+			self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
 			                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
 		except OSError:
 			pass
@@ -172,7 +172,7 @@ def run_reference(args):
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument('--gpus', type=int, default=1)
-	ap.add_argument('--steps', type=int, default=20)
+	ap.add_argument('--steps', type=int, default=200)
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='ours')
 	ap.add_argument('--no-newton', action='store_true')
@@ -257,13 +257,13 @@ def main():
 	t_pass = ctx.time_assemble(what, repeats=max(args.steps, 10), flush_l2=True)
 	ctx.assemble(u_dev, want_F=True, want_J=True, F=F_dev, J=False)       # make the resident J valid again
 	t_spmv = ctx.time_spmv(repeats=50, flush_l2=True)
-	clocks.stop()
 	for _ in range(args.warmup):
 		step_e2e()
 	t0 = time.perf_counter()
 	for _ in range(args.steps):
 		step_e2e()
 	t_e2e = (time.perf_counter() - t0) / args.steps
+	clocks.stop()
 	clk = clocks.summary()
 	clocks.close()
 
@@ -282,7 +282,7 @@ def main():
 	                   "state": "converged Newton solution x (1 + 1e-3 N(0,1))" if newton and newton['converged'] else "synthetic sheared flow"},
 	        "e2e": {"value": nt / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * u_host.size, "d2h_bytes_per_step": 8 * u_host.size},
 	        "gpu_launches": int(launches),
-	        "roofline": {"kernel": "k_cell<F,J>", "bound": "hbm", "achieved": b_cell / (t_cell * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+	        "roofline": {"kernel": "k_rows<F,J> (cell assembly, row gather)", "bound": "hbm", "achieved": b_cell / (t_cell * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
 	                     "frac": b_cell / (t_cell * 1e-3) / 1e9 / peak, "traffic": None,
 	                     "peak_source": "measured" if peaks else "fallback", "bytes_per_tet": b_cell / nt, "ms": t_cell,
 	                     "pass_ms": t_pass, "pass_frac": b_full / (t_pass * 1e-3) / 1e9 / peak},

@@ -260,12 +260,15 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	double Fx = 0.0, Fy = 0.0;
 	const int slice = i >> 5, lane = i & 31;
 	const int e0 = active ? inc_slice[slice] : 0, e1 = active ? inc_slice[slice + 1] : 0;
-	// software pipeline: the index words of incidence e+32 are requested before the
-	// arithmetic of incidence e, its vertex data as soon as the raw data of e is consumed
+	// software pipeline, two stages deep on the index words (tet code, block positions, four
+	// vertex ids: coalesced SELL-32 streams) and one stage on the gathered vertex data:
+	//   iteration e computes on data(e), requests data(e+1) from idx(e+1) once its raw inputs
+	//   are consumed, and requests idx(e+2) at the top.
 	int e = e0 + lane;
 	int code = (e < e1) ? inc_code[e] : -1;
-	uint32_t pk = 0;
-	int vid[4] = { 0, 0, 0, 0 };
+	uint32_t pk = 0, pk1 = 0;
+	int vid[4] = { 0, 0, 0, 0 }, vid1[4] = { 0, 0, 0, 0 };
+	int code1 = -1;
 	double4 p[4];
 	double2 uu[4];
 	double A[4];
@@ -273,6 +276,12 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		pk = inc_pos[e];
 		#pragma unroll
 		for (int j = 0; j < 4; ++j) vid[j] = inc_v[j * nslot + e];
+		if (e + 32 < e1) {                           // padding slots hold code -1, vertex 0: safe to load
+			code1 = inc_code[e + 32];
+			pk1 = inc_pos[e + 32];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) vid1[j] = inc_v[j * nslot + e + 32];
+		}
 		#pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
@@ -284,12 +293,17 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		const int a = code & 3;
 		const uint32_t pk_cur = pk;
 		e += 32;
-		int code_n = -1;
-		if (e < e1) {                                // padding slots hold code -1, vertex 0: safe to load
-			code_n = inc_code[e];
-			pk = inc_pos[e];
+		// stage idx(e+1) -> current "next", request idx(e+2)
+		const int code_n = code1;
+		pk = pk1;
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) vid[j] = vid1[j];
+		code1 = -1;
+		if (e + 32 < e1) {
+			code1 = inc_code[e + 32];
+			pk1 = inc_pos[e + 32];
 			#pragma unroll
-			for (int j = 0; j < 4; ++j) vid[j] = inc_v[j * nslot + e];
+			for (int j = 0; j < 4; ++j) vid1[j] = inc_v[j * nslot + e + 32];
 		}
 		const double e1x = p[1].x - p[0].x, e1y = p[1].y - p[0].y, e1z = p[1].z - p[0].z;
 		const double e2x = p[2].x - p[0].x, e2y = p[2].y - p[0].y, e2z = p[2].z - p[0].z;
