@@ -172,11 +172,14 @@ def run_reference(args):
 def main():
 	ap = argparse.ArgumentParser()
 	ap.add_argument('--gpus', type=int, default=1)
-	ap.add_argument('--steps', type=int, default=200)
+	ap.add_argument('--steps', type=int, default=500)
 	ap.add_argument('--warmup', type=int, default=3)
 	ap.add_argument('--impl', default='ours')
 	ap.add_argument('--no-newton', action='store_true')
 	ap.add_argument('--no-cpu', action='store_true')
+	ap.add_argument('--exp', default='C', help='ISMIP-HOM experiment of the multi-rank arm: C (default, L=20 km per 260 columns) or A (L=80 km total)')
+	ap.add_argument('--nx', type=int, default=0, help='multi-rank arm: TOTAL columns in x (default 260 per GPU); strong-scaling studies fix it')
+	ap.add_argument('--ny', type=int, default=0)
 	args = ap.parse_args()
 	args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
 	if args.impl == 'reference':
