@@ -42,7 +42,8 @@ class bp_params(C.Structure):
 	            ('error_on_nonconvergence', C.c_int32),
 	            ('krylov_rtol', C.c_double), ('krylov_atol', C.c_double),
 	            ('krylov_maxit', C.c_int32), ('pc', C.c_int32), ('pc_degree', C.c_int32),
-	            ('verbose', C.c_int32), ('assembly', C.c_int32), ('pc_eig_ratio', C.c_double)]
+	            ('verbose', C.c_int32), ('assembly', C.c_int32), ('pc_eig_ratio', C.c_double),
+	            ('n_quad_aux', C.c_int32), ('quad_points_aux', c_f64p), ('quad_weights_aux', c_f64p)]
 
 
 class bp_stats(C.Structure):
@@ -69,7 +70,7 @@ SYMBOLS = ['bp_create', 'bp_destroy', 'bp_last_error', 'bp_set_params', 'bp_set_
            'bp_set_field', 'bp_get_sizes', 'bp_csr_pattern', 'bp_assemble', 'bp_spmv',
            'bp_krylov_solve', 'bp_newton_solve', 'bp_time_assemble', 'bp_time_spmv',
            'bp_launch_count', 'bp_comm_unique_id', 'bp_comm_init',
-           'bp_newton_solve_group', 'bp_assemble_group']
+           'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure']
 
 _lib = None
 
@@ -99,6 +100,7 @@ def load_library():
 	lib.bp_spmv.argtypes = [vp, vp, vp, C.c_int]
 	lib.bp_krylov_solve.argtypes = [vp, vp, vp, C.c_int, c_i32p, c_f64p]
 	lib.bp_newton_solve.argtypes = [vp, vp, C.c_int, C.POINTER(bp_stats)]
+	lib.bp_solve_pressure.argtypes = [vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_time_assemble.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_f64p]
 	lib.bp_time_spmv.argtypes = [vp, C.c_int, C.c_int, c_f64p]
 	lib.bp_launch_count.argtypes = [vp]
@@ -221,6 +223,13 @@ class BPContext(object):
 		p.n_quad = len(wts)
 		p.quad_points = pts.ctypes.data_as(c_f64p)
 		p.quad_weights = wts.ctypes.data_as(c_f64p)
+		pa, wa = tetrahedron_rule(int(d.get('projection_quadrature_degree', 6)))
+		pa = np.ascontiguousarray(pa, dtype=np.float64)
+		wa = np.ascontiguousarray(wa, dtype=np.float64)
+		self._quad_aux = (pa, wa)
+		p.n_quad_aux = len(wa)
+		p.quad_points_aux = pa.ctypes.data_as(c_f64p)
+		p.quad_weights_aux = wa.ctypes.data_as(c_f64p)
 		p.newton_rtol = d.get('relative_tolerance', 1e-9)
 		p.newton_atol = d.get('absolute_tolerance', 1e-10)
 		p.newton_maxit = int(d.get('maximum_iterations', 25))
@@ -343,6 +352,21 @@ class BPContext(object):
 		if rc == BP_ERR_NONCONV:
 			raise BPError(rc, self.lib.bp_last_error(self.h).decode())
 		return d
+
+	def solve_pressure(self, u, p=None):
+		"""BP pressure (one value per mesh vertex) from the velocity dofs ``u``."""
+		pu, dev, ku = _ptr(u)
+		if p is None:
+			if dev:
+				import torch
+				p = torch.empty(self.n_vertices, dtype=torch.float64, device=ku.device)
+			else:
+				p = np.empty(self.n_vertices)
+		pp, _, kp = _ptr(p)
+		it = C.c_int32()
+		self._check(self.lib.bp_solve_pressure(self.h, pu, pp, dev, C.byref(it)))
+		self.last_projection_iterations = it.value
+		return p
 
 	def time_assemble(self, what=ASSEMBLE_F | ASSEMBLE_J, repeats=20, flush_l2=True):
 		ms = C.c_double()

@@ -27,6 +27,7 @@ static int check_params(bp_ctx* c, const bp_params* p)
 	double s = 0;
 	for (int q = 0; q < p->n_quad; ++q) s += p->quad_weights[q];
 	if (std::fabs(s - 1.0) > 1e-12) return bp_fail(c, BP_ERR_ARG, "bp_params: quadrature weights sum to %.17g, not 1", s);
+	if (p->n_quad_aux < 0 || p->n_quad_aux > BP_MAX_QUAD) return bp_fail(c, BP_ERR_ARG, "bp_params: n_quad_aux must be in [0,%d]", BP_MAX_QUAD);
 	if (p->assembly < BP_ASM_AUTO || p->assembly > BP_ASM_GATHER) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown assembly mode %d", p->assembly);
 	if (p->pc < BP_PC_NONE || p->pc > BP_PC_COLUMN) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown preconditioner %d", p->pc);
 	return BP_OK;
@@ -39,6 +40,12 @@ static void store_params(bp_ctx* c, const bp_params* p)
 	c->quad_wts.assign(p->quad_weights, p->quad_weights + p->n_quad);
 	c->prm.quad_points = c->quad_pts.data();
 	c->prm.quad_weights = c->quad_wts.data();
+	if (p->n_quad_aux > 0 && p->quad_points_aux && p->quad_weights_aux) {
+		c->quad_pts_aux.assign(p->quad_points_aux, p->quad_points_aux + 4 * p->n_quad_aux);
+		c->quad_wts_aux.assign(p->quad_weights_aux, p->quad_weights_aux + p->n_quad_aux);
+	} else { c->quad_pts_aux = c->quad_pts; c->quad_wts_aux = c->quad_wts; c->prm.n_quad_aux = c->prm.n_quad; }
+	c->prm.quad_points_aux = c->quad_pts_aux.data();
+	c->prm.quad_weights_aux = c->quad_wts_aux.data();
 }
 
 struct GroupStream {   // an in-process group runs on the first context's stream
@@ -484,6 +491,35 @@ int bp_assemble_group(bp_ctx** cs, int n, int what, const double** u, double** F
 	if (F) for (int r = 0; r < n; ++r) if (F[r] && (rc = vec_out(cs[r], cs[r]->d_F, F[r], on_device))) return rc;
 	BP_CUDA(cs[0], cudaStreamSynchronize(cs[0]->stream));
 	BP_CUDA(cs[0], cudaGetLastError());
+	return BP_OK;
+}
+
+int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_device, int32_t* iterations)
+{
+	if (!c || !u || !p_vertex) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = ready(c);
+	if (rc) return rc;
+	if (c->prm.assembly == BP_ASM_SCATTER || (size_t)4 * c->max_row * 128 * sizeof(double) > 200 * 1024)
+		return bp_fail(c, BP_ERR_STATE, "bp_solve_pressure needs the row-gather assembly path");
+	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
+	bp_ctx* cs[1] = { c };
+	if ((rc = bp_comm_halo(cs, 1, 0))) return rc;
+	bp_launch_rows_aux(c, 0);
+	c->have_J = false;
+	// mass-matrix solve: block-Jacobi PCG to 1e-13 (dolfin's project() uses a direct solver)
+	const bp_params saved = c->prm;
+	c->prm.pc = BP_PC_BLOCK_JACOBI; c->prm.krylov_rtol = 1e-13; c->prm.krylov_atol = 0.0; c->prm.krylov_maxit = 2000;
+	int it = 0;
+	rc = group_pcg(cs, 1, &it, nullptr);
+	c->prm = saved;
+	if (rc) return rc;
+	if (iterations) *iterations = it;
+	double* out = on_device ? p_vertex : c->d_io;
+	bp_launch_node_to_vertex(c, c->d_dx, 0, out);
+	if (!on_device) BP_CUDA(c, cudaMemcpyAsync(p_vertex, c->d_io, (size_t)c->nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
 	return BP_OK;
 }
 

@@ -32,7 +32,7 @@ struct bp_ctx {
 	bool         own_stream = false;
 	std::string  err;
 	bp_params    prm{};
-	std::vector<double> quad_pts, quad_wts;
+	std::vector<double> quad_pts, quad_wts, quad_pts_aux, quad_wts_aux;
 
 	// sizes
 	int64_t nv = 0, nt = 0, nd_ext = 0;
@@ -139,7 +139,9 @@ void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const
 void bp_launch_apply_dinv(bp_ctx* c, double* v);           // v <- D^-1 v
 void bp_launch_scale_inv_norm(bp_ctx* c, double* v, int sc_slot);   // v <- v / sqrt(d_sc[slot])
 void bp_launch_fill_probe(bp_ctx* c, double* v);
-void bp_launch_gershgorin(bp_ctx* c, int sc_slot);        // upper bound of lmax(D^-1 J) -> d_sc[slot]
+void bp_launch_gershgorin(bp_ctx* c, int sc_slot);
+void bp_launch_rows_aux(bp_ctx* c, int kind);              // projection systems (mass matrix + rhs) -> d_val, d_F
+void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out);        // upper bound of lmax(D^-1 J) -> d_sc[slot]
 
 // comm (bp_comm.cu)
 int  bp_comm_halo(bp_ctx** ctxs, int n, int which_vec);   // 0:u 1:p

@@ -11,6 +11,8 @@
 
 __constant__ double c_qw[BP_MAX_QUAD];
 __constant__ double c_ql[BP_MAX_QUAD * 4];
+__constant__ double c_qw2[BP_MAX_QUAD];          // projection right-hand sides (degree 6)
+__constant__ double c_ql2[BP_MAX_QUAD * 4];
 
 struct AsmParams;
 static AsmParams make_params_fwd(const bp_ctx* c);
@@ -401,6 +403,97 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	}
 }
 
+// ---------------------------------------------------------------- projection systems
+// Same row-gather mapping as k_rows for the scalar P1 systems behind the follow-on solves
+// of cslvr/momentumbp.py:205-229: the mass matrix int(phi_i phi_j) = |T|(1+delta)/20 goes
+// into both diagonal entries of the 2x2 node blocks (so the block PCG solves two copies,
+// the second with a zero right-hand side) and the right-hand side into F[2i].
+// KIND 0: solve_pressure, rhs_i = int (rho g (S - z) - 2 eta(u) (u_x,x + u_y,y)) phi_i.
+template <int KIND>
+__global__ void __launch_bounds__(RTPB)
+k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restrict__ inc_code,
+           const uint32_t* __restrict__ inc_pos, const int32_t* __restrict__ inc_v, size_t nslot,
+           const double* __restrict__ soa, size_t nv, const double2* __restrict__ u, const double* __restrict__ Av,
+           const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
+           double* __restrict__ F, double* __restrict__ val, AsmParams P, int nq)
+{
+	extern __shared__ double acc[];                  // [max_row][RTPB]
+	const int tid = threadIdx.x;
+	const int i = blockIdx.x * RTPB + tid;
+	if (i >= nrows) return;
+	const int len = rowlen[i];
+	for (int k = 0; k < len; ++k) acc[k * RTPB + tid] = 0.0;
+	double rhs = 0.0;
+	const int slice = i >> 5, lane = i & 31;
+	const int e0 = inc_slice[slice], e1 = inc_slice[slice + 1];
+	for (int e = e0 + lane; e < e1; e += 32) {
+		const int code = inc_code[e];
+		if (code < 0) break;
+		const uint32_t pk = inc_pos[e];
+		const int a = code & 3;
+		double4 p[4]; double2 uu[4]; double A[4];
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int v = inc_v[j * nslot + e];
+			p[j] = make_double4(soa[v], soa[nv + v], soa[2 * nv + v], soa[3 * nv + v]);
+			A[j] = Av[v]; uu[j] = u[v];
+		}
+		const double e1x = p[1].x - p[0].x, e1y = p[1].y - p[0].y, e1z = p[1].z - p[0].z;
+		const double e2x = p[2].x - p[0].x, e2y = p[2].y - p[0].y, e2z = p[2].z - p[0].z;
+		const double e3x = p[3].x - p[0].x, e3y = p[3].y - p[0].y, e3z = p[3].z - p[0].z;
+		double X[4], Y[4], Z[4];
+		X[1] = e2y * e3z - e2z * e3y; Y[1] = e2z * e3x - e2x * e3z; Z[1] = e2x * e3y - e2y * e3x;
+		X[2] = e3y * e1z - e3z * e1y; Y[2] = e3z * e1x - e3x * e1z; Z[2] = e3x * e1y - e3y * e1x;
+		X[3] = e1y * e2z - e1z * e2y; Y[3] = e1z * e2x - e1x * e2z; Z[3] = e1x * e2y - e1y * e2x;
+		const double det = e1x * X[1] + e1y * Y[1] + e1z * Z[1];
+		const double idet = 1.0 / det;
+		#pragma unroll
+		for (int j = 1; j < 4; ++j) { X[j] *= idet; Y[j] *= idet; Z[j] *= idet; }
+		X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
+		const double vol = fabs(det) * (1.0 / 6.0);
+		const double m = vol * (1.0 / 20.0);
+		#pragma unroll
+		for (int b = 0; b < 4; ++b) acc[((pk >> (8 * b)) & 255) * RTPB + tid] += (b == 0) ? 2.0 * m : m;
+		if (KIND == 0) {
+			double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0;
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				g00 += uu[j].x * X[j]; g01 += uu[j].x * Y[j]; g02 += uu[j].x * Z[j];
+				g10 += uu[j].y * X[j]; g11 += uu[j].y * Y[j]; g12 += uu[j].y * Z[j];
+			}
+			const double sh = 0.5 * (g01 + g10);
+			const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
+			const double two_eta_e = P.n_is_3 ? rcbrt(ed) : pow(ed, (1.0 - P.n) / (2.0 * P.n));
+			double wq;                                   // sum_q w_q lambda_i(q) A_q^(-1/n)
+			if (A[0] == A[1] && A[0] == A[2] && A[0] == A[3]) wq = 0.25 * pow_m1n(A[0], P);
+			else {
+				double Ao[4];
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) Ao[(a + j) & 3] = A[j];
+				wq = 0.0;
+				for (int q = 0; q < nq; ++q) {
+					const double aq = c_ql2[4 * q] * Ao[0] + c_ql2[4 * q + 1] * Ao[1] + c_ql2[4 * q + 2] * Ao[2] + c_ql2[4 * q + 3] * Ao[3];
+					wq += c_qw2[q] * c_ql2[4 * q + a] * pow_m1n(aq, P);
+				}
+			}
+			const double sz0 = p[0].w - p[0].z, szs = sz0 + (p[1].w - p[1].z) + (p[2].w - p[2].z) + (p[3].w - p[3].z);
+			rhs += P.rho_g * m * (szs + sz0) - (g00 + g11) * two_eta_e * vol * wq;
+		}
+	}
+	F[2 * i] = rhs; F[2 * i + 1] = 0.0;
+	double2* out = (double2*)val + 2 * ((size_t)sell_ptr[slice] + lane);
+	for (int k = 0; k < len; ++k) {
+		const double mv = acc[k * RTPB + tid];
+		out[64 * (size_t)k] = make_double2(mv, 0.0);
+		out[64 * (size_t)k + 1] = make_double2(0.0, mv);
+	}
+}
+
+__global__ void k_node_to_vertex(int nv, const int32_t* __restrict__ v2n, const double* __restrict__ nodevec, int comp, double* __restrict__ out)
+{
+	for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < nv; v += gridDim.x * blockDim.x) out[v] = nodevec[2 * (v2n ? v2n[v] : v) + comp];
+}
+
 // ---------------------------------------------------------------- facet kernel
 // Basal sliding  +1/2 beta u.u dGamma_b  and water pressure  -f_w u.n_h  on
 // dGamma_bw / dGamma_lt (cslvr/momentumbp.py:473-491), exact P1 mass integrals.
@@ -499,6 +592,8 @@ void bp_upload_quadrature(bp_ctx* c)
 {
 	cudaMemcpyToSymbol(c_qw, c->quad_wts.data(), c->quad_wts.size() * sizeof(double));
 	cudaMemcpyToSymbol(c_ql, c->quad_pts.data(), c->quad_pts.size() * sizeof(double));
+	cudaMemcpyToSymbol(c_qw2, c->quad_wts_aux.data(), c->quad_wts_aux.size() * sizeof(double));
+	cudaMemcpyToSymbol(c_ql2, c->quad_pts_aux.data(), c->quad_pts_aux.size() * sizeof(double));
 }
 
 // u per vertex for the row-gather kernel (periodic images read their master's value)
@@ -513,6 +608,23 @@ static const double2* bp_vertex_u(bp_ctx* c)
 	k_expand_u<<<red_blocks_fwd(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, c->d_v2n, (const double2*)c->d_u, (double2*)c->d_uvert);
 	c->launches++;
 	return (const double2*)c->d_uvert;
+}
+
+void bp_launch_rows_aux(bp_ctx* c, int kind)
+{
+	const AsmParams P = make_params(c);
+	const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
+	const size_t sm = (size_t)c->max_row * RTPB * sizeof(double);
+	const double2* uvert = bp_vertex_u(c);
+	if (kind == 0)
+		k_rows_aux<0><<<gr, RTPB, sm, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots,
+			c->d_soa, (size_t)c->nv, uvert, c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, (int)c->quad_wts_aux.size());
+	c->launches++;
+}
+void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out)
+{
+	k_node_to_vertex<<<red_blocks_fwd(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, c->d_v2n, node_vec, comp, vertex_out);
+	c->launches++;
 }
 
 void bp_launch_proxy(bp_ctx* c);

@@ -151,7 +151,14 @@ class MomentumBPBase(Momentum):
 	# ---- cslvr/momentumbp.py:205-253 ------------------------
 	def solve_pressure(self, annotate=False):
 		print_text("::: solving BP pressure :::", cls=self)
-		print_text(">>> solve_pressure is not on the B200 path yet (SURVEY.md §8f rank 2); model.p unchanged <<<", 'red', 1)
+		if annotate:
+			raise NotImplementedError("annotate=True cannot be served by an external solver")
+		# p = project(rho g (S - z) - 2 eta (u_x,x + u_y,y), Q), eta = eta(model.u) which at
+		# this point holds the velocity just solved (cslvr/momentumbp.py:216-223)
+		c = self._context()
+		p_vertex = c.solve_pressure(self.get_unknown().values)
+		self.model.p.values[:] = p_vertex[self.model.node_vertex]
+		print_min_max(self.model.p, 'p', cls=self)
 
 	def solve_vert_velocity(self, annotate=False):
 		print_text("::: solving BP vertical velocity :::", cls=self)

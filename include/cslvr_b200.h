@@ -120,7 +120,11 @@ typedef struct {
 	int32_t pc_degree;         /* Chebyshev degree                                */
 	int32_t verbose;
 	int32_t assembly;          /* BP_ASM_*                                        */
-	double  pc_eig_ratio;      /* Chebyshev: interval [lmax/ratio, 1.1 lmax] of D^-1 J (30)  */
+	double  pc_eig_ratio;      /* Chebyshev: interval [lmax/ratio, lmax] of D^-1 J (100)     */
+	/* quadrature of the projection right-hand sides (solve_pressure: UFL degree 6)          */
+	int32_t       n_quad_aux;
+	const double* quad_points_aux;
+	const double* quad_weights_aux;
 } bp_params;
 
 typedef struct {
@@ -175,6 +179,12 @@ int  bp_krylov_solve(bp_ctx* ctx, const double* b, double* dx, int on_device,
 
 /* the whole dolfin.solve(F == 0, u, J=J) call: damped Newton from u_inout         */
 int  bp_newton_solve(bp_ctx* ctx, double* u_inout, int on_device, bp_stats* stats);
+
+/* ---- cslvr/momentumbp.py:205-229, MomentumBPBase.solve_pressure ------------------
+ * p = project(rho g (S - z) - 2 eta(u) (u_x,x + u_y,y), model.Q): P1 mass-matrix solve
+ * (dolfin project() = LU; here block-Jacobi PCG to 1e-13).  u: caller's dofs;
+ * p_vertex: one value per mesh vertex.  The resident Jacobian is overwritten.          */
+int  bp_solve_pressure(bp_ctx* ctx, const double* u, double* p_vertex, int on_device, int32_t* iterations);
 
 /* ---- timing of the kernels themselves (CUDA events on the context's stream) --- */
 /* flush_l2 != 0: a 512 MiB buffer is written before every timed launch            */

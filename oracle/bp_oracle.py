@@ -441,6 +441,45 @@ class BPProblem(object):
 		indptr, indices = self.pattern()
 		return sp.csr_matrix((self.jacobian(u), indices, indptr), shape=(self.n_dofs,) * 2)
 
+	# ---- solve_pressure, cslvr/momentumbp.py:205-229 ---------------------------
+	def scalar_pattern(self):
+		"""node-level (model.Q) CSR pattern and per-cell node ids; Q dof = node = cell_dofs[:, :4] // 2
+		for the canonical blocked numbering."""
+		nd = self.cell_dofs[:, :4] // 2
+		return csr_pattern(nd, self.n_dofs // 2), nd
+
+	def mass_matrix(self):
+		"""assemble(u*v*dx) on model.Q (degree-2 rule is exact: |T| (1 + delta_ab) / 20)."""
+		(ip, ix), nd = self.scalar_pattern()
+		nn = self.n_dofs // 2
+		Me = (self.vol[:, None, None] / 20.0) * (np.ones((4, 4)) + np.eye(4))[None]
+		M = sp.coo_matrix((Me.ravel(), (np.repeat(nd, 4, axis=1).ravel(), np.tile(nd, (1, 4)).ravel())), shape=(nn, nn)).tocsr()
+		return M
+
+	def pressure(self, u, quad_degree=6):
+		"""p = project(rho g (S - z) - 2 eta (u_x,x + u_y,y), Q) with eta = eta(model.u)
+		(momentumbp.py:216-223, Appendix B quirk: always the 'linear' viscosity of the
+		velocity just solved).  UFL degree estimate: 1 (v) + 3 (A^(-1/n)) + 2 ((.)^p) = 6
+		-> Keast 24-point rule; dolfin's project() solves the mass system directly."""
+		n, eps0 = self.c['n'], self.c['eps_reg']
+		rho_g = self.c['rho_i'] * self.c['g']
+		pts, wts = tetrahedron_rule(quad_degree)
+		g = self._grad_u(u)
+		ed = self._epsdot(g) + eps0
+		div = g[:, 0, 0] + g[:, 1, 1]
+		Av = self.A[self.cells]
+		Sz = self.S[self.cells] - self.coords[self.cells, 2]
+		b = np.zeros((self.cells.shape[0], 4))
+		for lam, w in zip(pts, wts):
+			dx = w * self.vol
+			eta = 0.5 * (Av @ lam) ** (-1.0 / n) * ed ** ((1 - n) / (2 * n))
+			pf = rho_g * (Sz @ lam) - 2.0 * eta * div
+			b += (dx * pf)[:, None] * lam[None, :]
+		(_, _), nd = self.scalar_pattern()
+		rhs = np.zeros(self.n_dofs // 2)
+		np.add.at(rhs, nd.ravel(), b.ravel())
+		return spla.spsolve(self.mass_matrix().tocsc(), rhs)
+
 	# ---- Newton (dolfin NewtonSolver semantics, SURVEY A-N) ----------------
 	def newton(self, u0=None, rtol=1e-9, atol=1e-10, maxit=25, relax=1.0,
 	           linear_solver='direct', krylov_rtol=1e-5, verbose=False):

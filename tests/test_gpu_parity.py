@@ -246,3 +246,28 @@ def test_newton_with_other_preconditioners(pc):
 	st = c.newton_solve(u)
 	assert st['converged'] and relerr(u, uo) < TOL_U
 	c.close()
+
+
+@pytest.mark.parametrize('builder', [lambda: ismip_model('A', n=(9, 8, 4)), lambda: marine_model(n=(7, 6, 4))])
+def test_solve_pressure_matches_oracle(builder):
+	"""SURVEY §8f rank 2, cslvr/momentumbp.py:205-229: L2 projection of the BP pressure."""
+	m = builder()
+	P = oracle_problem(m)
+	u = state(P.n_dofs, 41)
+	po = P.pressure(u)                                   # per node (model.Q dofs)
+	c = product_context(m)
+	pv = c.solve_pressure(u)
+	assert relerr(pv[m.node_vertex], po) < TOL_U, relerr(pv[m.node_vertex], po)
+	assert np.array_equal(pv, pv[m.node_vertex][m.vertex_to_node])     # periodic images carry the master value
+	assert c.last_projection_iterations > 0
+	c.close()
+
+
+def test_solve_runs_pressure_step_like_the_reference():
+	from cslvr_b200 import MomentumDukowiczBP
+	m = ismip_model('A', n=(8, 8, 4))
+	mom = MomentumDukowiczBP(m)
+	mom.solve_params['solve_vert_velocity'] = False
+	mom.solve()
+	P = oracle_problem(m)
+	assert relerr(m.p.values, P.pressure(mom.get_unknown().values)) < TOL_U
