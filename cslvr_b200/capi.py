@@ -12,7 +12,7 @@ import numpy as np
 from . import _build
 
 BP_OK, BP_ERR_ARG, BP_ERR_CUDA, BP_ERR_STATE, BP_ERR_COMM, BP_ERR_NONCONV = range(6)
-FIELD_S, FIELD_A, FIELD_BETA = 0, 1, 2
+FIELD_S, FIELD_A, FIELD_BETA, FIELD_B, FIELD_B_RING = 0, 1, 2, 3, 4
 ASSEMBLE_F, ASSEMBLE_J = 1, 2
 PC = {'none': 0, 'jacobi': 1, 'block_jacobi': 2, 'chebyshev': 3, 'column': 4}
 
@@ -70,7 +70,7 @@ SYMBOLS = ['bp_create', 'bp_destroy', 'bp_last_error', 'bp_set_params', 'bp_set_
            'bp_set_field', 'bp_get_sizes', 'bp_csr_pattern', 'bp_assemble', 'bp_spmv',
            'bp_krylov_solve', 'bp_newton_solve', 'bp_time_assemble', 'bp_time_spmv',
            'bp_launch_count', 'bp_comm_unique_id', 'bp_comm_init',
-           'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure']
+           'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity']
 
 _lib = None
 
@@ -101,6 +101,7 @@ def load_library():
 	lib.bp_krylov_solve.argtypes = [vp, vp, vp, C.c_int, c_i32p, c_f64p]
 	lib.bp_newton_solve.argtypes = [vp, vp, C.c_int, C.POINTER(bp_stats)]
 	lib.bp_solve_pressure.argtypes = [vp, vp, vp, C.c_int, c_i32p]
+	lib.bp_solve_vert_velocity.argtypes = [vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_time_assemble.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_f64p]
 	lib.bp_time_spmv.argtypes = [vp, C.c_int, C.c_int, c_f64p]
 	lib.bp_launch_count.argtypes = [vp]
@@ -367,6 +368,21 @@ class BPContext(object):
 		self._check(self.lib.bp_solve_pressure(self.h, pu, pp, dev, C.byref(it)))
 		self.last_projection_iterations = it.value
 		return p
+
+	def solve_vert_velocity(self, u, uz=None):
+		"""u_z (one value per mesh vertex) from continuity; needs FIELD_B."""
+		pu, dev, ku = _ptr(u)
+		if uz is None:
+			if dev:
+				import torch
+				uz = torch.empty(self.n_vertices, dtype=torch.float64, device=ku.device)
+			else:
+				uz = np.empty(self.n_vertices)
+		pz, _, kz = _ptr(uz)
+		it = C.c_int32()
+		self._check(self.lib.bp_solve_vert_velocity(self.h, pu, pz, dev, C.byref(it)))
+		self.last_vert_iterations = it.value
+		return uz
 
 	def time_assemble(self, what=ASSEMBLE_F | ASSEMBLE_J, repeats=20, flush_l2=True):
 		ms = C.c_double()

@@ -302,7 +302,7 @@ void bp_destroy(bp_ctx* c)
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
-		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
+		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_bcnode, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -350,6 +350,12 @@ int bp_set_field(bp_ctx* c, int field, const double* values, int64_t nvals, int 
 	case BP_FIELD_BETA:
 		BP_CUDA(c, cudaMemcpyAsync(c->d_beta, values, nvals * sizeof(double), kind, c->stream));
 		c->have_beta = true; break;
+	case BP_FIELD_B:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_Bv, values, nvals * sizeof(double), kind, c->stream));
+		c->have_B = true; break;
+	case BP_FIELD_B_RING:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_Bring, values, nvals * sizeof(double), kind, c->stream));
+		break;
 	default:
 		return bp_fail(c, BP_ERR_ARG, "bp_set_field: unknown field %d", field);
 	}
@@ -518,6 +524,86 @@ int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_devic
 	double* out = on_device ? p_vertex : c->d_io;
 	bp_launch_node_to_vertex(c, c->d_dx, 0, out);
 	if (!on_device) BP_CUDA(c, cudaMemcpyAsync(p_vertex, c->d_io, (size_t)c->nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return BP_OK;
+}
+
+int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on_device, int32_t* iterations)
+{
+	if (!c || !u || !uz_vertex) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = ready(c);
+	if (rc) return rc;
+	if (!c->have_B) return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity: BP_FIELD_B (bed height) not set");
+	if (c->n_nbr > 0) return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity is not available on partitioned contexts yet");
+	if (c->max_layers > 64) return bp_fail(c, BP_ERR_ARG, "bp_solve_vert_velocity supports at most 64 nodes per ice column");
+	if (c->prm.assembly == BP_ASM_SCATTER || (size_t)4 * c->max_row * 128 * sizeof(double) > 200 * 1024)
+		return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity needs the row-gather assembly path");
+	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
+	bp_ctx* cs[1] = { c };
+	// 1. u_z_b = project(kinematic basal condition, Q): mass-matrix PCG
+	bp_launch_rows_aux(c, 1);
+	c->have_J = false;
+	{
+		const bp_params saved = c->prm;
+		c->prm.pc = BP_PC_BLOCK_JACOBI; c->prm.krylov_rtol = 1e-13; c->prm.krylov_atol = 0.0; c->prm.krylov_maxit = 2000;
+		rc = group_pcg(cs, 1, nullptr, nullptr);
+		c->prm = saved;
+		if (rc) return rc;
+	}
+	BP_CUDA(c, cudaMemcpyAsync(c->d_aux, c->d_dx, (size_t)2 * c->nn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+	// 2. the continuity system with Dirichlet rows -> d_val (component 0 of the blocks), d_F
+	bp_launch_rows_aux(c, 2);
+	// 3. BiCGStab, right-preconditioned by the pivoted tridiagonal solve of every column
+	const size_t nb = (size_t)2 * c->nn * sizeof(double);
+	double *x = c->d_dx, *r = c->d_r, *rh = c->d_z2, *p = c->d_p, *v = c->d_Ap, *y = c->d_z, *sv = c->d_cd, *t = c->d_io, *zz = c->d_io2;
+	auto dot = [&](const double* a, const double* b, double* out) -> int {
+		bp_launch_dot_owned(c, a, b, SC_TMP);
+		int r_ = read_scalars(c);
+		*out = c->h_sc[SC_TMP];
+		return r_;
+	};
+	BP_CUDA(c, cudaMemsetAsync(x, 0, nb, c->stream));
+	BP_CUDA(c, cudaMemsetAsync(p, 0, nb, c->stream));
+	BP_CUDA(c, cudaMemsetAsync(v, 0, nb, c->stream));
+	BP_CUDA(c, cudaMemcpyAsync(r, c->d_F, nb, cudaMemcpyDeviceToDevice, c->stream));
+	BP_CUDA(c, cudaMemcpyAsync(rh, c->d_F, nb, cudaMemcpyDeviceToDevice, c->stream));
+	double bnorm2, rho = 1.0, alpha = 1.0, omega = 1.0, rnorm2;
+	if ((rc = dot(r, r, &bnorm2))) return rc;
+	rnorm2 = bnorm2;
+	int it = 0;
+	const int maxit = 500;
+	while (it < maxit && bnorm2 > 0.0 && rnorm2 > 1e-24 * bnorm2) {
+		double rho_n, rhv, ts, tt;
+		if ((rc = dot(rh, r, &rho_n))) return rc;
+		if (rho_n == 0.0 || !std::isfinite(rho_n)) return bp_fail(c, BP_ERR_STATE, "BiCGStab breakdown (rho) in the u_z solve at iteration %d", it);
+		const double beta = (rho_n / rho) * (alpha / omega);
+		bp_launch_lincomb(c, p, 1.0, r, beta, p, -beta * omega, v);          // p = r + beta (p - omega v)
+		bp_launch_col_gtsv(c, p, y);                                          // y = M^-1 p
+		bp_launch_spmv(c, y, v, 0);                                           // v = A y
+		if ((rc = dot(rh, v, &rhv))) return rc;
+		if (rhv == 0.0 || !std::isfinite(rhv)) return bp_fail(c, BP_ERR_STATE, "BiCGStab breakdown (alpha) in the u_z solve at iteration %d", it);
+		alpha = rho_n / rhv;
+		bp_launch_lincomb(c, sv, 1.0, r, -alpha, v, 0.0, v);                  // s = r - alpha v
+		bp_launch_col_gtsv(c, sv, zz);                                        // z = M^-1 s
+		bp_launch_spmv(c, zz, t, 0);                                          // t = A z
+		if ((rc = dot(t, sv, &ts))) return rc;
+		if ((rc = dot(t, t, &tt))) return rc;
+		omega = (tt > 0.0) ? ts / tt : 0.0;
+		bp_launch_lincomb(c, x, 1.0, x, alpha, y, omega, zz);                 // x += alpha y + omega z
+		bp_launch_lincomb(c, r, 1.0, sv, -omega, t, 0.0, t);                  // r = s - omega t
+		if ((rc = dot(r, r, &rnorm2))) return rc;
+		rho = rho_n;
+		++it;
+		if (omega == 0.0) break;
+	}
+	if (bnorm2 > 0.0 && !(rnorm2 <= 1e-20 * bnorm2))
+		return bp_fail(c, BP_ERR_NONCONV, "u_z solve: BiCGStab stopped at relative residual %.3e after %d iterations", std::sqrt(rnorm2 / bnorm2), it);
+	if (iterations) *iterations = it;
+	double* out = on_device ? uz_vertex : c->d_io;
+	bp_launch_node_to_vertex(c, x, 0, out);
+	if (!on_device) BP_CUDA(c, cudaMemcpyAsync(uz_vertex, c->d_io, (size_t)c->nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	BP_CUDA(c, cudaStreamSynchronize(c->stream));
 	BP_CUDA(c, cudaGetLastError());
 	return BP_OK;

@@ -55,6 +55,9 @@ struct bp_ctx {
 	double4* d_geo = nullptr;            // per vertex {x, y, z, S}
 	double*  d_A = nullptr;              // per vertex
 	double*  d_beta = nullptr;           // per vertex
+	double  *d_Bv = nullptr, *d_Bring = nullptr;   // bed height / basal melt per vertex (u_z solve only)
+	uint8_t* d_bcnode = nullptr;         // owned node lies on a basal facet (Dirichlet dof of the u_z system)
+	double*  d_aux = nullptr;            // [2*nn] u_z_b per node
 	int4*    d_tets = nullptr;
 	int32_t* d_v2n = nullptr;            // nullptr when identity
 	int32_t* d_tet_blk = nullptr;        // [16][nt] block slot of (a,b), -1 = row not owned
@@ -101,7 +104,7 @@ struct bp_ctx {
 	int64_t  n_send = 0;
 	bp_comm_state* comm = nullptr;
 
-	bool have_S = false, have_A = false, have_beta = false, have_J = false;
+	bool have_S = false, have_A = false, have_beta = false, have_J = false, have_B = false;
 	int64_t launches = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
@@ -141,7 +144,9 @@ void bp_launch_scale_inv_norm(bp_ctx* c, double* v, int sc_slot);   // v <- v / 
 void bp_launch_fill_probe(bp_ctx* c, double* v);
 void bp_launch_gershgorin(bp_ctx* c, int sc_slot);
 void bp_launch_rows_aux(bp_ctx* c, int kind);              // projection systems (mass matrix + rhs) -> d_val, d_F
-void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out);        // upper bound of lmax(D^-1 J) -> d_sc[slot]
+void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out);
+void bp_launch_col_gtsv(bp_ctx* c, const double* r, double* z);   // scalar pivoted tridiagonal solve per column
+void bp_launch_lincomb(bp_ctx* c, double* out, double a, const double* x, double b, const double* y, double cc, const double* z);        // upper bound of lmax(D^-1 J) -> d_sc[slot]
 
 // comm (bp_comm.cu)
 int  bp_comm_halo(bp_ctx** ctxs, int n, int which_vec);   // 0:u 1:p

@@ -409,13 +409,20 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 // into both diagonal entries of the 2x2 node blocks (so the block PCG solves two copies,
 // the second with a zero right-hand side) and the right-hand side into F[2i].
 // KIND 0: solve_pressure, rhs_i = int (rho g (S - z) - 2 eta(u) (u_x,x + u_y,y)) phi_i.
+// KIND 1: projection of the basal kinematic condition (cslvr/momentumbp.py:68-72),
+//         rhs_i = int ((-B_ring - u_x n_b0 - u_y n_b1) / n_b2) phi_i, n_b = (grad B - k)/|.|.
+// KIND 2: the continuity system of solve_vert_velocity (momentumbp.py:75, 244-248):
+//         A_ij = int dz(phi_j) phi_i = Z_j |T|/4 (NOT symmetric), b_i = -int (u_x,x + u_y,y) phi_i,
+//         rows of the basal nodes replaced by identity with the projected u_z_b as value.
 template <int KIND>
 __global__ void __launch_bounds__(RTPB)
 k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restrict__ inc_code,
            const uint32_t* __restrict__ inc_pos, const int32_t* __restrict__ inc_v, size_t nslot,
            const double* __restrict__ soa, size_t nv, const double2* __restrict__ u, const double* __restrict__ Av,
            const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
-           double* __restrict__ F, double* __restrict__ val, AsmParams P, int nq)
+           double* __restrict__ F, double* __restrict__ val, AsmParams P, int nq,
+           const double* __restrict__ Bv, const double* __restrict__ Bring,
+           const double2* __restrict__ uzb, const uint8_t* __restrict__ bcnode)
 {
 	extern __shared__ double acc[];                  // [max_row][RTPB]
 	const int tid = threadIdx.x;
@@ -423,6 +430,7 @@ k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __re
 	if (i >= nrows) return;
 	const int len = rowlen[i];
 	for (int k = 0; k < len; ++k) acc[k * RTPB + tid] = 0.0;
+	int kd = 0;
 	double rhs = 0.0;
 	const int slice = i >> 5, lane = i & 31;
 	const int e0 = inc_slice[slice], e1 = inc_slice[slice + 1];
@@ -452,8 +460,37 @@ k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __re
 		X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
 		const double vol = fabs(det) * (1.0 / 6.0);
 		const double m = vol * (1.0 / 20.0);
-		#pragma unroll
-		for (int b = 0; b < 4; ++b) acc[((pk >> (8 * b)) & 255) * RTPB + tid] += (b == 0) ? 2.0 * m : m;
+		if (KIND != 2) {
+			#pragma unroll
+			for (int b = 0; b < 4; ++b) acc[((pk >> (8 * b)) & 255) * RTPB + tid] += (b == 0) ? 2.0 * m : m;
+		}
+		if (KIND == 1) {
+			double bx = 0, by = 0, bz = 0, Bj[4], Rj[4];
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const int v = inc_v[j * nslot + e];
+				Bj[j] = Bv[v]; Rj[j] = Bring[v];
+				bx += Bj[j] * X[j]; by += Bj[j] * Y[j]; bz += Bj[j] * Z[j];
+			}
+			const double nz = bz - 1.0, imag = rsqrt(1.0 + bx * bx + by * by + bz * bz);   // n_b_mag = sqrt(1 + grad B . grad B), momentumbp.py:69
+			const double n0 = bx * imag, n1 = by * imag, n2 = nz * imag;
+			double fs = 0.0, f0 = 0.0;
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const double f = (-Rj[j] - uu[j].x * n0 - uu[j].y * n1) / n2;
+				fs += f; if (j == 0) f0 = f;
+			}
+			rhs += m * (fs + f0);
+		}
+		if (KIND == 2) {
+			double div = 0.0;
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) div += uu[j].x * X[j] + uu[j].y * Y[j];
+			#pragma unroll
+			for (int b = 0; b < 4; ++b) acc[((pk >> (8 * b)) & 255) * RTPB + tid] += Z[b] * vol * 0.25;
+			rhs -= div * vol * 0.25;
+			kd = (int)(pk & 255);                                     // position of the diagonal block in the row
+		}
 		if (KIND == 0) {
 			double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0;
 			#pragma unroll
@@ -479,6 +516,10 @@ k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __re
 			const double sz0 = p[0].w - p[0].z, szs = sz0 + (p[1].w - p[1].z) + (p[2].w - p[2].z) + (p[3].w - p[3].z);
 			rhs += P.rho_g * m * (szs + sz0) - (g00 + g11) * two_eta_e * vol * wq;
 		}
+	}
+	if (KIND == 2 && bcnode[i]) {                  // DirichletBC row: identity, value u_z_b
+		for (int k = 0; k < len; ++k) acc[k * RTPB + tid] = (k == kd) ? 1.0 : 0.0;
+		rhs = uzb[i].x;
 	}
 	F[2 * i] = rhs; F[2 * i + 1] = 0.0;
 	double2* out = (double2*)val + 2 * ((size_t)sell_ptr[slice] + lane);
@@ -616,9 +657,10 @@ void bp_launch_rows_aux(bp_ctx* c, int kind)
 	const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
 	const size_t sm = (size_t)c->max_row * RTPB * sizeof(double);
 	const double2* uvert = bp_vertex_u(c);
-	if (kind == 0)
-		k_rows_aux<0><<<gr, RTPB, sm, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots,
-			c->d_soa, (size_t)c->nv, uvert, c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, (int)c->quad_wts_aux.size());
+	#define AUX(K) k_rows_aux<K><<<gr, RTPB, sm, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, \
+			c->d_soa, (size_t)c->nv, uvert, c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, (int)c->quad_wts_aux.size(), \
+			c->d_Bv, c->d_Bring, (const double2*)c->d_aux, c->d_bcnode)
+	if (kind == 0) AUX(0); else if (kind == 1) AUX(1); else AUX(2);
 	c->launches++;
 }
 void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out)
@@ -1139,6 +1181,67 @@ void bp_launch_col_solve(bp_ctx* c, const double* r, double* z)
 {
 	k_col_solve<<<(int)((c->n_cols + 127) / 128), 128, 0, c->stream>>>((int)c->n_cols, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l,
 		c->d_val, (const double2*)r, (double2*)z);
+	c->launches++;
+}
+
+// scalar tridiagonal solve with partial pivoting per ice column (LAPACK dgtsv recurrences) on
+// component 0 of the blocks: the continuity matrix has zero diagonals in the interior, so the
+// unpivoted Thomas algorithm of k_col_solve cannot be used.  z = T^-1 r, second component 0.
+__global__ void __launch_bounds__(128)
+k_col_gtsv(int ncol, const int32_t* __restrict__ colptr, const int32_t* __restrict__ colnode,
+           const int32_t* __restrict__ tri_d, const int32_t* __restrict__ tri_u, const int32_t* __restrict__ tri_l,
+           const double* __restrict__ val, const double2* __restrict__ r, double2* __restrict__ z)
+{
+	const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cidx >= ncol) return;
+	const int j0 = colptr[cidx], n = colptr[cidx + 1] - j0;
+	double d[BP_MAX_LAYERS], du[BP_MAX_LAYERS], dl[BP_MAX_LAYERS], b[BP_MAX_LAYERS];
+	for (int k = 0; k < n; ++k) {
+		const int j = j0 + k;
+		d[k] = val[4 * (size_t)tri_d[j]];
+		du[k] = (k < n - 1 && tri_u[j] >= 0) ? val[4 * (size_t)tri_u[j]] : 0.0;
+		dl[k] = (k < n - 1 && tri_l[j + 1] >= 0) ? val[4 * (size_t)tri_l[j + 1]] : 0.0;   // entry (k+1, k)
+		b[k] = r[colnode[j]].x;
+	}
+	for (int k = 0; k < n - 1; ++k) {
+		if (dl[k] == 0.0) continue;
+		if (fabs(d[k]) >= fabs(dl[k])) {
+			const double mult = dl[k] / d[k];
+			d[k + 1] -= mult * du[k]; b[k + 1] -= mult * b[k];
+			if (k < n - 2) dl[k] = 0.0;
+		} else {
+			const double mult = d[k] / dl[k];
+			d[k] = dl[k];
+			double temp = d[k + 1];
+			d[k + 1] = du[k] - mult * temp;
+			if (k < n - 2) { dl[k] = du[k + 1]; du[k + 1] = -mult * dl[k]; }
+			du[k] = temp;
+			temp = b[k]; b[k] = b[k + 1]; b[k + 1] = temp - mult * b[k + 1];
+		}
+	}
+	b[n - 1] /= d[n - 1];
+	if (n > 1) b[n - 2] = (b[n - 2] - du[n - 2] * b[n - 1]) / d[n - 2];
+	for (int k = n - 3; k >= 0; --k) b[k] = (b[k] - du[k] * b[k + 1] - dl[k] * b[k + 2]) / d[k];
+	for (int k = 0; k < n; ++k) z[colnode[j0 + k]] = make_double2(b[k], 0.0);
+}
+void bp_launch_col_gtsv(bp_ctx* c, const double* r, double* z)
+{
+	k_col_gtsv<<<(int)((c->n_cols + 127) / 128), 128, 0, c->stream>>>((int)c->n_cols, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l,
+		c->d_val, (const double2*)r, (double2*)z);
+	c->launches++;
+}
+__global__ void k_lincomb(int n, double* out, double a, const double* x, double b, const double* y, double cc, const double* z)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		double v = a * x[i] + b * y[i];
+		if (cc != 0.0) v += cc * z[i];
+		out[i] = v;
+	}
+}
+void bp_launch_lincomb(bp_ctx* c, double* out, double a, const double* x, double b, const double* y, double cc, const double* z)
+{
+	const int n = (int)(2 * c->nn_owned);
+	k_lincomb<<<red_blocks(n, 1024), 256, 0, c->stream>>>(n, out, a, x, b, y, cc, z);
 	c->launches++;
 }
 

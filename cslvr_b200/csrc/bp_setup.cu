@@ -268,6 +268,13 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		finfo.push_back(lf | (basal << 8) | (press << 9));
 	}
 	c->nf = (int64_t)fcell.size();
+	{	// Dirichlet dofs of the u_z system: nodes of the basal facets (cslvr/momentumbp.py:79-85)
+		static const int LOC[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
+		std::vector<uint8_t> bc((size_t)std::max<int64_t>(no, 1), 0);
+		for (size_t f = 0; f < fcell.size(); ++f) if ((finfo[f] >> 8) & 1)
+			for (int k = 0; k < 3; ++k) { const int32_t nd_ = cn[(int64_t)fcell[f] * 4 + LOC[finfo[f] & 0xff][k]]; if (nd_ < no) bc[nd_] = 1; }
+		UP(c->d_bcnode, bc.data(), bc.size());
+	}
 
 	// ---- ice columns (vertical-line preconditioner): owned nodes with the same (x, y),
 	// ordered bottom to top; slots of the diagonal and of the up / down coupling blocks
@@ -343,6 +350,9 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	}
 	UP(c->d_A, (const double*)nullptr, nv);
 	UP(c->d_beta, (const double*)nullptr, nv);
+	UP(c->d_Bv, (const double*)nullptr, nv);
+	UP(c->d_Bring, (const double*)nullptr, nv);
+	BP_CUDA(c, cudaMemset(c->d_Bring, 0, (size_t)nv * sizeof(double)));
 	UP(c->d_tets, (const int4*)m->cells, nt);
 	if (!c->identity_v2n) { UP(c->d_v2n, v2n.data(), nv); UP(c->d_uvert, (const double*)nullptr, (size_t)2 * nv); }
 	UP(c->d_tet_blk, tet_blk.data(), (size_t)nt * 16);
@@ -355,7 +365,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	c->h_sell_ptr = sell_ptr;
 	UP(c->d_diag, diag.data(), no);
 	UP(c->d_val, (const double*)nullptr, (size_t)c->n_slots * 4);
-	double** vecs[] = { &c->d_u, &c->d_F, &c->d_dx, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap, &c->d_io, &c->d_io2, &c->d_z2, &c->d_cd };
+	double** vecs[] = { &c->d_u, &c->d_F, &c->d_dx, &c->d_r, &c->d_z, &c->d_p, &c->d_Ap, &c->d_io, &c->d_io2, &c->d_z2, &c->d_cd, &c->d_aux };
 	for (double** v : vecs) {
 		size_t len = std::max<size_t>((size_t)2 * nn, (size_t)std::max<int64_t>(std::max<int64_t>(c->nd_ext, nv), 1));
 		UP(*v, (const double*)nullptr, len);

@@ -162,7 +162,19 @@ class MomentumBPBase(Momentum):
 
 	def solve_vert_velocity(self, annotate=False):
 		print_text("::: solving BP vertical velocity :::", cls=self)
-		print_text(">>> solve_vert_velocity is not on the B200 path yet (SURVEY.md §8f rank 1); u_z unchanged <<<", 'red', 1)
+		if annotate:
+			raise NotImplementedError("annotate=True cannot be served by an external solver")
+		# project the basal kinematic condition, assemble the continuity system, apply the
+		# basal Dirichlet rows and solve (cslvr/momentumbp.py:231-253) -- all on the device
+		m = self.model
+		c = self._context()
+		c.set_field(capi.FIELD_B, m.vertex_field(m.B))
+		if getattr(m, 'B_ring', None) is not None:
+			c.set_field(capi.FIELD_B_RING, m.vertex_field(m.B_ring))
+		uz_vertex = c.solve_vert_velocity(self.get_unknown().values)
+		self.u_z.values[:] = uz_vertex[m.node_vertex]
+		m.u.values[2::3] = self.u_z.values
+		print_min_max(self.u_z, 'w')
 
 	def solve(self, annotate=False):
 		"""Newton solve of the first-order equations, cslvr/momentumbp.py:255-273:

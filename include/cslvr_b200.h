@@ -34,6 +34,8 @@ extern "C" {
 #define BP_FIELD_S      0   /* surface height S      cslvr/model.py:2511, momentumbp.py:467 */
 #define BP_FIELD_A      1   /* rate factor A         cslvr/model.py:2530, momentum.py:181   */
 #define BP_FIELD_BETA   2   /* basal traction beta   cslvr/model.py:2527, momentumbp.py:473 */
+#define BP_FIELD_B      3   /* bed height B          cslvr/model.py:2512, momentumbp.py:65 (u_z only)   */
+#define BP_FIELD_B_RING 4   /* basal melt B_ring     momentumbp.py:66 (u_z only; default 0)             */
 
 /* what bp_assemble computes */
 #define BP_ASSEMBLE_F   1
@@ -185,6 +187,14 @@ int  bp_newton_solve(bp_ctx* ctx, double* u_inout, int on_device, bp_stats* stat
  * (dolfin project() = LU; here block-Jacobi PCG to 1e-13).  u: caller's dofs;
  * p_vertex: one value per mesh vertex.  The resident Jacobian is overwritten.          */
 int  bp_solve_pressure(bp_ctx* ctx, const double* u, double* p_vertex, int on_device, int32_t* iterations);
+
+/* ---- cslvr/momentumbp.py:60-85, 231-253, MomentumBPBase.solve_vert_velocity ----------
+ * u_z from continuity exactly as the reference poses it: u_z_b = project(basal kinematic
+ * condition, Q); A_ij = int dz(phi_j) phi_i, b_i = -int (u_x,x + u_y,y) phi_i; Dirichlet
+ * rows u_z = u_z_b on the basal facets' dofs; the reference factorises A with MUMPS, here
+ * BiCGStab right-preconditioned by an exact pivoted tridiagonal solve per ice column, to a
+ * relative residual of 1e-12.  Needs BP_FIELD_B; uz_vertex: one value per mesh vertex.    */
+int  bp_solve_vert_velocity(bp_ctx* ctx, const double* u, double* uz_vertex, int on_device, int32_t* iterations);
 
 /* ---- timing of the kernels themselves (CUDA events on the context's stream) --- */
 /* flush_l2 != 0: a 512 MiB buffer is written before every timed launch            */

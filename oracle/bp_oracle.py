@@ -480,6 +480,50 @@ class BPProblem(object):
 		np.add.at(rhs, nd.ravel(), b.ravel())
 		return spla.spsolve(self.mass_matrix().tocsc(), rhs)
 
+	# ---- solve_vert_velocity, cslvr/momentumbp.py:60-85, 231-253 ----------------
+	def vert_velocity(self, u, B, B_ring=None):
+		"""u_z from the continuity equation the way the reference does it:
+
+		1. u_z_b = project((-B_ring - u_x n_b0 - u_y n_b1) / n_b2, Q) with
+		   n_b = (grad B - k) / |grad B - k|  (momentumbp.py:68-72, 240);
+		2. A_ij = int d(phi_j)/dz phi_i dx,  b_i = -int (u_x,x + u_y,y) phi_i dx
+		   (lhs/rhs of u_z_F, momentumbp.py:75, 244-245);
+		3. DirichletBC(Q, u_z_b, ff, GAMMA_B_GND / GAMMA_B_FLT) applied to (A, b): rows of the
+		   basal dofs become identity rows (momentumbp.py:79-85, 246-248);
+		4. direct solve (LUSolver('mumps'), momentumbp.py:249-250).
+		Returns (u_z, u_z_b), both per node of model.Q."""
+		(ip, ix), nd = self.scalar_pattern()
+		nn = self.n_dofs // 2
+		nt = self.cells.shape[0]
+		B = np.asarray(B, dtype=np.float64)
+		Br = np.zeros_like(B) if B_ring is None else np.asarray(B_ring, dtype=np.float64) * np.ones_like(B)
+		gB = np.einsum('ta,taj->tj', B[self.cells], self.G)
+		mag = np.sqrt(1.0 + (gB ** 2).sum(axis=1))
+		nb = np.stack([gB[:, 0], gB[:, 1], gB[:, 2] - 1.0], axis=1) / mag[:, None]
+		Uloc = u[self.cell_dofs].reshape(-1, 2, 4)
+		M = self.mass_matrix()
+		Me = (self.vol[:, None, None] / 20.0) * (np.ones((4, 4)) + np.eye(4))[None]
+		# nodal values of the (cell-wise) integrand: P1 in u and B_ring, cell-constant normal
+		f = (-Br[self.cells] - Uloc[:, 0, :] * nb[:, 0:1] - Uloc[:, 1, :] * nb[:, 1:2]) / nb[:, 2:3]
+		rhs = np.zeros(nn)
+		np.add.at(rhs, nd.ravel(), np.einsum('tab,tb->ta', Me, f).ravel())
+		uzb = spla.spsolve(M.tocsc(), rhs)
+		# the continuity system
+		g = self._grad_u(u)
+		div = g[:, 0, 0] + g[:, 1, 1]
+		Ae = (self.vol / 4.0)[:, None, None] * np.broadcast_to(self.G[:, None, :, 2], (nt, 4, 4))   # [t, i, j] = dz(phi_j) |T|/4
+		A = sp.coo_matrix((Ae.ravel(), (np.repeat(nd, 4, axis=1).ravel(), np.tile(nd, (1, 4)).ravel())), shape=(nn, nn)).tolil()
+		b = np.zeros(nn)
+		np.add.at(b, nd.ravel(), np.repeat(-div * self.vol / 4.0, 4))
+		loc = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])
+		basal = np.isin(self.ff, (GAMMA_B_GND, GAMMA_B_FLT))
+		bn = np.unique(nd[self.fc[basal]][np.arange(basal.sum())[:, None], loc[self.fl[basal]]])
+		for i in bn:
+			A.rows[i] = [i]
+			A.data[i] = [1.0]
+		b[bn] = uzb[bn]
+		return spla.spsolve(A.tocsc(), b), uzb
+
 	# ---- Newton (dolfin NewtonSolver semantics, SURVEY A-N) ----------------
 	def newton(self, u0=None, rtol=1e-9, atol=1e-10, maxit=25, relax=1.0,
 	           linear_solver='direct', krylov_rtol=1e-5, verbose=False):

@@ -271,3 +271,30 @@ def test_solve_runs_pressure_step_like_the_reference():
 	mom.solve()
 	P = oracle_problem(m)
 	assert relerr(m.p.values, P.pressure(mom.get_unknown().values)) < TOL_U
+
+
+@pytest.mark.parametrize('builder', [lambda: ismip_model('A', n=(9, 8, 4)), lambda: ismip_model('C', L=20000.0, n=(8, 8, 5)),
+                                     lambda: marine_model(n=(7, 6, 4))])
+def test_solve_vert_velocity_matches_oracle(builder):
+	"""SURVEY §8f rank 1, cslvr/momentumbp.py:231-253: u_z from the continuity system."""
+	from cslvr_b200 import capi
+	m = builder()
+	P = oracle_problem(m)
+	u = state(P.n_dofs, 43)
+	uzo, uzbo = P.vert_velocity(u, m.vertex_field(m.B))
+	c = product_context(m)
+	c.set_field(capi.FIELD_B, m.vertex_field(m.B))
+	uz = c.solve_vert_velocity(u)
+	assert relerr(uz[m.node_vertex], uzo) < TOL_U, (relerr(uz[m.node_vertex], uzo), c.last_vert_iterations)
+	c.close()
+
+
+def test_default_solve_runs_all_three_steps():
+	"""MomentumBPBase.solve(): Newton, then u_z, then p (cslvr/momentumbp.py:255-273)."""
+	from cslvr_b200 import MomentumDukowiczBP
+	m = ismip_model('A', n=(8, 8, 4))
+	mom = MomentumDukowiczBP(m)
+	mom.solve()
+	P = oracle_problem(m)
+	uzo, _ = P.vert_velocity(mom.get_unknown().values, m.vertex_field(m.B))
+	assert relerr(m.u.sub(2), uzo) < 1e-7 and relerr(m.p.values, P.pressure(mom.get_unknown().values)) < TOL_U
