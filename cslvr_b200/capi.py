@@ -70,7 +70,7 @@ SYMBOLS = ['bp_create', 'bp_destroy', 'bp_last_error', 'bp_set_params', 'bp_set_
            'bp_set_field', 'bp_get_sizes', 'bp_csr_pattern', 'bp_assemble', 'bp_spmv',
            'bp_krylov_solve', 'bp_newton_solve', 'bp_time_assemble', 'bp_time_spmv',
            'bp_launch_count', 'bp_comm_unique_id', 'bp_comm_init',
-           'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity']
+           'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity', 'bp_linear_solve']
 
 _lib = None
 
@@ -100,6 +100,7 @@ def load_library():
 	lib.bp_spmv.argtypes = [vp, vp, vp, C.c_int]
 	lib.bp_krylov_solve.argtypes = [vp, vp, vp, C.c_int, c_i32p, c_f64p]
 	lib.bp_newton_solve.argtypes = [vp, vp, C.c_int, C.POINTER(bp_stats)]
+	lib.bp_linear_solve.argtypes = [vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_solve_pressure.argtypes = [vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_solve_vert_velocity.argtypes = [vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_time_assemble.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_f64p]
@@ -353,6 +354,21 @@ class BPContext(object):
 		if rc == BP_ERR_NONCONV:
 			raise BPError(rc, self.lib.bp_last_error(self.h).decode())
 		return d
+
+	def linear_solve(self, u_lin, u_out=None):
+		"""one linear solve with the viscosity frozen at eta(u_lin) (``linear=True``)."""
+		pl, dev, kl = _ptr(u_lin)
+		if u_out is None:
+			if dev:
+				import torch
+				u_out = torch.empty_like(kl)
+			else:
+				u_out = np.empty(self.n_dofs)
+		po, _, ko = _ptr(u_out)
+		it = C.c_int32()
+		self._check(self.lib.bp_linear_solve(self.h, pl, po, dev, C.byref(it)))
+		self.last_linear_iterations = it.value
+		return u_out
 
 	def solve_pressure(self, u, p=None):
 		"""BP pressure (one value per mesh vertex) from the velocity dofs ``u``."""

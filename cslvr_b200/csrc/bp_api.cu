@@ -500,6 +500,26 @@ int bp_assemble_group(bp_ctx** cs, int n, int what, const double** u, double** F
 	return BP_OK;
 }
 
+int bp_linear_solve(bp_ctx* c, const double* u_lin, double* u_out, int on_device, int32_t* iterations)
+{
+	if (!c || !u_lin || !u_out) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = ready(c);
+	if (rc) return rc;
+	if ((rc = vec_in(c, u_lin, on_device, c->d_u))) return rc;
+	bp_ctx* cs[1] = { c };
+	if ((rc = group_assemble(cs, 1, BP_ASSEMBLE_F | BP_ASSEMBLE_J | 16))) return rc;     // K(u_lin), f
+	int it = 0;
+	if ((rc = group_pcg(cs, 1, &it, nullptr))) return rc;                                  // dx = K^-1 f
+	if (iterations) *iterations = it;
+	BP_CUDA(c, cudaMemsetAsync(c->d_u, 0, (size_t)2 * c->nn * sizeof(double), c->stream));
+	bp_launch_axpy(c, -1.0, c->d_dx, c->d_u);                                              // u = -dx
+	if ((rc = vec_out(c, c->d_u, u_out, on_device))) return rc;
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return BP_OK;
+}
+
 int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_device, int32_t* iterations)
 {
 	if (!c || !u || !p_vertex) return BP_ERR_ARG;

@@ -20,6 +20,7 @@ struct AsmParams {
 	double n, eps_reg, rho_g, rho_sw_g;
 	int    n_quad;
 	int    n_is_3;
+	int    picard;      // linear=True: viscosity frozen at the given state, no eta' term, F = u-independent part
 };
 
 #define TPB 128
@@ -106,7 +107,7 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 		two_eta = pow(ed, e);
 		two_eta_p = e * two_eta / ed;
 	}
-	const double alpha = wbar * two_eta, gamma = wbar * two_eta_p;
+	const double alpha = wbar * two_eta, gamma = P.picard ? 0.0 : wbar * two_eta_p;
 	const double cxx = 2.0 * g00 + g11, cyy = 2.0 * g11 + g00, hz0 = 0.5 * g02, hz1 = 0.5 * g12;
 	double dx[4], dy[4];
 	#pragma unroll
@@ -120,8 +121,9 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 		#pragma unroll
 		for (int a = 0; a < 4; ++a) {
 			if (nd[a] < nn_owned) {
-				atomicAdd(&F[2 * nd[a]], alpha * dx[a] + grav * sx);
-				atomicAdd(&F[2 * nd[a] + 1], alpha * dy[a] + grav * sy);
+				const double af = P.picard ? 0.0 : alpha;
+				atomicAdd(&F[2 * nd[a]], af * dx[a] + grav * sx);
+				atomicAdd(&F[2 * nd[a] + 1], af * dy[a] + grav * sy);
 			}
 		}
 	}
@@ -362,14 +364,15 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 			two_eta = pow(ed, ex);
 			two_eta_p = ex * two_eta / ed;
 		}
-		const double alpha = wbar * two_eta, gamma = wbar * two_eta_p;
+		const double alpha = wbar * two_eta, gamma = P.picard ? 0.0 : wbar * two_eta_p;
 		const double cxx = 2.0 * g00 + g11, cyy = 2.0 * g11 + g00, hz0 = 0.5 * g02, hz1 = 0.5 * g12;
 		const double dx0 = cxx * X[0] + sh * Y[0] + hz0 * Z[0];
 		const double dy0 = cyy * Y[0] + sh * X[0] + hz1 * Z[0];
 		if (WANT_F) {
 			const double grav = P.rho_g * vol * 0.25;
-			Fx += alpha * dx0 + grav * sx;
-			Fy += alpha * dy0 + grav * sy;
+			const double af = P.picard ? 0.0 : alpha;
+			Fx += af * dx0 + grav * sx;
+			Fy += af * dy0 + grav * sy;
 		}
 		if (WANT_J) {
 			const double Pa = 2.0 * alpha * X[0], Qa = 0.5 * alpha * Y[0], Ra = 0.5 * alpha * Z[0];
@@ -591,7 +594,7 @@ k_facet(int nf, int nt, const int32_t* __restrict__ fcell, const int32_t* __rest
 		for (int a = 0; a < 3; ++a)
 			#pragma unroll
 			for (int b = 0; b < 3; ++b) {
-				Fx[a] += K[a][b] * uu[b].x; Fy[a] += K[a][b] * uu[b].y;
+				if (!P.picard) { Fx[a] += K[a][b] * uu[b].x; Fy[a] += K[a][b] * uu[b].y; }
 				if (WANT_J) {
 					const int slot = tet_blk[(la[a] * 4 + la[b]) * nt + cell];
 					if (slot >= 0) { atomicAdd(val + 4 * (size_t)slot, K[a][b]); atomicAdd(val + 4 * (size_t)slot + 3, K[a][b]); }
@@ -624,6 +627,7 @@ static AsmParams make_params(const bp_ctx* c)
 	P.rho_g = c->prm.rho_i * c->prm.g; P.rho_sw_g = c->prm.rho_sw * c->prm.g;
 	P.n_quad = (int)c->quad_wts.size();
 	P.n_is_3 = (c->prm.n == 3.0);
+	P.picard = 0;
 	return P;
 }
 
@@ -672,7 +676,8 @@ void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, doubl
 void bp_launch_proxy(bp_ctx* c);
 void bp_launch_assemble(bp_ctx* c, int what)
 {
-	const AsmParams P = make_params(c);
+	AsmParams P = make_params(c);
+	P.picard = (what & 16) ? 1 : 0;
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
 	if (what & 8) { bp_launch_proxy(c); return; }
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)

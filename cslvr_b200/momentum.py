@@ -50,6 +50,29 @@ class Momentum(Physics):
 		self.initialize(model=self.model, solve_params=self.solve_params_s, linear=self.linear_s,
 		                use_lat_bcs=self.use_lat_bcs_s, use_pressure_bc=self.use_pressure_bc_s, **self.kwargs)
 
+	def linearize_viscosity(self, reset_orig_config=True):
+		"""linearize the viscosity using the velocity stored in ``model.u``
+		(cslvr/momentum.py:97-138): re-initialise with linear=True, 2 Newton iterations max,
+		relaxation 1.0, no u_z / p solves."""
+		print_text("::: RE-INITIALIZING MOMENTUM PHYSICS WITH LINEAR VISCOSITY :::", cls=self)
+		mom_params = deepcopy(self.solve_params_s)
+		new_params = mom_params['solver']['newton_solver']
+		mom_params['solve_vert_velocity']     = False
+		mom_params['solve_pressure']          = False
+		new_params['relaxation_parameter']    = 1.0
+		new_params['maximum_iterations']      = 2
+		new_params['error_on_nonconvergence'] = False
+		print_text("::: altering solver parameters for optimal convergence :::", cls=self)
+		print_text(json.dumps(mom_params, sort_keys=True, indent=2), '230')
+		if reset_orig_config:
+			print_text("::: reseting the original config to use linear viscosity :::", cls=self)
+			self.linear_s       = True
+			self.solve_params_s = mom_params
+		self.linear = True
+		self.solve_params = mom_params
+		self.initialize(model=self.model, solve_params=mom_params, linear=True,
+		                use_lat_bcs=self.use_lat_bcs_s, use_pressure_bc=self.use_pressure_bc_s, **self.kwargs)
+
 	def color(self):
 		return 'cyan'
 

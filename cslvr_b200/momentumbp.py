@@ -133,6 +133,23 @@ class MomentumBPBase(Momentum):
 		stats = c.newton_solve(u.values)
 		return stats
 
+	def _linear_solve(self, sp):
+		"""linear=True: viscosity from model.u (cslvr/momentumbp.py:91-93)."""
+		c = self._context()
+		# after linearize_viscosity() the dictionary still has the non-linear layout
+		# (cslvr/momentum.py:105-118), so look for the Krylov settings at both levels
+		sp = sp if isinstance(sp, dict) else {}
+		inner = sp.get('newton_solver', sp)
+		pc = inner.get('preconditioner', 'default')
+		ks = inner.get('krylov_solver', {})
+		c.set_params(krylov_rtol=ks.get('relative_tolerance', 1e-5), krylov_atol=ks.get('absolute_tolerance', 1e-50),
+		             krylov_maxit=ks.get('maximum_iterations', 10000), preconditioner=self._PC_MAP.get(pc, 'chebyshev'),
+		             quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		ul = np.empty(self.Q.dim())
+		ul[0::2], ul[1::2] = self.model.u.values[0::3], self.model.u.values[1::3]
+		self.get_unknown().values[:] = c.linear_solve(ul)
+		return dict(converged=True, iterations=1, krylov_iterations=c.last_linear_iterations)
+
 	# ---- assemble(residual) / assemble(jacobian) ------------------------------
 	def assemble_residual(self, u=None):
 		c = self._context()

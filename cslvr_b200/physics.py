@@ -64,7 +64,13 @@ class Physics(object):
 			                          "cannot be served by an external solver")
 		t0 = time()
 		if self.linear:
-			raise NotImplementedError("linear=True (cslvr/physics.py:655-661) is not on the B200 path yet")
+			# cslvr/physics.py:655-661: solve(lhs == rhs, u, bcs, solver_parameters=params['solver'])
+			print_text("::: solving linear equations :::", cls=self)
+			self.stats = self._linear_solve(params['solver'])
+			t_tot = time() - t0
+			print_text("time to solve: %02d:%02d:%02d:%03d" % (t_tot / 3600, (t_tot / 60) % 60, t_tot % 60, (t_tot % 1) * 1000), 'red', 1)
+			self.update_model_var(self.get_unknown(), annotate=annotate)
+			return
 		ns     = params['solver']['newton_solver']
 		rtol   = ns['relative_tolerance']
 		maxit  = ns['maximum_iterations']
@@ -87,4 +93,7 @@ class Physics(object):
 		raise NotImplementedError
 
 	def _newton_solve(self, newton_params):
+		raise NotImplementedError
+
+	def _linear_solve(self, solver_params):
 		raise NotImplementedError

@@ -182,6 +182,11 @@ int  bp_krylov_solve(bp_ctx* ctx, const double* b, double* dx, int on_device,
 /* the whole dolfin.solve(F == 0, u, J=J) call: damped Newton from u_inout         */
 int  bp_newton_solve(bp_ctx* ctx, double* u_inout, int on_device, bp_stats* stats);
 
+/* ---- linear=True (cslvr/momentumbp.py:91-93, 396, 503; physics.py:655-661; used by
+ * Momentum.linearize_viscosity, momentum.py:97-138): ONE linear solve lhs == rhs with the
+ * viscosity frozen at eta(u_lin) (u_lin = model.u).  u_out = K(u_lin)^-1 (-f).            */
+int  bp_linear_solve(bp_ctx* ctx, const double* u_lin, double* u_out, int on_device, int32_t* iterations);
+
 /* ---- cslvr/momentumbp.py:205-229, MomentumBPBase.solve_pressure ------------------
  * p = project(rho g (S - z) - 2 eta(u) (u_x,x + u_y,y), model.Q): P1 mass-matrix solve
  * (dolfin project() = LU; here block-Jacobi PCG to 1e-13).  u: caller's dofs;

@@ -290,7 +290,7 @@ class BPProblem(object):
 		return H
 
 	# ---- cell integrals ---------------------------------------------------
-	def cell_tensors(self, u, want_J=True, form='dukowicz'):
+	def cell_tensors(self, u, want_J=True, form='dukowicz', picard=False):
 		"""element action, residual [nt,8] and Jacobian [nt,8,8] by quadrature.
 
 		Dukowicz: momentumbp.py:460-500 with Vd from momentum.py:187-222;
@@ -338,7 +338,7 @@ class BPProblem(object):
 			grav = np.concatenate([np.outer(gS[:, 0], lam), np.outer(gS[:, 1], lam)], axis=1)
 			F += dx[:, None] * (Fv + rho_g * grav)
 			if want_J:
-				two_eta_p = Ainv * ((1 - n) / (2 * n)) * ed ** ((1 - n) / (2 * n) - 1)
+				two_eta_p = 0.0 * Ainv if picard else Ainv * ((1 - n) / (2 * n)) * ed ** ((1 - n) / (2 * n) - 1)
 				J += dx[:, None, None] * (two_eta[:, None, None] * H + two_eta_p[:, None, None] * dede)
 		return act, F, J
 
@@ -523,6 +523,44 @@ class BPProblem(object):
 			A.data[i] = [1.0]
 		b[bn] = uzb[bn]
 		return spla.spsolve(A.tocsc(), b), uzb
+
+	# ---- linear=True, cslvr/momentumbp.py:396 / 503, physics.py:655-661 ----------
+	def linear_solve(self, u_l):
+		"""one linear solve with the viscosity frozen at eta(u_l) (``linear=True``:
+		Vd = 2 eta(model.u) epsdot(u), momentumbp.py:91-93 / momentum.py:213-216; the
+		residual with u_h replaced by the trial function splits into lhs == rhs).
+		K = second variation without the eta' term, f = the u-independent part of F."""
+		_, Fc, Jc = self.cell_tensors(u_l, want_J=True, picard=True)
+		indptr, indices = self.pattern()
+		nd = self.n_dofs
+		rows = np.repeat(self.cell_dofs, 8, axis=1).ravel()
+		cols = np.tile(self.cell_dofs, (1, 8)).ravel()
+		vals = Jc.ravel()
+		zero = np.zeros(nd)
+		f = self.residual(zero) - self._viscous_residual(zero)        # gravity + water pressure only
+		if self.fc.size:
+			_, _, Jf = self.facet_tensors(u_l)
+			cd = self.cell_dofs[self.fc]
+			rows = np.concatenate([rows, np.repeat(cd, 8, axis=1).ravel()])
+			cols = np.concatenate([cols, np.tile(cd, (1, 8)).ravel()])
+			vals = np.concatenate([vals, Jf.ravel()])
+		K = sp.coo_matrix((vals, (rows, cols)), shape=(nd, nd)).tocsc()
+		return spla.spsolve(K, -f)
+
+	def _viscous_residual(self, u):
+		"""int 2 eta(u) d(epsdot)(u; v): the part of F that is not gravity / facets."""
+		n, eps0 = self.c['n'], self.c['eps_reg']
+		pts, wts = tetrahedron_rule(self.quad_degree)
+		g = self._grad_u(u)
+		ed = self._epsdot(g) + eps0
+		de = self._depsdot(g)
+		Av = self.A[self.cells]
+		F = np.zeros((self.cells.shape[0], 8))
+		for lam, w in zip(pts, wts):
+			F += (w * self.vol * (Av @ lam) ** (-1.0 / n) * ed ** ((1 - n) / (2 * n)))[:, None] * de
+		out = np.zeros(self.n_dofs)
+		np.add.at(out, self.cell_dofs.ravel(), F.ravel())
+		return out
 
 	# ---- Newton (dolfin NewtonSolver semantics, SURVEY A-N) ----------------
 	def newton(self, u0=None, rtol=1e-9, atol=1e-10, maxit=25, relax=1.0,

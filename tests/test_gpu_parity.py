@@ -298,3 +298,34 @@ def test_default_solve_runs_all_three_steps():
 	P = oracle_problem(m)
 	uzo, _ = P.vert_velocity(mom.get_unknown().values, m.vertex_field(m.B))
 	assert relerr(m.u.sub(2), uzo) < 1e-7 and relerr(m.p.values, P.pressure(mom.get_unknown().values)) < TOL_U
+
+
+@pytest.mark.parametrize('mode', ['gather', 'scatter'])
+def test_linear_solve_matches_oracle(mode):
+	"""linear=True -- one solve with eta frozen at eta(model.u)."""
+	m = marine_model(n=(7, 6, 4))
+	P = oracle_problem(m)
+	ul = state(P.n_dofs, 51, 20.0)
+	ref = P.linear_solve(ul)
+	c = product_context(m, krylov_rtol=1e-13, assembly=mode)
+	out = c.linear_solve(ul)
+	assert relerr(out, ref) < TOL_U, relerr(out, ref)
+	c.close()
+
+
+def test_linearize_viscosity_like_the_reference():
+	"""Momentum.linearize_viscosity (cslvr/momentum.py:97-138): after a non-linear solve, the
+	linearised problem at model.u reproduces that velocity (fixed point) in ONE linear solve."""
+	from cslvr_b200 import MomentumDukowiczBP
+	m = ismip_model('A', n=(8, 8, 4))
+	mom = MomentumDukowiczBP(m)
+	mom.solve_params['solver']['newton_solver']['relative_tolerance'] = 1e-12
+	mom.solve_params['solver']['newton_solver']['krylov_solver'] = {'relative_tolerance': 1e-13}
+	mom.solve()
+	u_nl = mom.get_unknown().values.copy()
+	mom.linearize_viscosity()
+	assert mom.linear and mom.solve_params['solve_pressure'] is False and mom.solve_params['solve_vert_velocity'] is False
+	mom.solve()
+	assert relerr(mom.get_unknown().values, u_nl) < 1e-4       # linearize_viscosity restores the ORIGINAL params: Krylov rtol 1e-5
+	P = oracle_problem(m)
+	assert relerr(mom.get_unknown().values, P.linear_solve(u_nl)) < 1e-4      # default Krylov rtol 1e-5 on the linear path
