@@ -12,7 +12,7 @@ import numpy as np
 from . import _build
 
 BP_OK, BP_ERR_ARG, BP_ERR_CUDA, BP_ERR_STATE, BP_ERR_COMM, BP_ERR_NONCONV = range(6)
-FIELD_S, FIELD_A, FIELD_BETA, FIELD_B, FIELD_B_RING = 0, 1, 2, 3, 4
+FIELD_S, FIELD_A, FIELD_BETA, FIELD_B, FIELD_B_RING, FIELD_TP, FIELD_W, FIELD_E = range(8)
 ASSEMBLE_F, ASSEMBLE_J = 1, 2
 PC = {'none': 0, 'jacobi': 1, 'block_jacobi': 2, 'chebyshev': 3, 'column': 4}
 
@@ -43,7 +43,9 @@ class bp_params(C.Structure):
 	            ('krylov_rtol', C.c_double), ('krylov_atol', C.c_double),
 	            ('krylov_maxit', C.c_int32), ('pc', C.c_int32), ('pc_degree', C.c_int32),
 	            ('verbose', C.c_int32), ('assembly', C.c_int32), ('pc_eig_ratio', C.c_double),
-	            ('n_quad_aux', C.c_int32), ('quad_points_aux', c_f64p), ('quad_weights_aux', c_f64p)]
+	            ('n_quad_aux', C.c_int32), ('quad_points_aux', c_f64p), ('quad_weights_aux', c_f64p),
+	            ('energy_dependent', C.c_int32), ('a_T_l', C.c_double), ('a_T_u', C.c_double),
+	            ('Q_T_l', C.c_double), ('Q_T_u', C.c_double), ('R_gas', C.c_double)]
 
 
 class bp_stats(C.Structure):
@@ -218,7 +220,12 @@ class BPContext(object):
 		p.g = d.get('g', 9.80665)
 		p.periodic = int(bool(d.get('periodic', False)))
 		p.use_pressure_bc = int(bool(d.get('use_pressure_bc', True)))
-		pts, wts = tetrahedron_rule(int(d.get('quadrature_degree', 5)))
+		p.energy_dependent = int(bool(d.get('energy_dependent_rate_factor', False)))
+		spy = 31556926.0
+		p.a_T_l, p.a_T_u = d.get('a_T_l', 3.985e-13 * spy), d.get('a_T_u', 1.916e3 * spy)
+		p.Q_T_l, p.Q_T_u, p.R_gas = d.get('Q_T_l', 6e4), d.get('Q_T_u', 13.9e4), d.get('R', 8.3144621)
+		# UFL's degree estimate: 5 with a P1 rate factor, 9 with the energy-dependent expression (SURVEY A-Q)
+		pts, wts = tetrahedron_rule(int(d.get('quadrature_degree', 9 if p.energy_dependent else 5)))
 		pts = np.ascontiguousarray(pts, dtype=np.float64)
 		wts = np.ascontiguousarray(wts, dtype=np.float64)
 		self._quad = (pts, wts)

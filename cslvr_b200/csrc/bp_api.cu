@@ -56,8 +56,10 @@ struct GroupStream {   // an in-process group runs on the first context's stream
 
 static int ready(bp_ctx* c)
 {
-	if (!c->have_S || !c->have_A || !c->have_beta)
-		return bp_fail(c, BP_ERR_STATE, "fields not set: S=%d A=%d beta=%d (bp_set_field)", (int)c->have_S, (int)c->have_A, (int)c->have_beta);
+	const bool haveA = c->prm.energy_dependent ? c->have_Tp : c->have_A;
+	if (!c->have_S || !haveA || !c->have_beta)
+		return bp_fail(c, BP_ERR_STATE, "fields not set: S=%d %s=%d beta=%d (bp_set_field)", (int)c->have_S,
+		               c->prm.energy_dependent ? "T'" : "A", (int)haveA, (int)c->have_beta);
 	return BP_OK;
 }
 
@@ -302,7 +304,7 @@ void bp_destroy(bp_ctx* c)
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
-		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_bcnode, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
+		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -319,6 +321,7 @@ int bp_set_params(bp_ctx* c, const bp_params* p)
 	if ((p->periodic != c->prm.periodic) || (p->use_pressure_bc != c->prm.use_pressure_bc))
 		return bp_fail(c, BP_ERR_ARG, "bp_set_params: periodic / use_pressure_bc select the facet sets at bp_create and cannot change");
 	store_params(c, p);
+	c->ainv_dirty = true;
 	cudaSetDevice(c->device);
 	bp_upload_quadrature(c);
 	return BP_OK;
@@ -346,7 +349,16 @@ int bp_set_field(bp_ctx* c, int field, const double* values, int64_t nvals, int 
 		c->have_S = true; break;
 	case BP_FIELD_A:
 		BP_CUDA(c, cudaMemcpyAsync(c->d_A, values, nvals * sizeof(double), kind, c->stream));
-		c->have_A = true; break;
+		c->have_A = true; c->ainv_dirty = true; break;
+	case BP_FIELD_TP:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_Tp, values, nvals * sizeof(double), kind, c->stream));
+		c->have_Tp = true; c->ainv_dirty = true; break;
+	case BP_FIELD_W:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_W, values, nvals * sizeof(double), kind, c->stream));
+		c->ainv_dirty = true; break;
+	case BP_FIELD_E:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_E, values, nvals * sizeof(double), kind, c->stream));
+		c->ainv_dirty = true; break;
 	case BP_FIELD_BETA:
 		BP_CUDA(c, cudaMemcpyAsync(c->d_beta, values, nvals * sizeof(double), kind, c->stream));
 		c->have_beta = true; break;
@@ -528,6 +540,8 @@ int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_devic
 	if (rc) return rc;
 	if (c->prm.assembly == BP_ASM_SCATTER || (size_t)4 * c->max_row * 128 * sizeof(double) > 200 * 1024)
 		return bp_fail(c, BP_ERR_STATE, "bp_solve_pressure needs the row-gather assembly path");
+	if (c->prm.energy_dependent)
+		return bp_fail(c, BP_ERR_STATE, "bp_solve_pressure with the energy-dependent rate factor is not available yet");
 	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
 	bp_ctx* cs[1] = { c };
 	if ((rc = bp_comm_halo(cs, 1, 0))) return rc;

@@ -55,6 +55,9 @@ struct bp_ctx {
 	double4* d_geo = nullptr;            // per vertex {x, y, z, S}
 	double*  d_A = nullptr;              // per vertex
 	double*  d_beta = nullptr;           // per vertex
+	double  *d_Tp = nullptr, *d_W = nullptr, *d_E = nullptr;   // energy-dependent rate factor inputs, per vertex
+	double*  d_ainv = nullptr;           // [nt] sum_q w_q A_q^(-1/n) per tet (k_tet_ainv)
+	bool     ainv_dirty = true, have_Tp = false;
 	double  *d_Bv = nullptr, *d_Bring = nullptr;   // bed height / basal melt per vertex (u_z solve only)
 	uint8_t* d_bcnode = nullptr;         // owned node lies on a basal facet (Dirichlet dof of the u_z system)
 	double*  d_aux = nullptr;            // [2*nn] u_z_b per node
@@ -120,6 +123,7 @@ int bp_build_csr_export(bp_ctx* c);
 
 // kernels (bp_kernels.cu)
 void bp_launch_assemble(bp_ctx* c, int what);                 // d_u -> d_F / d_val
+void bp_update_ainv(bp_ctx* c);
 void bp_launch_spmv(bp_ctx* c, const double* x, double* y, int with_dot);
 void bp_launch_gather_in(bp_ctx* c, const double* ext, double* internal);   // caller -> internal
 void bp_launch_scatter_out(bp_ctx* c, const double* internal, double* ext); // internal -> caller

@@ -31,6 +31,52 @@ __device__ __forceinline__ double pow_m1n(double a, const AsmParams& P)
 	return P.n_is_3 ? rcbrt(a) : pow(a, -1.0 / P.n);
 }
 
+// ---------------------------------------------------------------- rate-factor quadrature
+// ainv[t] = sum_q w_q A(x_q)^(-1/n): the only quadrature of the BP cell integrals (the strain
+// rate of a P1 velocity is cell-constant).  It does not depend on u, so it is evaluated once
+// per coefficient change, not once per Newton iteration.
+//   ENERGY = false: A is the P1 Function model.A (cslvr/model.py:2530);
+//   ENERGY = true : A = E a_T (1 + 181.25 min(W, 0.01)) exp(-Q_T / (R T')) evaluated at the
+//                   quadrature points from the P1 fields T', W, E with a_T, Q_T switching at
+//                   T' = 263.15 K (Model.form_energy_dependent_rate_factor, model.py:1815-1859).
+struct RateLaw { double a_T_l, a_T_u, Q_T_l, Q_T_u, R; };
+template <bool ENERGY>
+__global__ void __launch_bounds__(128)
+k_tet_ainv(int nt, const int4* __restrict__ tets, const double* __restrict__ Av, const double* __restrict__ Tp,
+           const double* __restrict__ W, const double* __restrict__ E, RateLaw L, AsmParams P, double* __restrict__ ainv)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nt) return;
+	const int4 tv = tets[t];
+	const int vid[4] = { tv.x, tv.y, tv.z, tv.w };
+	if (!ENERGY) {
+		double A[4];
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) A[a] = Av[vid[a]];
+		if (A[0] == A[1] && A[0] == A[2] && A[0] == A[3]) { ainv[t] = pow_m1n(A[0], P); return; }
+		double s = 0.0;
+		for (int q = 0; q < P.n_quad; ++q)
+			s += c_qw[q] * pow_m1n(c_ql[4 * q] * A[0] + c_ql[4 * q + 1] * A[1] + c_ql[4 * q + 2] * A[2] + c_ql[4 * q + 3] * A[3], P);
+		ainv[t] = s;
+	} else {
+		double T[4], Wv[4], Ev[4];
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) { T[a] = Tp[vid[a]]; Wv[a] = W[vid[a]]; Ev[a] = E[vid[a]]; }
+		double s = 0.0;
+		for (int q = 0; q < P.n_quad; ++q) {
+			const double l0 = c_ql[4 * q], l1 = c_ql[4 * q + 1], l2 = c_ql[4 * q + 2], l3 = c_ql[4 * q + 3];
+			const double Tq = l0 * T[0] + l1 * T[1] + l2 * T[2] + l3 * T[3];
+			const double Wq = l0 * Wv[0] + l1 * Wv[1] + l2 * Wv[2] + l3 * Wv[3];
+			const double Eq = l0 * Ev[0] + l1 * Ev[1] + l2 * Ev[2] + l3 * Ev[3];
+			const bool cold = Tq < 263.15;
+			const double aT = cold ? L.a_T_l : L.a_T_u, QT = cold ? L.Q_T_l : L.Q_T_u;
+			const double WT = (Wq < 0.01) ? Wq : 0.01;
+			s += c_qw[q] * pow_m1n(Eq * aT * (1.0 + 181.25 * WT) * exp(-QT / (L.R * Tq)), P);
+		}
+		ainv[t] = s;
+	}
+}
+
 // ---------------------------------------------------------------- cell kernel
 // One thread per tetrahedron.  Loads: int4 connectivity, 4 x {x,y,z,S} (32 B each),
 // 4 x {u_x,u_y} (16 B), 4 x A.  Builds F_cell (8) and J_cell (8x8, symmetric) in
@@ -49,12 +95,10 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 	double4 p[4];
 	int nd[4];
 	double2 uu[4];
-	double A[4];
 	#pragma unroll
 	for (int a = 0; a < 4; ++a) {
 		p[a] = geo[vid[a]];
 		nd[a] = v2n ? v2n[vid[a]] : vid[a];
-		A[a] = Av[vid[a]];
 	}
 	#pragma unroll
 	for (int a = 0; a < 4; ++a) uu[a] = u[nd[a]];
@@ -74,18 +118,8 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 	X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
 	const double vol = fabs(det) * (1.0 / 6.0);
 
-	// wbar = |T| * sum_q w_q A_q^(-1/n); one evaluation when A is constant on the cell
-	double wbar;
-	if (A[0] == A[1] && A[0] == A[2] && A[0] == A[3]) {
-		wbar = vol * pow_m1n(A[0], P);
-	} else {
-		double s = 0.0;
-		for (int q = 0; q < P.n_quad; ++q) {
-			const double aq = c_ql[4 * q] * A[0] + c_ql[4 * q + 1] * A[1] + c_ql[4 * q + 2] * A[2] + c_ql[4 * q + 3] * A[3];
-			s += c_qw[q] * pow_m1n(aq, P);
-		}
-		wbar = vol * s;
-	}
+	// wbar = |T| * sum_q w_q A_q^(-1/n): the quadrature sum does not depend on u and is kept per tet (k_tet_ainv)
+	const double wbar = vol * Av[t];
 
 	// velocity gradient g[c][j] and surface gradient
 	double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, sx = 0, sy = 0;
@@ -167,9 +201,9 @@ k_proxy_smem(int nt, const int4* __restrict__ tets, const double4* __restrict__ 
 	for (int t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
 		const int4 tv = tets[t];
 		const int vid[4] = { tv.x, tv.y, tv.z, tv.w };
-		double4 p[4]; int nd[4]; double2 uu[4]; double A[4];
+		double4 p[4]; int nd[4]; double2 uu[4];
 		#pragma unroll
-		for (int a = 0; a < 4; ++a) { p[a] = geo[vid[a]]; nd[a] = v2n ? v2n[vid[a]] : vid[a]; A[a] = Av[vid[a]]; }
+		for (int a = 0; a < 4; ++a) { p[a] = geo[vid[a]]; nd[a] = v2n ? v2n[vid[a]] : vid[a]; }
 		#pragma unroll
 		for (int a = 0; a < 4; ++a) uu[a] = u[nd[a]];
 		const double e1x = p[1].x - p[0].x, e1y = p[1].y - p[0].y, e1z = p[1].z - p[0].z;
@@ -185,7 +219,7 @@ k_proxy_smem(int nt, const int4* __restrict__ tets, const double4* __restrict__ 
 		for (int a = 1; a < 4; ++a) { X[a] *= idet; Y[a] *= idet; Z[a] *= idet; }
 		X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
 		const double vol = fabs(det) * (1.0 / 6.0);
-		const double wbar = vol * pow_m1n(A[0], P);
+		const double wbar = vol * Av[t];
 		double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, sx = 0, sy = 0;
 		#pragma unroll
 		for (int a = 0; a < 4; ++a) {
@@ -232,7 +266,7 @@ void bp_launch_proxy(bp_ctx* c)
 	const AsmParams P = make_params_fwd(c);
 	const int nacc = 25000;
 	cudaFuncSetAttribute(k_proxy_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, nacc * 8);
-	k_proxy_smem<<<148, 384, nacc * 8, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_tet_blk, P, nacc, c->d_part);
+	k_proxy_smem<<<148, 384, nacc * 8, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_ainv, c->d_tet_blk, P, nacc, c->d_part);
 	c->launches++;
 }
 
@@ -275,7 +309,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	int code1 = -1;
 	double4 p[4];
 	double2 uu[4];
-	double A[4];
+	double ai = 0.0;                                 // sum_q w_q A_q^(-1/n) of the tet (k_tet_ainv)
 	if (code >= 0) {
 		pk = inc_pos[e];
 		#pragma unroll
@@ -289,12 +323,11 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		#pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
-			A[j] = Av[vid[j]];
 			uu[j] = u[vid[j]];
 		}
+		ai = Av[code >> 2];
 	}
 	while (code >= 0) {
-		const int a = code & 3;
 		const uint32_t pk_cur = pk;
 		e += 32;
 		// stage idx(e+1) -> current "next", request idx(e+2)
@@ -322,21 +355,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		for (int j = 1; j < 4; ++j) { X[j] *= idet; Y[j] *= idet; Z[j] *= idet; }
 		X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
 		const double vol = fabs(det) * (1.0 / 6.0);
-		double wbar;
-		if (A[0] == A[1] && A[0] == A[2] && A[0] == A[3]) {
-			wbar = vol * pow_m1n(A[0], P);
-		} else {
-			// the quadrature points are stored for the tet's own vertex order: undo the rotation
-			double Ao[4];
-			#pragma unroll
-			for (int j = 0; j < 4; ++j) Ao[(a + j) & 3] = A[j];
-			double sacc = 0.0;
-			for (int q = 0; q < P.n_quad; ++q) {
-				const double aq = c_ql[4 * q] * Ao[0] + c_ql[4 * q + 1] * Ao[1] + c_ql[4 * q + 2] * Ao[2] + c_ql[4 * q + 3] * Ao[3];
-				sacc += c_qw[q] * pow_m1n(aq, P);
-			}
-			wbar = vol * sacc;
-		}
+		const double wbar = vol * ai;
 		double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, sx = 0, sy = 0;
 		#pragma unroll
 		for (int j = 0; j < 4; ++j) {
@@ -349,9 +368,9 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 			#pragma unroll
 			for (int j = 0; j < 4; ++j) {
 				p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
-				A[j] = Av[vid[j]];
 				uu[j] = u[vid[j]];
 			}
+			ai = Av[code_n >> 2];
 		}
 		const double sh = 0.5 * (g01 + g10);
 		const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
@@ -674,10 +693,23 @@ void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, doubl
 }
 
 void bp_launch_proxy(bp_ctx* c);
+void bp_update_ainv(bp_ctx* c)
+{
+	if (!c->ainv_dirty) return;
+	const AsmParams P = make_params(c);
+	RateLaw L = { c->prm.a_T_l, c->prm.a_T_u, c->prm.Q_T_l, c->prm.Q_T_u, c->prm.R_gas };
+	const int g = (int)((c->nt + 127) / 128);
+	if (c->prm.energy_dependent) k_tet_ainv<true><<<g, 128, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_A, c->d_Tp, c->d_W, c->d_E, L, P, c->d_ainv);
+	else k_tet_ainv<false><<<g, 128, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_A, c->d_Tp, c->d_W, c->d_E, L, P, c->d_ainv);
+	c->launches++;
+	c->ainv_dirty = false;
+}
+
 void bp_launch_assemble(bp_ctx* c, int what)
 {
 	AsmParams P = make_params(c);
 	P.picard = (what & 16) ? 1 : 0;
+	bp_update_ainv(c);
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
 	if (what & 8) { bp_launch_proxy(c); return; }
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
@@ -685,10 +717,10 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
 			cudaFuncSetAttribute(k_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			k_rows<true, true><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
-				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P);
+				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P);
 		} else {
 			const int gc = (int)((c->nt + TPB - 1) / TPB);
-			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P);
+			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P);
 		}
 		c->launches++;
 		c->have_J = false;
@@ -708,7 +740,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		}
 		const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
 		const double2* uvert = bp_vertex_u(c);
-		#define ROWS(WF, WJ, SM) k_rows<WF, WJ><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P)
+		#define ROWS(WF, WJ, SM) k_rows<WF, WJ><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P)
 		if (wf && wj) ROWS(true, true, row_smem);
 		else if (wf)  ROWS(true, false, 0);
 		else if (wj)  ROWS(false, true, row_smem);
@@ -716,7 +748,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		if (wf) cudaMemsetAsync(c->d_F, 0, 2 * c->nn * sizeof(double), c->stream);
 		if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->n_slots * 4 * sizeof(double), c->stream);
 		const int gc = (int)((c->nt + TPB - 1) / TPB);
-		#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_A, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
+		#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
 		if (wf && wj) CELL(true, true);
 		else if (wf)  CELL(true, false);
 		else if (wj)  CELL(false, true);

@@ -350,6 +350,11 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	}
 	UP(c->d_A, (const double*)nullptr, nv);
 	UP(c->d_beta, (const double*)nullptr, nv);
+	UP(c->d_Tp, (const double*)nullptr, nv);
+	UP(c->d_W, (const double*)nullptr, nv);
+	BP_CUDA(c, cudaMemset(c->d_W, 0, (size_t)nv * sizeof(double)));
+	{ std::vector<double> ones(nv, 1.0); UP(c->d_E, ones.data(), nv); }
+	UP(c->d_ainv, (const double*)nullptr, nt);
 	UP(c->d_Bv, (const double*)nullptr, nv);
 	UP(c->d_Bring, (const double*)nullptr, nv);
 	BP_CUDA(c, cudaMemset(c->d_Bring, 0, (size_t)nv * sizeof(double)));

@@ -204,6 +204,10 @@ class D3Model(object):
 		self.E      = Function(self.Q, 'E')
 		self.A      = Function(self.Q, 'A')
 		self.sigma  = Function(self.Q_non_periodic, 'sigma')
+		self.T      = Function(self.Q, 'T')             # cslvr/model.py:2544-2551
+		self.Tp     = Function(self.Q, 'Tp')
+		self.W      = Function(self.Q, 'W')
+		self.E.values[:] = 1.0
 		self.ff = None
 
 	# ---- coefficient setters: cslvr/model.py:486-497, 691-733, 2166-2221 ---
@@ -248,6 +252,25 @@ class D3Model(object):
 	def init_E(self, E):
 		print_text("::: initializing enhancement factor over grounded and shelves :::", cls=self)
 		self.assign_variable(self.E, E)
+
+	def init_T(self, T):
+		print_text("::: initializing absolute temperature :::", cls=self)
+		self.assign_variable(self.T, T)
+
+	def init_Tp(self, Tp):
+		print_text("::: initializing pressure-adjusted temperature :::", cls=self)
+		self.assign_variable(self.Tp, Tp)
+
+	def init_W(self, W):
+		print_text("::: initializing water content :::", cls=self)
+		self.assign_variable(self.W, W)
+
+	def form_energy_dependent_rate_factor(self):
+		"""A = E a_T (1 + 181.25 min(W, 0.01)) exp(-Q_T / (R T')) as an expression of the P1
+		fields T', W, E, evaluated at the quadrature points of the momentum forms instead of a
+		nodal A (cslvr/model.py:1815-1859)."""
+		print_text("::: formulating energy-dependent rate-factor :::", cls=self)
+		self.energy_dependent_rate_factor = True
 
 	def init_mask(self, mask):
 		print_text("::: initializing shelf mask :::", cls=self)

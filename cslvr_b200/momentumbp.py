@@ -84,12 +84,14 @@ class MomentumBPBase(Momentum):
 		m = self.model
 		X = m.mesh.coordinates()
 		key = (id(m.mesh), float(X[:, 2].sum()), float(np.abs(X[:, 2]).sum()), int(m.ff.sum()),
-		       bool(self.use_pressure_bc))
+		       bool(self.use_pressure_bc), bool(m.energy_dependent_rate_factor))
 		if self._ctx is None or key != self._ctx_key:
 			if self._ctx is not None:
 				self._ctx.close()
 			params = dict(n=m.n, eps_reg=m.eps_reg, rho_i=m.rho_i, rhosw=m.rhosw, g=m.g,
-			              periodic=m.use_periodic, use_pressure_bc=self.use_pressure_bc)
+			              periodic=m.use_periodic, use_pressure_bc=self.use_pressure_bc,
+			              energy_dependent_rate_factor=m.energy_dependent_rate_factor,
+			              a_T_l=m.a_T_l, a_T_u=m.a_T_u, Q_T_l=m.Q_T_l, Q_T_u=m.Q_T_u, R=m.R)
 			self._ctx = capi.BPContext(X, m.mesh.cells(), self.Q.dim(),
 			                           (m.facet_cell, m.facet_local, m.ff), params,
 			                           vertex_to_node=m.vertex_to_node if m.use_periodic else None,
@@ -97,7 +99,12 @@ class MomentumBPBase(Momentum):
 			self._ctx_key = key
 		c = self._ctx
 		c.set_field(capi.FIELD_S, m.vertex_field(m.S))
-		c.set_field(capi.FIELD_A, m.vertex_field(m.A))
+		if m.energy_dependent_rate_factor:
+			c.set_field(capi.FIELD_TP, m.vertex_field(m.Tp))
+			c.set_field(capi.FIELD_W, m.vertex_field(m.W))
+			c.set_field(capi.FIELD_E, m.vertex_field(m.E))
+		else:
+			c.set_field(capi.FIELD_A, m.vertex_field(m.A))
 		c.set_field(capi.FIELD_BETA, m.vertex_field(m.beta))
 		return c
 
@@ -123,7 +130,7 @@ class MomentumBPBase(Momentum):
 		          krylov_maxit=ks.get('maximum_iterations', 10000),
 		          preconditioner=self._PC_MAP.get(pc, 'chebyshev'),
 		          verbose=ks.get('monitor_convergence', False) or ns.get('report', False),
-		          quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		          quadrature_degree=self.solve_params.get('quadrature_degree', 9 if self.model.energy_dependent_rate_factor else 5))
 		return kw
 
 	def _newton_solve(self, ns):

@@ -36,6 +36,9 @@ extern "C" {
 #define BP_FIELD_BETA   2   /* basal traction beta   cslvr/model.py:2527, momentumbp.py:473 */
 #define BP_FIELD_B      3   /* bed height B          cslvr/model.py:2512, momentumbp.py:65 (u_z only)   */
 #define BP_FIELD_B_RING 4   /* basal melt B_ring     momentumbp.py:66 (u_z only; default 0)             */
+#define BP_FIELD_TP     5   /* pressure-adjusted temperature T'   } energy-dependent rate factor,      */
+#define BP_FIELD_W      6   /* water content W (default 0)        } Model.form_energy_dependent_rate_  */
+#define BP_FIELD_E      7   /* enhancement factor E (default 1)   } factor, cslvr/model.py:1815-1859   */
 
 /* what bp_assemble computes */
 #define BP_ASSEMBLE_F   1
@@ -127,6 +130,10 @@ typedef struct {
 	int32_t       n_quad_aux;
 	const double* quad_points_aux;
 	const double* quad_weights_aux;
+	/* model.energy_dependent_rate_factor: A = E a_T (1 + 181.25 min(W, .01)) exp(-Q_T/(R T')) at
+	 * the quadrature points instead of the P1 field A (constants cslvr/model.py:275-285, 263)   */
+	int32_t energy_dependent;
+	double  a_T_l, a_T_u, Q_T_l, Q_T_u, R_gas;
 } bp_params;
 
 typedef struct {

@@ -208,7 +208,7 @@ class BPProblem(object):
 	"""
 
 	def __init__(self, coords, cells, cell_dofs, n_dofs, fc, fl, ff, S, A, beta,
-	             periodic, use_pressure_bc=True, quad_degree=None, consts=None):
+	             periodic, use_pressure_bc=True, quad_degree=None, consts=None, energy=None):
 		self.coords = np.asarray(coords, dtype=np.float64)
 		self.cells = np.asarray(cells, dtype=np.int64)
 		self.cell_dofs = np.asarray(cell_dofs, dtype=np.int64)
@@ -226,7 +226,13 @@ class BPProblem(object):
 		self.c = c
 		# UFL degree estimation, SURVEY A-Q: P1 A -> 5; constant A is still a
 		# P1 Function in cslvr (model.py:2530) so the estimate does not change
-		self.quad_degree = 5 if quad_degree is None else int(quad_degree)
+		# energy = dict(Tp=, W=, E=) switches to Model.form_energy_dependent_rate_factor
+		# (model.py:1815-1859): A is then a UFL expression evaluated at the quadrature points and
+		# the estimated degree rises to 9 (SURVEY A-Q)
+		self.energy = None
+		if energy is not None:
+			self.energy = {k: np.asarray(energy[k], dtype=np.float64) * np.ones(nv) for k in ('Tp', 'W', 'E')}
+		self.quad_degree = (9 if energy is not None else 5) if quad_degree is None else int(quad_degree)
 		self._geometry()
 		self._pattern = None
 
@@ -289,6 +295,19 @@ class BPProblem(object):
 		H[:, 4:, :4] = np.transpose(H[:, :4, 4:], (0, 2, 1))
 		return H
 
+	def _A_at(self, lam, Av):
+		if self.energy is None:
+			return Av @ lam                                # P1 interpolant of model.A
+		spy = 31556926.0                                   # model.py:190, 275-285
+		a_T_l, a_T_u, Q_T_l, Q_T_u, R = 3.985e-13 * spy, 1.916e3 * spy, 6e4, 13.9e4, 8.3144621
+		Tp = self.energy['Tp'][self.cells] @ lam
+		W = self.energy['W'][self.cells] @ lam
+		E = self.energy['E'][self.cells] @ lam
+		a_T = np.where(Tp < 263.15, a_T_l, a_T_u)
+		Q_T = np.where(Tp < 263.15, Q_T_l, Q_T_u)
+		W_T = np.where(W < 0.01, W, 0.01)
+		return E * a_T * (1 + 181.25 * W_T) * np.exp(-Q_T / (R * Tp))
+
 	# ---- cell integrals ---------------------------------------------------
 	def cell_tensors(self, u, want_J=True, form='dukowicz', picard=False):
 		"""element action, residual [nt,8] and Jacobian [nt,8,8] by quadrature.
@@ -324,7 +343,7 @@ class BPProblem(object):
 			q[:, 1, 2] = 0.5 * g[:, 1, 2]
 		for lam, w in zip(pts, wts):
 			dx = w * self.vol
-			Aq = Av @ lam                                  # P1 interpolant of A at the point
+			Aq = self._A_at(lam, Av)                       # A at the point
 			uq = Uloc @ lam                                # [nt,2]
 			Ainv = Aq ** (-1.0 / n)
 			act += dx * ((2 * n) / (n + 1) * Ainv * ed ** ((n + 1) / (2 * n))

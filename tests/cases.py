@@ -48,14 +48,14 @@ def marine_model(n=(8, 7, 4), L=40000.0, variable_A=True):
 	return model
 
 
-def oracle_problem(model, use_pressure_bc=True, quad_degree=None, cell_dofs=None, n_dofs=None):
+def oracle_problem(model, use_pressure_bc=True, quad_degree=None, cell_dofs=None, n_dofs=None, energy=None):
 	return bo.BPProblem(model.mesh.coordinates(), model.mesh.cells(),
 	                    model.cell_dofs if cell_dofs is None else cell_dofs,
 	                    2 * model.n_nodes if n_dofs is None else n_dofs,
 	                    model.facet_cell, model.facet_local, model.ff,
 	                    model.vertex_field(model.S), model.vertex_field(model.A),
 	                    model.vertex_field(model.beta), periodic=model.use_periodic,
-	                    use_pressure_bc=use_pressure_bc, quad_degree=quad_degree,
+	                    use_pressure_bc=use_pressure_bc, quad_degree=quad_degree, energy=energy,
 	                    consts=dict(n=model.n, eps_reg=model.eps_reg, rho_i=model.rho_i,
 	                                rhosw=model.rhosw, g=model.g))
 

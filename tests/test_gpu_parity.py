@@ -329,3 +329,47 @@ def test_linearize_viscosity_like_the_reference():
 	assert relerr(mom.get_unknown().values, u_nl) < 1e-4       # linearize_viscosity restores the ORIGINAL params: Krylov rtol 1e-5
 	P = oracle_problem(m)
 	assert relerr(mom.get_unknown().values, P.linear_solve(u_nl)) < 1e-4      # default Krylov rtol 1e-5 on the linear path
+
+
+@pytest.mark.parametrize('deg', [None, 4])
+def test_energy_dependent_rate_factor_at_quadrature_points(deg):
+	"""A(T', W, E) evaluated at the quadrature points
+	(cslvr/model.py:1815-1859), UFL degree 9 (125-point rule) unless the script sets it
+	(simulations/greenland/nioghalvfjerdsbrae/data_assimilation.py:5 uses 4)."""
+	from cslvr_b200 import capi
+	m = marine_model(n=(6, 5, 3))
+	X = m.mesh.coordinates()
+	Tp = 250.0 + 20.0 * (1.0 - (X[:, 2] + 500.0) / 1100.0) + 4.0 * np.sin(5 * X[:, 0] / 40000.0)     # straddles 263.15 K
+	W = np.clip(0.02 * (Tp - 262.0) / 8.0, 0.0, 0.03)                                                # straddles 0.01
+	E = 1.0 + 0.5 * np.cos(3 * X[:, 1] / 40000.0)
+	P = oracle_problem(m, energy=dict(Tp=Tp, W=W, E=E), quad_degree=deg)
+	kw = dict(energy_dependent_rate_factor=True)
+	if deg is not None:
+		kw['quadrature_degree'] = deg
+	for mode in ('gather', 'scatter'):
+		c = product_context(m, assembly=mode, **kw)
+		for f, v in ((capi.FIELD_TP, Tp), (capi.FIELD_W, W), (capi.FIELD_E, E)):
+			c.set_field(f, v)
+		u = state(P.n_dofs, 61)
+		F, J = c.assemble(u, want_F=True, want_J=True)
+		assert relerr(F, P.residual(u)) < TOL_ASM and relerr(J, P.jacobian(u)) < TOL_ASM
+		c.close()
+
+
+def test_energy_dependent_model_through_the_mirror():
+	from cslvr_b200 import MomentumDukowiczBP
+	m = ismip_model('A', n=(7, 7, 4))
+	X = m.mesh.coordinates()[m.node_vertex]
+	m.init_Tp(255.0 + 12.0 * (m.S.values[m.node_vertex] - X[:, 2]) / 1500.0)
+	m.init_T(m.Tp.values)
+	m.init_W(0.0)
+	m.init_E(1.0)
+	m.form_energy_dependent_rate_factor()
+	mom = MomentumDukowiczBP(m)
+	assert mom.solve_params['solver']['newton_solver']['relaxation_parameter'] == 0.7     # non-uniform T: momentumbp.py:169-175
+	mom.solve_params['solve_pressure'] = False
+	mom.solve_params['solver']['newton_solver']['maximum_iterations'] = 60
+	mom.solve()
+	P = oracle_problem(m, energy=dict(Tp=m.vertex_field(m.Tp), W=m.vertex_field(m.W), E=m.vertex_field(m.E)))
+	uo, io = P.newton(relax=0.7, maxit=60)
+	assert mom.stats['converged'] and relerr(mom.get_unknown().values, uo) < 1e-6
