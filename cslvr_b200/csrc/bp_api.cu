@@ -555,6 +555,7 @@ int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_devic
 	c->prm = saved;
 	if (rc) return rc;
 	if (iterations) *iterations = it;
+	if ((rc = bp_comm_halo(cs, 1, 5))) return rc;                 // ghost nodes get their owner's value
 	double* out = on_device ? p_vertex : c->d_io;
 	bp_launch_node_to_vertex(c, c->d_dx, 0, out);
 	if (!on_device) BP_CUDA(c, cudaMemcpyAsync(p_vertex, c->d_io, (size_t)c->nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -570,12 +571,12 @@ int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on
 	int rc = ready(c);
 	if (rc) return rc;
 	if (!c->have_B) return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity: BP_FIELD_B (bed height) not set");
-	if (c->n_nbr > 0) return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity is not available on partitioned contexts yet");
 	if (c->max_layers > 64) return bp_fail(c, BP_ERR_ARG, "bp_solve_vert_velocity supports at most 64 nodes per ice column");
 	if (c->prm.assembly == BP_ASM_SCATTER || (size_t)4 * c->max_row * 128 * sizeof(double) > 200 * 1024)
 		return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity needs the row-gather assembly path");
 	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
 	bp_ctx* cs[1] = { c };
+	if ((rc = bp_comm_halo(cs, 1, 0))) return rc;
 	// 1. u_z_b = project(kinematic basal condition, Q): mass-matrix PCG
 	bp_launch_rows_aux(c, 1);
 	c->have_J = false;
@@ -594,7 +595,8 @@ int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on
 	double *x = c->d_dx, *r = c->d_r, *rh = c->d_z2, *p = c->d_p, *v = c->d_Ap, *y = c->d_z, *sv = c->d_cd, *t = c->d_io, *zz = c->d_io2;
 	auto dot = [&](const double* a, const double* b, double* out) -> int {
 		bp_launch_dot_owned(c, a, b, SC_TMP);
-		int r_ = read_scalars(c);
+		int r_ = bp_comm_allreduce(cs, 1, SC_TMP, 1);
+		if (!r_) r_ = read_scalars(c);
 		*out = c->h_sc[SC_TMP];
 		return r_;
 	};
@@ -615,12 +617,14 @@ int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on
 		const double beta = (rho_n / rho) * (alpha / omega);
 		bp_launch_lincomb(c, p, 1.0, r, beta, p, -beta * omega, v);          // p = r + beta (p - omega v)
 		bp_launch_col_gtsv(c, p, y);                                          // y = M^-1 p
+		if ((rc = bp_comm_halo(cs, 1, 2))) return rc;                         // ghosts of y (= d_z)
 		bp_launch_spmv(c, y, v, 0);                                           // v = A y
 		if ((rc = dot(rh, v, &rhv))) return rc;
 		if (rhv == 0.0 || !std::isfinite(rhv)) return bp_fail(c, BP_ERR_STATE, "BiCGStab breakdown (alpha) in the u_z solve at iteration %d", it);
 		alpha = rho_n / rhv;
 		bp_launch_lincomb(c, sv, 1.0, r, -alpha, v, 0.0, v);                  // s = r - alpha v
 		bp_launch_col_gtsv(c, sv, zz);                                        // z = M^-1 s
+		if ((rc = bp_comm_halo(cs, 1, 4))) return rc;                         // ghosts of z (= d_io2)
 		bp_launch_spmv(c, zz, t, 0);                                          // t = A z
 		if ((rc = dot(t, sv, &ts))) return rc;
 		if ((rc = dot(t, t, &tt))) return rc;
@@ -635,6 +639,7 @@ int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on
 	if (bnorm2 > 0.0 && !(rnorm2 <= 1e-20 * bnorm2))
 		return bp_fail(c, BP_ERR_NONCONV, "u_z solve: BiCGStab stopped at relative residual %.3e after %d iterations", std::sqrt(rnorm2 / bnorm2), it);
 	if (iterations) *iterations = it;
+	if ((rc = bp_comm_halo(cs, 1, 5))) return rc;                 // x is d_dx: ghost nodes get their owner's value
 	double* out = on_device ? uz_vertex : c->d_io;
 	bp_launch_node_to_vertex(c, x, 0, out);
 	if (!on_device) BP_CUDA(c, cudaMemcpyAsync(uz_vertex, c->d_io, (size_t)c->nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));

@@ -93,7 +93,7 @@ void bp_comm_free(bp_ctx* c)
 
 double* bp_vec(bp_ctx* c, int which)
 {
-	switch (which) { case 0: return c->d_u; case 1: return c->d_p; case 2: return c->d_z; case 3: return c->d_z2; default: return c->d_p; }
+	switch (which) { case 0: return c->d_u; case 1: return c->d_p; case 2: return c->d_z; case 3: return c->d_z2; case 4: return c->d_io2; case 5: return c->d_dx; default: return c->d_p; }
 }
 
 // ghost values of vector `which` (0: u, 1: p) from the owning ranks

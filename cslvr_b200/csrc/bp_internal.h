@@ -57,7 +57,7 @@ struct bp_ctx {
 	double*  d_beta = nullptr;           // per vertex
 	double  *d_Tp = nullptr, *d_W = nullptr, *d_E = nullptr;   // energy-dependent rate factor inputs, per vertex
 	double*  d_ainv = nullptr;           // [nt] sum_q w_q A_q^(-1/n) per tet (k_tet_ainv)
-	bool     ainv_dirty = true, have_Tp = false;
+	bool     ainv_dirty = true, have_Tp = false, smem_attr_set = false;
 	double  *d_Bv = nullptr, *d_Bring = nullptr;   // bed height / basal melt per vertex (u_z solve only)
 	uint8_t* d_bcnode = nullptr;         // owned node lies on a basal facet (Dirichlet dof of the u_z system)
 	double*  d_aux = nullptr;            // [2*nn] u_z_b per node

@@ -732,11 +732,10 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
 	#define FACET(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
 	if (gather) {
-		static bool attr_set = false;
-		if (!attr_set) {
+		if (!c->smem_attr_set) {                     // function attributes are per device
 			cudaFuncSetAttribute(k_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			cudaFuncSetAttribute(k_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-			attr_set = true;
+			c->smem_attr_set = true;
 		}
 		const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
 		const double2* uvert = bp_vertex_u(c);

@@ -60,14 +60,14 @@ def oracle_problem(model, use_pressure_bc=True, quad_degree=None, cell_dofs=None
 	                                rhosw=model.rhosw, g=model.g))
 
 
-def product_context(model, use_pressure_bc=True, cell_dofs=None, **params):
+def product_context(model, use_pressure_bc=True, cell_dofs=None, device=0, **params):
 	from cslvr_b200 import capi
 	p = dict(n=model.n, eps_reg=model.eps_reg, rho_i=model.rho_i, rhosw=model.rhosw, g=model.g,
 	         periodic=model.use_periodic, use_pressure_bc=use_pressure_bc)
 	p.update(params)
 	c = capi.BPContext(model.mesh.coordinates(), model.mesh.cells(), 2 * model.n_nodes,
 	                   (model.facet_cell, model.facet_local, model.ff), p,
-	                   cell_dofs=cell_dofs,
+	                   cell_dofs=cell_dofs, device=device,
 	                   vertex_to_node=(model.vertex_to_node if (model.use_periodic and cell_dofs is None) else None))
 	c.set_field(capi.FIELD_S, model.vertex_field(model.S))
 	c.set_field(capi.FIELD_A, model.vertex_field(model.A))
