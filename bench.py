@@ -177,6 +177,7 @@ def main():
 	ap.add_argument('--impl', default='ours')
 	ap.add_argument('--no-newton', action='store_true')
 	ap.add_argument('--no-cpu', action='store_true')
+	ap.add_argument('--pc', default='', help='preconditioner of the Newton solve (default: the library default)')
 	ap.add_argument('--exp', default='C', help='ISMIP-HOM experiment of the multi-rank arm: C (default, L=20 km per 260 columns) or A (L=80 km total)')
 	ap.add_argument('--nx', type=int, default=0, help='multi-rank arm: TOTAL columns in x (default 260 per GPU); strong-scaling studies fix it')
 	ap.add_argument('--ny', type=int, default=0)
@@ -211,7 +212,7 @@ def main():
 	# ---- Newton solve (reference defaults: rtol 1e-9, relax 1.0, Krylov rtol 1e-5), cold start
 	newton = None
 	if not args.no_newton:
-		ctx.set_params(relative_tolerance=1e-9, maximum_iterations=25, relaxation_parameter=1.0, krylov_rtol=1e-5)
+		ctx.set_params(relative_tolerance=1e-9, maximum_iterations=25, relaxation_parameter=1.0, krylov_rtol=1e-5, **({'preconditioner': args.pc} if args.pc else {}))
 		un = torch.full((2 * model.n_nodes,), 3e-16, dtype=torch.float64, device=dev)
 		torch.cuda.synchronize()
 		t0 = time.perf_counter()
@@ -224,7 +225,7 @@ def main():
 		t_e2e = time.perf_counter() - t0
 		newton = {"solve_s": t_dev, "e2e_s": t_e2e, "converged": st['converged'], "newton_iterations": st['iterations'],
 		          "krylov_iterations": st['krylov_iterations'], "assemble_ms": st['t_assemble_ms'], "krylov_ms": st['t_krylov_ms'],
-		          "preconditioner": "%s(degree %d, ratio %g)" % (ctx.params.get('preconditioner', 'chebyshev'), ctx.params.get('pc_degree', 8), ctx.params.get('pc_eig_ratio', 100.0)), "rtol": 1e-9, "krylov_rtol": 1e-5,
+		          "preconditioner": ctx.pc_label(), "rtol": 1e-9, "krylov_rtol": 1e-5,
 		          "gpu_launches": st['gpu_launches']}
 		if st['converged']:
 			u_host = uh * (1.0 + 1e-3 * np.random.default_rng(1234).normal(size=uh.size))

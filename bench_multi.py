@@ -15,6 +15,8 @@ def run_multi(args, rank, world, local):
 	from cslvr_b200.partition import boxmesh_slab
 	import bench as B
 	dev = torch.device('cuda', local)
+	if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+		os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 	dist.init_process_group('nccl', device_id=dev)
 	NXT = args.nx if args.nx > 0 else B.NX * world
 	NYT = args.ny if args.ny > 0 else B.NY
@@ -58,7 +60,8 @@ def run_multi(args, rank, world, local):
 	ctx.assemble(u_host, want_F=True, want_J=True, J=False)          # untimed: first halo exchange sets up the NCCL channels
 	newton = None
 	if not args.no_newton:
-		ctx.set_params(relative_tolerance=1e-9, maximum_iterations=1, relaxation_parameter=1.0, krylov_rtol=1e-5, krylov_maxit=8)
+		pck = {'preconditioner': args.pc} if args.pc else {}
+		ctx.set_params(relative_tolerance=1e-9, maximum_iterations=1, relaxation_parameter=1.0, krylov_rtol=1e-5, krylov_maxit=8, **pck)
 		ctx.newton_solve(torch.full((2 * rm.n_nodes,), 3e-16, dtype=torch.float64, device=dev))   # untimed: sets up every NCCL collective used
 		ctx.set_params(relative_tolerance=1e-9, maximum_iterations=25, relaxation_parameter=1.0, krylov_rtol=1e-5, krylov_maxit=10000)
 		un = torch.full((2 * rm.n_nodes,), 3e-16, dtype=torch.float64, device=dev)
@@ -69,7 +72,7 @@ def run_multi(args, rank, world, local):
 		t = torch.tensor([time.perf_counter() - t0], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 		newton = {"solve_s": t.item(), "converged": st['converged'], "newton_iterations": st['iterations'],
 		          "krylov_iterations": st['krylov_iterations'], "assemble_ms": st['t_assemble_ms'], "krylov_ms": st['t_krylov_ms'],
-		          "preconditioner": "%s(degree %d, ratio %g)" % (ctx.params.get('preconditioner', 'chebyshev'), ctx.params.get('pc_degree', 8), ctx.params.get('pc_eig_ratio', 100.0)), "rtol": 1e-9, "krylov_rtol": 1e-5}
+		          "preconditioner": ctx.pc_label(), "rtol": 1e-9, "krylov_rtol": 1e-5}
 
 	u_dev = torch.from_numpy(u_host).to(dev)
 	F_dev = torch.empty_like(u_dev)

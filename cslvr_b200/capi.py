@@ -14,7 +14,7 @@ from . import _build
 BP_OK, BP_ERR_ARG, BP_ERR_CUDA, BP_ERR_STATE, BP_ERR_COMM, BP_ERR_NONCONV = range(6)
 FIELD_S, FIELD_A, FIELD_BETA, FIELD_B, FIELD_B_RING, FIELD_TP, FIELD_W, FIELD_E = range(8)
 ASSEMBLE_F, ASSEMBLE_J = 1, 2
-PC = {'none': 0, 'jacobi': 1, 'block_jacobi': 2, 'chebyshev': 3, 'column': 4}
+PC = {'none': 0, 'jacobi': 1, 'block_jacobi': 2, 'chebyshev': 3, 'column': 4, 'mg': 5}
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
@@ -247,13 +247,22 @@ class BPContext(object):
 		p.krylov_rtol = d.get('krylov_rtol', 1e-5)
 		p.krylov_atol = d.get('krylov_atol', 1e-50)
 		p.krylov_maxit = int(d.get('krylov_maxit', 10000))
-		pc = d.get('preconditioner', 'chebyshev')
+		pc = d.get('preconditioner', 'mg')
 		p.pc = PC[pc] if isinstance(pc, str) else int(pc)
-		p.pc_degree = int(d.get('pc_degree', 8))
-		p.pc_eig_ratio = float(d.get('pc_eig_ratio', 100.0))
+		is_mg = (pc == 'mg' or pc == 5)          # Chebyshev as a smoother wants a short interval
+		p.pc_degree = int(d.get('pc_degree', 3 if is_mg else 8))
+		p.pc_eig_ratio = float(d.get('pc_eig_ratio', 6.0 if is_mg else 100.0))
 		p.verbose = int(bool(d.get('verbose', False)))
 		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
+		self._last_params = p
 		return p
+
+	def pc_label(self):
+		"""human-readable preconditioner of the last parameter set (for logs / bench lines)."""
+		names = {v: k for k, v in PC.items()}
+		p = self._last_params
+		nm = names.get(p.pc, str(p.pc))
+		return nm if p.pc <= 2 or p.pc == 4 else "%s(degree %d, ratio %g)" % (nm, p.pc_degree, p.pc_eig_ratio)
 
 	def _check(self, rc, allow=()):
 		if rc != BP_OK and rc not in allow:

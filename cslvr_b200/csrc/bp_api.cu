@@ -29,7 +29,7 @@ static int check_params(bp_ctx* c, const bp_params* p)
 	if (std::fabs(s - 1.0) > 1e-12) return bp_fail(c, BP_ERR_ARG, "bp_params: quadrature weights sum to %.17g, not 1", s);
 	if (p->n_quad_aux < 0 || p->n_quad_aux > BP_MAX_QUAD) return bp_fail(c, BP_ERR_ARG, "bp_params: n_quad_aux must be in [0,%d]", BP_MAX_QUAD);
 	if (p->assembly < BP_ASM_AUTO || p->assembly > BP_ASM_GATHER) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown assembly mode %d", p->assembly);
-	if (p->pc < BP_PC_NONE || p->pc > BP_PC_COLUMN) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown preconditioner %d", p->pc);
+	if (p->pc < BP_PC_NONE || p->pc > BP_PC_MG) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown preconditioner %d", p->pc);
 	return BP_OK;
 }
 
@@ -124,6 +124,8 @@ static int group_pc_prepare(bp_ctx** cs, int n)
 		if (!(lmax > 0.0) || !std::isfinite(lmax)) return bp_fail(cs[0], BP_ERR_STATE, "Chebyshev: eigenvalue bound failed (%g)", lmax);
 		for (int r = 0; r < n; ++r) cs[r]->cheb_lmax = lmax;
 	}
+	if (cs[0]->prm.pc == BP_PC_MG)
+		for (int r = 0; r < n; ++r) if ((rc = bp_mg_prepare(cs[r]))) { if (r) cs[0]->err = cs[r]->err; return rc; }
 	if (cs[0]->prm.pc == BP_PC_COLUMN)
 		for (int r = 0; r < n; ++r) if (cs[r]->max_layers > 64)
 			return bp_fail(cs[0], BP_ERR_ARG, "column preconditioner supports at most 64 nodes per ice column (mesh has %d)", cs[r]->max_layers);
@@ -136,6 +138,10 @@ static int group_pc_apply(bp_ctx** cs, int n)
 	int rc;
 	if (cs[0]->prm.pc == BP_PC_COLUMN) {
 		for (int r = 0; r < n; ++r) bp_launch_col_solve(cs[r], cs[r]->d_r, cs[r]->d_z);
+		return BP_OK;
+	}
+	if (cs[0]->prm.pc == BP_PC_MG) {
+		for (int r = 0; r < n; ++r) if ((rc = bp_mg_apply(cs[r]))) return rc;
 		return BP_OK;
 	}
 	// Chebyshev on [b / ratio, b], b = 1.1 lmax
@@ -301,6 +307,7 @@ void bp_destroy(bp_ctx* c)
 {
 	if (!c) return;
 	cudaSetDevice(c->device);
+	bp_mg_free(c);
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,

@@ -25,6 +25,7 @@ enum {
 };
 
 struct bp_comm_state;   // NCCL binding (bp_comm.cu)
+struct bp_mg;           // multigrid hierarchy (bp_mg.cu)
 
 struct bp_ctx {
 	int          device = 0;
@@ -106,6 +107,9 @@ struct bp_ctx {
 	double*  d_sendbuf = nullptr;
 	int64_t  n_send = 0;
 	bp_comm_state* comm = nullptr;
+	bp_mg*   mg = nullptr;
+	std::vector<int32_t> h_colptr, h_colnode;      // ice columns on the host (first multigrid aggregation)
+	int      grid_spmv0 = 0, grid_spmv1 = 0, grid_cheb = 0;   // one-wave launch grids, per context
 
 	bool have_S = false, have_A = false, have_beta = false, have_J = false, have_B = false;
 	int64_t launches = 0;
@@ -151,6 +155,11 @@ void bp_launch_rows_aux(bp_ctx* c, int kind);              // projection systems
 void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out);
 void bp_launch_col_gtsv(bp_ctx* c, const double* r, double* z);   // scalar pivoted tridiagonal solve per column
 void bp_launch_lincomb(bp_ctx* c, double* out, double a, const double* x, double b, const double* y, double cc, const double* z);        // upper bound of lmax(D^-1 J) -> d_sc[slot]
+
+// multigrid (bp_mg.cu)
+int  bp_mg_prepare(bp_ctx* c);      // numeric set-up for the current resident Jacobian
+int  bp_mg_apply(bp_ctx* c);        // d_z = M^-1 d_r
+void bp_mg_free(bp_ctx* c);
 
 // comm (bp_comm.cu)
 int  bp_comm_halo(bp_ctx** ctxs, int n, int which_vec);   // 0:u 1:p

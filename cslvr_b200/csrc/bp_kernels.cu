@@ -888,13 +888,11 @@ static int one_wave(K kernel, int block, int64_t n_items, int per_block)
 void bp_launch_spmv(bp_ctx* c, const double* x, double* y, int with_dot)
 {
 	const int rows_per_block = 256;
-	static int g1 = 0, g0 = 0;
-	static int64_t n_cached = -1;
-	if (n_cached != c->nn_owned) {
-		g1 = one_wave(k_spmv<true>, 256, c->nn_owned, rows_per_block);
-		g0 = one_wave(k_spmv<false>, 256, c->nn_owned, rows_per_block);
-		n_cached = c->nn_owned;
+	if (!c->grid_spmv0) {
+		c->grid_spmv1 = one_wave(k_spmv<true>, 256, c->nn_owned, rows_per_block);
+		c->grid_spmv0 = one_wave(k_spmv<false>, 256, c->nn_owned, rows_per_block);
 	}
+	const int g1 = c->grid_spmv1, g0 = c->grid_spmv0;
 	if (with_dot)
 		k_spmv<true><<<g1, 256, 0, c->stream>>>((int)c->nn_owned, c->d_sell_ptr, c->d_col, (const double2*)c->d_val,
 			(const double2*)x, (double2*)y, c->d_sc, c->d_part, c->d_counter, c->d_sc + SC_PAP);
@@ -1328,9 +1326,8 @@ void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z)
 }
 void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew)
 {
-	static int g = 0; static int64_t nc = -1;
-	if (nc != c->nn_owned) { g = one_wave(k_cheb_step, 256, c->nn_owned, 256); nc = c->nn_owned; }
-	k_cheb_step<<<g, 256, 0, c->stream>>>((int)c->nn_owned, c1, c2, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, c->d_dinv,
+	if (!c->grid_cheb) c->grid_cheb = one_wave(k_cheb_step, 256, c->nn_owned, 256);
+	k_cheb_step<<<c->grid_cheb, 256, 0, c->stream>>>((int)c->nn_owned, c1, c2, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, c->d_dinv,
 		(const double2*)r, (const double2*)zold, (double2*)znew, (double2*)c->d_cd);
 	c->launches++;
 }

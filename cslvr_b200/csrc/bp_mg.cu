@@ -1,0 +1,415 @@
+// bp_mg.cu -- aggregation multigrid preconditioner (BP_PC_MG) for the BP Jacobian.
+//
+// The reference preconditions KSPCG with hypre BoomerAMG (cslvr/momentumbp.py:183-184).
+// This is the device-resident counterpart built for extruded ice meshes:
+//   level 0 -> 1 : every ice column becomes one coarse node (the SSA-like, vertically
+//                  constant space; thin-ice physics makes this the natural first coarsening);
+//   level l -> l+1: greedy aggregation of the 2-D footprint graph (root + all its free
+//                  neighbours), until <= 64 nodes remain;
+//   prolongation : piecewise constant (2x2 identity per node), so the Galerkin product is a
+//                  scatter-add of fine blocks into coarse blocks through a precomputed slot
+//                  map -- no SpGEMM, and it is redone on the device every Newton step;
+//   smoother     : Chebyshev polynomial in D^-1 A (same fused SpMV kernel as BP_PC_CHEBYSHEV),
+//                  pre from a zero guess, post continuing from the corrected iterate;
+//   coarsest     : dense inverse computed on the host (<= 128 x 128), applied by one kernel.
+// All levels store 2x2 blocks in the same SELL-32 layout, so k_spmv / k_cheb_step / k_pc_setup
+// / k_gershgorin are reused unchanged through light-weight level contexts.
+// With several ranks the hierarchy is rank-local (ghost columns are ignored: block-Jacobi
+// over the slabs with a multigrid V-cycle inside) and needs no communication.
+#include "bp_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+struct bp_mg_level {
+	bp_ctx* M = nullptr;                 // matrix + vectors of this level (level 0: the real context)
+	int64_t n = 0;
+	std::vector<int32_t> h_rowptr, h_col, h_sell_ptr;      // node-level pattern on the host
+	// transfer to the next coarser level
+	int32_t *d_agg = nullptr, *d_galmap = nullptr, *d_aggptr = nullptr, *d_aggidx = nullptr;
+	double lmax = 0.0;
+};
+struct bp_mg {
+	std::vector<bp_mg_level> lv;
+	double* d_dense = nullptr;           // inverse of the coarsest matrix, row-major
+	std::vector<double> h_dense, h_val;
+	int nc = 0;                          // coarsest dofs
+};
+
+template <class T>
+static int up(bp_ctx* c, T** dst, const T* src, size_t n)
+{
+	*dst = nullptr;
+	if (n == 0) n = 1;
+	BP_CUDA(c, cudaMalloc((void**)dst, n * sizeof(T)));
+	if (src) BP_CUDA(c, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+	else BP_CUDA(c, cudaMemset(*dst, 0, n * sizeof(T)));
+	return BP_OK;
+}
+#define UPM(dst, src, n) do { int rc_ = up(c, &(dst), (src), (size_t)(n)); if (rc_) return rc_; } while (0)
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_mg_galerkin(int64_t nslots, const int32_t* __restrict__ galmap, const double* __restrict__ vf, double* vc)
+{
+	for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < nslots; s += (int64_t)gridDim.x * blockDim.x) {
+		const int32_t cs = galmap[s];
+		if (cs < 0) continue;
+		const double2 a = ((const double2*)vf)[2 * s], b = ((const double2*)vf)[2 * s + 1];
+		double* o = vc + 4 * (size_t)cs;
+		atomicAdd(o, a.x); atomicAdd(o + 1, a.y); atomicAdd(o + 2, b.x); atomicAdd(o + 3, b.y);
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_mg_residual(int nrows, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ col, const double2* __restrict__ val,
+              const double2* __restrict__ b, const double2* __restrict__ z, double2* __restrict__ out)
+{
+	const int lane = threadIdx.x & 31;
+	const int nsl = (nrows + 31) >> 5;
+	for (int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slice < nsl; slice += (gridDim.x * blockDim.x) >> 5) {
+		const int b0 = sell_ptr[slice], w = (sell_ptr[slice + 1] - b0) >> 5;
+		const int row = (slice << 5) + lane;
+		const int32_t* cp = col + b0 + lane;
+		const double2* vp = val + 2 * ((size_t)b0 + lane);
+		double s0 = 0.0, s1 = 0.0;
+		#pragma unroll 4
+		for (int k = 0; k < w; ++k) {
+			const double2 a01 = vp[64 * (size_t)k], a23 = vp[64 * (size_t)k + 1];
+			const double2 xv = z[cp[32 * k]];
+			s0 += a01.x * xv.x + a01.y * xv.y; s1 += a23.x * xv.x + a23.y * xv.y;
+		}
+		if (row < nrows) { const double2 bv = b[row]; out[row] = make_double2(bv.x - s0, bv.y - s1); }
+	}
+}
+
+__global__ void k_mg_restrict(int nc, const int32_t* __restrict__ aggptr, const int32_t* __restrict__ aggidx,
+                              const double2* __restrict__ rf, double2* __restrict__ bc)
+{
+	for (int I = blockIdx.x * blockDim.x + threadIdx.x; I < nc; I += gridDim.x * blockDim.x) {
+		double s0 = 0.0, s1 = 0.0;
+		for (int k = aggptr[I]; k < aggptr[I + 1]; ++k) { const double2 v = rf[aggidx[k]]; s0 += v.x; s1 += v.y; }
+		bc[I] = make_double2(s0, s1);
+	}
+}
+
+__global__ void k_mg_prolong_add(int nf, const int32_t* __restrict__ agg, const double2* __restrict__ xc, double2* __restrict__ zf)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
+		const int I = agg[i];
+		if (I < 0) continue;
+		const double2 e = xc[I];
+		double2 z = zf[i];
+		z.x += e.x; z.y += e.y;
+		zf[i] = z;
+	}
+}
+
+__global__ void k_mg_dense(int n, const double* __restrict__ Ainv, const double* __restrict__ b, double* __restrict__ x)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	double s = 0.0;
+	for (int j = 0; j < n; ++j) s += Ainv[(size_t)i * n + j] * b[j];
+	x[i] = s;
+}
+
+static inline int blocks(int64_t n, int per)
+{
+	int64_t b = (n + per - 1) / per;
+	return (int)std::min<int64_t>(std::max<int64_t>(b, 1), 148 * 8);
+}
+
+// ------------------------------------------------------------------ symbolic set-up (host, once)
+static void greedy_aggregate(const std::vector<int32_t>& rp, const std::vector<int32_t>& ci, int64_t n, std::vector<int32_t>& agg, int32_t& na)
+{
+	agg.assign(n, -1);
+	na = 0;
+	for (int64_t i = 0; i < n; ++i) {                // roots: nodes whose whole neighbourhood is free
+		if (agg[i] >= 0) continue;
+		bool free_nb = true;
+		for (int32_t k = rp[i]; k < rp[i + 1]; ++k) if (agg[ci[k]] >= 0) { free_nb = false; break; }
+		if (!free_nb) continue;
+		for (int32_t k = rp[i]; k < rp[i + 1]; ++k) agg[ci[k]] = na;
+		agg[i] = na++;
+	}
+	for (int64_t i = 0; i < n; ++i) {                // leftovers join a neighbouring aggregate
+		if (agg[i] >= 0) continue;
+		for (int32_t k = rp[i]; k < rp[i + 1]; ++k) if (agg[ci[k]] >= 0 && ci[k] != i) { agg[i] = agg[ci[k]]; break; }
+		if (agg[i] < 0) agg[i] = na++;
+	}
+}
+
+static int make_level_ctx(bp_ctx* c, bp_mg_level& L, const std::vector<int32_t>& diag_slot, const std::vector<int32_t>& sell_col, int64_t n_slots)
+{
+	bp_ctx* M = new bp_ctx();
+	L.M = M;
+	M->device = c->device; M->stream = c->stream; M->prm = c->prm;
+	M->prm.pc = BP_PC_BLOCK_JACOBI;
+	M->nn = M->nn_owned = L.n;
+	M->n_slots = n_slots;
+	UPM(M->d_sell_ptr, L.h_sell_ptr.data(), L.h_sell_ptr.size());
+	UPM(M->d_col, sell_col.data(), n_slots);
+	UPM(M->d_diag, diag_slot.data(), L.n);
+	UPM(M->d_val, (const double*)nullptr, (size_t)n_slots * 4);
+	UPM(M->d_dinv, (const double*)nullptr, (size_t)L.n * 4);
+	double** vecs[] = { &M->d_F, &M->d_z, &M->d_z2, &M->d_cd, &M->d_io };
+	for (double** v : vecs) UPM(*v, (const double*)nullptr, (size_t)2 * L.n);
+	UPM(M->d_sc, (const double*)nullptr, SC_COUNT);
+	UPM(M->d_part, (const double*)nullptr, 4 * 4096);
+	UPM(M->d_counter, (const unsigned*)nullptr, 16);
+	BP_CUDA(c, cudaMallocHost((void**)&M->h_sc, SC_COUNT * sizeof(double)));
+	return BP_OK;
+}
+
+static int mg_symbolic(bp_ctx* c)
+{
+	bp_mg* mg = new bp_mg();
+	c->mg = mg;
+	const int64_t no = c->nn_owned;
+	mg->lv.emplace_back();
+	{
+		bp_mg_level& L0 = mg->lv.back();
+		L0.M = c; L0.n = no;
+		L0.h_rowptr = c->h_rowptr; L0.h_col = c->h_col; L0.h_sell_ptr = c->h_sell_ptr;
+	}
+	// first aggregation: ice columns
+	std::vector<int32_t> agg(no, -1);
+	int32_t na = (int32_t)c->n_cols;
+	for (int64_t cc = 0; cc < c->n_cols; ++cc)
+		for (int32_t j = c->h_colptr[cc]; j < c->h_colptr[cc + 1]; ++j) agg[c->h_colnode[j]] = (int32_t)cc;
+	for (int guard = 0; guard < 20; ++guard) {
+		bp_mg_level& F = mg->lv.back();
+		const int64_t nf = F.n;
+		// members of every aggregate
+		std::vector<int32_t> aggptr(na + 1, 0), aggidx;
+		for (int64_t i = 0; i < nf; ++i) if (agg[i] >= 0) aggptr[agg[i] + 1]++;
+		for (int32_t I = 0; I < na; ++I) aggptr[I + 1] += aggptr[I];
+		aggidx.resize(aggptr[na]);
+		{
+			std::vector<int32_t> fill(aggptr.begin(), aggptr.end() - 1);
+			for (int64_t i = 0; i < nf; ++i) if (agg[i] >= 0) aggidx[fill[agg[i]]++] = (int32_t)i;
+		}
+		// coarse pattern: I ~ J iff some fine i in I has a column j in J (owned columns only)
+		bp_mg_level C;
+		C.n = na;
+		C.h_rowptr.assign(na + 1, 0);
+		std::vector<std::vector<int32_t>> rows(na);
+		#pragma omp parallel for schedule(dynamic, 64)
+		for (int32_t I = 0; I < na; ++I) {
+			std::vector<int32_t>& r = rows[I];
+			for (int32_t m = aggptr[I]; m < aggptr[I + 1]; ++m) {
+				const int32_t i = aggidx[m];
+				for (int32_t k = F.h_rowptr[i]; k < F.h_rowptr[i + 1]; ++k) {
+					const int32_t j = F.h_col[k];
+					if (j < nf && agg[j] >= 0) r.push_back(agg[j]);
+				}
+			}
+			std::sort(r.begin(), r.end());
+			r.erase(std::unique(r.begin(), r.end()), r.end());
+		}
+		for (int32_t I = 0; I < na; ++I) C.h_rowptr[I + 1] = C.h_rowptr[I] + (int32_t)rows[I].size();
+		C.h_col.resize(C.h_rowptr[na]);
+		for (int32_t I = 0; I < na; ++I) std::copy(rows[I].begin(), rows[I].end(), C.h_col.begin() + C.h_rowptr[I]);
+		// SELL-32 slots of the coarse level
+		const int64_t nsl = ((int64_t)na + 31) / 32;
+		C.h_sell_ptr.assign(nsl + 1, 0);
+		for (int64_t s = 0; s < nsl; ++s) {
+			int32_t w = 0;
+			for (int64_t I = s * 32; I < std::min<int64_t>(na, s * 32 + 32); ++I) w = std::max(w, C.h_rowptr[I + 1] - C.h_rowptr[I]);
+			C.h_sell_ptr[s + 1] = C.h_sell_ptr[s] + 32 * w;
+		}
+		const int64_t nslots_c = C.h_sell_ptr[nsl];
+		auto slot_c = [&](int64_t I, int32_t k) -> int32_t { return C.h_sell_ptr[I >> 5] + 32 * k + (int32_t)(I & 31); };
+		std::vector<int32_t> sell_col((size_t)std::max<int64_t>(nslots_c, 1), 0), diag(na, -1);
+		for (int64_t I = 0; I < nsl * 32; ++I) {
+			const int32_t w = (C.h_sell_ptr[(I >> 5) + 1] - C.h_sell_ptr[I >> 5]) >> 5;
+			const int32_t len = I < na ? C.h_rowptr[I + 1] - C.h_rowptr[I] : 0;
+			for (int32_t k = 0; k < w; ++k) {
+				const int32_t cj = (k < len) ? C.h_col[C.h_rowptr[I] + k] : (I < na ? (int32_t)I : 0);
+				sell_col[slot_c(I, k)] = cj;
+				if (k < len && cj == I) diag[I] = slot_c(I, k);
+			}
+		}
+		// fine slot -> coarse slot
+		const int64_t nslots_f = F.h_sell_ptr.back();
+		std::vector<int32_t> galmap((size_t)std::max<int64_t>(nslots_f, 1), -1);
+		#pragma omp parallel for schedule(static)
+		for (int64_t i = 0; i < nf; ++i) {
+			const int32_t I = agg[i];
+			if (I < 0) continue;
+			const int32_t* lo = C.h_col.data() + C.h_rowptr[I];
+			const int32_t* hi = C.h_col.data() + C.h_rowptr[I + 1];
+			for (int32_t k = F.h_rowptr[i]; k < F.h_rowptr[i + 1]; ++k) {
+				const int32_t j = F.h_col[k];
+				if (j >= nf || agg[j] < 0) continue;
+				const int32_t kc = (int32_t)(std::lower_bound(lo, hi, agg[j]) - lo);
+				galmap[F.h_sell_ptr[i >> 5] + 32 * (k - F.h_rowptr[i]) + (i & 31)] = slot_c(I, kc);
+			}
+		}
+		UPM(F.d_agg, agg.data(), nf);
+		UPM(F.d_galmap, galmap.data(), galmap.size());
+		UPM(F.d_aggptr, aggptr.data(), aggptr.size());
+		UPM(F.d_aggidx, aggidx.data(), aggidx.size());
+		int rc = make_level_ctx(c, C, diag, sell_col, nslots_c);
+		if (rc) return rc;
+		mg->lv.push_back(std::move(C));
+		if (na <= 64) break;
+		int32_t na2;
+		greedy_aggregate(mg->lv.back().h_rowptr, mg->lv.back().h_col, na, agg, na2);
+		if (na2 >= na) break;                         // no coarsening possible
+		na = na2;
+	}
+	mg->nc = (int)(2 * mg->lv.back().n);
+	if (mg->nc > 4096) return bp_fail(c, BP_ERR_STATE, "multigrid: coarsest level has %d dofs (aggregation stalled)", mg->nc);
+	mg->h_dense.resize((size_t)mg->nc * mg->nc);
+	UPM(mg->d_dense, (const double*)nullptr, (size_t)mg->nc * mg->nc);
+	if (c->prm.verbose) {
+		printf("multigrid levels:");
+		for (auto& L : mg->lv) printf(" %lld", (long long)L.n);
+		printf(" nodes\n");
+	}
+	return BP_OK;
+}
+
+// ------------------------------------------------------------------ numeric set-up (every Newton step)
+int bp_mg_prepare(bp_ctx* c)
+{
+	int rc;
+	if (!c->mg && (rc = mg_symbolic(c))) return rc;
+	bp_mg* mg = c->mg;
+	const int nl = (int)mg->lv.size();
+	for (int l = 0; l < nl; ++l) mg->lv[l].M->stream = c->stream;
+	// ghosts of the fine iterates are zero: the hierarchy is rank-local
+	if (c->nn > c->nn_owned) {
+		const size_t off = (size_t)2 * c->nn_owned, nb = (size_t)2 * (c->nn - c->nn_owned) * sizeof(double);
+		BP_CUDA(c, cudaMemsetAsync(c->d_z + off, 0, nb, c->stream));
+		BP_CUDA(c, cudaMemsetAsync(c->d_z2 + off, 0, nb, c->stream));
+	}
+	for (int l = 0; l + 1 < nl; ++l) {
+		bp_mg_level& F = mg->lv[l];
+		bp_ctx* C = mg->lv[l + 1].M;
+		BP_CUDA(c, cudaMemsetAsync(C->d_val, 0, (size_t)C->n_slots * 4 * sizeof(double), c->stream));
+		const int64_t ns = F.h_sell_ptr.back();
+		k_mg_galerkin<<<blocks(ns, 256), 256, 0, c->stream>>>(ns, F.d_galmap, F.M->d_val, C->d_val);
+		c->launches++;
+	}
+	for (int l = 0; l < nl; ++l) {
+		bp_ctx* M = mg->lv[l].M;
+		if (l > 0) bp_launch_pc_setup(M);             // level 0: done by the caller
+		bp_launch_gershgorin(M, SC_TMP);
+	}
+	for (int l = 0; l < nl; ++l) {
+		bp_ctx* M = mg->lv[l].M;
+		BP_CUDA(c, cudaMemcpyAsync(M->h_sc, M->d_sc, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	}
+	// coarsest matrix -> host, dense inverse
+	bp_mg_level& Lc = mg->lv.back();
+	mg->h_val.resize((size_t)Lc.M->n_slots * 4);
+	BP_CUDA(c, cudaMemcpyAsync(mg->h_val.data(), Lc.M->d_val, mg->h_val.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	for (int l = 0; l < nl; ++l) {
+		mg->lv[l].lmax = mg->lv[l].M->h_sc[SC_TMP];
+		if (!(mg->lv[l].lmax > 0.0) || !std::isfinite(mg->lv[l].lmax))
+			return bp_fail(c, BP_ERR_STATE, "multigrid: eigenvalue bound of level %d failed (%g)", l, mg->lv[l].lmax);
+	}
+	const int n = mg->nc;
+	std::vector<double> A((size_t)n * n, 0.0);
+	for (int64_t I = 0; I < Lc.n; ++I)
+		for (int32_t k = Lc.h_rowptr[I]; k < Lc.h_rowptr[I + 1]; ++k) {
+			const int32_t J = Lc.h_col[k];
+			const double* v = mg->h_val.data() + 4 * (size_t)(Lc.h_sell_ptr[I >> 5] + 32 * (k - Lc.h_rowptr[I]) + (I & 31));
+			A[(size_t)(2 * I) * n + 2 * J] = v[0]; A[(size_t)(2 * I) * n + 2 * J + 1] = v[1];
+			A[(size_t)(2 * I + 1) * n + 2 * J] = v[2]; A[(size_t)(2 * I + 1) * n + 2 * J + 1] = v[3];
+		}
+	// Gauss-Jordan with partial pivoting
+	std::vector<double>& Inv = mg->h_dense;
+	std::fill(Inv.begin(), Inv.end(), 0.0);
+	for (int i = 0; i < n; ++i) Inv[(size_t)i * n + i] = 1.0;
+	for (int col = 0; col < n; ++col) {
+		int piv = col;
+		for (int r = col + 1; r < n; ++r) if (std::fabs(A[(size_t)r * n + col]) > std::fabs(A[(size_t)piv * n + col])) piv = r;
+		if (A[(size_t)piv * n + col] == 0.0) return bp_fail(c, BP_ERR_STATE, "multigrid: coarsest matrix is singular");
+		if (piv != col) for (int j = 0; j < n; ++j) { std::swap(A[(size_t)piv * n + j], A[(size_t)col * n + j]); std::swap(Inv[(size_t)piv * n + j], Inv[(size_t)col * n + j]); }
+		const double ip = 1.0 / A[(size_t)col * n + col];
+		for (int j = 0; j < n; ++j) { A[(size_t)col * n + j] *= ip; Inv[(size_t)col * n + j] *= ip; }
+		for (int r = 0; r < n; ++r) {
+			if (r == col) continue;
+			const double f = A[(size_t)r * n + col];
+			if (f == 0.0) continue;
+			for (int j = 0; j < n; ++j) { A[(size_t)r * n + j] -= f * A[(size_t)col * n + j]; Inv[(size_t)r * n + j] -= f * Inv[(size_t)col * n + j]; }
+		}
+	}
+	BP_CUDA(c, cudaMemcpyAsync(mg->d_dense, Inv.data(), Inv.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	return BP_OK;
+}
+
+// ------------------------------------------------------------------ V-cycle
+static void cheb_smooth(bp_ctx* M, double lmax, int deg, double ratio, const double* r, bool zero_init)
+{
+	const double b = lmax, a = b / ratio, theta = 0.5 * (b + a), delta = 0.5 * (b - a), sigma = theta / delta;
+	double rho = 1.0 / sigma;
+	if (zero_init) bp_launch_cheb_first(M, 1.0 / theta, r, M->d_z);
+	else { bp_launch_cheb_step(M, 0.0, 1.0 / theta, r, M->d_z, M->d_z2); std::swap(M->d_z, M->d_z2); }
+	for (int k = 1; k < deg; ++k) {
+		const double rho_n = 1.0 / (2.0 * sigma - rho);
+		bp_launch_cheb_step(M, rho_n * rho, 2.0 * rho_n / delta, r, M->d_z, M->d_z2);
+		std::swap(M->d_z, M->d_z2);
+		rho = rho_n;
+	}
+}
+
+static void vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs)
+{
+	bp_mg_level& L = mg->lv[l];
+	bp_ctx* M = L.M;
+	const int nl = (int)mg->lv.size();
+	if (l == nl - 1) {
+		k_mg_dense<<<(mg->nc + 127) / 128, 128, 0, c->stream>>>(mg->nc, mg->d_dense, rhs, M->d_z);
+		c->launches++;
+		return;
+	}
+	const int deg = std::max(c->prm.pc_degree, 1);
+	const double ratio = std::max(c->prm.pc_eig_ratio, 1.5);
+	cheb_smooth(M, L.lmax, deg, ratio, rhs, true);
+	k_mg_residual<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, M->d_sell_ptr, M->d_col, (const double2*)M->d_val,
+		(const double2*)rhs, (const double2*)M->d_z, (double2*)M->d_io);
+	bp_ctx* C = mg->lv[l + 1].M;
+	k_mg_restrict<<<blocks(C->nn_owned, 128), 128, 0, c->stream>>>((int)C->nn_owned, L.d_aggptr, L.d_aggidx, (const double2*)M->d_io, (double2*)C->d_F);
+	c->launches += 2;
+	vcycle(c, mg, l + 1, C->d_F);
+	k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, L.d_agg, (const double2*)C->d_z, (double2*)M->d_z);
+	c->launches++;
+	cheb_smooth(M, L.lmax, deg, ratio, rhs, false);
+}
+
+// z = M^-1 r with r = c->d_r, z = c->d_z
+int bp_mg_apply(bp_ctx* c)
+{
+	if (!c->mg) return bp_fail(c, BP_ERR_STATE, "multigrid preconditioner not prepared");
+	const int64_t l0 = c->launches;
+	for (size_t l = 1; l < c->mg->lv.size(); ++l) c->mg->lv[l].M->launches = 0;
+	vcycle(c, c->mg, 0, c->d_r);
+	for (size_t l = 1; l < c->mg->lv.size(); ++l) c->launches += c->mg->lv[l].M->launches;
+	(void)l0;
+	return BP_OK;
+}
+
+void bp_mg_free(bp_ctx* c)
+{
+	if (!c->mg) return;
+	for (size_t l = 0; l < c->mg->lv.size(); ++l) {
+		bp_mg_level& L = c->mg->lv[l];
+		void* t[] = { L.d_agg, L.d_galmap, L.d_aggptr, L.d_aggidx };
+		for (void* p : t) if (p) cudaFree(p);
+		if (l > 0 && L.M) {
+			bp_ctx* M = L.M;
+			void* ptrs[] = { M->d_sell_ptr, M->d_col, M->d_diag, M->d_val, M->d_dinv, M->d_F, M->d_z, M->d_z2, M->d_cd, M->d_io, M->d_sc, M->d_part, M->d_counter };
+			for (void* p : ptrs) if (p) cudaFree(p);
+			if (M->h_sc) cudaFreeHost(M->h_sc);
+			delete M;
+		}
+	}
+	if (c->mg->d_dense) cudaFree(c->mg->d_dense);
+	delete c->mg;
+	c->mg = nullptr;
+}

@@ -313,6 +313,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 				if (j > colptr[cc]) tri_l[j] = find_slot(colnode[j], colnode[j - 1]);
 			}
 		}
+		c->h_colptr = colptr; c->h_colnode = colnode;
 		UP(c->d_colptr, colptr.data(), colptr.size());
 		UP(c->d_colnode, colnode.data(), no);
 		UP(c->d_tri_d, tri_d.data(), no);

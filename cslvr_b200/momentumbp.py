@@ -109,8 +109,9 @@ class MomentumBPBase(Momentum):
 		return c
 
 	# the reference asks PETSc for hypre BoomerAMG; the device PCG offers Jacobi-type,
-	# Chebyshev-polynomial and vertical-line preconditioners -- AMG requests get Chebyshev
-	_PC_MAP = {'hypre_amg': 'chebyshev', 'amg': 'chebyshev', 'default': 'chebyshev',
+	# Chebyshev-polynomial, vertical-line and aggregation-multigrid preconditioners -- AMG
+	# requests get the multigrid V-cycle
+	_PC_MAP = {'hypre_amg': 'mg', 'amg': 'mg', 'default': 'mg', 'mg': 'mg',
 	           'none': 'none', 'jacobi': 'jacobi', 'block_jacobi': 'block_jacobi',
 	           'chebyshev': 'chebyshev', 'column': 'column'}
 
@@ -128,7 +129,7 @@ class MomentumBPBase(Momentum):
 		          krylov_rtol=ks.get('relative_tolerance', 1e-5),
 		          krylov_atol=ks.get('absolute_tolerance', 1e-50),
 		          krylov_maxit=ks.get('maximum_iterations', 10000),
-		          preconditioner=self._PC_MAP.get(pc, 'chebyshev'),
+		          preconditioner=self._PC_MAP.get(pc, 'mg'),
 		          verbose=ks.get('monitor_convergence', False) or ns.get('report', False),
 		          quadrature_degree=self.solve_params.get('quadrature_degree', 9 if self.model.energy_dependent_rate_factor else 5))
 		return kw
@@ -150,7 +151,7 @@ class MomentumBPBase(Momentum):
 		pc = inner.get('preconditioner', 'default')
 		ks = inner.get('krylov_solver', {})
 		c.set_params(krylov_rtol=ks.get('relative_tolerance', 1e-5), krylov_atol=ks.get('absolute_tolerance', 1e-50),
-		             krylov_maxit=ks.get('maximum_iterations', 10000), preconditioner=self._PC_MAP.get(pc, 'chebyshev'),
+		             krylov_maxit=ks.get('maximum_iterations', 10000), preconditioner=self._PC_MAP.get(pc, 'mg'),
 		             quadrature_degree=self.solve_params.get('quadrature_degree', 5))
 		ul = np.empty(self.Q.dim())
 		ul[0::2], ul[1::2] = self.model.u.values[0::3], self.model.u.values[1::3]

@@ -61,6 +61,10 @@ extern "C" {
 #define BP_ASM_SCATTER  1   /* one thread per tetrahedron, FP64 atomics into F and J           */
 #define BP_ASM_GATHER   2   /* one thread per Jacobian block row, no atomics, deterministic    */
 
+#define BP_PC_MG            5   /* aggregation multigrid V-cycle: ice columns -> footprint nodes ->
+                                   greedy 2-D aggregates, Chebyshev smoothing (pc_degree, pc_eig_ratio),
+                                   Galerkin coarse operators rebuilt on the device per Newton step     */
+
 typedef struct bp_ctx bp_ctx;
 
 /* The mesh and the P1xP1 dof map: what the adapter pulls out of dolfin

@@ -203,12 +203,12 @@ def test_empty_and_ragged_inputs_are_rejected():
 	c.close(); c2.close()
 
 
-@pytest.mark.parametrize('pc', ['none', 'jacobi', 'block_jacobi', 'chebyshev', 'column'])
+@pytest.mark.parametrize('pc', ['none', 'jacobi', 'block_jacobi', 'chebyshev', 'column', 'mg'])
 def test_every_preconditioner_solves_the_same_system(pc):
 	"""bp_krylov_solve with each BP_PC_* against a sparse direct solve of the exported J."""
 	import scipy.sparse.linalg as spla
 	m = ismip_model('A', n=(10, 8, 5))                     # dx = 8 km >> dz = 200 m: strongly anisotropic
-	c = product_context(m, krylov_rtol=1e-12, preconditioner=pc, pc_degree=4)
+	c = product_context(m, krylov_rtol=1e-12, preconditioner=pc, **({} if pc == 'mg' else dict(pc_degree=4)))
 	u = state(2 * m.n_nodes, 31)
 	F, J = c.assemble(u, want_F=True, want_J=True)
 	ip, ix = c.csr_pattern()
@@ -236,7 +236,7 @@ def test_preconditioner_quality_ordering():
 	assert its['chebyshev'] * 2 < its['block_jacobi'], its
 
 
-@pytest.mark.parametrize('pc', ['chebyshev', 'column'])
+@pytest.mark.parametrize('pc', ['chebyshev', 'column', 'mg'])
 def test_newton_with_other_preconditioners(pc):
 	m = ismip_model('C', L=20000.0, n=(10, 10, 4))
 	P = oracle_problem(m)
@@ -373,3 +373,20 @@ def test_energy_dependent_model_through_the_mirror():
 	P = oracle_problem(m, energy=dict(Tp=m.vertex_field(m.Tp), W=m.vertex_field(m.W), E=m.vertex_field(m.E)))
 	uo, io = P.newton(relax=0.7, maxit=60)
 	assert mom.stats['converged'] and relerr(mom.get_unknown().values, uo) < 1e-6
+
+
+def test_multigrid_iteration_count_is_nearly_mesh_independent():
+	"""the point of BP_PC_MG: refining the footprint 2x must not double the CG iterations."""
+	its = {}
+	for nxy in (24, 48):
+		m = ismip_model('C', L=20000.0 * nxy / 260, n=(nxy, nxy, 5))
+		u = state(2 * m.n_nodes, 71, 5.0) + 20.0
+		out = {}
+		for pc in ('mg', 'chebyshev'):
+			c = product_context(m, krylov_rtol=1e-8, preconditioner=pc)
+			F, _ = c.assemble(u, want_F=True, want_J=True, J=False)
+			_, out[pc], _ = c.krylov_solve(F)
+			c.close()
+		its[nxy] = out
+	assert its[48]['mg'] <= 1.35 * its[24]['mg'] + 3, its
+	assert its[48]['mg'] < its[48]['chebyshev'], its
