@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
 	       '-gencode', 'arch=compute_100a,code=sm_100a',
 	       '-Xcompiler', '-fPIC,-fopenmp,-O3', '-shared',
 	       '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(HERE, 'csrc'),
-	       '-Xptxas', '-v' if verbose else '-O3',
+	       '-Xptxas', '-v' if verbose else '-O3'] + (['-DBP_EXPERIMENTS'] if os.environ.get('BP_EXPERIMENTS') == '1' else []) + [
 	       '-o', LIB] + SRC + ['-lcudart', '-ldl', '-lgomp']
 	r = subprocess.run(cmd, capture_output=True, text=True)
 	if r.returncode != 0:

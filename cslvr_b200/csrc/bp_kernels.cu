@@ -184,6 +184,7 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 	}
 }
 
+#ifdef BP_EXPERIMENTS
 // ---------------------------------------------------------------- EXPERIMENT (timing only)
 // Thread-per-tet element computation with the 64 + 8 contributions accumulated by
 // shared-memory atomicAdd(double) (ATOMS.CAST.SPIN.64) at slot-derived addresses in a
@@ -270,6 +271,8 @@ void bp_launch_proxy(bp_ctx* c)
 	c->launches++;
 }
 
+#endif  // BP_EXPERIMENTS
+
 // ---------------------------------------------------------------- row-gather kernel
 // One thread per Jacobian block row (= owned node i).  The thread walks the tets that
 // touch node i (SELL-32 incidence list), rebuilds each tet's cell-constant quantities
@@ -296,6 +299,8 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	const int len = active ? rowlen[i] : 0;
 	if (WANT_J) for (int k = 0; k < 4 * len; ++k) acc[k * RTPB + tid] = 0.0;
 	double Fx = 0.0, Fy = 0.0;
+	double dg0 = 0.0, dg1 = 0.0, dg2 = 0.0, dg3 = 0.0;    // diagonal block
+	int kdiag = -1;
 	const int slice = i >> 5, lane = i & 31;
 	const int e0 = active ? inc_slice[slice] : 0, e1 = active ? inc_slice[slice + 1] : 0;
 	// software pipeline, two stages deep on the index words (tet code, block positions, four
@@ -402,12 +407,17 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 			for (int b = 0; b < 4; ++b) {
 				const double dxb = cxx * X[b] + sh * Y[b] + hz0 * Z[b];
 				const double dyb = cyy * Y[b] + sh * X[b] + hz1 * Z[b];
-				const int k = (pk_cur >> (8 * b)) & 255;
-				double* s4 = acc + (4 * k) * RTPB + tid;
-				s4[0]        += Pa * X[b] + Qa * Y[b] + Ra * Z[b] + Ea * dxb;
-				s4[RTPB]     += Ua * Y[b] + Qa * X[b] + Ea * dyb;
-				s4[2 * RTPB] += Wa * X[b] + Ta * Y[b] + Ga * dxb;
-				s4[3 * RTPB] += Sa * Y[b] + Ta * X[b] + Ra * Z[b] + Ga * dyb;
+				const double jxx = Pa * X[b] + Qa * Y[b] + Ra * Z[b] + Ea * dxb;
+				const double jxy = Ua * Y[b] + Qa * X[b] + Ea * dyb;
+				const double jyx = Wa * X[b] + Ta * Y[b] + Ga * dxb;
+				const double jyy = Sa * Y[b] + Ta * X[b] + Ra * Z[b] + Ga * dyb;
+				if (b == 0) {                             // the diagonal block gets a term from every tet: keep it in registers
+					dg0 += jxx; dg1 += jxy; dg2 += jyx; dg3 += jyy;
+					kdiag = (int)(pk_cur & 255);
+				} else {
+					double* s4 = acc + (4 * ((pk_cur >> (8 * b)) & 255)) * RTPB + tid;
+					s4[0] += jxx; s4[RTPB] += jxy; s4[2 * RTPB] += jyx; s4[3 * RTPB] += jyy;
+				}
 			}
 		}
 		code = code_n;
@@ -419,8 +429,9 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		double2* out = (double2*)val + 2 * ((size_t)sell_ptr[slice] + lane);
 		for (int k = 0; k < len; ++k) {
 			const double* s4 = acc + (4 * k) * RTPB + tid;
-			out[64 * (size_t)k]     = make_double2(s4[0], s4[RTPB]);
-			out[64 * (size_t)k + 1] = make_double2(s4[2 * RTPB], s4[3 * RTPB]);
+			const bool dgk = (k == kdiag);
+			out[64 * (size_t)k]     = dgk ? make_double2(dg0, dg1) : make_double2(s4[0], s4[RTPB]);
+			out[64 * (size_t)k + 1] = dgk ? make_double2(dg2, dg3) : make_double2(s4[2 * RTPB], s4[3 * RTPB]);
 		}
 	}
 }
@@ -711,7 +722,9 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	P.picard = (what & 16) ? 1 : 0;
 	bp_update_ainv(c);
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
+#ifdef BP_EXPERIMENTS
 	if (what & 8) { bp_launch_proxy(c); return; }
+#endif
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
 		const size_t rs = (size_t)4 * c->max_row * RTPB * sizeof(double);
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {

@@ -1,3 +1,4 @@
+# needs the library built with BP_EXPERIMENTS=1 (python cslvr_b200/_build.py) for the proxy kernel (flag 8)
 import sys, os
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests'); os.environ['CSLVR_B200_QUIET']='1'
 import numpy as np, bench
