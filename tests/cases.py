@@ -81,3 +81,45 @@ def state(n_dofs, seed=1234, scale=30.0):
 
 def relerr(a, b):
 	return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+def delaunay_extruded_model(n_pts=60, n_layers=4, seed=3, L=30000.0):
+	"""an UNSTRUCTURED extruded mesh, the other tet layout D3Model meshes come in
+	(cslvr/meshing.py:771-860: gmsh footprint triangles extruded to prisms, each prism split
+	into 3 tets by comparing vertex ids): random Delaunay footprint x layers, non-periodic,
+	floating part, variable A.  No BoxMesh structure anywhere: vertex ids are shuffled."""
+	from scipy.spatial import Delaunay
+	from cslvr_b200 import Mesh
+	rng = np.random.default_rng(seed)
+	pts = rng.uniform(0.05, 0.95, size=(n_pts, 2)) * L
+	pts = np.vstack([pts, [[0, 0], [L, 0], [0, L], [L, L]], np.column_stack([np.linspace(0, L, 7)[1:-1], np.zeros(5)]),
+	                 np.column_stack([np.linspace(0, L, 7)[1:-1], L * np.ones(5)])])
+	tri = Delaunay(pts).simplices
+	nf = pts.shape[0]
+	perm = rng.permutation(nf * (n_layers + 1))                 # shuffled vertex numbering
+	vid = lambda p, k: perm[k * nf + p]
+	coords = np.zeros((nf * (n_layers + 1), 3))
+	for k in range(n_layers + 1):
+		coords[vid(np.arange(nf), k), 0:2] = pts
+		coords[vid(np.arange(nf), k), 2] = k / n_layers
+	cells = []
+	for t in tri:
+		for k in range(n_layers):
+			b = [vid(p, k) for p in t]
+			tp = [vid(p, k + 1) for p in t]
+			# split the prism (b0 b1 b2 | t0 t1 t2) into 3 tets, diagonals chosen by the smaller
+			# footprint vertex id so that neighbouring prisms agree on their shared quad faces
+			o = np.argsort(t)
+			b = [b[i] for i in o]; tp = [tp[i] for i in o]
+			cells += [[b[0], b[1], b[2], tp[2]], [b[0], b[1], tp[2], tp[1]], [b[0], tp[1], tp[2], tp[0]]]
+	cells = np.sort(np.array(cells), axis=1)
+	model = D3Model(Mesh(coords, cells), use_periodic=False)
+	S = lambda x, y, z: 500.0 - 450.0 * x / L + 40.0 * np.sin(4 * y / L)
+	B = lambda x, y, z: -150.0 - 250.0 * x / L + 60.0 * np.cos(6 * x / L) * np.sin(5 * y / L)
+	model.calculate_boundaries()
+	model.deform_mesh_to_geometry(S, B)
+	model.calculate_boundaries(mask=lambda x, y, z: np.where(x > 0.65 * L, 2.0, 1.0))
+	model.init_beta(lambda x, y, z: 300.0 + 200.0 * np.sin(6 * x / L) * np.cos(4 * y / L))
+	X = model.mesh.coordinates()
+	model.init_A(model.rate_factor(252.0 + 15.0 * (1.0 - (X[:, 2] + 400.0) / 900.0)))
+	return model

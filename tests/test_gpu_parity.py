@@ -390,3 +390,33 @@ def test_multigrid_iteration_count_is_nearly_mesh_independent():
 		its[nxy] = out
 	assert its[48]['mg'] <= 1.35 * its[24]['mg'] + 3, its
 	assert its[48]['mg'] < its[48]['chebyshev'], its
+
+
+def test_unstructured_extruded_mesh_all_paths():
+	"""nothing in the library may depend on BoxMesh structure or vertex numbering: random
+	Delaunay footprint, prism -> 3 tets split, shuffled vertex ids, floating tongue, P1 A."""
+	from cases import delaunay_extruded_model
+	from cslvr_b200 import capi
+	m = delaunay_extruded_model()
+	assert m.N_GAMMA_B_FLT > 0 and m.N_GAMMA_L_UDR > 0
+	P = oracle_problem(m)
+	for mode in ('gather', 'scatter'):
+		c = product_context(m, assembly=mode)
+		ip, ix = c.csr_pattern()
+		assert np.array_equal(ip, P.pattern()[0]) and np.array_equal(ix, P.pattern()[1])
+		u = state(P.n_dofs, 81)
+		F, J = c.assemble(u, want_F=True, want_J=True)
+		assert relerr(F, P.residual(u)) < TOL_ASM and relerr(J, P.jacobian(u)) < TOL_ASM
+		c.close()
+	uo, io = P.newton(rtol=1e-10, relax=0.7, maxit=80)
+	for pc in ('mg', 'chebyshev', 'column'):
+		c = product_context(m, relative_tolerance=1e-10, relaxation_parameter=0.7, maximum_iterations=80, krylov_rtol=1e-12, preconditioner=pc)
+		u = np.full(P.n_dofs, 3e-16)
+		st = c.newton_solve(u)
+		assert st['converged'] and relerr(u, uo) < 1e-7, (pc, relerr(u, uo))
+		c.close()
+	c = product_context(m)
+	c.set_field(capi.FIELD_B, m.vertex_field(m.B))
+	assert relerr(c.solve_pressure(uo)[m.node_vertex], P.pressure(uo)) < TOL_U
+	assert relerr(c.solve_vert_velocity(uo)[m.node_vertex], P.vert_velocity(uo, m.vertex_field(m.B))[0]) < 1e-7
+	c.close()
