@@ -21,6 +21,7 @@ enum {
 	SC_BREAKDOWN,   // 1.0 if p.Ap <= 0 or NaN
 	SC_FF,          // F.F (Newton residual norm squared)
 	SC_TMP,
+	SC_LMAX,        // bound of lmax(D^-1 A) (multigrid levels: read by the Chebyshev kernels on the device)
 	SC_COUNT = 16
 };
 
@@ -145,8 +146,9 @@ void bp_launch_pcg_init2(bp_ctx* c);                       // x = 0, r = b (prec
 void bp_launch_pcg_update2(bp_ctx* c, int par);            // x += alpha p, r -= alpha Ap
 void bp_launch_dots3(bp_ctx* c, int slot, int guard);      // {r.z, z.z, r.r} -> d_sc[slot..]
 void bp_launch_col_solve(bp_ctx* c, const double* r, double* z);
-void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z);
-void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew);
+// lmax_dev != nullptr: c0 / c2 are given for lmax = 1 and scaled by 1 / *lmax_dev on the device
+void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z, const double* lmax_dev = nullptr);
+void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew, const double* lmax_dev = nullptr);
 void bp_launch_apply_dinv(bp_ctx* c, double* v);           // v <- D^-1 v
 void bp_launch_scale_inv_norm(bp_ctx* c, double* v, int sc_slot);   // v <- v / sqrt(d_sc[slot])
 void bp_launch_fill_probe(bp_ctx* c, double* v);

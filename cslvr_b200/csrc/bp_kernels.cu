@@ -1295,8 +1295,9 @@ void bp_launch_lincomb(bp_ctx* c, double* out, double a, const double* x, double
 // Chebyshev polynomial in D^-1 J: first step d = c0 D^-1 r, z = d; further steps fused with
 // the SpMV: res = r - J z_old; d = c1 d + c2 D^-1 res; z_new = z_old + d.
 __global__ void __launch_bounds__(256)
-k_cheb_first(int nrows, double c0, const double* __restrict__ dinv, const double2* __restrict__ r, double2* z, double2* d)
+k_cheb_first(int nrows, double c0, const double* __restrict__ dinv, const double2* __restrict__ r, double2* z, double2* d, const double* __restrict__ lmax_dev)
 {
+	if (lmax_dev) c0 /= *lmax_dev;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nrows; i += gridDim.x * blockDim.x) {
 		const double2 v = apply_dinv(dinv, i, r[i]);
 		const double2 dv = make_double2(c0 * v.x, c0 * v.y);
@@ -1306,8 +1307,9 @@ k_cheb_first(int nrows, double c0, const double* __restrict__ dinv, const double
 __global__ void __launch_bounds__(256)
 k_cheb_step(int nrows, double c1, double c2, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ col,
             const double2* __restrict__ val, const double* __restrict__ dinv, const double2* __restrict__ r,
-            const double2* __restrict__ zold, double2* __restrict__ znew, double2* __restrict__ d)
+            const double2* __restrict__ zold, double2* __restrict__ znew, double2* __restrict__ d, const double* __restrict__ lmax_dev)
 {
+	if (lmax_dev) c2 /= *lmax_dev;
 	const int lane = threadIdx.x & 31;
 	const int nsl = (nrows + 31) >> 5;
 	for (int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slice < nsl; slice += (gridDim.x * blockDim.x) >> 5) {
@@ -1331,17 +1333,17 @@ k_cheb_step(int nrows, double c1, double c2, const int32_t* __restrict__ sell_pt
 		}
 	}
 }
-void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z)
+void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z, const double* lmax_dev)
 {
 	const int n = (int)c->nn_owned;
-	k_cheb_first<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, c0, c->d_dinv, (const double2*)r, (double2*)z, (double2*)c->d_cd);
+	k_cheb_first<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, c0, c->d_dinv, (const double2*)r, (double2*)z, (double2*)c->d_cd, lmax_dev);
 	c->launches++;
 }
-void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew)
+void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew, const double* lmax_dev)
 {
 	if (!c->grid_cheb) c->grid_cheb = one_wave(k_cheb_step, 256, c->nn_owned, 256);
 	k_cheb_step<<<c->grid_cheb, 256, 0, c->stream>>>((int)c->nn_owned, c1, c2, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, c->d_dinv,
-		(const double2*)r, (const double2*)zold, (double2*)znew, (double2*)c->d_cd);
+		(const double2*)r, (const double2*)zold, (double2*)znew, (double2*)c->d_cd, lmax_dev);
 	c->launches++;
 }
 

@@ -32,6 +32,10 @@ struct bp_mg_level {
 struct bp_mg {
 	std::vector<bp_mg_level> lv;
 	double* d_dense = nullptr;           // inverse of the coarsest matrix, row-major
+	// the V-cycle is a fixed sequence of ~50 mostly tiny launches: captured once as a CUDA graph
+	cudaGraphExec_t graph = nullptr;
+	const double *g_r = nullptr; double *g_z = nullptr, *g_z2 = nullptr;
+	int g_deg = 0; double g_ratio = 0.0; int64_t g_launches = 0;
 	std::vector<double> h_dense, h_val;
 	int nc = 0;                          // coarsest dofs
 };
@@ -296,7 +300,7 @@ int bp_mg_prepare(bp_ctx* c)
 	for (int l = 0; l < nl; ++l) {
 		bp_ctx* M = mg->lv[l].M;
 		if (l > 0) bp_launch_pc_setup(M);             // level 0: done by the caller
-		bp_launch_gershgorin(M, SC_TMP);
+		bp_launch_gershgorin(M, SC_LMAX);
 	}
 	for (int l = 0; l < nl; ++l) {
 		bp_ctx* M = mg->lv[l].M;
@@ -308,7 +312,7 @@ int bp_mg_prepare(bp_ctx* c)
 	BP_CUDA(c, cudaMemcpyAsync(mg->h_val.data(), Lc.M->d_val, mg->h_val.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	BP_CUDA(c, cudaStreamSynchronize(c->stream));
 	for (int l = 0; l < nl; ++l) {
-		mg->lv[l].lmax = mg->lv[l].M->h_sc[SC_TMP];
+		mg->lv[l].lmax = mg->lv[l].M->h_sc[SC_LMAX];
 		if (!(mg->lv[l].lmax > 0.0) || !std::isfinite(mg->lv[l].lmax))
 			return bp_fail(c, BP_ERR_STATE, "multigrid: eigenvalue bound of level %d failed (%g)", l, mg->lv[l].lmax);
 	}
@@ -344,21 +348,28 @@ int bp_mg_prepare(bp_ctx* c)
 }
 
 // ------------------------------------------------------------------ V-cycle
-static void cheb_smooth(bp_ctx* M, double lmax, int deg, double ratio, const double* r, bool zero_init)
+// Chebyshev smoothing for the interval [lmax / ratio, lmax]; lmax is read on the device
+// (d_sc[SC_LMAX] of the level), so the launch sequence does not depend on the matrix values
+// and can be replayed as a graph.  Iterates ping-pong between za and zb; returns the buffer
+// that holds the result.
+static double* cheb_smooth(bp_ctx* M, int deg, double ratio, const double* r, double* za, double* zb, bool zero_init)
 {
-	const double b = lmax, a = b / ratio, theta = 0.5 * (b + a), delta = 0.5 * (b - a), sigma = theta / delta;
+	const double a = 1.0 / ratio, theta = 0.5 * (1.0 + a), delta = 0.5 * (1.0 - a), sigma = theta / delta;
+	const double* lm = M->d_sc + SC_LMAX;
 	double rho = 1.0 / sigma;
-	if (zero_init) bp_launch_cheb_first(M, 1.0 / theta, r, M->d_z);
-	else { bp_launch_cheb_step(M, 0.0, 1.0 / theta, r, M->d_z, M->d_z2); std::swap(M->d_z, M->d_z2); }
+	if (zero_init) bp_launch_cheb_first(M, 1.0 / theta, r, za, lm);
+	else { bp_launch_cheb_step(M, 0.0, 1.0 / theta, r, za, zb, lm); std::swap(za, zb); }
 	for (int k = 1; k < deg; ++k) {
 		const double rho_n = 1.0 / (2.0 * sigma - rho);
-		bp_launch_cheb_step(M, rho_n * rho, 2.0 * rho_n / delta, r, M->d_z, M->d_z2);
-		std::swap(M->d_z, M->d_z2);
+		bp_launch_cheb_step(M, rho_n * rho, 2.0 * rho_n / delta, r, za, zb, lm);
+		std::swap(za, zb);
 		rho = rho_n;
 	}
+	return za;
 }
 
-static void vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs)
+// returns the buffer of level l that holds the correction
+static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, double ratio)
 {
 	bp_mg_level& L = mg->lv[l];
 	bp_ctx* M = L.M;
@@ -366,31 +377,50 @@ static void vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs)
 	if (l == nl - 1) {
 		k_mg_dense<<<(mg->nc + 127) / 128, 128, 0, c->stream>>>(mg->nc, mg->d_dense, rhs, M->d_z);
 		c->launches++;
-		return;
+		return M->d_z;
 	}
-	const int deg = std::max(c->prm.pc_degree, 1);
-	const double ratio = std::max(c->prm.pc_eig_ratio, 1.5);
-	cheb_smooth(M, L.lmax, deg, ratio, rhs, true);
+	double* z = cheb_smooth(M, deg, ratio, rhs, M->d_z, M->d_z2, true);
+	double* other = (z == M->d_z) ? M->d_z2 : M->d_z;
 	k_mg_residual<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, M->d_sell_ptr, M->d_col, (const double2*)M->d_val,
-		(const double2*)rhs, (const double2*)M->d_z, (double2*)M->d_io);
+		(const double2*)rhs, (const double2*)z, (double2*)M->d_io);
 	bp_ctx* C = mg->lv[l + 1].M;
 	k_mg_restrict<<<blocks(C->nn_owned, 128), 128, 0, c->stream>>>((int)C->nn_owned, L.d_aggptr, L.d_aggidx, (const double2*)M->d_io, (double2*)C->d_F);
 	c->launches += 2;
-	vcycle(c, mg, l + 1, C->d_F);
-	k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, L.d_agg, (const double2*)C->d_z, (double2*)M->d_z);
+	const double* xc = vcycle(c, mg, l + 1, C->d_F, deg, ratio);
+	k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, L.d_agg, (const double2*)xc, (double2*)z);
 	c->launches++;
-	cheb_smooth(M, L.lmax, deg, ratio, rhs, false);
+	return cheb_smooth(M, deg, ratio, rhs, z, other, false);
 }
 
 // z = M^-1 r with r = c->d_r, z = c->d_z
 int bp_mg_apply(bp_ctx* c)
 {
 	if (!c->mg) return bp_fail(c, BP_ERR_STATE, "multigrid preconditioner not prepared");
-	const int64_t l0 = c->launches;
-	for (size_t l = 1; l < c->mg->lv.size(); ++l) c->mg->lv[l].M->launches = 0;
-	vcycle(c, c->mg, 0, c->d_r);
-	for (size_t l = 1; l < c->mg->lv.size(); ++l) c->launches += c->mg->lv[l].M->launches;
-	(void)l0;
+	bp_mg* mg = c->mg;
+	const int deg = std::max(c->prm.pc_degree, 1);
+	const double ratio = std::max(c->prm.pc_eig_ratio, 1.5);
+	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio)) {
+		cudaGraphExecDestroy(mg->graph);
+		mg->graph = nullptr;
+	}
+	if (!mg->graph) {
+		int64_t l0 = c->launches;
+		for (size_t l = 1; l < mg->lv.size(); ++l) { mg->lv[l].M->launches = 0; mg->lv[l].M->stream = c->stream; }
+		cudaGraph_t g = nullptr;
+		BP_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+		double* out = vcycle(c, mg, 0, c->d_r, deg, ratio);
+		if (out != c->d_z) cudaMemcpyAsync(c->d_z, out, (size_t)2 * c->nn_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+		BP_CUDA(c, cudaStreamEndCapture(c->stream, &g));
+		cudaError_t e = cudaGraphInstantiate(&mg->graph, g, 0);
+		cudaGraphDestroy(g);
+		BP_CUDA(c, e);
+		mg->g_launches = c->launches - l0;
+		for (size_t l = 1; l < mg->lv.size(); ++l) mg->g_launches += mg->lv[l].M->launches;
+		c->launches = l0;
+		mg->g_r = c->d_r; mg->g_z = c->d_z; mg->g_z2 = c->d_z2; mg->g_deg = deg; mg->g_ratio = ratio;
+	}
+	BP_CUDA(c, cudaGraphLaunch(mg->graph, c->stream));
+	c->launches += mg->g_launches;
 	return BP_OK;
 }
 
@@ -409,6 +439,7 @@ void bp_mg_free(bp_ctx* c)
 			delete M;
 		}
 	}
+	if (c->mg->graph) cudaGraphExecDestroy(c->mg->graph);
 	if (c->mg->d_dense) cudaFree(c->mg->d_dense);
 	delete c->mg;
 	c->mg = nullptr;
