@@ -123,3 +123,51 @@ def delaunay_extruded_model(n_pts=60, n_layers=4, seed=3, L=30000.0):
 	X = model.mesh.coordinates()
 	model.init_A(model.rate_factor(252.0 + 15.0 * (1.0 - (X[:, 2] + 400.0) / 900.0)))
 	return model
+
+
+def eismint_dome_model(n=(14, 14, 4), L=750000.0):
+	"""BASELINE config 3 at test size: EISMINT-II-style dome (simulations/eismint_ii/
+	eismint_ii_a.py:50-65, gen_vars.py:7-12): flat bed, beta = 1e9 (frozen), Vialov-type surface
+	clipped to 1 m thickness, non-periodic, use_pressure_bc=False, nodal A(T) from a depth-linear
+	temperature (our synthetic choices)."""
+	mesh = BoxMesh(Point(-L, -L, 0), Point(L, L, 1), *n)
+	model = D3Model(mesh, use_periodic=False)
+	H0, R = 3500.0, 700000.0
+	def S(x, y, z):
+		r = np.minimum(np.sqrt(x ** 2 + y ** 2) / R, 1.0)
+		return np.maximum(H0 * (1.0 - r ** (4.0 / 3.0)) ** (3.0 / 8.0), 1.0)
+	B = lambda x, y, z: 0.0 * x
+	model.calculate_boundaries()
+	model.deform_mesh_to_geometry(S, B)
+	model.init_beta(1e9)
+	X = mesh.coordinates()
+	Sv = model.vertex_field(model.S)
+	Ts = 238.15 + 1.67e-5 * np.sqrt(X[:, 0] ** 2 + X[:, 1] ** 2)
+	depth = np.clip((Sv - X[:, 2]) / np.maximum(Sv, 1.0), 0.0, 1.0)
+	Tm = 273.15 - 9.8e-8 * 910.0 * 9.80665 * Sv
+	model.init_A(model.rate_factor(Ts + (Tm - Ts) * depth))
+	return model
+
+
+def greenland_like_model(n=(12, 16, 4)):
+	"""BASELINE config 4 at test size: an elliptical dome 1200 x 2400 km on a rough bed with a
+	marine margin below sea level (D > 0, dGamma_lt water pressure, relax 0.7), smooth
+	beta in [10, 1e4], nodal A(T) -- entirely synthetic."""
+	Lx, Ly = 600000.0, 1200000.0
+	mesh = BoxMesh(Point(-Lx, -Ly, 0), Point(Lx, Ly, 1), *n)
+	model = D3Model(mesh, use_periodic=False)
+	def S(x, y, z):
+		r2 = np.minimum((x / (0.95 * Lx)) ** 2 + (y / (0.95 * Ly)) ** 2, 1.0)
+		return np.maximum(3200.0 * (1.0 - r2) ** 0.5, 60.0)
+	def B(x, y, z):
+		r2 = (x / Lx) ** 2 + (y / Ly) ** 2
+		return 200.0 * np.sin(7 * x / Lx) * np.cos(5 * y / Ly) - 900.0 * r2 ** 2 - 50.0
+	model.calculate_boundaries()
+	model.deform_mesh_to_geometry(S, B)
+	model.init_beta(lambda x, y, z: 10.0 ** (1.0 + 3.0 * (0.5 + 0.5 * np.sin(4 * x / Lx) * np.cos(3 * y / Ly))))
+	X = mesh.coordinates()
+	Sv = model.vertex_field(model.S)
+	Bv = model.vertex_field(model.B)
+	depth = np.clip((Sv - X[:, 2]) / np.maximum(Sv - Bv, 1.0), 0.0, 1.0)
+	model.init_A(model.rate_factor(243.0 + 28.0 * depth))
+	return model

@@ -420,3 +420,26 @@ def test_unstructured_extruded_mesh_all_paths():
 	assert relerr(c.solve_pressure(uo)[m.node_vertex], P.pressure(uo)) < TOL_U
 	assert relerr(c.solve_vert_velocity(uo)[m.node_vertex], P.vert_velocity(uo, m.vertex_field(m.B))[0]) < 1e-7
 	c.close()
+
+
+@pytest.mark.parametrize('name', ['eismint', 'greenland'])
+def test_baseline_configs_3_and_4_at_test_size(name):
+	"""BASELINE.json configs[2] (EISMINT-II-style dome, thermomechanical A, frozen bed, no
+	lateral pressure) and configs[3] (Greenland-shaped, marine margin, variable beta):
+	assembly parity and a converged Newton velocity against the oracle."""
+	from cases import eismint_dome_model, greenland_like_model
+	m = eismint_dome_model() if name == 'eismint' else greenland_like_model()
+	upb = (name != 'eismint')                                  # eismint_ii_a.py: use_pressure_bc=False
+	P = oracle_problem(m, use_pressure_bc=upb)
+	if name == 'greenland':
+		assert m.N_GAMMA_L_UDR > 0 and (P.D > 0).any()         # water pressure on the lateral boundary is active
+	c = product_context(m, use_pressure_bc=upb, relative_tolerance=1e-10, relaxation_parameter=0.7, maximum_iterations=100, krylov_rtol=1e-12)
+	u = state(P.n_dofs, 91, 5.0)
+	F, J = c.assemble(u, want_F=True, want_J=True)
+	assert relerr(F, P.residual(u)) < TOL_ASM and relerr(J, P.jacobian(u)) < TOL_ASM
+	uo, io = P.newton(rtol=1e-10, relax=0.7, maxit=100)
+	un = np.full(P.n_dofs, 3e-16)
+	st = c.newton_solve(un)
+	assert io['converged'] and st['converged'] and abs(st['iterations'] - io['iterations']) <= 1
+	assert relerr(un, uo) < 1e-7, relerr(un, uo)
+	c.close()
