@@ -45,7 +45,8 @@ class bp_params(C.Structure):
 	            ('verbose', C.c_int32), ('assembly', C.c_int32), ('pc_eig_ratio', C.c_double),
 	            ('n_quad_aux', C.c_int32), ('quad_points_aux', c_f64p), ('quad_weights_aux', c_f64p),
 	            ('energy_dependent', C.c_int32), ('a_T_l', C.c_double), ('a_T_u', C.c_double),
-	            ('Q_T_l', C.c_double), ('Q_T_u', C.c_double), ('R_gas', C.c_double)]
+	            ('Q_T_l', C.c_double), ('Q_T_u', C.c_double), ('R_gas', C.c_double),
+	            ('krylov_norm_preconditioned', C.c_int32), ('mg_smoother', C.c_int32)]
 
 
 class bp_stats(C.Structure):
@@ -253,6 +254,8 @@ class BPContext(object):
 		p.pc_degree = int(d.get('pc_degree', 3 if is_mg else 8))
 		p.pc_eig_ratio = float(d.get('pc_eig_ratio', 6.0 if is_mg else 100.0))
 		p.verbose = int(bool(d.get('verbose', False)))
+		p.krylov_norm_preconditioned = int(d.get('krylov_norm', 'unpreconditioned') == 'preconditioned')
+		p.mg_smoother = {'auto': -1, 'block': 0, 'column': 1}[d.get('mg_smoother', 'auto')]
 		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
 		self._last_params = p
 		return p

@@ -6,8 +6,8 @@
 //     b = F(u); r0 = |b|
 //     while not (|b|/r0 < rtol or |b| < atol) and it < maxit:
 //         assemble J(u); solve J dx = b; u <- u - relax dx; b = F(u)
-// and PETSc KSPCG semantics for the inner solve (zero initial guess, preconditioned
-// residual norm, rtol 1e-5 by default).
+// and a PETSc-KSPCG-like inner solve (zero initial guess, rtol 1e-5 by default; the stopping
+// test is on the true residual norm unless krylov_norm_preconditioned asks for PETSc's default).
 #include "bp_internal.h"
 #include <algorithm>
 #include <cmath>

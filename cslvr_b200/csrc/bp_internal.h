@@ -92,7 +92,8 @@ struct bp_ctx {
 	double  *d_z2 = nullptr, *d_cd = nullptr;   // Chebyshev ping-pong iterate and direction
 	// vertical-line preconditioner: owned nodes grouped by ice column, bottom to top
 	int64_t  n_cols = 0;
-	int32_t  max_layers = 0;
+	int32_t  max_layers = 0, col_touch_max = 4;
+	double   aspect = 1.0;               // median horizontal / vertical extent of the tets
 	int32_t *d_colptr = nullptr, *d_colnode = nullptr, *d_tri_d = nullptr, *d_tri_u = nullptr, *d_tri_l = nullptr;
 	double   cheb_lmax = 0.0;
 	double*  d_dinv = nullptr;           // [nn_owned*4] preconditioner blocks
@@ -146,6 +147,8 @@ void bp_launch_pcg_init2(bp_ctx* c);                       // x = 0, r = b (prec
 void bp_launch_pcg_update2(bp_ctx* c, int par);            // x += alpha p, r -= alpha Ap
 void bp_launch_dots3(bp_ctx* c, int slot, int guard);      // {r.z, z.z, r.r} -> d_sc[slot..]
 void bp_launch_col_solve(bp_ctx* c, const double* r, double* z);
+// Chebyshev step on the column splitting: delta = T^-1 res; d = c1 d + c2 delta; znew = zold + d
+void bp_launch_col_cheb(bp_ctx* c, double c1, double c2, const double* res, const double* zold, double* znew);
 // lmax_dev != nullptr: c0 / c2 are given for lmax = 1 and scaled by 1 / *lmax_dev on the device
 void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z, const double* lmax_dev = nullptr);
 void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew, const double* lmax_dev = nullptr);

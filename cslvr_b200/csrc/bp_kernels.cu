@@ -1025,7 +1025,7 @@ void bp_launch_pc_setup(bp_ctx* c)
 }
 
 // ---------------------------------------------------------------- PCG kernels
-// PETSc KSPCG semantics: zero initial guess, preconditioned residual norm ||z||_2,
+// KSPCG-like: zero initial guess; norm = |r|_2 (default) or PETSc's preconditioned |z|_2,
 // converged when ||z|| <= max(rtol * ||z_0||, atol).
 __device__ __forceinline__ double2 apply_dinv(const double* __restrict__ dinv, int i, double2 r)
 {
@@ -1076,13 +1076,13 @@ k_pcg_update(int nrows, int par, const double* __restrict__ dinv, const double2*
 // the only writer of SC_DONE, and blocks that already see it set skip the same work the
 // others skip because they evaluate the same predicate.
 __global__ void __launch_bounds__(256)
-k_pcg_p(int nrows, int first, int par, double rtol, double atol, const double2* __restrict__ z, double2* p, double* sc)
+k_pcg_p(int nrows, int first, int par, double rtol, double atol, int precond_norm, const double2* __restrict__ z, double2* p, double* sc)
 {
 	if (!first && sc[SC_DONE] != 0.0) return;
 	const double* Told = sc + (par ? SC_T1 : SC_T0);
 	const double* Tnew = first ? sc + SC_T0 : sc + (par ? SC_T0 : SC_T1);
-	const double rz = Told[0], rz_next = Tnew[0], zz = Tnew[1], pAp = sc[SC_PAP];
-	const double norm = sqrt(zz);
+	const double rz = Told[0], rz_next = Tnew[0], pAp = sc[SC_PAP];
+	const double norm = sqrt(precond_norm ? Tnew[1] : Tnew[2]);        // |M^-1 r| or |r|
 	const double norm0 = first ? norm : sc[SC_NORM0];
 	const bool bad = !first && !(pAp > 0.0);
 	const bool conv = bad || !(norm > fmax(rtol * norm0, atol));     // also stops on NaN
@@ -1119,7 +1119,7 @@ void bp_launch_pcg_update(bp_ctx* c, int par)
 void bp_launch_pcg_p(bp_ctx* c, int first, int par)
 {
 	const int n = (int)c->nn_owned;
-	k_pcg_p<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, first, par, c->prm.krylov_rtol, c->prm.krylov_atol, (const double2*)c->d_z, (double2*)c->d_p, c->d_sc);
+	k_pcg_p<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, first, par, c->prm.krylov_rtol, c->prm.krylov_atol, c->prm.krylov_norm_preconditioned, (const double2*)c->d_z, (double2*)c->d_p, c->d_sc);
 	c->launches++;
 }
 
@@ -1228,6 +1228,76 @@ void bp_launch_col_solve(bp_ctx* c, const double* r, double* z)
 {
 	k_col_solve<<<(int)((c->n_cols + 127) / 128), 128, 0, c->stream>>>((int)c->n_cols, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l,
 		c->d_val, (const double2*)r, (double2*)z);
+	c->launches++;
+}
+
+// Chebyshev step with the column (line) splitting: per ice column solve T delta = res with the
+// block Thomas algorithm, then d = c1 d + c2 delta and znew = zold + d (multigrid level-0 smoother).
+// MAXL bounds the column height at compile time so that the eliminated blocks stay in registers.
+template <int MAXL>
+__global__ void __launch_bounds__(128)
+k_col_cheb(int ncol, double c1, double c2, const int32_t* __restrict__ colptr, const int32_t* __restrict__ colnode,
+           const int32_t* __restrict__ tri_d, const int32_t* __restrict__ tri_u, const int32_t* __restrict__ tri_l,
+           const double2* __restrict__ val, const double2* __restrict__ res, const double2* __restrict__ zold,
+           double2* __restrict__ znew, double2* __restrict__ d)
+{
+	const int cidx = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cidx >= ncol) return;
+	const int j0 = colptr[cidx], n = colptr[cidx + 1] - j0;
+	double Di[MAXL][4];
+	double2 rr[MAXL];
+	int nd[MAXL];
+	#pragma unroll
+	for (int k = 0; k < MAXL; ++k) {
+		if (k < n) {
+			const int j = j0 + k;
+			nd[k] = colnode[j];
+			const double2 D01 = val[2 * (size_t)tri_d[j]], D23 = val[2 * (size_t)tri_d[j] + 1];
+			double a = D01.x, b = D01.y, cc = D23.x, dd = D23.y;
+			double2 rv = res[nd[k]];
+			const int sl = tri_l[j], su = (k > 0) ? tri_u[j - 1] : -1;
+			if (k > 0 && sl >= 0 && su >= 0) {
+				const double2 L01 = val[2 * (size_t)sl], L23 = val[2 * (size_t)sl + 1];
+				const double2 U01 = val[2 * (size_t)su], U23 = val[2 * (size_t)su + 1];
+				const double m0 = L01.x * Di[k - 1][0] + L01.y * Di[k - 1][2], m1 = L01.x * Di[k - 1][1] + L01.y * Di[k - 1][3];
+				const double m2 = L23.x * Di[k - 1][0] + L23.y * Di[k - 1][2], m3 = L23.x * Di[k - 1][1] + L23.y * Di[k - 1][3];
+				a -= m0 * U01.x + m1 * U23.x; b -= m0 * U01.y + m1 * U23.y;
+				cc -= m2 * U01.x + m3 * U23.x; dd -= m2 * U01.y + m3 * U23.y;
+				rv.x -= m0 * rr[k - 1].x + m1 * rr[k - 1].y; rv.y -= m2 * rr[k - 1].x + m3 * rr[k - 1].y;
+			}
+			inv2(a, b, cc, dd, Di[k][0], Di[k][1], Di[k][2], Di[k][3]);
+			rr[k] = rv;
+		}
+	}
+	double2 zn = make_double2(0.0, 0.0);
+	#pragma unroll
+	for (int k = MAXL - 1; k >= 0; --k) {
+		if (k < n) {
+			const int j = j0 + k;
+			double2 rv = rr[k];
+			const int su = tri_u[j];
+			if (k < n - 1 && su >= 0) {
+				const double2 U01 = val[2 * (size_t)su], U23 = val[2 * (size_t)su + 1];
+				rv.x -= U01.x * zn.x + U01.y * zn.y; rv.y -= U23.x * zn.x + U23.y * zn.y;
+			}
+			zn = make_double2(Di[k][0] * rv.x + Di[k][1] * rv.y, Di[k][2] * rv.x + Di[k][3] * rv.y);
+			double2 dv = make_double2(c2 * zn.x, c2 * zn.y);
+			if (c1 != 0.0) { const double2 dold = d[nd[k]]; dv.x += c1 * dold.x; dv.y += c1 * dold.y; }
+			d[nd[k]] = dv;
+			if (zold) { const double2 zo = zold[nd[k]]; znew[nd[k]] = make_double2(zo.x + dv.x, zo.y + dv.y); }
+			else znew[nd[k]] = dv;
+		}
+	}
+}
+void bp_launch_col_cheb(bp_ctx* c, double c1, double c2, const double* res, const double* zold, double* znew)
+{
+	const int g = (int)((c->n_cols + 127) / 128);
+	#define COLCHEB(M) k_col_cheb<M><<<g, 128, 0, c->stream>>>((int)c->n_cols, c1, c2, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, \
+		(const double2*)c->d_val, (const double2*)res, (const double2*)zold, (double2*)znew, (double2*)c->d_cd)
+	if (c->max_layers <= 8) COLCHEB(8);
+	else if (c->max_layers <= 16) COLCHEB(16);
+	else if (c->max_layers <= 32) COLCHEB(32);
+	else COLCHEB(64);
 	c->launches++;
 }
 

@@ -35,7 +35,7 @@ struct bp_mg {
 	// the V-cycle is a fixed sequence of ~50 mostly tiny launches: captured once as a CUDA graph
 	cudaGraphExec_t graph = nullptr;
 	const double *g_r = nullptr; double *g_z = nullptr, *g_z2 = nullptr;
-	int g_deg = 0; double g_ratio = 0.0; int64_t g_launches = 0;
+	int g_deg = 0, g_smoother = -1; double g_ratio = 0.0; int64_t g_launches = 0;
 	std::vector<double> h_dense, h_val;
 	int nc = 0;                          // coarsest dofs
 };
@@ -368,6 +368,31 @@ static double* cheb_smooth(bp_ctx* M, int deg, double ratio, const double* r, do
 	return za;
 }
 
+// level-0 line smoother: Chebyshev on the column splitting J = T + N, T = the exact coupling
+// inside every ice column.  lmax(T^-1 J) <= (columns a tet touches) = 3 on extruded meshes
+// (J is a sum of positive semi-definite element matrices), a fixed number: graph-safe.
+static double* col_cheb_smooth(bp_ctx* c, int deg, double ratio, const double* rhs, double* za, double* zb, bool zero_init, int64_t n)
+{
+	const double b = (double)c->col_touch_max, a = b / ratio, theta = 0.5 * (b + a), delta = 0.5 * (b - a), sigma = theta / delta;
+	double rho = 1.0 / sigma;
+	if (zero_init) bp_launch_col_cheb(c, 0.0, 1.0 / theta, rhs, nullptr, za);
+	else {
+		k_mg_residual<<<blocks(n, 256), 256, 0, c->stream>>>((int)n, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, (const double2*)rhs, (const double2*)za, (double2*)c->d_io);
+		c->launches++;
+		bp_launch_col_cheb(c, 0.0, 1.0 / theta, c->d_io, za, zb);
+		std::swap(za, zb);
+	}
+	for (int k = 1; k < deg; ++k) {
+		const double rho_n = 1.0 / (2.0 * sigma - rho);
+		k_mg_residual<<<blocks(n, 256), 256, 0, c->stream>>>((int)n, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, (const double2*)rhs, (const double2*)za, (double2*)c->d_io);
+		c->launches++;
+		bp_launch_col_cheb(c, rho_n * rho, 2.0 * rho_n / delta, c->d_io, za, zb);
+		std::swap(za, zb);
+		rho = rho_n;
+	}
+	return za;
+}
+
 // returns the buffer of level l that holds the correction
 static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, double ratio)
 {
@@ -379,7 +404,11 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 		c->launches++;
 		return M->d_z;
 	}
-	double* z = cheb_smooth(M, deg, ratio, rhs, M->d_z, M->d_z2, true);
+	// line smoother when asked for, or (auto) when the elements are flat: dx >= 3 dz
+	const bool want_line = c->prm.mg_smoother == 1 || (c->prm.mg_smoother < 0 && c->aspect >= 3.0);
+	const bool line = (l == 0) && want_line && c->max_layers <= 64 && c->n_cols < c->nn_owned;
+	double* z = line ? col_cheb_smooth(c, deg, ratio, rhs, M->d_z, M->d_z2, true, L.n)
+	                 : cheb_smooth(M, deg, ratio, rhs, M->d_z, M->d_z2, true);
 	double* other = (z == M->d_z) ? M->d_z2 : M->d_z;
 	k_mg_residual<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, M->d_sell_ptr, M->d_col, (const double2*)M->d_val,
 		(const double2*)rhs, (const double2*)z, (double2*)M->d_io);
@@ -389,7 +418,7 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 	const double* xc = vcycle(c, mg, l + 1, C->d_F, deg, ratio);
 	k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, L.d_agg, (const double2*)xc, (double2*)z);
 	c->launches++;
-	return cheb_smooth(M, deg, ratio, rhs, z, other, false);
+	return line ? col_cheb_smooth(c, deg, ratio, rhs, z, other, false, L.n) : cheb_smooth(M, deg, ratio, rhs, z, other, false);
 }
 
 // z = M^-1 r with r = c->d_r, z = c->d_z
@@ -399,7 +428,7 @@ int bp_mg_apply(bp_ctx* c)
 	bp_mg* mg = c->mg;
 	const int deg = std::max(c->prm.pc_degree, 1);
 	const double ratio = std::max(c->prm.pc_eig_ratio, 1.5);
-	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio)) {
+	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_smoother != c->prm.mg_smoother)) {
 		cudaGraphExecDestroy(mg->graph);
 		mg->graph = nullptr;
 	}
@@ -417,7 +446,7 @@ int bp_mg_apply(bp_ctx* c)
 		mg->g_launches = c->launches - l0;
 		for (size_t l = 1; l < mg->lv.size(); ++l) mg->g_launches += mg->lv[l].M->launches;
 		c->launches = l0;
-		mg->g_r = c->d_r; mg->g_z = c->d_z; mg->g_z2 = c->d_z2; mg->g_deg = deg; mg->g_ratio = ratio;
+		mg->g_r = c->d_r; mg->g_z = c->d_z; mg->g_z2 = c->d_z2; mg->g_deg = deg; mg->g_ratio = ratio; mg->g_smoother = c->prm.mg_smoother;
 	}
 	BP_CUDA(c, cudaGraphLaunch(mg->graph, c->stream));
 	c->launches += mg->g_launches;

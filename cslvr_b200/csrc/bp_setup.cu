@@ -314,6 +314,31 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 			}
 		}
 		c->h_colptr = colptr; c->h_colnode = colnode;
+		{	// largest number of ice columns one tet touches: lmax(T^-1 J) <= that number for the
+			// column-block splitting (J is a sum of positive semi-definite element matrices)
+			std::vector<int32_t> col_of(nn, -1);
+			for (int64_t cc = 0; cc < c->n_cols; ++cc) for (int32_t j = colptr[cc]; j < colptr[cc + 1]; ++j) col_of[colnode[j]] = (int32_t)cc;
+			int mx = 1;
+			for (int64_t t = 0; t < nt; ++t) {
+				int32_t cs[4]; int k = 0;
+				for (int a = 0; a < 4; ++a) { const int32_t q = col_of[cn[t * 4 + a]]; bool seen = false; for (int b = 0; b < k; ++b) seen |= (cs[b] == q); if (!seen) cs[k++] = q; }
+				mx = std::max(mx, k);
+			}
+			c->col_touch_max = mx;
+			// mesh anisotropy: median over (a sample of) the tets of horizontal extent / vertical extent
+			std::vector<double> asp;
+			const int64_t stride = std::max<int64_t>(1, nt / 20000);
+			for (int64_t t = 0; t < nt; t += stride) {
+				double lo3[3] = { 1e300, 1e300, 1e300 }, hi3[3] = { -1e300, -1e300, -1e300 };
+				for (int a = 0; a < 4; ++a) for (int d2 = 0; d2 < 3; ++d2) {
+					const double v = m->coords[3 * (int64_t)m->cells[t * 4 + a] + d2];
+					lo3[d2] = std::min(lo3[d2], v); hi3[d2] = std::max(hi3[d2], v);
+				}
+				asp.push_back(std::max(hi3[0] - lo3[0], hi3[1] - lo3[1]) / std::max(hi3[2] - lo3[2], 1e-300));
+			}
+			std::nth_element(asp.begin(), asp.begin() + asp.size() / 2, asp.end());
+			c->aspect = asp[asp.size() / 2];
+		}
 		UP(c->d_colptr, colptr.data(), colptr.size());
 		UP(c->d_colnode, colnode.data(), no);
 		UP(c->d_tri_d, tri_d.data(), no);

@@ -138,6 +138,13 @@ typedef struct {
 	 * the quadrature points instead of the P1 field A (constants cslvr/model.py:275-285, 263)   */
 	int32_t energy_dependent;
 	double  a_T_l, a_T_u, Q_T_l, Q_T_u, R_gas;
+	/* CG stopping test: 0 = true residual |r|_2 <= max(rtol |b|_2, atol) (default: the Newton
+	 * step is then resolved to rtol whatever the preconditioner), 1 = PETSc's default
+	 * preconditioned norm |M^-1 r|_2 (only safe with a spectrally tight preconditioner)         */
+	int32_t krylov_norm_preconditioned;
+	int32_t mg_smoother;       /* BP_PC_MG level 0: 0 = Chebyshev on 2x2 node blocks, 1 = Chebyshev on exact
+	                              ice-column solves (line smoother), -1 = line iff the tets are flat
+	                              (median horizontal/vertical extent >= 3; default)              */
 } bp_params;
 
 typedef struct {

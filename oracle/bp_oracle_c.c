@@ -190,8 +190,8 @@ void bpo_assemble_facets(int64_t nf, const int32_t* fcell, const int32_t* flocal
 	}
 }
 
-/* y = A x (CSR) and Jacobi-preconditioned CG with PETSc-like stopping (preconditioned
- * residual norm, zero initial guess): the Krylov part of cslvr/physics.py:673-678.    */
+/* y = A x (CSR) and Jacobi-preconditioned CG (zero initial guess, stop on the true residual
+ * norm): the Krylov part of cslvr/physics.py:673-678.                                  */
 void bpo_spmv(int64_t n, const int64_t* indptr, const int32_t* indices, const double* v, const double* x, double* y)
 {
 	#pragma omp parallel for schedule(static)
@@ -221,7 +221,7 @@ int bpo_pcg_jacobi(int64_t n, const int64_t* indptr, const int32_t* indices, con
 		dinv[i] = 1.0 / d; x[i] = 0.0; r[i] = b[i]; z[i] = dinv[i] * r[i]; p[i] = z[i];
 	}
 	double rz = dotp(n, r, z);
-	const double norm0 = sqrt(dotp(n, z, z));
+	const double norm0 = sqrt(dotp(n, r, r));          /* true residual norm, as the product */
 	if (!(norm0 > atol)) return 0;
 	int it = 0;
 	while (it < maxit) {
@@ -229,7 +229,7 @@ int bpo_pcg_jacobi(int64_t n, const int64_t* indptr, const int32_t* indices, con
 		const double alpha = rz / dotp(n, p, Ap);
 		#pragma omp parallel for schedule(static)
 		for (int64_t i = 0; i < n; ++i) { x[i] += alpha * p[i]; r[i] -= alpha * Ap[i]; z[i] = dinv[i] * r[i]; }
-		const double rz1 = dotp(n, r, z), nz = sqrt(dotp(n, z, z));
+		const double rz1 = dotp(n, r, z), nz = sqrt(dotp(n, r, r));
 		++it;
 		if (!(nz > fmax(rtol * norm0, atol))) break;
 		const double bt = rz1 / rz;
