@@ -12,7 +12,7 @@ import numpy as np
 from . import _build
 
 BP_OK, BP_ERR_ARG, BP_ERR_CUDA, BP_ERR_STATE, BP_ERR_COMM, BP_ERR_NONCONV = range(6)
-FIELD_S, FIELD_A, FIELD_BETA, FIELD_B, FIELD_B_RING, FIELD_TP, FIELD_W, FIELD_E = range(8)
+FIELD_S, FIELD_A, FIELD_BETA, FIELD_B, FIELD_B_RING, FIELD_TP, FIELD_W, FIELD_E, FIELD_UZ = range(9)
 ASSEMBLE_F, ASSEMBLE_J = 1, 2
 PC = {'none': 0, 'jacobi': 1, 'block_jacobi': 2, 'chebyshev': 3, 'column': 4, 'mg': 5}
 
@@ -46,7 +46,8 @@ class bp_params(C.Structure):
 	            ('n_quad_aux', C.c_int32), ('quad_points_aux', c_f64p), ('quad_weights_aux', c_f64p),
 	            ('energy_dependent', C.c_int32), ('a_T_l', C.c_double), ('a_T_u', C.c_double),
 	            ('Q_T_l', C.c_double), ('Q_T_u', C.c_double), ('R_gas', C.c_double),
-	            ('krylov_norm_preconditioned', C.c_int32), ('mg_smoother', C.c_int32)]
+	            ('krylov_norm_preconditioned', C.c_int32), ('mg_smoother', C.c_int32),
+	            ('reduced_stokes', C.c_int32)]
 
 
 class bp_stats(C.Structure):
@@ -73,7 +74,8 @@ SYMBOLS = ['bp_create', 'bp_destroy', 'bp_last_error', 'bp_set_params', 'bp_set_
            'bp_set_field', 'bp_get_sizes', 'bp_csr_pattern', 'bp_assemble', 'bp_spmv',
            'bp_krylov_solve', 'bp_newton_solve', 'bp_time_assemble', 'bp_time_spmv',
            'bp_launch_count', 'bp_comm_unique_id', 'bp_comm_init',
-           'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity', 'bp_linear_solve']
+           'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity', 'bp_linear_solve',
+           'bp_rs_newton_solve', 'bp_rs_solve_pressure']
 
 _lib = None
 
@@ -106,6 +108,8 @@ def load_library():
 	lib.bp_linear_solve.argtypes = [vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_solve_pressure.argtypes = [vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_solve_vert_velocity.argtypes = [vp, vp, vp, C.c_int, c_i32p]
+	lib.bp_rs_newton_solve.argtypes = [vp, vp, vp, C.c_int, C.c_double, C.c_int, C.POINTER(bp_stats)]
+	lib.bp_rs_solve_pressure.argtypes = [vp, vp, vp, vp, C.c_int, c_i32p]
 	lib.bp_time_assemble.argtypes = [vp, C.c_int, C.c_int, C.c_int, c_f64p]
 	lib.bp_time_spmv.argtypes = [vp, C.c_int, C.c_int, c_f64p]
 	lib.bp_launch_count.argtypes = [vp]
@@ -257,6 +261,7 @@ class BPContext(object):
 		p.krylov_norm_preconditioned = int(d.get('krylov_norm', 'unpreconditioned') == 'preconditioned')
 		p.mg_smoother = {'auto': -1, 'block': 0, 'column': 1}[d.get('mg_smoother', 'auto')]
 		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
+		p.reduced_stokes = int(bool(d.get('reduced_stokes', False)))
 		self._last_params = p
 		return p
 
@@ -418,6 +423,41 @@ class BPContext(object):
 		self._check(self.lib.bp_solve_vert_velocity(self.h, pu, pz, dev, C.byref(it)))
 		self.last_vert_iterations = it.value
 		return uz
+
+	def rs_newton_solve(self, u, uz=None, atol=1e-6, callback=True):
+		"""``Model.home_rolled_newton_method`` with ``solve_vert_velocity`` as the callback
+		(MomentumDukowiczStokesReduced.solve): in place on ``u`` and on ``uz`` (per-vertex
+		u_z: start value in, last callback's value out; None keeps the context's field)."""
+		if not _is_torch(u) and not (isinstance(u, np.ndarray) and u.dtype == np.float64 and u.flags.c_contiguous):
+			raise ValueError("u must be a contiguous float64 numpy array or a torch tensor (updated in place)")
+		if uz is not None and not _is_torch(uz) and not (isinstance(uz, np.ndarray) and uz.dtype == np.float64 and uz.flags.c_contiguous):
+			raise ValueError("uz must be a contiguous float64 numpy array or a torch tensor (updated in place)")
+		pu, dev, ku = _ptr(u)
+		pz, _, kz = _ptr(uz)
+		st = bp_stats()
+		rc = self._check(self.lib.bp_rs_newton_solve(self.h, pu, pz, dev, float(atol), int(bool(callback)), C.byref(st)),
+		                 allow=(BP_ERR_NONCONV,))
+		d = st.as_dict()
+		d['residuals'] = d['residuals'][:d['iterations']]
+		if rc == BP_ERR_NONCONV:
+			raise BPError(rc, self.lib.bp_last_error(self.h).decode())
+		return d
+
+	def rs_solve_pressure(self, u, u_model, p=None):
+		"""pressure with the viscosity of ``u_model`` (+ the context's u_z) and the divergence of ``u``."""
+		pu, dev, ku = _ptr(u)
+		pm, _, km = _ptr(u_model)
+		if p is None:
+			if dev:
+				import torch
+				p = torch.empty(self.n_vertices, dtype=torch.float64, device=ku.device)
+			else:
+				p = np.empty(self.n_vertices)
+		pp, _, kp = _ptr(p)
+		it = C.c_int32()
+		self._check(self.lib.bp_rs_solve_pressure(self.h, pu, pm, pp, dev, C.byref(it)))
+		self.last_projection_iterations = it.value
+		return p
 
 	def time_assemble(self, what=ASSEMBLE_F | ASSEMBLE_J, repeats=20, flush_l2=True):
 		ms = C.c_double()

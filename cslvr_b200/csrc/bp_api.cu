@@ -311,7 +311,7 @@ void bp_destroy(bp_ctx* c)
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_val, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
-		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
+		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -374,6 +374,9 @@ int bp_set_field(bp_ctx* c, int field, const double* values, int64_t nvals, int 
 		c->have_B = true; break;
 	case BP_FIELD_B_RING:
 		BP_CUDA(c, cudaMemcpyAsync(c->d_Bring, values, nvals * sizeof(double), kind, c->stream));
+		break;
+	case BP_FIELD_UZ:
+		BP_CUDA(c, cudaMemcpyAsync(c->d_uz, values, nvals * sizeof(double), kind, c->stream));
 		break;
 	default:
 		return bp_fail(c, BP_ERR_ARG, "bp_set_field: unknown field %d", field);
@@ -539,7 +542,7 @@ int bp_linear_solve(bp_ctx* c, const double* u_lin, double* u_out, int on_device
 	return BP_OK;
 }
 
-int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_device, int32_t* iterations)
+static int solve_pressure_impl(bp_ctx* c, const double* u, const double* u_model, double* p_vertex, int on_device, int32_t* iterations)
 {
 	if (!c || !u || !p_vertex) return BP_ERR_ARG;
 	BP_CUDA(c, cudaSetDevice(c->device));
@@ -549,10 +552,15 @@ int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_devic
 		return bp_fail(c, BP_ERR_STATE, "bp_solve_pressure needs the row-gather assembly path");
 	if (c->prm.energy_dependent)
 		return bp_fail(c, BP_ERR_STATE, "bp_solve_pressure with the energy-dependent rate factor is not available yet");
-	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
 	bp_ctx* cs[1] = { c };
+	if (u_model) {                        // viscosity state of the reduced-Stokes solve(): per-vertex copy in d_uvert2
+		if (c->comm || c->nn != c->nn_owned) return bp_fail(c, BP_ERR_STATE, "bp_rs_solve_pressure runs on unpartitioned contexts only");
+		if ((rc = vec_in(c, u_model, on_device, c->d_u))) return rc;
+		bp_launch_expand_to_vertex(c, c->d_u, c->d_uvert2);
+	}
+	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
 	if ((rc = bp_comm_halo(cs, 1, 0))) return rc;
-	bp_launch_rows_aux(c, 0);
+	bp_launch_rows_aux(c, 0, u_model ? (const double2*)c->d_uvert2 : nullptr, c->prm.reduced_stokes ? c->d_uz : nullptr);
 	c->have_J = false;
 	// mass-matrix solve: block-Jacobi PCG to 1e-13 (dolfin's project() uses a direct solver)
 	const bp_params saved = c->prm;
@@ -571,17 +579,26 @@ int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_devic
 	return BP_OK;
 }
 
-int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on_device, int32_t* iterations)
+int bp_solve_pressure(bp_ctx* c, const double* u, double* p_vertex, int on_device, int32_t* iterations)
 {
-	if (!c || !u || !uz_vertex) return BP_ERR_ARG;
-	BP_CUDA(c, cudaSetDevice(c->device));
-	int rc = ready(c);
-	if (rc) return rc;
+	return solve_pressure_impl(c, u, nullptr, p_vertex, on_device, iterations);
+}
+
+int bp_rs_solve_pressure(bp_ctx* c, const double* u, const double* u_model, double* p_vertex, int on_device, int32_t* iterations)
+{
+	if (!c || !u_model) return BP_ERR_ARG;
+	if (!c->prm.reduced_stokes) return bp_fail(c, BP_ERR_STATE, "bp_rs_solve_pressure: bp_params.reduced_stokes is not set");
+	return solve_pressure_impl(c, u, u_model, p_vertex, on_device, iterations);
+}
+
+// u_z from d_u (cslvr/momentumbp.py:231-253); the result is left per node in d_dx[2*i] (ghosts filled)
+static int vert_velocity_core(bp_ctx* c, int32_t* iterations)
+{
+	int rc;
 	if (!c->have_B) return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity: BP_FIELD_B (bed height) not set");
 	if (c->max_layers > 64) return bp_fail(c, BP_ERR_ARG, "bp_solve_vert_velocity supports at most 64 nodes per ice column");
 	if (c->prm.assembly == BP_ASM_SCATTER || (size_t)4 * c->max_row * 128 * sizeof(double) > 200 * 1024)
 		return bp_fail(c, BP_ERR_STATE, "bp_solve_vert_velocity needs the row-gather assembly path");
-	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
 	bp_ctx* cs[1] = { c };
 	if ((rc = bp_comm_halo(cs, 1, 0))) return rc;
 	// 1. u_z_b = project(kinematic basal condition, Q): mass-matrix PCG
@@ -647,12 +664,99 @@ int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on
 		return bp_fail(c, BP_ERR_NONCONV, "u_z solve: BiCGStab stopped at relative residual %.3e after %d iterations", std::sqrt(rnorm2 / bnorm2), it);
 	if (iterations) *iterations = it;
 	if ((rc = bp_comm_halo(cs, 1, 5))) return rc;                 // x is d_dx: ghost nodes get their owner's value
+	return BP_OK;
+}
+
+int bp_solve_vert_velocity(bp_ctx* c, const double* u, double* uz_vertex, int on_device, int32_t* iterations)
+{
+	if (!c || !u || !uz_vertex) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = ready(c);
+	if (rc) return rc;
+	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
+	if ((rc = vert_velocity_core(c, iterations))) return rc;
 	double* out = on_device ? uz_vertex : c->d_io;
-	bp_launch_node_to_vertex(c, x, 0, out);
+	bp_launch_node_to_vertex(c, c->d_dx, 0, out);
 	if (!on_device) BP_CUDA(c, cudaMemcpyAsync(uz_vertex, c->d_io, (size_t)c->nv * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
 	BP_CUDA(c, cudaStreamSynchronize(c->stream));
 	BP_CUDA(c, cudaGetLastError());
 	return BP_OK;
+}
+
+// ---- MomentumDukowiczStokesReduced.solve: Model.home_rolled_newton_method (cslvr/model.py:2676-2729)
+int bp_rs_newton_solve(bp_ctx* c, double* u, double* uz_vertex, int on_device, double atol, int run_callback, bp_stats* st)
+{
+	if (!c || !u) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	int rc = ready(c);
+	if (rc) return rc;
+	if (!c->prm.reduced_stokes) return bp_fail(c, BP_ERR_STATE, "bp_rs_newton_solve: bp_params.reduced_stokes is not set");
+	if (c->comm || c->nn != c->nn_owned) return bp_fail(c, BP_ERR_STATE, "bp_rs_newton_solve runs on unpartitioned contexts only");
+	if (run_callback && !c->have_B) return bp_fail(c, BP_ERR_STATE, "bp_rs_newton_solve: BP_FIELD_B (bed height) not set");
+	const bp_params& P = c->prm;
+	bp_stats s;
+	memset(&s, 0, sizeof(s));
+	const int64_t l0 = c->launches;
+	if (uz_vertex)
+		BP_CUDA(c, cudaMemcpyAsync(c->d_uz, uz_vertex, (size_t)c->nv * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
+	bp_ctx* cs[1] = { c };
+	cudaEvent_t eA, eB, eT0, eT1;
+	cudaEventCreate(&eA); cudaEventCreate(&eB); cudaEventCreate(&eT0); cudaEventCreate(&eT1);
+	float ms;
+	cudaEventRecord(eT0, c->stream);
+	double rn = 0.0, r0 = 0.0;
+	while (!s.converged && s.newton_iterations < P.newton_maxit) {
+		// A, b = assemble_system(J, -R): the residual and the Jacobian at the current (u, u_z)
+		cudaEventRecord(eA, c->stream);
+		rc = group_assemble(cs, 1, BP_ASSEMBLE_F | BP_ASSEMBLE_J);
+		cudaEventRecord(eB, c->stream);
+		if (rc) break;
+		cudaEventSynchronize(eB); cudaEventElapsedTime(&ms, eA, eB); s.t_assemble_ms += ms; s.n_assemblies++;
+		if ((rc = group_norm_F(cs, 1, &rn))) break;
+		if (!std::isfinite(rn)) { rc = bp_fail(c, BP_ERR_STATE, "residual became non-finite at Newton iteration %d", s.newton_iterations); break; }
+		if (s.newton_iterations == 0) { r0 = rn; s.residual_norm0 = rn; }
+		if (s.newton_iterations < 64) s.residual_history[s.newton_iterations] = rn;
+		// solve(A, d, b): d = -J^-1 R; the step is taken in the converging iteration as well
+		int kit = 0;
+		if (rn > 0.0) {
+			cudaEventRecord(eA, c->stream);
+			rc = group_pcg(cs, 1, &kit, nullptr);
+			cudaEventRecord(eB, c->stream);
+			cudaEventSynchronize(eB); cudaEventElapsedTime(&ms, eA, eB); s.t_krylov_ms += ms;
+			if (rc) break;
+			s.krylov_iterations += kit;
+			bp_launch_axpy(c, -P.newton_relax, c->d_dx, c->d_u);
+		}
+		s.converged = (rn < atol) || (r0 > 0.0 && rn / r0 < P.newton_rtol);
+		s.newton_iterations++;
+		if (P.verbose)
+			printf("Newton iteration %d: r (abs) = %.3e (tol = %.3e) r (rel) = %.3e (tol = %.3e)  [krylov %d]\n",
+			       s.newton_iterations, rn, atol, r0 > 0.0 ? rn / r0 : 0.0, P.newton_rtol, kit);
+		if (run_callback) {            // cb_ftn = solve_vert_velocity (momentumstokes.py:468)
+			if ((rc = vert_velocity_core(c, nullptr))) break;
+			bp_launch_node_to_vertex(c, c->d_dx, 0, c->d_uz);
+		}
+	}
+	s.residual_norm = rn;
+	if (!rc && !s.converged && P.error_on_nonconvergence)
+		rc = bp_fail(c, BP_ERR_NONCONV, "Newton solver did not converge in %d iterations (|F| = %.3e)", s.newton_iterations, rn);
+	cudaEventRecord(eT1, c->stream);
+	cudaEventSynchronize(eT1);
+	cudaEventElapsedTime(&ms, eT0, eT1);
+	s.t_total_ms = ms;
+	cudaEventDestroy(eA); cudaEventDestroy(eB); cudaEventDestroy(eT0); cudaEventDestroy(eT1);
+	s.gpu_launches = (int32_t)(c->launches - l0);
+	if (st) *st = s;
+	if (rc && rc != BP_ERR_NONCONV) return rc;
+	int rc2 = vec_out(c, c->d_u, u, on_device);
+	if (rc2) return rc2;
+	if (uz_vertex)
+		BP_CUDA(c, cudaMemcpyAsync(uz_vertex, c->d_uz, (size_t)c->nv * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	c->have_J = false;
+	return rc;
 }
 
 // ---- timing on the context's stream with CUDA events -------------------------

@@ -61,6 +61,8 @@ struct bp_ctx {
 	double*  d_ainv = nullptr;           // [nt] sum_q w_q A_q^(-1/n) per tet (k_tet_ainv)
 	bool     ainv_dirty = true, have_Tp = false, smem_attr_set = false;
 	double  *d_Bv = nullptr, *d_Bring = nullptr;   // bed height / basal melt per vertex (u_z solve only)
+	double*  d_uz = nullptr;             // frozen vertical velocity per vertex (reduced-Stokes model, BP_FIELD_UZ)
+	double*  d_uvert2 = nullptr;         // [2*nv] second per-vertex velocity (viscosity state of bp_rs_solve_pressure)
 	uint8_t* d_bcnode = nullptr;         // owned node lies on a basal facet (Dirichlet dof of the u_z system)
 	double*  d_aux = nullptr;            // [2*nn] u_z_b per node
 	int4*    d_tets = nullptr;
@@ -75,7 +77,7 @@ struct bp_ctx {
 	double*  d_soa = nullptr;            // [4][nv] x | y | z | S (struct-of-arrays copy of d_geo)
 	int32_t  max_row = 0;                // longest block row
 	int32_t* d_fac_cell = nullptr;       // [nf]
-	int32_t* d_fac_info = nullptr;       // [nf] local facet | basal<<8 | pressure<<9
+	int32_t* d_fac_info = nullptr;       // [nf] local facet | basal<<8 | pressure<<9 | grounded<<10
 	int32_t* d_ext_dof = nullptr;        // nullptr when identity
 	// device: resident Jacobian, BSR 2x2, owned rows
 	int32_t* d_sell_ptr = nullptr;       // [slices+1] first slot of every 32-row slice
@@ -156,7 +158,8 @@ void bp_launch_apply_dinv(bp_ctx* c, double* v);           // v <- D^-1 v
 void bp_launch_scale_inv_norm(bp_ctx* c, double* v, int sc_slot);   // v <- v / sqrt(d_sc[slot])
 void bp_launch_fill_probe(bp_ctx* c, double* v);
 void bp_launch_gershgorin(bp_ctx* c, int sc_slot);
-void bp_launch_rows_aux(bp_ctx* c, int kind);              // projection systems (mass matrix + rhs) -> d_val, d_F
+void bp_launch_rows_aux(bp_ctx* c, int kind, const double2* u_eta_vertex = nullptr, const double* uz_vertex = nullptr);              // projection systems (mass matrix + rhs) -> d_val, d_F
+void bp_launch_expand_to_vertex(bp_ctx* c, const double* node_vec2, double* vertex_vec2);   // [2*node+c] -> [2*vertex+c]
 void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out);
 void bp_launch_col_gtsv(bp_ctx* c, const double* r, double* z);   // scalar pivoted tridiagonal solve per column
 void bp_launch_lincomb(bp_ctx* c, double* out, double a, const double* x, double b, const double* y, double cc, const double* z);        // upper bound of lmax(D^-1 J) -> d_sc[slot]

@@ -21,6 +21,7 @@ struct AsmParams {
 	int    n_quad;
 	int    n_is_3;
 	int    picard;      // linear=True: viscosity frozen at the given state, no eta' term, F = u-independent part
+	int    rs;          // MomentumDukowiczStokesReduced: u_z in the strain rate, u_z_b in the sliding term
 };
 
 #define TPB 128
@@ -86,7 +87,8 @@ __global__ void __launch_bounds__(TPB)
 k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
        const int32_t* __restrict__ v2n, const double2* __restrict__ u,
        const double* __restrict__ Av, const int32_t* __restrict__ tet_blk,
-       int nn_owned, double* __restrict__ F, double* __restrict__ val, AsmParams P)
+       int nn_owned, double* __restrict__ F, double* __restrict__ val, AsmParams P,
+       const double* __restrict__ uzv)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= nt) return;
@@ -129,6 +131,12 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 		g10 += uu[a].y * X[a]; g11 += uu[a].y * Y[a]; g12 += uu[a].y * Z[a];
 		sx += p[a].w * X[a]; sy += p[a].w * Y[a];
 	}
+	double wx = 0.0, wy = 0.0;
+	if (P.rs) {   // eps_02 = (u_x,z + u_z,x)/2, eps_12 = (u_y,z + u_z,y)/2 (cslvr/momentumstokes.py:406-418)
+		#pragma unroll
+		for (int a = 0; a < 4; ++a) { const double w = uzv[vid[a]]; wx += w * X[a]; wy += w * Y[a]; }
+		g02 += wx; g12 += wy;
+	}
 	const double sh = 0.5 * (g01 + g10);
 	const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
 	// 2 eta = ed^((1-n)/(2n)),  2 eta' = (1-n)/(2n) ed^((1-n)/(2n) - 1)
@@ -155,9 +163,11 @@ k_cell(int nt, const int4* __restrict__ tets, const double4* __restrict__ geo,
 		#pragma unroll
 		for (int a = 0; a < 4; ++a) {
 			if (nd[a] < nn_owned) {
-				const double af = P.picard ? 0.0 : alpha;
-				atomicAdd(&F[2 * nd[a]], af * dx[a] + grav * sx);
-				atomicAdd(&F[2 * nd[a] + 1], af * dy[a] + grav * sy);
+				// linear=True keeps the u-independent part: gravity and, in the reduced-Stokes model, the u_z part of d(epsdot)
+				const double fx = P.picard ? alpha * 0.5 * wx * Z[a] : alpha * dx[a];
+				const double fy = P.picard ? alpha * 0.5 * wy * Z[a] : alpha * dy[a];
+				atomicAdd(&F[2 * nd[a]], fx + grav * sx);
+				atomicAdd(&F[2 * nd[a] + 1], fy + grav * sy);
 			}
 		}
 	}
@@ -283,14 +293,14 @@ void bp_launch_proxy(bp_ctx* c)
 // reproducible.  The price is that the cell-constant part of a tet is recomputed by
 // each of its four nodes.
 #define RTPB 128
-template <bool WANT_F, bool WANT_J>
+template <bool WANT_F, bool WANT_J, bool RS>
 __global__ void __launch_bounds__(RTPB)
 k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restrict__ inc_code,
        const uint32_t* __restrict__ inc_pos, const int32_t* __restrict__ inc_v, size_t nslot,
        const double* __restrict__ soa, size_t nv,
        const double2* __restrict__ u /* per VERTEX */, const double* __restrict__ Av,
        const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
-       double* __restrict__ F, double* __restrict__ val, AsmParams P)
+       double* __restrict__ F, double* __restrict__ val, AsmParams P, const double* __restrict__ uzv)
 {
 	extern __shared__ double acc[];                  // [4*max_row][RTPB]
 	const int tid = threadIdx.x;
@@ -314,6 +324,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	int code1 = -1;
 	double4 p[4];
 	double2 uu[4];
+	double ww[4] = { 0.0, 0.0, 0.0, 0.0 };           // u_z at the vertices (reduced-Stokes model only)
 	double ai = 0.0;                                 // sum_q w_q A_q^(-1/n) of the tet (k_tet_ainv)
 	if (code >= 0) {
 		pk = inc_pos[e];
@@ -329,6 +340,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		for (int j = 0; j < 4; ++j) {
 			p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
 			uu[j] = u[vid[j]];
+			if (RS) ww[j] = uzv[vid[j]];
 		}
 		ai = Av[code >> 2];
 	}
@@ -368,12 +380,19 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 			g10 += uu[j].y * X[j]; g11 += uu[j].y * Y[j]; g12 += uu[j].y * Z[j];
 			sx += p[j].w * X[j]; sy += p[j].w * Y[j];
 		}
+		double wx = 0.0, wy = 0.0;
+		if (RS) {   // eps_02 = (u_x,z + u_z,x)/2, eps_12 = (u_y,z + u_z,y)/2 (cslvr/momentumstokes.py:406-418)
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) { wx += ww[j] * X[j]; wy += ww[j] * Y[j]; }
+			g02 += wx; g12 += wy;
+		}
 		// raw vertex data of this incidence is consumed: request the next incidence's
 		if (code_n >= 0) {
 			#pragma unroll
 			for (int j = 0; j < 4; ++j) {
 				p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
 				uu[j] = u[vid[j]];
+				if (RS) ww[j] = uzv[vid[j]];
 			}
 			ai = Av[code_n >> 2];
 		}
@@ -394,9 +413,9 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		const double dy0 = cyy * Y[0] + sh * X[0] + hz1 * Z[0];
 		if (WANT_F) {
 			const double grav = P.rho_g * vol * 0.25;
-			const double af = P.picard ? 0.0 : alpha;
-			Fx += af * dx0 + grav * sx;
-			Fy += af * dy0 + grav * sy;
+			// linear=True keeps the u-independent part: gravity and, in the reduced-Stokes model, the u_z part of d(epsdot)
+			Fx += (P.picard ? alpha * 0.5 * wx * Z[0] : alpha * dx0) + grav * sx;
+			Fy += (P.picard ? alpha * 0.5 * wy * Z[0] : alpha * dy0) + grav * sy;
 		}
 		if (WANT_J) {
 			const double Pa = 2.0 * alpha * X[0], Qa = 0.5 * alpha * Y[0], Ra = 0.5 * alpha * Z[0];
@@ -455,7 +474,8 @@ k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __re
            const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
            double* __restrict__ F, double* __restrict__ val, AsmParams P, int nq,
            const double* __restrict__ Bv, const double* __restrict__ Bring,
-           const double2* __restrict__ uzb, const uint8_t* __restrict__ bcnode)
+           const double2* __restrict__ uzb, const uint8_t* __restrict__ bcnode,
+           const double2* __restrict__ u_eta, const double* __restrict__ uzv)
 {
 	extern __shared__ double acc[];                  // [max_row][RTPB]
 	const int tid = threadIdx.x;
@@ -525,11 +545,17 @@ k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __re
 			kd = (int)(pk & 255);                                     // position of the diagonal block in the row
 		}
 		if (KIND == 0) {
-			double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0;
+			// viscosity state: u itself (BP: model.u was just updated) or, for the reduced-Stokes solve(), the
+			// velocity the model still holds plus the frozen u_z (bp_rs_solve_pressure)
+			double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, div = 0;
 			#pragma unroll
 			for (int j = 0; j < 4; ++j) {
-				g00 += uu[j].x * X[j]; g01 += uu[j].x * Y[j]; g02 += uu[j].x * Z[j];
-				g10 += uu[j].y * X[j]; g11 += uu[j].y * Y[j]; g12 += uu[j].y * Z[j];
+				const int v = inc_v[j * nslot + e];
+				const double2 ue = u_eta ? u_eta[v] : uu[j];
+				const double w = uzv ? uzv[v] : 0.0;
+				g00 += ue.x * X[j]; g01 += ue.x * Y[j]; g02 += ue.x * Z[j] + w * X[j];
+				g10 += ue.y * X[j]; g11 += ue.y * Y[j]; g12 += ue.y * Z[j] + w * Y[j];
+				div += uu[j].x * X[j] + uu[j].y * Y[j];
 			}
 			const double sh = 0.5 * (g01 + g10);
 			const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
@@ -547,7 +573,7 @@ k_rows_aux(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __re
 				}
 			}
 			const double sz0 = p[0].w - p[0].z, szs = sz0 + (p[1].w - p[1].z) + (p[2].w - p[2].z) + (p[3].w - p[3].z);
-			rhs += P.rho_g * m * (szs + sz0) - (g00 + g11) * two_eta_e * vol * wq;
+			rhs += P.rho_g * m * (szs + sz0) - div * two_eta_e * vol * wq;
 		}
 	}
 	if (KIND == 2 && bcnode[i]) {                  // DirichletBC row: identity, value u_z_b
@@ -577,13 +603,15 @@ k_facet(int nf, int nt, const int32_t* __restrict__ fcell, const int32_t* __rest
         const int4* __restrict__ tets, const double4* __restrict__ geo,
         const int32_t* __restrict__ v2n, const double2* __restrict__ u,
         const double* __restrict__ beta, const int32_t* __restrict__ tet_blk,
-        int nn_owned, double* __restrict__ F, double* __restrict__ val, AsmParams P)
+        int nn_owned, double* __restrict__ F, double* __restrict__ val, AsmParams P,
+        const double* __restrict__ Bring)
 {
 	const int f = blockIdx.x * blockDim.x + threadIdx.x;
 	if (f >= nf) return;
 	const int cell = fcell[f], info = finfo[f];
 	const int lf = info & 0xff;
-	const bool basal = (info >> 8) & 1, press = (info >> 9) & 1;
+	// sliding: dGamma_b (markers 3, 5) for the BP classes, dGamma_bg (3) for the reduced-Stokes model (momentumstokes.py:381)
+	const bool basal = P.rs ? ((info >> 10) & 1) : ((info >> 8) & 1), press = (info >> 9) & 1;
 	const int4 tv = tets[cell];
 	const int vid[4] = { tv.x, tv.y, tv.z, tv.w };
 	int la[3], k = 0;
@@ -592,11 +620,12 @@ k_facet(int nf, int nt, const int32_t* __restrict__ fcell, const int32_t* __rest
 	double4 p[3];
 	int nd[3];
 	double2 uu[3];
-	double bt[3];
+	double bt[3], br[3] = { 0.0, 0.0, 0.0 };
 	#pragma unroll
 	for (int a = 0; a < 3; ++a) {
 		const int v = vid[la[a]];
 		p[a] = geo[v]; nd[a] = v2n ? v2n[v] : v; uu[a] = u[nd[a]]; bt[a] = beta[v];
+		if (P.rs) br[a] = Bring[v];
 	}
 	const double4 po = geo[vid[lf]];
 	const double ax = p[1].x - p[0].x, ay = p[1].y - p[0].y, az = p[1].z - p[0].z;
@@ -607,7 +636,7 @@ k_facet(int nf, int nt, const int32_t* __restrict__ fcell, const int32_t* __rest
 	// outward: away from the opposite vertex
 	const double side = nx * (po.x - p[0].x) + ny * (po.y - p[0].y) + nz * (po.z - p[0].z);
 	const double sgn = (side > 0.0 ? -1.0 : 1.0) / nrm;
-	nx *= sgn; ny *= sgn;
+	nx *= sgn; ny *= sgn; nz *= sgn;
 
 	double Fx[3] = { 0, 0, 0 }, Fy[3] = { 0, 0, 0 };
 	if (basal) {
@@ -620,14 +649,22 @@ k_facet(int nf, int nt, const int32_t* __restrict__ fcell, const int32_t* __rest
 			for (int b = 0; b < 3; ++b)
 				K[a][b] = (a == b) ? area * (bt[a] * (1.0 / 10.0) + (bs - bt[a]) * (1.0 / 30.0))
 				                   : area * ((bt[a] + bt[b]) * (1.0 / 30.0) + (bs - bt[a] - bt[b]) * (1.0 / 60.0));
+		// reduced-Stokes: 1/2 beta u_z_b^2 with u_z_b = (-B_ring - u_h.n_h)/n_z (momentumstokes.py:369-370):
+		// second variation beta (delta_cd + n_c n_d / n_z^2), first variation beta (u_c + (n_c/n_z)(B_ring/n_z + u_h.n_h/n_z))
+		const double cx = P.rs ? nx / nz : 0.0, cy = P.rs ? ny / nz : 0.0, inz = P.rs ? 1.0 / nz : 0.0;
 		#pragma unroll
 		for (int a = 0; a < 3; ++a)
 			#pragma unroll
 			for (int b = 0; b < 3; ++b) {
+				const double t = P.rs ? br[b] * inz + (P.picard ? 0.0 : cx * uu[b].x + cy * uu[b].y) : 0.0;
 				if (!P.picard) { Fx[a] += K[a][b] * uu[b].x; Fy[a] += K[a][b] * uu[b].y; }
+				if (P.rs) { Fx[a] += K[a][b] * cx * t; Fy[a] += K[a][b] * cy * t; }
 				if (WANT_J) {
 					const int slot = tet_blk[(la[a] * 4 + la[b]) * nt + cell];
-					if (slot >= 0) { atomicAdd(val + 4 * (size_t)slot, K[a][b]); atomicAdd(val + 4 * (size_t)slot + 3, K[a][b]); }
+					if (slot >= 0) {
+						atomicAdd(val + 4 * (size_t)slot, K[a][b] * (1.0 + cx * cx)); atomicAdd(val + 4 * (size_t)slot + 3, K[a][b] * (1.0 + cy * cy));
+						if (P.rs) { atomicAdd(val + 4 * (size_t)slot + 1, K[a][b] * cx * cy); atomicAdd(val + 4 * (size_t)slot + 2, K[a][b] * cx * cy); }
+					}
 				}
 			}
 	}
@@ -658,6 +695,7 @@ static AsmParams make_params(const bp_ctx* c)
 	P.n_quad = (int)c->quad_wts.size();
 	P.n_is_3 = (c->prm.n == 3.0);
 	P.picard = 0;
+	P.rs = c->prm.reduced_stokes ? 1 : 0;
 	return P;
 }
 
@@ -685,7 +723,14 @@ static const double2* bp_vertex_u(bp_ctx* c)
 	return (const double2*)c->d_uvert;
 }
 
-void bp_launch_rows_aux(bp_ctx* c, int kind)
+void bp_launch_expand_to_vertex(bp_ctx* c, const double* node_vec2, double* vertex_vec2)
+{
+	if (!c->d_v2n) { cudaMemcpyAsync(vertex_vec2, node_vec2, (size_t)2 * c->nv * sizeof(double), cudaMemcpyDeviceToDevice, c->stream); return; }
+	k_expand_u<<<red_blocks_fwd(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, c->d_v2n, (const double2*)node_vec2, (double2*)vertex_vec2);
+	c->launches++;
+}
+
+void bp_launch_rows_aux(bp_ctx* c, int kind, const double2* u_eta_vertex, const double* uz_vertex)
 {
 	const AsmParams P = make_params(c);
 	const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
@@ -693,7 +738,7 @@ void bp_launch_rows_aux(bp_ctx* c, int kind)
 	const double2* uvert = bp_vertex_u(c);
 	#define AUX(K) k_rows_aux<K><<<gr, RTPB, sm, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, \
 			c->d_soa, (size_t)c->nv, uvert, c->d_A, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, (int)c->quad_wts_aux.size(), \
-			c->d_Bv, c->d_Bring, (const double2*)c->d_aux, c->d_bcnode)
+			c->d_Bv, c->d_Bring, (const double2*)c->d_aux, c->d_bcnode, u_eta_vertex, uz_vertex)
 	if (kind == 0) AUX(0); else if (kind == 1) AUX(1); else AUX(2);
 	c->launches++;
 }
@@ -728,12 +773,12 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
 		const size_t rs = (size_t)4 * c->max_row * RTPB * sizeof(double);
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
-			cudaFuncSetAttribute(k_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-			k_rows<true, true><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
-				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P);
+			cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			k_rows<true, true, false><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
+				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz);
 		} else {
 			const int gc = (int)((c->nt + TPB - 1) / TPB);
-			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P);
+			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_uz);
 		}
 		c->launches++;
 		c->have_J = false;
@@ -743,16 +788,19 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	const double2* u2 = (const double2*)c->d_u;
 	const size_t row_smem = (size_t)4 * c->max_row * RTPB * sizeof(double);
 	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
-	#define FACET(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
+	#define FACET(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring)
 	if (gather) {
 		if (!c->smem_attr_set) {                     // function attributes are per device
-			cudaFuncSetAttribute(k_rows<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-			cudaFuncSetAttribute(k_rows<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			cudaFuncSetAttribute(k_rows<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			cudaFuncSetAttribute(k_rows<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+			cudaFuncSetAttribute(k_rows<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			c->smem_attr_set = true;
 		}
 		const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
 		const double2* uvert = bp_vertex_u(c);
-		#define ROWS(WF, WJ, SM) k_rows<WF, WJ><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P)
+		#define ROWS(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz); \
+			else k_rows<WF, WJ, false><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz); } while (0)
 		if (wf && wj) ROWS(true, true, row_smem);
 		else if (wf)  ROWS(true, false, 0);
 		else if (wj)  ROWS(false, true, row_smem);
@@ -760,7 +808,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		if (wf) cudaMemsetAsync(c->d_F, 0, 2 * c->nn * sizeof(double), c->stream);
 		if (wj) cudaMemsetAsync(c->d_val, 0, (size_t)c->n_slots * 4 * sizeof(double), c->stream);
 		const int gc = (int)((c->nt + TPB - 1) / TPB);
-		#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P)
+		#define CELL(WF, WJ) k_cell<WF, WJ><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_uz)
 		if (wf && wj) CELL(true, true);
 		else if (wf)  CELL(true, false);
 		else if (wj)  CELL(false, true);

@@ -265,7 +265,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		if (!basal && !press) continue;
 		c->n_basal += basal;
 		fcell.push_back(cell);
-		finfo.push_back(lf | (basal << 8) | (press << 9));
+		finfo.push_back(lf | (basal << 8) | (press << 9) | ((mk == 3) << 10));   // bit 10: dGamma_bg (grounded bed), the reduced-Stokes sliding set
 	}
 	c->nf = (int64_t)fcell.size();
 	{	// Dirichlet dofs of the u_z system: nodes of the basal facets (cslvr/momentumbp.py:79-85)
@@ -384,6 +384,9 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	UP(c->d_Bv, (const double*)nullptr, nv);
 	UP(c->d_Bring, (const double*)nullptr, nv);
 	BP_CUDA(c, cudaMemset(c->d_Bring, 0, (size_t)nv * sizeof(double)));
+	UP(c->d_uz, (const double*)nullptr, nv);
+	BP_CUDA(c, cudaMemset(c->d_uz, 0, (size_t)nv * sizeof(double)));
+	UP(c->d_uvert2, (const double*)nullptr, 2 * nv);
 	UP(c->d_tets, (const int4*)m->cells, nt);
 	if (!c->identity_v2n) { UP(c->d_v2n, v2n.data(), nv); UP(c->d_uvert, (const double*)nullptr, (size_t)2 * nv); }
 	UP(c->d_tet_blk, tet_blk.data(), (size_t)nt * 16);

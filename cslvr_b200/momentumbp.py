@@ -24,6 +24,8 @@ from .momentum import Momentum
 
 class MomentumBPBase(Momentum):
 
+	_reduced_stokes = False      # MomentumDukowiczStokesReduced (momentumstokes.py) flips this
+
 	def __init__(self, model, solve_params=None, linear=False, use_lat_bcs=False,
 	             use_pressure_bc=True, device=0):
 		print_text("::: INITIALIZING BP VELOCITY BASE PHYSICS :::", cls=self)
@@ -91,6 +93,7 @@ class MomentumBPBase(Momentum):
 			params = dict(n=m.n, eps_reg=m.eps_reg, rho_i=m.rho_i, rhosw=m.rhosw, g=m.g,
 			              periodic=m.use_periodic, use_pressure_bc=self.use_pressure_bc,
 			              energy_dependent_rate_factor=m.energy_dependent_rate_factor,
+			              reduced_stokes=self._reduced_stokes,
 			              a_T_l=m.a_T_l, a_T_u=m.a_T_u, Q_T_l=m.Q_T_l, Q_T_u=m.Q_T_u, R=m.R)
 			self._ctx = capi.BPContext(X, m.mesh.cells(), self.Q.dim(),
 			                           (m.facet_cell, m.facet_local, m.ff), params,
@@ -106,6 +109,12 @@ class MomentumBPBase(Momentum):
 		else:
 			c.set_field(capi.FIELD_A, m.vertex_field(m.A))
 		c.set_field(capi.FIELD_BETA, m.vertex_field(m.beta))
+		if self._reduced_stokes:
+			# the frozen u_z of the strain-rate tensor and B_ring of u_z_b (cslvr/momentumstokes.py:322, 361-370)
+			c.set_field(capi.FIELD_UZ, m.vertex_field(self.u_z))
+			c.set_field(capi.FIELD_B, m.vertex_field(m.B))
+			if getattr(m, 'B_ring', None) is not None:
+				c.set_field(capi.FIELD_B_RING, m.vertex_field(m.B_ring))
 		return c
 
 	# the reference asks PETSc for hypre BoomerAMG; the device PCG offers Jacobi-type,

@@ -39,6 +39,8 @@ extern "C" {
 #define BP_FIELD_TP     5   /* pressure-adjusted temperature T'   } energy-dependent rate factor,      */
 #define BP_FIELD_W      6   /* water content W (default 0)        } Model.form_energy_dependent_rate_  */
 #define BP_FIELD_E      7   /* enhancement factor E (default 1)   } factor, cslvr/model.py:1815-1859   */
+#define BP_FIELD_UZ     8   /* frozen vertical velocity u_z of MomentumDukowiczStokesReduced (default 0),
+                               cslvr/momentumstokes.py:361, 406-418; read iff bp_params.reduced_stokes   */
 
 /* what bp_assemble computes */
 #define BP_ASSEMBLE_F   1
@@ -145,6 +147,10 @@ typedef struct {
 	int32_t mg_smoother;       /* BP_PC_MG level 0: 0 = Chebyshev on 2x2 node blocks, 1 = Chebyshev on exact
 	                              ice-column solves (line smoother), -1 = line iff the tets are flat
 	                              (median horizontal/vertical extent >= 3; default)              */
+	/* MomentumDukowiczStokesReduced (cslvr/momentumstokes.py:300-400) instead of the Blatter-Pattyn
+	 * forms: BP_FIELD_UZ enters the strain-rate tensor (eps_02 = (u_x,z + u_z,x)/2, eps_12 likewise),
+	 * sliding acts on the grounded bed only (dGamma_bg) and carries u_z_b = (-B_ring - u_h.n_h)/n_z   */
+	int32_t reduced_stokes;
 } bp_params;
 
 typedef struct {
@@ -218,6 +224,21 @@ int  bp_solve_pressure(bp_ctx* ctx, const double* u, double* p_vertex, int on_de
  * BiCGStab right-preconditioned by an exact pivoted tridiagonal solve per ice column, to a
  * relative residual of 1e-12.  Needs BP_FIELD_B; uz_vertex: one value per mesh vertex.    */
 int  bp_solve_vert_velocity(bp_ctx* ctx, const double* u, double* uz_vertex, int on_device, int32_t* iterations);
+
+/* ---- MomentumDukowiczStokesReduced.solve, cslvr/momentumstokes.py:449-486 ------------------
+ * Model.home_rolled_newton_method (cslvr/model.py:2610-2730) with solve_vert_velocity as the
+ * per-iteration callback: loop { assemble J, b = -R at (u, u_z); solve J d = b; r = |b|;
+ * converged = r < atol or r/r0 < rtol; u += relax d; u_z = solve_vert_velocity(u) }.
+ * Needs reduced_stokes != 0 and BP_FIELD_B.  uz_vertex_inout: the starting u_z (NULL = keep the
+ * one set with BP_FIELD_UZ) and, on return, the u_z of the last callback (per mesh vertex).
+ * run_callback = 0 leaves u_z frozen (cb_ftn = None).                                          */
+int  bp_rs_newton_solve(bp_ctx* ctx, double* u_inout, double* uz_vertex_inout, int on_device,
+                        double atol, int run_callback, bp_stats* stats);
+/* solve_pressure as that solve() reaches it (momentumstokes.py:478 runs BEFORE update_model_var):
+ * p = project(rho g (S - z) - 2 eta(u_model, u_z) (u_x,x + u_y,y), Q) with the viscosity of the
+ * velocity the model holds (self.eta, cslvr/momentumbp.py:92, 219) and the divergence of u.    */
+int  bp_rs_solve_pressure(bp_ctx* ctx, const double* u, const double* u_model, double* p_vertex,
+                          int on_device, int32_t* iterations);
 
 /* ---- timing of the kernels themselves (CUDA events on the context's stream) --- */
 /* flush_l2 != 0: a 512 MiB buffer is written before every timed launch            */

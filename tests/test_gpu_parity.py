@@ -443,3 +443,117 @@ def test_baseline_configs_3_and_4_at_test_size(name):
 	assert io['converged'] and st['converged'] and abs(st['iterations'] - io['iterations']) <= 1
 	assert relerr(un, uo) < 1e-7, relerr(un, uo)
 	c.close()
+
+
+# ---- SURVEY §8f rank 4 (second half): MomentumDukowiczStokesReduced ------------------------
+def _rs_context(m, **params):
+	from cslvr_b200 import capi
+	c = product_context(m, reduced_stokes=True, **params)
+	c.set_field(capi.FIELD_B, m.vertex_field(m.B))
+	return c
+
+
+@pytest.mark.parametrize('builder', [lambda: ismip_model('A', n=(9, 8, 4)), lambda: marine_model(n=(7, 6, 4)),
+                                     lambda: ismip_model('A', n=(7, 6, 3), periodic=False)])
+def test_reduced_stokes_assembly_matches_oracle(builder):
+	"""cslvr/momentumstokes.py:300-400: u_z in the strain-rate tensor, u_z_b in the sliding term
+	(grounded bed only), F and J to 1e-12, both assembly modes, sparsity unchanged."""
+	from cases import rs_problem
+	from cslvr_b200 import capi
+	m = builder()
+	rng = np.random.default_rng(61)
+	Br = rng.normal(size=m.num_vertices) * 0.2
+	P = rs_problem(m, B_ring=Br)
+	uz = rng.normal(size=P.n_dofs // 2)[m.vertex_to_node] * 4.0       # a P1 function on model.Q, per vertex
+	P.set_uz(uz)
+	for mode in ('gather', 'scatter'):
+		c = _rs_context(m, assembly=mode)
+		c.set_field(capi.FIELD_UZ, uz)
+		c.set_field(capi.FIELD_B_RING, Br)
+		ip, ix = c.csr_pattern()
+		assert np.array_equal(ip, P.pattern()[0]) and np.array_equal(ix, P.pattern()[1])
+		for seed, scale in ((1, 30.0), (2, 1e-3), (3, 0.0)):
+			u = state(P.n_dofs, seed, scale)
+			F, J = c.assemble(u, want_F=True, want_J=True)
+			assert relerr(F, P.residual(u)) < TOL_ASM, (mode, seed, relerr(F, P.residual(u)))
+			assert relerr(J, P.jacobian(u)) < TOL_ASM, (mode, seed, relerr(J, P.jacobian(u)))
+			F2, _ = c.assemble(u, want_F=True, want_J=False)
+			_, J2 = c.assemble(u, want_F=False, want_J=True)
+			assert relerr(F2, F) < 1e-14 and relerr(J2, J) < 1e-14
+		# the same context serves the BP forms again once the flag is cleared
+		c.set_params(reduced_stokes=False)
+		Pb = oracle_problem(m)
+		u = state(P.n_dofs, 4)
+		F, J = c.assemble(u, want_F=True, want_J=True)
+		assert relerr(F, Pb.residual(u)) < TOL_ASM and relerr(J, Pb.jacobian(u)) < TOL_ASM
+		c.close()
+
+
+@pytest.mark.parametrize('builder,cb', [(lambda: ismip_model('A', n=(8, 7, 4)), True), (lambda: marine_model(n=(7, 6, 4)), True),
+                                        (lambda: ismip_model('A', n=(8, 7, 4)), False)])
+def test_reduced_stokes_newton_matches_oracle(builder, cb):
+	"""Model.home_rolled_newton_method (cslvr/model.py:2610-2730) with solve_vert_velocity as the
+	callback: same iteration count, residual history, velocity (1e-8) and u_z."""
+	from cases import rs_problem
+	m = builder()
+	P = rs_problem(m)
+	uo, io = P.newton_rs(rtol=1e-9, atol=1e-6, maxit=50, relax=0.8, callback=cb)
+	c = _rs_context(m, relative_tolerance=1e-9, maximum_iterations=50, relaxation_parameter=0.8, krylov_rtol=1e-13)
+	u = np.zeros(P.n_dofs)
+	uz = np.zeros(m.num_vertices)
+	st = c.rs_newton_solve(u, uz, atol=1e-6, callback=cb)
+	assert st['converged'] and io['converged'] and st['iterations'] == io['iterations']
+	assert relerr(st['residuals'], io['residuals']) < 1e-6
+	assert relerr(u, uo) < TOL_U, relerr(u, uo)
+	assert relerr(uz, P.uz) < 1e-7 or not cb
+	c.close()
+
+
+def test_reduced_stokes_class_solves_like_the_reference():
+	"""MomentumDukowiczStokesReduced.solve() (cslvr/momentumstokes.py:449-486): Newton with the
+	u_z callback, the pressure with the viscosity of the velocity the model held BEFORE the solve,
+	then update_model_var."""
+	from cases import rs_problem
+	from cslvr_b200 import MomentumDukowiczStokesReduced
+	m = ismip_model('A', n=(8, 7, 4))
+	mom = MomentumDukowiczStokesReduced(m)
+	assert mom.solve_params['solver']['newton_solver']['relaxation_parameter'] == 0.8
+	assert mom.solve_params['solver']['newton_solver']['maximum_iterations'] == 50
+	mom.solve_params['solver']['newton_solver']['krylov_solver'] = {'relative_tolerance': 1e-13}
+	mom.solve()
+	P = rs_problem(m)
+	uo, io = P.newton_rs()
+	assert mom.stats['converged'] and mom.stats['iterations'] == io['iterations']
+	u = mom.get_unknown().values
+	assert relerr(u, uo) < TOL_U
+	assert relerr(m.u.sub(0), uo[0::2]) < TOL_U and relerr(m.u.sub(1), uo[1::2]) < TOL_U      # update_model_var
+	assert relerr(m.u.sub(2), P.uz[m.node_vertex]) < 1e-7                                         # the callback's u_z
+	po = P.pressure_rs(uo, np.zeros(P.n_dofs), P.uz)            # model.u was zero before the solve
+	assert relerr(m.p.values, po) < TOL_U, relerr(m.p.values, po)
+	# residual / Jacobian of the class (with the u_z it now holds)
+	ur = state(P.n_dofs, 7)
+	assert relerr(mom.assemble_residual(ur), P.residual(ur)) < TOL_ASM
+	ip, ix, J = mom.assemble_jacobian()
+	assert relerr(J, P.jacobian(u)) < TOL_ASM
+
+
+@pytest.mark.parametrize('mode', ['gather', 'scatter'])
+def test_reduced_stokes_linear_solve_matches_oracle(mode):
+	"""linear=True for the reduced model: viscosity frozen at (u_l, u_z), the right-hand side
+	keeps the u_z part of d(epsdot) and the B_ring part of the sliding term."""
+	from cases import rs_problem
+	from cslvr_b200 import capi
+	m = marine_model(n=(7, 6, 4))
+	rng = np.random.default_rng(71)
+	Br = rng.normal(size=m.num_vertices) * 0.2
+	P = rs_problem(m, B_ring=Br)
+	uz = rng.normal(size=P.n_dofs // 2)[m.vertex_to_node] * 2.0
+	P.set_uz(uz)
+	ul = state(P.n_dofs, 51, 20.0)
+	ref = P.linear_solve(ul)
+	c = _rs_context(m, krylov_rtol=1e-13, assembly=mode)
+	c.set_field(capi.FIELD_UZ, uz)
+	c.set_field(capi.FIELD_B_RING, Br)
+	out = c.linear_solve(ul)
+	assert relerr(out, ref) < TOL_U, relerr(out, ref)
+	c.close()

@@ -33,7 +33,7 @@ def test_sizes_of_config_1():
 	assert (Q.n_dofs, Q.pattern()[1].size) == (3072, 78424)
 
 
-def _sympy_element(coords, S, A, beta, u, basal_facet, press_facet, consts):
+def _sympy_element(coords, S, A, beta, u, basal_facet, press_facet, consts, uz=None, B_ring=None):
 	"""F and J of ONE tetrahedron by symbolic differentiation of the action
 	(cslvr/momentumbp.py:460-500), the cell integral with an exact degree-1 rule since A
 	is taken constant here, facet integrals by exact polynomial integration."""
@@ -46,6 +46,11 @@ def _sympy_element(coords, S, A, beta, u, basal_facet, press_facet, consts):
 	G = Minv[1:, :].T                    # grad lambda_a (rows)
 	vol = abs(M.det()) / 6
 	gu = [[sum(U[4 * c + a] * G[a, j] for a in range(4)) for j in range(3)] for c in range(2)]
+	if uz is not None:
+		# MomentumDukowiczStokesReduced.strain_rate_tensor (cslvr/momentumstokes.py:406-418):
+		# eps_02 = (u_x,z + u_z,x)/2, eps_12 = (u_y,z + u_z,y)/2 with the frozen P1 u_z
+		for c in range(2):
+			gu[c][2] = gu[c][2] + sum(sp.Float(uz[a], 30) * G[a, c] for a in range(4))
 	eps = sp.Matrix([[gu[0][0], (gu[0][1] + gu[1][0]) / 2, gu[0][2] / 2],
 	                 [(gu[0][1] + gu[1][0]) / 2, gu[1][1], gu[1][2] / 2],
 	                 [gu[0][2] / 2, gu[1][2] / 2, -gu[0][0] - gu[1][1]]])       # momentumbp.py:122-135
@@ -67,7 +72,16 @@ def _sympy_element(coords, S, A, beta, u, basal_facet, press_facet, consts):
 		integ = lambda f: sp.integrate(sp.integrate(f, (t, 0, 1 - s)), (s, 0, 1)) * area2
 		if kind == 'b':
 			bq = sum(lam[k] * beta[la[k]] for k in range(3))
-			action += integ(bq * (uq[0] ** 2 + uq[1] ** 2) / 2)                 # -Sl dGamma_b
+			if uz is None:
+				action += integ(bq * (uq[0] ** 2 + uq[1] ** 2) / 2)             # -Sl dGamma_b
+			else:
+				# -Sl_gnd dGamma_bg with u_z_b = (-B_ring - u_h.n_h) / n_z, momentumstokes.py:369-370
+				nrm = cr / area2
+				if nrm.dot((X[lf, :] - P0)) > 0:
+					nrm = -nrm
+				Brq = sum(lam[k] * sp.Float(B_ring[la[k]], 30) for k in range(3))
+				uzb = (-Brq - uq[0] * nrm[0] - uq[1] * nrm[1]) / nrm[2]
+				action += integ(bq * (uq[0] ** 2 + uq[1] ** 2 + uzb ** 2) / 2)
 		else:
 			nrm = cr / area2
 			if nrm.dot((X[lf, :] - P0)) > 0:
@@ -101,6 +115,63 @@ def test_single_tet_against_symbolic_differentiation(seed):
 	F, J = P.residual(u), P.jacobian_matrix(u).toarray()
 	assert relerr(F[perm], Fs) < 1e-12
 	assert relerr(J[np.ix_(perm, perm)], Js) < 1e-12
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_reduced_stokes_single_tet_against_symbolic_differentiation(seed):
+	"""MomentumDukowiczStokesReduced (cslvr/momentumstokes.py:300-400): the same symbolic
+	pipeline with u_z in the strain-rate tensor and u_z_b in the sliding term."""
+	from oracle.rs_oracle import RSProblem
+	rng = np.random.default_rng(10 + seed)
+	coords = np.array([[0, 0, 0], [1200.0, 30, -40], [100, 900.0, 60], [50, -80, 350.0]]) + rng.normal(size=(4, 3)) * 20
+	cells = np.array([[0, 1, 2, 3]])
+	S = coords[:, 2] + 500 + rng.normal(size=4) * 30
+	beta = 800 + rng.uniform(size=4) * 400
+	A = 3.3e-17
+	coords[:, 2] -= 300.0
+	uz = rng.normal(size=4) * 5
+	Br = rng.normal(size=4) * 0.3
+	cd = bo.canonical_cell_dofs(cells, np.arange(4))
+	fc, fl = np.array([0, 0]), np.array([3, 1])
+	ff = np.array([bo.GAMMA_B_GND, bo.GAMMA_L_UDR])
+	P = RSProblem(coords, cells, cd, 8, fc, fl, ff, S, A, beta, periodic=False, use_pressure_bc=True, B=coords[:, 2], B_ring=Br)
+	P.set_uz(uz)
+	u8 = rng.normal(size=8) * 40
+	u = np.empty(8); u[0::2] = u8[:4]; u[1::2] = u8[4:]
+	Fs, Js = _sympy_element(coords.tolist(), S.tolist(), A, beta.tolist(), u8.tolist(), 3, 1, P.c, uz=uz.tolist(), B_ring=Br.tolist())
+	perm = np.array([0, 2, 4, 6, 1, 3, 5, 7])
+	F, J = P.residual(u), P.jacobian_matrix(u).toarray()
+	assert relerr(F[perm], Fs) < 1e-12
+	assert relerr(J[np.ix_(perm, perm)], Js) < 1e-12
+	# a floating bed carries no sliding term in this model (dGamma_bg only)
+	P2 = RSProblem(coords, cells, cd, 8, fc, fl, np.array([bo.GAMMA_B_FLT, bo.GAMMA_L_UDR]), S, A, beta, periodic=False, B=coords[:, 2])
+	_, _, Jf = P2.facet_tensors(u)
+	assert np.all(Jf == 0.0)
+
+
+def test_reduced_stokes_residual_and_jacobian_are_derivatives_of_the_action():
+	from cases import rs_problem
+	P = rs_problem(marine_model(n=(5, 4, 3)))
+	rng = np.random.default_rng(4)
+	P.set_uz(rng.normal(size=P.coords.shape[0]) * 3)
+	u = rng.normal(size=P.n_dofs) * 20
+	F, J = P.residual(u), P.jacobian_matrix(u)
+	for k in range(4):
+		v = rng.normal(size=P.n_dofs)
+		h = 1e-4
+		dA = (P.action(u + h * v) - P.action(u - h * v)) / (2 * h)
+		assert abs(dA - F @ v) < 1e-7 * max(abs(dA), abs(F @ v))
+		dF = (P.residual(u + h * v) - P.residual(u - h * v)) / (2 * h)
+		assert relerr(J @ v, dF) < 1e-6
+	assert abs(J - J.T).max() < 1e-12 * abs(J).max()
+	# with u_z = 0 the cell integrals are Blatter-Pattyn's; the sliding term is not (u_z_b)
+	Q = rs_problem(ismip_model('A', n=(5, 4, 3)))
+	Pb = oracle_problem(ismip_model('A', n=(5, 4, 3)))
+	ub = state(Q.n_dofs, 2)
+	Q.set_uz(np.zeros(Q.coords.shape[0]))
+	fq, fb = Q.residual(ub), Pb.residual(ub)
+	assert relerr(fq, fb) > 1e-6          # the bed of ISMIP-HOM A is bumpy: u_z_b couples u_x and u_y
+	assert relerr(Q.cell_tensors(ub)[1], Pb.cell_tensors(ub)[1]) == 0.0
 
 
 @pytest.mark.parametrize('builder', [lambda: ismip_model('A', n=(5, 4, 3)), lambda: marine_model(n=(5, 4, 3))])
