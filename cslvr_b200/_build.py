@@ -8,7 +8,7 @@ ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, 'csrc', f) for f in
        ('bp_setup.cu', 'bp_kernels.cu', 'bp_mg.cu', 'bp_comm.cu', 'bp_api.cu')]
 HDR = [os.path.join(HERE, 'csrc', 'bp_internal.h'), os.path.join(ROOT, 'include', 'cslvr_b200.h')]
-LIB = os.path.join(HERE, 'lib', 'libcslvr_b200.so')
+LIB = os.environ.get('BP_LIB_PATH') or os.path.join(HERE, 'lib', 'libcslvr_b200.so')
 
 
 def lib_path():
@@ -32,7 +32,7 @@ def build(force=False, verbose=False):
 	       '-gencode', 'arch=compute_100a,code=sm_100a',
 	       '-Xcompiler', '-fPIC,-fopenmp,-O3', '-shared',
 	       '-I', os.path.join(ROOT, 'include'), '-I', os.path.join(HERE, 'csrc'),
-	       '-Xptxas', '-v' if verbose else '-O3'] + (['-DBP_EXPERIMENTS'] if os.environ.get('BP_EXPERIMENTS') == '1' else []) + [
+	       '-Xptxas', '-v' if verbose else '-O3'] + (['-DBP_EXPERIMENTS'] if os.environ.get('BP_EXPERIMENTS') == '1' else []) + os.environ.get('BP_NVCC_FLAGS', '').split() + [
 	       '-o', LIB] + SRC + ['-lcudart', '-ldl', '-lgomp']
 	r = subprocess.run(cmd, capture_output=True, text=True)
 	if r.returncode != 0:

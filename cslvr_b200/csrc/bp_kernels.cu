@@ -292,9 +292,14 @@ void bp_launch_proxy(bp_ctx* c)
 // and every F entry is then written exactly once: no atomics, no zero-fill, bitwise
 // reproducible.  The price is that the cell-constant part of a tet is recomputed by
 // each of its four nodes.
+#ifndef RTPB
 #define RTPB 128
+#endif
+#ifndef ROWS_MIN_CTAS
+#define ROWS_MIN_CTAS 3
+#endif
 template <bool WANT_F, bool WANT_J, bool RS>
-__global__ void __launch_bounds__(RTPB)
+__global__ void __launch_bounds__(RTPB, ROWS_MIN_CTAS)
 k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restrict__ inc_code,
        const uint32_t* __restrict__ inc_pos, const int32_t* __restrict__ inc_v, size_t nslot,
        const double* __restrict__ soa, size_t nv,
@@ -302,15 +307,15 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
        const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
        double* __restrict__ F, double* __restrict__ val, AsmParams P, const double* __restrict__ uzv)
 {
-	extern __shared__ double acc[];                  // [4*max_row][RTPB]
+	extern __shared__ double acc[];                  // [4*(max_row-1)][RTPB]: off-diagonal blocks, strip slot = row position minus (position > diagonal's)
 	const int tid = threadIdx.x;
 	const int i = blockIdx.x * RTPB + tid;
 	const bool active = i < nrows;
 	const int len = active ? rowlen[i] : 0;
-	if (WANT_J) for (int k = 0; k < 4 * len; ++k) acc[k * RTPB + tid] = 0.0;
+	if (WANT_J) for (int k = 0; k < 4 * (len - 1); ++k) acc[k * RTPB + tid] = 0.0;
 	double Fx = 0.0, Fy = 0.0;
 	double dg0 = 0.0, dg1 = 0.0, dg2 = 0.0, dg3 = 0.0;    // diagonal block
-	int kdiag = -1;
+	int kdiag = 1 << 30;
 	const int slice = i >> 5, lane = i & 31;
 	const int e0 = active ? inc_slice[slice] : 0, e1 = active ? inc_slice[slice + 1] : 0;
 	// software pipeline, two stages deep on the index words (tet code, block positions, four
@@ -328,6 +333,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	double ai = 0.0;                                 // sum_q w_q A_q^(-1/n) of the tet (k_tet_ainv)
 	if (code >= 0) {
 		pk = inc_pos[e];
+		kdiag = (int)(pk & 255);                     // position of the diagonal block: the same in every incidence of the row
 		#pragma unroll
 		for (int j = 0; j < 4; ++j) vid[j] = inc_v[j * nslot + e];
 		if (e + 32 < e1) {                           // padding slots hold code -1, vertex 0: safe to load
@@ -344,6 +350,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		}
 		ai = Av[code >> 2];
 	}
+	int own = vid[0];                                // vertex whose data sits in p[0] / uu[0]
 	while (code >= 0) {
 		const uint32_t pk_cur = pk;
 		e += 32;
@@ -367,7 +374,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		X[2] = e3y * e1z - e3z * e1y; Y[2] = e3z * e1x - e3x * e1z; Z[2] = e3x * e1y - e3y * e1x;
 		X[3] = e1y * e2z - e1z * e2y; Y[3] = e1z * e2x - e1x * e2z; Z[3] = e1x * e2y - e1y * e2x;
 		const double det = e1x * X[1] + e1y * Y[1] + e1z * Z[1];
-		const double idet = 1.0 / det;
+		const double idet = __drcp_rn(det);
 		#pragma unroll
 		for (int j = 1; j < 4; ++j) { X[j] *= idet; Y[j] *= idet; Z[j] *= idet; }
 		X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
@@ -386,14 +393,17 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 			for (int j = 0; j < 4; ++j) { wx += ww[j] * X[j]; wy += ww[j] * Y[j]; }
 			g02 += wx; g12 += wy;
 		}
-		// raw vertex data of this incidence is consumed: request the next incidence's
+		// raw vertex data of this incidence is consumed: request the next incidence's (the row's own
+		// vertex only when it changes: periodic images)
 		if (code_n >= 0) {
 			#pragma unroll
 			for (int j = 0; j < 4; ++j) {
+				if (j == 0 && vid[0] == own) continue;
 				p[j] = make_double4(soa[vid[j]], soa[nv + vid[j]], soa[2 * nv + vid[j]], soa[3 * nv + vid[j]]);
 				uu[j] = u[vid[j]];
 				if (RS) ww[j] = uzv[vid[j]];
 			}
+			own = vid[0];
 			ai = Av[code_n >> 2];
 		}
 		const double sh = 0.5 * (g01 + g10);
@@ -432,9 +442,9 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 				const double jyy = Sa * Y[b] + Ta * X[b] + Ra * Z[b] + Ga * dyb;
 				if (b == 0) {                             // the diagonal block gets a term from every tet: keep it in registers
 					dg0 += jxx; dg1 += jxy; dg2 += jyx; dg3 += jyy;
-					kdiag = (int)(pk_cur & 255);
 				} else {
-					double* s4 = acc + (4 * ((pk_cur >> (8 * b)) & 255)) * RTPB + tid;
+					const int pos = (int)((pk_cur >> (8 * b)) & 255);
+					double* s4 = acc + (4 * (pos - (pos > kdiag))) * RTPB + tid;
 					s4[0] += jxx; s4[RTPB] += jxy; s4[2 * RTPB] += jyx; s4[3 * RTPB] += jyy;
 				}
 			}
@@ -447,10 +457,12 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		// SELL-32: block k of the 32 rows of a slice is contiguous -> coalesced 1 KB stores
 		double2* out = (double2*)val + 2 * ((size_t)sell_ptr[slice] + lane);
 		for (int k = 0; k < len; ++k) {
-			const double* s4 = acc + (4 * k) * RTPB + tid;
 			const bool dgk = (k == kdiag);
-			out[64 * (size_t)k]     = dgk ? make_double2(dg0, dg1) : make_double2(s4[0], s4[RTPB]);
-			out[64 * (size_t)k + 1] = dgk ? make_double2(dg2, dg3) : make_double2(s4[2 * RTPB], s4[3 * RTPB]);
+			const double* s4 = acc + (4 * (dgk ? 0 : k - (k > kdiag))) * RTPB + tid;
+			double2 lo = make_double2(dg0, dg1), hi = make_double2(dg2, dg3);
+			if (!dgk) { lo = make_double2(s4[0], s4[RTPB]); hi = make_double2(s4[2 * RTPB], s4[3 * RTPB]); }
+			out[64 * (size_t)k]     = lo;
+			out[64 * (size_t)k + 1] = hi;
 		}
 	}
 }
@@ -771,7 +783,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	if (what & 8) { bp_launch_proxy(c); return; }
 #endif
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
-		const size_t rs = (size_t)4 * c->max_row * RTPB * sizeof(double);
+		const size_t rs = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
 			cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			k_rows<true, true, false><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
@@ -786,7 +798,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	}
 	const int gf = (int)((c->nf + TPB - 1) / TPB);
 	const double2* u2 = (const double2*)c->d_u;
-	const size_t row_smem = (size_t)4 * c->max_row * RTPB * sizeof(double);
+	const size_t row_smem = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);   // the diagonal block lives in registers
 	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
 	#define FACET(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring)
 	if (gather) {
