@@ -47,7 +47,7 @@ class bp_params(C.Structure):
 	            ('energy_dependent', C.c_int32), ('a_T_l', C.c_double), ('a_T_u', C.c_double),
 	            ('Q_T_l', C.c_double), ('Q_T_u', C.c_double), ('R_gas', C.c_double),
 	            ('krylov_norm_preconditioned', C.c_int32), ('mg_smoother', C.c_int32),
-	            ('reduced_stokes', C.c_int32)]
+	            ('reduced_stokes', C.c_int32), ('mg_coarse_scale', C.c_double)]
 
 
 class bp_stats(C.Structure):
@@ -262,6 +262,7 @@ class BPContext(object):
 		p.mg_smoother = {'auto': -1, 'block': 0, 'column': 1}[d.get('mg_smoother', 'auto')]
 		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
 		p.reduced_stokes = int(bool(d.get('reduced_stokes', False)))
+		p.mg_coarse_scale = float(d.get('mg_coarse_scale', 0.0))
 		self._last_params = p
 		return p
 

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 struct bp_mg_level {
 	bp_ctx* M = nullptr;                 // matrix + vectors of this level (level 0: the real context)
@@ -35,9 +36,10 @@ struct bp_mg {
 	// the V-cycle is a fixed sequence of ~50 mostly tiny launches: captured once as a CUDA graph
 	cudaGraphExec_t graph = nullptr;
 	const double *g_r = nullptr; double *g_z = nullptr, *g_z2 = nullptr;
-	int g_deg = 0, g_smoother = -1; double g_ratio = 0.0; int64_t g_launches = 0;
+	int g_deg = 0, g_smoother = -1; double g_ratio = 0.0, g_alpha = 0.0; int64_t g_launches = 0;
 	std::vector<double> h_dense, h_val;
 	int nc = 0;                          // coarsest dofs
+	int gamma = 1;                       // coarse-grid visits per level below the finest
 };
 
 template <class T>
@@ -96,14 +98,14 @@ __global__ void k_mg_restrict(int nc, const int32_t* __restrict__ aggptr, const 
 	}
 }
 
-__global__ void k_mg_prolong_add(int nf, const int32_t* __restrict__ agg, const double2* __restrict__ xc, double2* __restrict__ zf)
+__global__ void k_mg_prolong_add(int nf, const int32_t* __restrict__ agg, const double2* __restrict__ xc, double2* __restrict__ zf, double alpha)
 {
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += gridDim.x * blockDim.x) {
 		const int I = agg[i];
 		if (I < 0) continue;
 		const double2 e = xc[I];
 		double2 z = zf[i];
-		z.x += e.x; z.y += e.y;
+		z.x += alpha * e.x; z.y += alpha * e.y;
 		zf[i] = z;
 	}
 }
@@ -176,12 +178,76 @@ static int mg_symbolic(bp_ctx* c)
 		L0.M = c; L0.n = no;
 		L0.h_rowptr = c->h_rowptr; L0.h_col = c->h_col; L0.h_sell_ptr = c->h_sell_ptr;
 	}
-	// first aggregation: ice columns
-	std::vector<int32_t> agg(no, -1);
-	int32_t na = (int32_t)c->n_cols;
-	for (int64_t cc = 0; cc < c->n_cols; ++cc)
-		for (int32_t j = c->h_colptr[cc]; j < c->h_colptr[cc + 1]; ++j) agg[c->h_colnode[j]] = (int32_t)cc;
-	for (int guard = 0; guard < 20; ++guard) {
+	// Extruded structure of the current level: node -> (column, layer).  The order of the two kinds
+	// of coarsening follows the anisotropy (c->aspect = horizontal / vertical extent of the tets):
+	//   * flat elements (aspect >= 1, real ice sheets): the vertical coupling is the strong one, so
+	//     every ice column collapses into one node first (the SSA-like, vertically constant space);
+	//   * tall elements (ISMIP-HOM at high horizontal resolution): the strong coupling is horizontal;
+	//     collapsing columns would leave the horizontally smooth, vertically varying error to the
+	//     smoother, so the footprint is aggregated layer by layer (coarse node = 2-D aggregate x layer)
+	//     until the aggregates are wide enough, and only then do the columns collapse.
+	std::vector<int32_t> col_of(no, -1), lay_of(no, 0);
+	int64_t ncol = c->n_cols;
+	int32_t nlay = 0;
+	bool uniform = true;
+	for (int64_t cc = 0; cc < c->n_cols; ++cc) {
+		const int32_t len = c->h_colptr[cc + 1] - c->h_colptr[cc];
+		if (cc == 0) nlay = len; else if (len != nlay) uniform = false;
+		for (int32_t j = c->h_colptr[cc]; j < c->h_colptr[cc + 1]; ++j) { col_of[c->h_colnode[j]] = (int32_t)cc; lay_of[c->h_colnode[j]] = j - c->h_colptr[cc]; }
+	}
+	double aspect = c->aspect;
+	const char* ev_h = getenv("BP_MG_HORIZONTAL_FIRST");
+	const double aspect_switch = ev_h ? atof(ev_h) : 1.0;
+	std::vector<int32_t> agg;
+	int32_t na = 0;
+	auto next_aggregation = [&](const bp_mg_level& F) {
+		const int64_t nf = F.n;
+		if (nlay > 1 && uniform && aspect < aspect_switch) {
+			// footprint graph of the columns, aggregated; layers kept
+			std::vector<std::vector<int32_t>> nb(ncol);
+			for (int64_t i = 0; i < nf; ++i)
+				for (int32_t k = F.h_rowptr[i]; k < F.h_rowptr[i + 1]; ++k) {
+					const int32_t j = F.h_col[k];
+					if (j < nf && col_of[j] >= 0 && col_of[j] != col_of[i]) nb[col_of[i]].push_back(col_of[j]);
+				}
+			std::vector<int32_t> rp(ncol + 1, 0), ci;
+			for (int64_t cc = 0; cc < ncol; ++cc) {
+				std::sort(nb[cc].begin(), nb[cc].end());
+				nb[cc].erase(std::unique(nb[cc].begin(), nb[cc].end()), nb[cc].end());
+				rp[cc + 1] = rp[cc] + (int32_t)nb[cc].size();
+			}
+			ci.reserve(rp[ncol]);
+			for (int64_t cc = 0; cc < ncol; ++cc) ci.insert(ci.end(), nb[cc].begin(), nb[cc].end());
+			std::vector<int32_t> cagg;
+			int32_t nca = 0;
+			greedy_aggregate(rp, ci, ncol, cagg, nca);
+			agg.assign(nf, -1);
+			for (int64_t i = 0; i < nf; ++i) if (col_of[i] >= 0) agg[i] = cagg[col_of[i]] * nlay + lay_of[i];
+			na = nca * nlay;
+			aspect *= std::sqrt((double)ncol / std::max(nca, 1));
+			ncol = nca;
+			col_of.assign(na, 0); lay_of.assign(na, 0);
+			for (int32_t I = 0; I < na; ++I) { col_of[I] = I / nlay; lay_of[I] = I % nlay; }
+		} else if (nlay > 1 || !uniform) {
+			// ice columns -> one node each
+			agg.assign(col_of.begin(), col_of.begin() + nf);
+			na = (int32_t)ncol;
+			nlay = 1; uniform = true;
+			col_of.assign(na, 0); lay_of.assign(na, 0);
+			for (int32_t I = 0; I < na; ++I) col_of[I] = I;
+		} else {
+			greedy_aggregate(F.h_rowptr, F.h_col, nf, agg, na);
+			ncol = na;
+			col_of.assign(na, 0); lay_of.assign(na, 0);
+			for (int32_t I = 0; I < na; ++I) col_of[I] = I;
+		}
+	};
+	for (int guard = 0; guard < 24; ++guard) {
+		{
+			const int64_t n_before = mg->lv.back().n;
+			next_aggregation(mg->lv.back());
+			if (guard > 0 && na >= n_before) break;          // no coarsening possible
+		}
 		bp_mg_level& F = mg->lv.back();
 		const int64_t nf = F.n;
 		// members of every aggregate
@@ -258,10 +324,6 @@ static int mg_symbolic(bp_ctx* c)
 		if (rc) return rc;
 		mg->lv.push_back(std::move(C));
 		if (na <= 64) break;
-		int32_t na2;
-		greedy_aggregate(mg->lv.back().h_rowptr, mg->lv.back().h_col, na, agg, na2);
-		if (na2 >= na) break;                         // no coarsening possible
-		na = na2;
 	}
 	mg->nc = (int)(2 * mg->lv.back().n);
 	if (mg->nc > 4096) return bp_fail(c, BP_ERR_STATE, "multigrid: coarsest level has %d dofs (aggregation stalled)", mg->nc);
@@ -409,16 +471,27 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 	const bool line = (l == 0) && want_line && c->max_layers <= 64 && c->n_cols < c->nn_owned;
 	double* z = line ? col_cheb_smooth(c, deg, ratio, rhs, M->d_z, M->d_z2, true, L.n)
 	                 : cheb_smooth(M, deg, ratio, rhs, M->d_z, M->d_z2, true);
-	double* other = (z == M->d_z) ? M->d_z2 : M->d_z;
-	k_mg_residual<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, M->d_sell_ptr, M->d_col, (const double2*)M->d_val,
-		(const double2*)rhs, (const double2*)z, (double2*)M->d_io);
 	bp_ctx* C = mg->lv[l + 1].M;
-	k_mg_restrict<<<blocks(C->nn_owned, 128), 128, 0, c->stream>>>((int)C->nn_owned, L.d_aggptr, L.d_aggidx, (const double2*)M->d_io, (double2*)C->d_F);
-	c->launches += 2;
-	const double* xc = vcycle(c, mg, l + 1, C->d_F, deg, ratio);
-	k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, L.d_agg, (const double2*)xc, (double2*)z);
-	c->launches++;
-	return line ? col_cheb_smooth(c, deg, ratio, rhs, z, other, false, L.n) : cheb_smooth(M, deg, ratio, rhs, z, other, false);
+	// gamma coarse-grid visits per level below the finest (1 = V-cycle, 2 = W-cycle): plain
+	// aggregation has a stiff coarse operator, a second visit of the (tiny) coarser levels is cheap
+	const char* evg = getenv("BP_MG_GAMMA");
+	const int gamma = (l == 0) ? 1 : std::max(1, evg ? atoi(evg) : mg->gamma);
+	const char* ev = getenv(l == 0 ? "BP_MG_ALPHA0" : "BP_MG_ALPHA");
+	const double alpha_def = (c->prm.mg_coarse_scale > 0.0 && c->prm.mg_coarse_scale <= 2.0) ? c->prm.mg_coarse_scale : 1.8;
+	const double alpha = ev ? atof(ev) : alpha_def;
+	for (int g = 0; g < gamma; ++g) {
+		double* other = (z == M->d_z) ? M->d_z2 : M->d_z;
+		k_mg_residual<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, M->d_sell_ptr, M->d_col, (const double2*)M->d_val,
+			(const double2*)rhs, (const double2*)z, (double2*)M->d_io);
+		k_mg_restrict<<<blocks(C->nn_owned, 128), 128, 0, c->stream>>>((int)C->nn_owned, L.d_aggptr, L.d_aggidx, (const double2*)M->d_io, (double2*)C->d_F);
+		c->launches += 2;
+		const double* xc = vcycle(c, mg, l + 1, C->d_F, deg, ratio);
+		// over-relaxed coarse correction (piecewise-constant prolongation under-corrects)
+		k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, L.d_agg, (const double2*)xc, (double2*)z, alpha);
+		c->launches++;
+		z = line ? col_cheb_smooth(c, deg, ratio, rhs, z, other, false, L.n) : cheb_smooth(M, deg, ratio, rhs, z, other, false);
+	}
+	return z;
 }
 
 // z = M^-1 r with r = c->d_r, z = c->d_z
@@ -428,7 +501,7 @@ int bp_mg_apply(bp_ctx* c)
 	bp_mg* mg = c->mg;
 	const int deg = std::max(c->prm.pc_degree, 1);
 	const double ratio = std::max(c->prm.pc_eig_ratio, 1.5);
-	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_smoother != c->prm.mg_smoother)) {
+	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_smoother != c->prm.mg_smoother || mg->g_alpha != c->prm.mg_coarse_scale)) {
 		cudaGraphExecDestroy(mg->graph);
 		mg->graph = nullptr;
 	}
@@ -446,7 +519,7 @@ int bp_mg_apply(bp_ctx* c)
 		mg->g_launches = c->launches - l0;
 		for (size_t l = 1; l < mg->lv.size(); ++l) mg->g_launches += mg->lv[l].M->launches;
 		c->launches = l0;
-		mg->g_r = c->d_r; mg->g_z = c->d_z; mg->g_z2 = c->d_z2; mg->g_deg = deg; mg->g_ratio = ratio; mg->g_smoother = c->prm.mg_smoother;
+		mg->g_r = c->d_r; mg->g_z = c->d_z; mg->g_z2 = c->d_z2; mg->g_deg = deg; mg->g_ratio = ratio; mg->g_smoother = c->prm.mg_smoother; mg->g_alpha = c->prm.mg_coarse_scale;
 	}
 	BP_CUDA(c, cudaGraphLaunch(mg->graph, c->stream));
 	c->launches += mg->g_launches;
