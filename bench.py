@@ -205,6 +205,9 @@ def main():
 	model = build_model(1)
 	ctx = product_context(model)
 	ctx.device = local
+	# a non-default torch stream: the library runs on torch's current stream (so torch.cuda.Event sees its
+	# kernels) and that stream can be captured into CUDA graphs (the legacy default stream cannot)
+	torch.cuda.set_stream(torch.cuda.Stream(dev))
 	ctx.use_torch_stream()
 	nt = model.num_cells
 	u_host = synthetic_state(model)

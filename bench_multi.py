@@ -41,6 +41,7 @@ def run_multi(args, rank, world, local):
 	                     vertex_to_node=rm.vertex_to_node, partition=rm.partition, device=local)
 	for f, k in ((capi.FIELD_S, 'S'), (capi.FIELD_A, 'A'), (capi.FIELD_BETA, 'beta')):
 		ctx.set_field(f, rm.fields[k])
+	torch.cuda.set_stream(torch.cuda.Stream(dev))       # capturable (the legacy default stream is not), and torch.cuda.Event sees it
 	ctx.use_torch_stream()
 	ids = [capi.comm_unique_id() if rank == 0 else None]
 	dist.broadcast_object_list(ids, src=0, device=dev)

@@ -87,6 +87,7 @@ struct bp_ctx {
 	int32_t* d_col = nullptr;
 	int32_t* d_diag = nullptr;           // slot of the diagonal block of each owned row
 	double*  d_val = nullptr;            // [n_slots*4] 2x2 blocks {a00 a01 a10 a11}, SELL-32 slot order
+	float*   d_valf = nullptr;           // FP32 copy of d_val for the multigrid smoother (allocated on first use)
 	int32_t* d_csr_src = nullptr;        // CSR export gather map
 	// device: vectors in internal layout [2*node + c], length 2*nn
 	double *d_u = nullptr, *d_F = nullptr, *d_dx = nullptr, *d_r = nullptr, *d_z = nullptr,
@@ -153,7 +154,9 @@ void bp_launch_col_solve(bp_ctx* c, const double* r, double* z);
 void bp_launch_col_cheb(bp_ctx* c, double c1, double c2, const double* res, const double* zold, double* znew);
 // lmax_dev != nullptr: c0 / c2 are given for lmax = 1 and scaled by 1 / *lmax_dev on the device
 void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z, const double* lmax_dev = nullptr);
-void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew, const double* lmax_dev = nullptr);
+void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew, const double* lmax_dev = nullptr, bool f32 = false);
+int  bp_launch_val_to_float(bp_ctx* c);                    // d_val -> d_valf (FP32 copy read by the multigrid V-cycle)
+void bp_launch_residual(bp_ctx* c, const double* b, const double* z, double* out, bool f32);   // out = b - A z
 void bp_launch_apply_dinv(bp_ctx* c, double* v);           // v <- D^-1 v
 void bp_launch_scale_inv_norm(bp_ctx* c, double* v, int sc_slot);   // v <- v / sqrt(d_sc[slot])
 void bp_launch_fill_probe(bp_ctx* c, double* v);

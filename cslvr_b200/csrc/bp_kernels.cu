@@ -1434,9 +1434,17 @@ k_cheb_first(int nrows, double c0, const double* __restrict__ dinv, const double
 		d[i] = dv; z[i] = dv;
 	}
 }
+// 2x2 block {a00 a01 a10 a11} of the resident matrix: FP64 (double2 pairs) or the FP32 copy the
+// multigrid V-cycle reads (float4; accumulation stays FP64, vectors stay FP64)
+struct BlkD { typedef double2 T; static __device__ __forceinline__ void ld(const double2* v, size_t slot, double& a0, double& a1, double& a2, double& a3)
+	{ const double2 p = v[2 * slot], q = v[2 * slot + 1]; a0 = p.x; a1 = p.y; a2 = q.x; a3 = q.y; } };
+struct BlkF { typedef float4 T; static __device__ __forceinline__ void ld(const float4* v, size_t slot, double& a0, double& a1, double& a2, double& a3)
+	{ const float4 p = v[slot]; a0 = p.x; a1 = p.y; a2 = p.z; a3 = p.w; } };
+
+template <class B>
 __global__ void __launch_bounds__(256)
 k_cheb_step(int nrows, double c1, double c2, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ col,
-            const double2* __restrict__ val, const double* __restrict__ dinv, const double2* __restrict__ r,
+            const typename B::T* __restrict__ val, const double* __restrict__ dinv, const double2* __restrict__ r,
             const double2* __restrict__ zold, double2* __restrict__ znew, double2* __restrict__ d, const double* __restrict__ lmax_dev)
 {
 	if (lmax_dev) c2 /= *lmax_dev;
@@ -1446,13 +1454,14 @@ k_cheb_step(int nrows, double c1, double c2, const int32_t* __restrict__ sell_pt
 		const int b0 = sell_ptr[slice], w = (sell_ptr[slice + 1] - b0) >> 5;
 		const int row = (slice << 5) + lane;
 		const int32_t* cp = col + b0 + lane;
-		const double2* vp = val + 2 * ((size_t)b0 + lane);
+		const size_t s0_ = (size_t)b0 + lane;
 		double s0 = 0.0, s1 = 0.0;
 		#pragma unroll 4
 		for (int k = 0; k < w; ++k) {
-			const double2 a01 = vp[64 * (size_t)k], a23 = vp[64 * (size_t)k + 1];
+			double a0, a1, a2, a3;
+			B::ld(val, s0_ + 32 * (size_t)k, a0, a1, a2, a3);
 			const double2 xv = zold[cp[32 * k]];
-			s0 += a01.x * xv.x + a01.y * xv.y; s1 += a23.x * xv.x + a23.y * xv.y;
+			s0 += a0 * xv.x + a1 * xv.y; s1 += a2 * xv.x + a3 * xv.y;
 		}
 		if (row < nrows) {
 			const double2 rv = r[row], zo = zold[row], dv = d[row];
@@ -1463,17 +1472,67 @@ k_cheb_step(int nrows, double c1, double c2, const int32_t* __restrict__ sell_pt
 		}
 	}
 }
+// b - A z with either copy of the matrix (multigrid residual before restriction)
+template <class B>
+__global__ void __launch_bounds__(256)
+k_residual(int nrows, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ col, const typename B::T* __restrict__ val,
+           const double2* __restrict__ b, const double2* __restrict__ z, double2* __restrict__ out)
+{
+	const int lane = threadIdx.x & 31;
+	const int nsl = (nrows + 31) >> 5;
+	for (int slice = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slice < nsl; slice += (gridDim.x * blockDim.x) >> 5) {
+		const int b0 = sell_ptr[slice], w = (sell_ptr[slice + 1] - b0) >> 5;
+		const int row = (slice << 5) + lane;
+		const int32_t* cp = col + b0 + lane;
+		const size_t s0_ = (size_t)b0 + lane;
+		double s0 = 0.0, s1 = 0.0;
+		#pragma unroll 4
+		for (int k = 0; k < w; ++k) {
+			double a0, a1, a2, a3;
+			B::ld(val, s0_ + 32 * (size_t)k, a0, a1, a2, a3);
+			const double2 xv = z[cp[32 * k]];
+			s0 += a0 * xv.x + a1 * xv.y; s1 += a2 * xv.x + a3 * xv.y;
+		}
+		if (row < nrows) { const double2 bv = b[row]; out[row] = make_double2(bv.x - s0, bv.y - s1); }
+	}
+}
+__global__ void k_val_to_float(size_t n4, const double2* __restrict__ v, float4* __restrict__ f)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+		const double2 p = v[2 * i], q = v[2 * i + 1];
+		f[i] = make_float4((float)p.x, (float)p.y, (float)q.x, (float)q.y);
+	}
+}
+// refresh the FP32 copy of the resident matrix (allocated on first use)
+int bp_launch_val_to_float(bp_ctx* c)
+{
+	if (!c->d_valf) BP_CUDA(c, cudaMalloc((void**)&c->d_valf, (size_t)std::max<int64_t>(c->n_slots, 1) * sizeof(float4)));
+	k_val_to_float<<<red_blocks(c->n_slots, 256), 256, 0, c->stream>>>((size_t)c->n_slots, (const double2*)c->d_val, (float4*)c->d_valf);
+	c->launches++;
+	return BP_OK;
+}
+void bp_launch_residual(bp_ctx* c, const double* b, const double* z, double* out, bool f32)
+{
+	const int g = red_blocks(c->nn_owned, 256);
+	if (f32 && c->d_valf) k_residual<BlkF><<<g, 256, 0, c->stream>>>((int)c->nn_owned, c->d_sell_ptr, c->d_col, (const float4*)c->d_valf, (const double2*)b, (const double2*)z, (double2*)out);
+	else k_residual<BlkD><<<g, 256, 0, c->stream>>>((int)c->nn_owned, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, (const double2*)b, (const double2*)z, (double2*)out);
+	c->launches++;
+}
 void bp_launch_cheb_first(bp_ctx* c, double c0, const double* r, double* z, const double* lmax_dev)
 {
 	const int n = (int)c->nn_owned;
 	k_cheb_first<<<red_blocks(n, 512), 256, 0, c->stream>>>(n, c0, c->d_dinv, (const double2*)r, (double2*)z, (double2*)c->d_cd, lmax_dev);
 	c->launches++;
 }
-void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew, const double* lmax_dev)
+void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const double* zold, double* znew, const double* lmax_dev, bool f32)
 {
-	if (!c->grid_cheb) c->grid_cheb = one_wave(k_cheb_step, 256, c->nn_owned, 256);
-	k_cheb_step<<<c->grid_cheb, 256, 0, c->stream>>>((int)c->nn_owned, c1, c2, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, c->d_dinv,
-		(const double2*)r, (const double2*)zold, (double2*)znew, (double2*)c->d_cd, lmax_dev);
+	if (!c->grid_cheb) c->grid_cheb = one_wave(k_cheb_step<BlkD>, 256, c->nn_owned, 256);
+	if (f32 && c->d_valf)
+		k_cheb_step<BlkF><<<c->grid_cheb, 256, 0, c->stream>>>((int)c->nn_owned, c1, c2, c->d_sell_ptr, c->d_col, (const float4*)c->d_valf, c->d_dinv,
+			(const double2*)r, (const double2*)zold, (double2*)znew, (double2*)c->d_cd, lmax_dev);
+	else
+		k_cheb_step<BlkD><<<c->grid_cheb, 256, 0, c->stream>>>((int)c->nn_owned, c1, c2, c->d_sell_ptr, c->d_col, (const double2*)c->d_val, c->d_dinv,
+			(const double2*)r, (const double2*)zold, (double2*)znew, (double2*)c->d_cd, lmax_dev);
 	c->launches++;
 }
 

@@ -36,10 +36,12 @@ struct bp_mg {
 	// the V-cycle is a fixed sequence of ~50 mostly tiny launches: captured once as a CUDA graph
 	cudaGraphExec_t graph = nullptr;
 	const double *g_r = nullptr; double *g_z = nullptr, *g_z2 = nullptr;
-	int g_deg = 0, g_smoother = -1; double g_ratio = 0.0, g_alpha = 0.0; int64_t g_launches = 0;
+	int g_deg = 0, g_smoother = -1; double g_ratio = 0.0, g_alpha = 0.0; int64_t g_launches = 0; bool g_f32 = false;
 	std::vector<double> h_dense, h_val;
 	int nc = 0;                          // coarsest dofs
 	int gamma = 1;                       // coarse-grid visits per level below the finest
+	bool no_graph = false;               // the context's stream cannot be captured
+	bool f32 = true;                     // the V-cycle reads FP32 copies of the level matrices (vectors and accumulation stay FP64)
 };
 
 template <class T>
@@ -359,10 +361,18 @@ int bp_mg_prepare(bp_ctx* c)
 		k_mg_galerkin<<<blocks(ns, 256), 256, 0, c->stream>>>(ns, F.d_galmap, F.M->d_val, C->d_val);
 		c->launches++;
 	}
+	{
+		const char* e32 = getenv("BP_MG_FP32");
+		mg->f32 = e32 ? atoi(e32) != 0 : true;
+	}
 	for (int l = 0; l < nl; ++l) {
 		bp_ctx* M = mg->lv[l].M;
 		if (l > 0) bp_launch_pc_setup(M);             // level 0: done by the caller
 		bp_launch_gershgorin(M, SC_LMAX);
+		// FP32 copy of the level matrix for the smoother (the line smoother of level 0 keeps FP64)
+		const bool want_line = c->prm.mg_smoother == 1 || (c->prm.mg_smoother < 0 && c->aspect >= 3.0);
+		const bool line0 = (l == 0) && want_line && c->max_layers <= 64 && c->n_cols < c->nn_owned;
+		if (mg->f32 && !line0 && l + 1 < nl && (rc = bp_launch_val_to_float(M))) return rc;
 	}
 	for (int l = 0; l < nl; ++l) {
 		bp_ctx* M = mg->lv[l].M;
@@ -414,16 +424,16 @@ int bp_mg_prepare(bp_ctx* c)
 // (d_sc[SC_LMAX] of the level), so the launch sequence does not depend on the matrix values
 // and can be replayed as a graph.  Iterates ping-pong between za and zb; returns the buffer
 // that holds the result.
-static double* cheb_smooth(bp_ctx* M, int deg, double ratio, const double* r, double* za, double* zb, bool zero_init)
+static double* cheb_smooth(bp_ctx* M, int deg, double ratio, const double* r, double* za, double* zb, bool zero_init, bool f32)
 {
 	const double a = 1.0 / ratio, theta = 0.5 * (1.0 + a), delta = 0.5 * (1.0 - a), sigma = theta / delta;
 	const double* lm = M->d_sc + SC_LMAX;
 	double rho = 1.0 / sigma;
 	if (zero_init) bp_launch_cheb_first(M, 1.0 / theta, r, za, lm);
-	else { bp_launch_cheb_step(M, 0.0, 1.0 / theta, r, za, zb, lm); std::swap(za, zb); }
+	else { bp_launch_cheb_step(M, 0.0, 1.0 / theta, r, za, zb, lm, f32); std::swap(za, zb); }
 	for (int k = 1; k < deg; ++k) {
 		const double rho_n = 1.0 / (2.0 * sigma - rho);
-		bp_launch_cheb_step(M, rho_n * rho, 2.0 * rho_n / delta, r, za, zb, lm);
+		bp_launch_cheb_step(M, rho_n * rho, 2.0 * rho_n / delta, r, za, zb, lm, f32);
 		std::swap(za, zb);
 		rho = rho_n;
 	}
@@ -470,7 +480,7 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 	const bool want_line = c->prm.mg_smoother == 1 || (c->prm.mg_smoother < 0 && c->aspect >= 3.0);
 	const bool line = (l == 0) && want_line && c->max_layers <= 64 && c->n_cols < c->nn_owned;
 	double* z = line ? col_cheb_smooth(c, deg, ratio, rhs, M->d_z, M->d_z2, true, L.n)
-	                 : cheb_smooth(M, deg, ratio, rhs, M->d_z, M->d_z2, true);
+	                 : cheb_smooth(M, deg, ratio, rhs, M->d_z, M->d_z2, true, mg->f32);
 	bp_ctx* C = mg->lv[l + 1].M;
 	// gamma coarse-grid visits per level below the finest (1 = V-cycle, 2 = W-cycle): plain
 	// aggregation has a stiff coarse operator, a second visit of the (tiny) coarser levels is cheap
@@ -481,15 +491,18 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 	const double alpha = ev ? atof(ev) : alpha_def;
 	for (int g = 0; g < gamma; ++g) {
 		double* other = (z == M->d_z) ? M->d_z2 : M->d_z;
-		k_mg_residual<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, M->d_sell_ptr, M->d_col, (const double2*)M->d_val,
-			(const double2*)rhs, (const double2*)z, (double2*)M->d_io);
+		if (line) {
+			k_mg_residual<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, M->d_sell_ptr, M->d_col, (const double2*)M->d_val,
+				(const double2*)rhs, (const double2*)z, (double2*)M->d_io);
+			c->launches++;
+		} else bp_launch_residual(M, rhs, z, M->d_io, mg->f32);
 		k_mg_restrict<<<blocks(C->nn_owned, 128), 128, 0, c->stream>>>((int)C->nn_owned, L.d_aggptr, L.d_aggidx, (const double2*)M->d_io, (double2*)C->d_F);
-		c->launches += 2;
+		c->launches += 1;
 		const double* xc = vcycle(c, mg, l + 1, C->d_F, deg, ratio);
 		// over-relaxed coarse correction (piecewise-constant prolongation under-corrects)
 		k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, c->stream>>>((int)L.n, L.d_agg, (const double2*)xc, (double2*)z, alpha);
 		c->launches++;
-		z = line ? col_cheb_smooth(c, deg, ratio, rhs, z, other, false, L.n) : cheb_smooth(M, deg, ratio, rhs, z, other, false);
+		z = line ? col_cheb_smooth(c, deg, ratio, rhs, z, other, false, L.n) : cheb_smooth(M, deg, ratio, rhs, z, other, false, mg->f32);
 	}
 	return z;
 }
@@ -501,7 +514,7 @@ int bp_mg_apply(bp_ctx* c)
 	bp_mg* mg = c->mg;
 	const int deg = std::max(c->prm.pc_degree, 1);
 	const double ratio = std::max(c->prm.pc_eig_ratio, 1.5);
-	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_smoother != c->prm.mg_smoother || mg->g_alpha != c->prm.mg_coarse_scale)) {
+	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_smoother != c->prm.mg_smoother || mg->g_alpha != c->prm.mg_coarse_scale || mg->g_f32 != mg->f32)) {
 		cudaGraphExecDestroy(mg->graph);
 		mg->graph = nullptr;
 	}
@@ -509,7 +522,17 @@ int bp_mg_apply(bp_ctx* c)
 		int64_t l0 = c->launches;
 		for (size_t l = 1; l < mg->lv.size(); ++l) { mg->lv[l].M->launches = 0; mg->lv[l].M->stream = c->stream; }
 		cudaGraph_t g = nullptr;
-		BP_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+		// the legacy default stream (e.g. torch's default current stream handed over with bp_set_stream)
+		// cannot be captured: launch the V-cycle directly there
+		const cudaError_t eb = mg->no_graph ? cudaErrorStreamCaptureUnsupported : cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+		if (eb != cudaSuccess) {
+			cudaGetLastError();
+			mg->no_graph = true;
+			double* out = vcycle(c, mg, 0, c->d_r, deg, ratio);
+			if (out != c->d_z) BP_CUDA(c, cudaMemcpyAsync(c->d_z, out, (size_t)2 * c->nn_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+			for (size_t l = 1; l < mg->lv.size(); ++l) c->launches += mg->lv[l].M->launches;
+			return BP_OK;
+		}
 		double* out = vcycle(c, mg, 0, c->d_r, deg, ratio);
 		if (out != c->d_z) cudaMemcpyAsync(c->d_z, out, (size_t)2 * c->nn_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
 		BP_CUDA(c, cudaStreamEndCapture(c->stream, &g));
@@ -519,7 +542,7 @@ int bp_mg_apply(bp_ctx* c)
 		mg->g_launches = c->launches - l0;
 		for (size_t l = 1; l < mg->lv.size(); ++l) mg->g_launches += mg->lv[l].M->launches;
 		c->launches = l0;
-		mg->g_r = c->d_r; mg->g_z = c->d_z; mg->g_z2 = c->d_z2; mg->g_deg = deg; mg->g_ratio = ratio; mg->g_smoother = c->prm.mg_smoother; mg->g_alpha = c->prm.mg_coarse_scale;
+		mg->g_r = c->d_r; mg->g_z = c->d_z; mg->g_z2 = c->d_z2; mg->g_deg = deg; mg->g_ratio = ratio; mg->g_smoother = c->prm.mg_smoother; mg->g_alpha = c->prm.mg_coarse_scale; mg->g_f32 = mg->f32;
 	}
 	BP_CUDA(c, cudaGraphLaunch(mg->graph, c->stream));
 	c->launches += mg->g_launches;
@@ -535,7 +558,7 @@ void bp_mg_free(bp_ctx* c)
 		for (void* p : t) if (p) cudaFree(p);
 		if (l > 0 && L.M) {
 			bp_ctx* M = L.M;
-			void* ptrs[] = { M->d_sell_ptr, M->d_col, M->d_diag, M->d_val, M->d_dinv, M->d_F, M->d_z, M->d_z2, M->d_cd, M->d_io, M->d_sc, M->d_part, M->d_counter };
+			void* ptrs[] = { M->d_sell_ptr, M->d_col, M->d_diag, M->d_val, M->d_valf, M->d_dinv, M->d_F, M->d_z, M->d_z2, M->d_cd, M->d_io, M->d_sc, M->d_part, M->d_counter };
 			for (void* p : ptrs) if (p) cudaFree(p);
 			if (M->h_sc) cudaFreeHost(M->h_sc);
 			delete M;
