@@ -121,6 +121,155 @@ __global__ void k_mg_dense(int n, const double* __restrict__ Ainv, const double*
 	x[i] = s;
 }
 
+
+// ------------------------------------------------------------------ the small levels in ONE kernel
+// Below a few thousand nodes a level is one or two CTAs' worth of work and its ~12 launches per
+// visit cost more than their arithmetic.  k_mg_tail runs the whole lower part of the V-cycle
+// (pre-smoothing, residual, restriction ... dense coarsest solve ... prolongation, post-smoothing)
+// for the levels >= l_tail in a single CTA of 1024 threads, __syncthreads() between the phases.
+struct TailLevel {
+	int n, nc;                           // nodes of this level / of the next coarser one
+	const int32_t *sell_ptr, *col;
+	const float4* valf;                  // FP32 copy (or nullptr -> val)
+	const double2* val;
+	const double* dinv;
+	const double* lmax;                  // bound of lmax(D^-1 A), on the device
+	double2 *F, *z, *z2, *cd, *io;       // rhs (written by the level above), iterates, direction, residual
+	const int32_t *agg, *aggptr, *aggidx;
+};
+#define MG_TAIL_MAX 8
+struct TailArgs { TailLevel lv[MG_TAIL_MAX]; int nl; int deg; double ratio, alpha; const double* dense; int ndense; };
+
+__device__ __forceinline__ double2 tail_dinv(const double* dinv, int i, double2 r)
+{
+	const double2 d01 = ((const double2*)dinv)[2 * (size_t)i], d23 = ((const double2*)dinv)[2 * (size_t)i + 1];
+	return make_double2(d01.x * r.x + d01.y * r.y, d23.x * r.x + d23.y * r.y);
+}
+// s = A x for the 32 rows of one slice (one warp)
+__device__ __forceinline__ void tail_row(const TailLevel& L, int slice, int lane, const double2* x, double& s0, double& s1)
+{
+	const int b0 = L.sell_ptr[slice], w = (L.sell_ptr[slice + 1] - b0) >> 5;
+	const int32_t* cp = L.col + b0 + lane;
+	s0 = 0.0; s1 = 0.0;
+	for (int k = 0; k < w; ++k) {
+		double a0, a1, a2, a3;
+		const size_t slot = (size_t)b0 + lane + 32 * (size_t)k;
+		if (L.valf) { const float4 v = L.valf[slot]; a0 = v.x; a1 = v.y; a2 = v.z; a3 = v.w; }
+		else { const double2 p = L.val[2 * slot], q = L.val[2 * slot + 1]; a0 = p.x; a1 = p.y; a2 = q.x; a3 = q.y; }
+		const double2 xv = x[cp[32 * k]];
+		s0 += a0 * xv.x + a1 * xv.y; s1 += a2 * xv.x + a3 * xv.y;
+	}
+}
+__device__ void tail_cheb_step(const TailLevel& L, double c1, double c2, const double2* r, const double2* zold, double2* znew)
+{
+	const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31, nsl = (L.n + 31) >> 5;
+	for (int slice = warp; slice < nsl; slice += nw) {
+		double s0, s1;
+		tail_row(L, slice, lane, zold, s0, s1);
+		const int row = (slice << 5) + lane;
+		if (row < L.n) {
+			const double2 rv = r[row], zo = zold[row], dv = L.cd[row];
+			const double2 pr = tail_dinv(L.dinv, row, make_double2(rv.x - s0, rv.y - s1));
+			const double2 dn = make_double2(c1 * dv.x + c2 * pr.x, c1 * dv.y + c2 * pr.y);
+			L.cd[row] = dn;
+			znew[row] = make_double2(zo.x + dn.x, zo.y + dn.y);
+		}
+	}
+	__syncthreads();
+}
+// Chebyshev smoothing exactly as cheb_smooth(): returns the buffer holding the result
+__device__ double2* tail_smooth(const TailLevel& L, int deg, double ratio, const double2* r, double2* za, double2* zb, bool zero_init)
+{
+	const double a = 1.0 / ratio, theta = 0.5 * (1.0 + a), delta = 0.5 * (1.0 - a), sigma = theta / delta;
+	const double ilm = 1.0 / *L.lmax;
+	double rho = 1.0 / sigma;
+	if (zero_init) {
+		const double c0 = ilm / theta;
+		for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+			const double2 v = tail_dinv(L.dinv, i, r[i]);
+			const double2 dv = make_double2(c0 * v.x, c0 * v.y);
+			L.cd[i] = dv; za[i] = dv;
+		}
+		__syncthreads();
+	} else {
+		tail_cheb_step(L, 0.0, ilm / theta, r, za, zb);
+		double2* t = za; za = zb; zb = t;
+	}
+	for (int k = 1; k < deg; ++k) {
+		const double rho_n = 1.0 / (2.0 * sigma - rho);
+		tail_cheb_step(L, rho_n * rho, 2.0 * rho_n / delta * ilm, r, za, zb);
+		double2* t = za; za = zb; zb = t;
+		rho = rho_n;
+	}
+	return za;
+}
+__global__ void __launch_bounds__(1024, 1)
+k_mg_tail(const TailArgs A)
+{
+	__shared__ double2* zres[MG_TAIL_MAX];
+	const int nl = A.nl;                  // levels in the tail; the last one is the dense coarsest level
+	// ---- down
+	for (int l = 0; l + 1 < nl; ++l) {
+		const TailLevel& L = A.lv[l];
+		double2* z = tail_smooth(L, A.deg, A.ratio, L.F, L.z, L.z2, true);
+		if (threadIdx.x == 0) zres[l] = z;
+		// residual -> io
+		const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5, lane = threadIdx.x & 31, nsl = (L.n + 31) >> 5;
+		for (int slice = warp; slice < nsl; slice += nw) {
+			double s0, s1;
+			tail_row(L, slice, lane, z, s0, s1);
+			const int row = (slice << 5) + lane;
+			if (row < L.n) { const double2 bv = L.F[row]; L.io[row] = make_double2(bv.x - s0, bv.y - s1); }
+		}
+		__syncthreads();
+		// restriction -> rhs of the next level
+		double2* bc = A.lv[l + 1].F;
+		for (int I = threadIdx.x; I < L.nc; I += blockDim.x) {
+			double s0 = 0.0, s1 = 0.0;
+			for (int k = L.aggptr[I]; k < L.aggptr[I + 1]; ++k) { const double2 v = L.io[L.aggidx[k]]; s0 += v.x; s1 += v.y; }
+			bc[I] = make_double2(s0, s1);
+		}
+		__syncthreads();
+	}
+	// ---- coarsest: dense inverse
+	{
+		const TailLevel& C = A.lv[nl - 1];
+		const double* b = (const double*)C.F;
+		double* x = (double*)C.z;
+		for (int i = threadIdx.x; i < A.ndense; i += blockDim.x) {
+			double sacc = 0.0;
+			for (int j = 0; j < A.ndense; ++j) sacc += A.dense[(size_t)i * A.ndense + j] * b[j];
+			x[i] = sacc;
+		}
+		__syncthreads();
+	}
+	// ---- up
+	for (int l = nl - 2; l >= 0; --l) {
+		const TailLevel& L = A.lv[l];
+		double2* z = zres[l];
+		const double2* xc = (l + 1 == nl - 1) ? A.lv[l + 1].z : zres[l + 1];
+		for (int i = threadIdx.x; i < L.n; i += blockDim.x) {
+			const int I = L.agg[i];
+			if (I < 0) continue;
+			const double2 e = xc[I];
+			double2 v = z[i];
+			v.x += A.alpha * e.x; v.y += A.alpha * e.y;
+			z[i] = v;
+		}
+		__syncthreads();
+		double2* other = (z == L.z) ? L.z2 : L.z;
+		z = tail_smooth(L, A.deg, A.ratio, L.F, z, other, false);
+		if (threadIdx.x == 0) zres[l] = z;
+		__syncthreads();
+	}
+	// the level above reads the correction from lv[0].z
+	if (nl > 1) {
+		const TailLevel& L = A.lv[0];
+		double2* z = zres[0];
+		if (z != L.z) for (int i = threadIdx.x; i < L.n; i += blockDim.x) L.z[i] = z[i];
+	}
+}
+
 static inline int blocks(int64_t n, int per)
 {
 	int64_t b = (n + per - 1) / per;
@@ -475,6 +624,35 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 		k_mg_dense<<<(mg->nc + 127) / 128, 128, 0, c->stream>>>(mg->nc, mg->d_dense, rhs, M->d_z);
 		c->launches++;
 		return M->d_z;
+	}
+	{
+		const char* evg0 = getenv("BP_MG_GAMMA");
+		const char* evt = getenv("BP_MG_TAIL");
+		const int tail_nodes = evt ? atoi(evt) : 4096;
+		const bool v_only = std::max(1, evg0 ? atoi(evg0) : mg->gamma) == 1;
+		if (l > 0 && v_only && L.n <= tail_nodes && nl - l <= MG_TAIL_MAX && rhs == M->d_F) {
+			// this level and everything below it: one launch
+			TailArgs A;
+			memset(&A, 0, sizeof(A));
+			A.nl = nl - l; A.deg = deg; A.ratio = ratio;
+			const char* eva = getenv("BP_MG_ALPHA");
+			A.alpha = eva ? atof(eva) : ((c->prm.mg_coarse_scale > 0.0 && c->prm.mg_coarse_scale <= 2.0) ? c->prm.mg_coarse_scale : 1.8);
+			A.dense = mg->d_dense; A.ndense = mg->nc;
+			for (int k = l; k < nl; ++k) {
+				bp_mg_level& Lk = mg->lv[k];
+				bp_ctx* Mk = Lk.M;
+				TailLevel& T = A.lv[k - l];
+				T.n = (int)Lk.n; T.nc = (k + 1 < nl) ? (int)mg->lv[k + 1].n : 0;
+				T.sell_ptr = Mk->d_sell_ptr; T.col = Mk->d_col;
+				T.valf = (mg->f32 && k + 1 < nl) ? (const float4*)Mk->d_valf : nullptr;
+				T.val = (const double2*)Mk->d_val; T.dinv = Mk->d_dinv; T.lmax = Mk->d_sc + SC_LMAX;
+				T.F = (double2*)Mk->d_F; T.z = (double2*)Mk->d_z; T.z2 = (double2*)Mk->d_z2; T.cd = (double2*)Mk->d_cd; T.io = (double2*)Mk->d_io;
+				T.agg = Lk.d_agg; T.aggptr = Lk.d_aggptr; T.aggidx = Lk.d_aggidx;
+			}
+			k_mg_tail<<<1, 1024, 0, c->stream>>>(A);
+			c->launches++;
+			return M->d_z;
+		}
 	}
 	// line smoother when asked for, or (auto) when the elements are flat: dx >= 3 dz
 	const bool want_line = c->prm.mg_smoother == 1 || (c->prm.mg_smoother < 0 && c->aspect >= 3.0);
