@@ -43,6 +43,7 @@ def run_multi(args, rank, world, local):
 		ctx.set_field(f, rm.fields[k])
 	torch.cuda.set_stream(torch.cuda.Stream(dev))       # capturable (the legacy default stream is not), and torch.cuda.Event sees it
 	ctx.use_torch_stream()
+	clocks = B.ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs a moment before its first sample
 	ids = [capi.comm_unique_id() if rank == 0 else None]
 	dist.broadcast_object_list(ids, src=0, device=dev)
 	ctx.comm_init(ids[0], rank, world)
@@ -99,7 +100,6 @@ def run_multi(args, rank, world, local):
 		dist.all_reduce(t, op=dist.ReduceOp.MAX)
 		return t[0].item() / args.steps, t[1].item() / args.steps
 
-	clocks = B.ClockSampler(local) if rank == 0 else None
 	if clocks: clocks.start()
 	l0 = ctx.launch_count()
 	s_dev, _ = timed(step_dev)
