@@ -151,7 +151,8 @@ typedef struct {
 	 * forms: BP_FIELD_UZ enters the strain-rate tensor (eps_02 = (u_x,z + u_z,x)/2, eps_12 likewise),
 	 * sliding acts on the grounded bed only (dGamma_bg) and carries u_z_b = (-B_ring - u_h.n_h)/n_z   */
 	int32_t reduced_stokes;
-	/* BP_PC_MG: factor on every coarse-grid correction (0 = default 1.8).  The piecewise-constant
+	/* BP_PC_MG: factor on every coarse-grid correction (0 = default: 1.8, or 1.0 on the slabs of a
+	 * partitioned mesh).  The piecewise-constant
 	 * prolongation gives a coarse operator that is too stiff, so the plain correction under-shoots;
 	 * any factor in (0, 2] keeps the V-cycle symmetric positive definite.                          */
 	double  mg_coarse_scale;
