@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 std::string g_bp_create_error;
 void bp_upload_quadrature(bp_ctx* c);
@@ -316,6 +317,9 @@ void bp_destroy(bp_ctx* c)
 	if (c->h_sc) cudaFreeHost(c->h_sc);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+	if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+	for (auto e : c->pipe_ev) if (e) cudaEventDestroy(e);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -411,6 +415,72 @@ int bp_csr_pattern(bp_ctx* c, int64_t* nnz, const int64_t** indptr, const int32_
 	return BP_OK;
 }
 
+// Host-buffer assembly, pipelined: u travels to the device in pieces, each slice of the row-gather pass
+// starts as soon as the node prefix its incidences reference has arrived (h_blk_need_node, a prefix
+// maximum computed at set-up: with any locality in the numbering the first slices need only the first
+// part of u), and every slice of F starts its way back as soon as it is final -- right after the slice for
+// rows no facet integral touches, after the facet kernel for the others.  Three streams: copies in,
+// kernels, copies out (PCIe is full duplex).  Needs the caller's numbering to be the internal one.
+static int assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
+{
+	const int64_t no = c->nn_owned, nn = c->nn;
+	const int nblk = (int)((no + BP_ROWS_PER_CTA - 1) / BP_ROWS_PER_CTA);
+	const char* evk = getenv("BP_PIPE_K");
+	const int K = std::max(1, std::min(evk ? atoi(evk) : 4, std::min(8, nblk / 64)));
+	if (!c->s_h2d) {
+		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+		c->pipe_ev.resize(2 * 8 + 2);
+		for (auto& e : c->pipe_ev) BP_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	cudaEvent_t* e_h = c->pipe_ev.data();
+	cudaEvent_t* e_c = c->pipe_ev.data() + 8;
+	cudaEvent_t e_f = c->pipe_ev[16], e_0 = c->pipe_ev[17];
+	bp_update_ainv(c);
+	// the copy streams start after whatever the context's stream still has in flight
+	BP_CUDA(c, cudaEventRecord(e_0, c->stream));
+	BP_CUDA(c, cudaStreamWaitEvent(c->s_h2d, e_0, 0));
+	BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_0, 0));
+	int64_t prev = 0;
+	for (int k = 0; k < K; ++k) {
+		const int b1 = (int)((int64_t)(k + 1) * nblk / K);
+		const int64_t hi = (k == K - 1) ? nn : std::min<int64_t>(nn, c->h_blk_need_node[b1 - 1]);
+		if (hi > prev) {
+			BP_CUDA(c, cudaMemcpyAsync(c->d_u + 2 * prev, u + 2 * prev, (size_t)(hi - prev) * 2 * sizeof(double), cudaMemcpyHostToDevice, c->s_h2d));
+			prev = hi;
+		}
+		BP_CUDA(c, cudaEventRecord(e_h[k], c->s_h2d));
+	}
+	int vprev = 0;
+	for (int k = 0; k < K; ++k) {
+		const int b0 = (int)((int64_t)k * nblk / K), b1 = (int)((int64_t)(k + 1) * nblk / K);
+		const int vhi = (k == K - 1) ? (int)c->nv : std::max(vprev, (int)c->h_blk_need_vert[b1 - 1]);
+		BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_h[k], 0));
+		bp_launch_rows_chunk(c, what, b0, b1 - b0, vprev, vhi);
+		vprev = vhi;
+		BP_CUDA(c, cudaEventRecord(e_c[k], c->stream));
+	}
+	bp_launch_facets(c, what);
+	BP_CUDA(c, cudaEventRecord(e_f, c->stream));
+	if (what & BP_ASSEMBLE_J) c->have_J = true;
+	if (F && (what & BP_ASSEMBLE_F)) {
+		for (int pass = 0; pass < 2; ++pass)           // slices no facet touches first, the others after the facet kernel
+			for (int k = 0; k < K; ++k) {
+				const int b0 = (int)((int64_t)k * nblk / K), b1 = (int)((int64_t)(k + 1) * nblk / K);
+				bool touched = false;
+				for (int b = b0; b < b1 && !touched; ++b) touched = c->h_blk_facet[b] != 0;
+				if ((int)touched != pass) continue;
+				const int64_t r0 = (int64_t)b0 * BP_ROWS_PER_CTA, r1 = std::min<int64_t>(no, (int64_t)b1 * BP_ROWS_PER_CTA);
+				BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, touched ? e_f : e_c[k], 0));
+				BP_CUDA(c, cudaMemcpyAsync(F + 2 * r0, c->d_F + 2 * r0, (size_t)(r1 - r0) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
+			}
+		BP_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+	}
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return BP_OK;
+}
+
 int bp_assemble(bp_ctx* c, int what, const double* u, double* F, double* Jv, int on_device)
 {
 	if (!c || !u) return BP_ERR_ARG;
@@ -419,6 +489,9 @@ int bp_assemble(bp_ctx* c, int what, const double* u, double* F, double* Jv, int
 	int rc = ready(c);
 	if (rc) return rc;
 	if (Jv && (rc = bp_build_csr_export(c))) return rc;
+	if (!on_device && !Jv && c->identity_dofs && !c->comm && c->nn == c->nn_owned && c->nd_ext == 2 * c->nn && bp_rows_gather_mode(c)
+	    && !(what & ~(BP_ASSEMBLE_F | BP_ASSEMBLE_J)) && !getenv("BP_NO_PIPELINE"))
+		return assemble_pipelined(c, what, u, F);
 	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
 	bp_ctx* cs[1] = { c };
 	if ((rc = group_assemble(cs, 1, what))) return rc;

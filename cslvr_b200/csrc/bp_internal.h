@@ -8,6 +8,9 @@
 #include "cslvr_b200.h"
 
 #define BP_MAX_QUAD 128
+#ifndef BP_ROWS_PER_CTA
+#define BP_ROWS_PER_CTA 128       // block rows per CTA of the row-gather assembly kernel
+#endif
 
 // ---- device scalar block used by the Krylov loop (doubles) ------------------
 enum {
@@ -119,6 +122,12 @@ struct bp_ctx {
 	bool have_S = false, have_A = false, have_beta = false, have_J = false, have_B = false;
 	int64_t launches = 0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// host-buffer bp_assemble, pipelined: per CTA of the row-gather kernel, the vertex / node prefix its
+	// incidences reference (prefix maxima) and whether a facet integral touches one of its rows
+	std::vector<int32_t> h_blk_need_vert, h_blk_need_node;
+	std::vector<uint8_t> h_blk_facet;
+	cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+	std::vector<cudaEvent_t> pipe_ev;
 };
 
 // ---- helpers -------------------------------------------------------------
@@ -132,6 +141,9 @@ int bp_build_csr_export(bp_ctx* c);
 
 // kernels (bp_kernels.cu)
 void bp_launch_assemble(bp_ctx* c, int what);                 // d_u -> d_F / d_val
+bool bp_rows_gather_mode(const bp_ctx* c);                    // the row-gather kernel serves this context
+void bp_launch_rows_chunk(bp_ctx* c, int what, int blk0, int nblk, int v0, int v1);   // CTAs [blk0, blk0+nblk) of k_rows; u expanded for vertices [v0, v1) first
+void bp_launch_facets(bp_ctx* c, int what);
 void bp_update_ainv(bp_ctx* c);
 void bp_launch_spmv(bp_ctx* c, const double* x, double* y, int with_dot);
 void bp_launch_gather_in(bp_ctx* c, const double* ext, double* internal);   // caller -> internal

@@ -292,9 +292,7 @@ void bp_launch_proxy(bp_ctx* c)
 // and every F entry is then written exactly once: no atomics, no zero-fill, bitwise
 // reproducible.  The price is that the cell-constant part of a tet is recomputed by
 // each of its four nodes.
-#ifndef RTPB
-#define RTPB 128
-#endif
+#define RTPB BP_ROWS_PER_CTA
 #ifndef ROWS_MIN_CTAS
 #define ROWS_MIN_CTAS 3
 #endif
@@ -305,11 +303,11 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
        const double* __restrict__ soa, size_t nv,
        const double2* __restrict__ u /* per VERTEX */, const double* __restrict__ Av,
        const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
-       double* __restrict__ F, double* __restrict__ val, AsmParams P, const double* __restrict__ uzv)
+       double* __restrict__ F, double* __restrict__ val, AsmParams P, const double* __restrict__ uzv, int blk0)
 {
 	extern __shared__ double acc[];                  // [4*(max_row-1)][RTPB]: off-diagonal blocks, strip slot = row position minus (position > diagonal's)
 	const int tid = threadIdx.x;
-	const int i = blockIdx.x * RTPB + tid;
+	const int i = (blockIdx.x + blk0) * RTPB + tid;
 	const bool active = i < nrows;
 	const int len = active ? rowlen[i] : 0;
 	if (WANT_J) for (int k = 0; k < 4 * (len - 1); ++k) acc[k * RTPB + tid] = 0.0;
@@ -773,6 +771,58 @@ void bp_update_ainv(bp_ctx* c)
 	c->ainv_dirty = false;
 }
 
+__global__ void k_expand_u_range(int v0, int v1, const int32_t* __restrict__ v2n, const double2* __restrict__ u, double2* __restrict__ uv)
+{
+	for (int i = v0 + blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += gridDim.x * blockDim.x) uv[i] = u[v2n[i]];
+}
+
+bool bp_rows_gather_mode(const bp_ctx* c)
+{
+	const size_t row_smem = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);
+	return c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
+}
+
+// one slice of the row-gather pass (the pipelined host-buffer bp_assemble): CTAs [blk0, blk0 + nblk)
+void bp_launch_rows_chunk(bp_ctx* c, int what, int blk0, int nblk, int v0, int v1)
+{
+	AsmParams P = make_params(c);
+	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
+	const size_t row_smem = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);
+	if (!c->smem_attr_set) {
+		cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(k_rows<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(k_rows<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(k_rows<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		c->smem_attr_set = true;
+	}
+	const double2* uvert = (const double2*)c->d_u;
+	if (c->d_v2n) {
+		if (v1 > v0) { k_expand_u_range<<<red_blocks_fwd(v1 - v0, 256), 256, 0, c->stream>>>(v0, v1, c->d_v2n, (const double2*)c->d_u, (double2*)c->d_uvert); c->launches++; }
+		uvert = (const double2*)c->d_uvert;
+	}
+	if (nblk <= 0) return;
+	#define ROWSC(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<nblk, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, blk0); \
+		else k_rows<WF, WJ, false><<<nblk, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, blk0); } while (0)
+	if (wf && wj) ROWSC(true, true, row_smem);
+	else if (wf)  ROWSC(true, false, 0);
+	else if (wj)  ROWSC(false, true, row_smem);
+	c->launches++;
+}
+
+void bp_launch_facets(bp_ctx* c, int what)
+{
+	if (!c->nf) return;
+	AsmParams P = make_params(c);
+	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
+	const int gf = (int)((c->nf + TPB - 1) / TPB);
+	const double2* u2 = (const double2*)c->d_u;
+	#define FACETC(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring)
+	if (wf && wj) FACETC(true, true);
+	else if (wf)  FACETC(true, false);
+	else if (wj)  FACETC(false, true);
+	c->launches++;
+}
+
 void bp_launch_assemble(bp_ctx* c, int what)
 {
 	AsmParams P = make_params(c);
@@ -787,7 +837,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
 			cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			k_rows<true, true, false><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
-				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz);
+				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0);
 		} else {
 			const int gc = (int)((c->nt + TPB - 1) / TPB);
 			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_uz);
@@ -811,8 +861,8 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		}
 		const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
 		const double2* uvert = bp_vertex_u(c);
-		#define ROWS(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz); \
-			else k_rows<WF, WJ, false><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz); } while (0)
+		#define ROWS(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0); \
+			else k_rows<WF, WJ, false><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0); } while (0)
 		if (wf && wj) ROWS(true, true, row_smem);
 		else if (wf)  ROWS(true, false, 0);
 		else if (wj)  ROWS(false, true, row_smem);

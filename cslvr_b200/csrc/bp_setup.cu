@@ -245,6 +245,26 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 				}
 				pos[at] = pk;
 			}
+		{	// what the pipelined host-buffer bp_assemble needs per CTA of the row-gather kernel
+			const int64_t nblk = (no + BP_ROWS_PER_CTA - 1) / BP_ROWS_PER_CTA;
+			std::vector<int32_t> mxv(nblk, -1);
+			for (int64_t t = 0; t < nt; ++t)
+				for (int a = 0; a < 4; ++a) {
+					const int32_t i = cn[t * 4 + a];
+					if (i >= no) continue;
+					int32_t& mv = mxv[i / BP_ROWS_PER_CTA];
+					for (int j = 0; j < 4; ++j) mv = std::max(mv, m->cells[t * 4 + j]);
+				}
+			std::vector<int32_t> pmx(nv);                       // prefix maximum of the node of vertices 0..v
+			for (int64_t v = 0; v < nv; ++v) pmx[v] = std::max(v2n[v], v ? pmx[v - 1] : -1);
+			c->h_blk_need_vert.assign(nblk, 0); c->h_blk_need_node.assign(nblk, 0);
+			int32_t run = -1;
+			for (int64_t b = 0; b < nblk; ++b) {
+				run = std::max(run, mxv[b]);
+				c->h_blk_need_vert[b] = run + 1;
+				c->h_blk_need_node[b] = run >= 0 ? pmx[run] + 1 : 0;
+			}
+		}
 		UP(c->d_inc_slice, sl_ptr.data(), nsl + 1);
 		UP(c->d_inc_code, code.data(), code.size());
 		UP(c->d_inc_pos, pos.data(), pos.size());
@@ -268,6 +288,12 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		finfo.push_back(lf | (basal << 8) | (press << 9) | ((mk == 3) << 10));   // bit 10: dGamma_bg (grounded bed), the reduced-Stokes sliding set
 	}
 	c->nf = (int64_t)fcell.size();
+	{	// CTAs of the row-gather kernel with a row that a facet integral adds to
+		static const int LOCF[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
+		c->h_blk_facet.assign((size_t)((no + BP_ROWS_PER_CTA - 1) / BP_ROWS_PER_CTA), 0);
+		for (size_t f = 0; f < fcell.size(); ++f)
+			for (int k = 0; k < 3; ++k) { const int32_t nd_ = cn[(int64_t)fcell[f] * 4 + LOCF[finfo[f] & 0xff][k]]; if (nd_ < no) c->h_blk_facet[nd_ / BP_ROWS_PER_CTA] = 1; }
+	}
 	{	// Dirichlet dofs of the u_z system: nodes of the basal facets (cslvr/momentumbp.py:79-85)
 		static const int LOC[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
 		std::vector<uint8_t> bc((size_t)std::max<int64_t>(no, 1), 0);
