@@ -37,6 +37,28 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 os.environ.setdefault('CSLVR_B200_QUIET', '1')
+os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')      # stdout carries exactly one JSON line
+
+_JSON_FD = None
+
+
+def quiet_stdout():
+	"""stdout carries exactly ONE JSON line: everything else a library prints there (NCCL's version
+	banner, ...) is sent to stderr; emit() writes the line to the real stdout."""
+	global _JSON_FD
+	if _JSON_FD is None:
+		sys.stdout.flush()
+		_JSON_FD = os.dup(1)
+		os.dup2(2, 1)
+
+
+def emit(text):
+	sys.stdout.flush()
+	if _JSON_FD is None:
+		print(text, flush=True)
+	else:
+		os.write(_JSON_FD, (text + "\n").encode())
+
 
 METRIC = "BP residual+Jacobian assembly throughput"
 UNIT = "Mtets/s"
@@ -166,7 +188,7 @@ def run_reference(args):
 	        "cpu_baseline": base,
 	        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 	        "gpu_launches": 0}
-	print(json.dumps(line))
+	emit(json.dumps(line))
 
 
 def main():
@@ -182,6 +204,7 @@ def main():
 	ap.add_argument('--nx', type=int, default=0, help='multi-rank arm: TOTAL columns in x (default 260 per GPU); strong-scaling studies fix it')
 	ap.add_argument('--ny', type=int, default=0)
 	args = ap.parse_args()
+	quiet_stdout()
 	args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
 	if args.impl == 'reference':
 		return run_reference(args)
@@ -309,7 +332,7 @@ def main():
 	if not args.no_cpu:
 		base, _ = cpu_reference(model, u_host, sample_cells=None if nt <= 2500000 else 2000000, steps=1, warmup=0)
 		line["cpu_baseline"] = base
-	print(json.dumps(line))
+	emit(json.dumps(line))
 
 
 if __name__ == '__main__':

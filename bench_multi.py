@@ -138,7 +138,7 @@ def run_multi(args, rank, world, local):
 		        "clocks": clocks.summary()}
 		if newton:
 			line["newton"] = newton
-		print(json.dumps(line))
+		B.emit(json.dumps(line))
 	if clocks: clocks.close()
 	ctx.close()
 	dist.barrier()

@@ -37,5 +37,28 @@ def main():
 		print(name, P.n_dofs, ix.size, info['iterations'])
 
 
+def main_rs():
+	"""MomentumDukowiczStokesReduced (oracle/rs_oracle.py): residual and Jacobian at a random state with a
+	random frozen u_z and B_ring, and the home-rolled Newton solution with the u_z callback."""
+	from cases import rs_problem, state
+	os.environ['CSLVR_B200_QUIET'] = '1'
+	for base in ('ismip_a_6x5x3', 'marine_6x5x3'):
+		m = build(base)
+		rng = np.random.default_rng(7)
+		Br = rng.normal(size=m.num_vertices) * 0.2
+		uz = rng.normal(size=m.n_nodes)[m.vertex_to_node] * 3.0
+		P = rs_problem(m, B_ring=Br)
+		P.set_uz(uz)
+		u = state(P.n_dofs, 98)
+		F, J = P.residual(u), P.jacobian(u)
+		P.set_uz(np.zeros(m.num_vertices))
+		un, info = P.newton_rs(rtol=1e-9, atol=1e-6, maxit=50, relax=0.8)
+		assert info['converged']
+		np.savez_compressed(os.path.join(HERE, 'rs_' + base + '.npz'), u=u, uz=uz, B_ring=Br, F=F, J=J, u_newton=un,
+		                    uz_newton=P.uz, newton_iterations=info['iterations'], residuals=np.array(info['residuals']))
+		print('rs_' + base, P.n_dofs, info['iterations'])
+
+
 if __name__ == '__main__':
 	main()
+	main_rs()

@@ -557,3 +557,24 @@ def test_reduced_stokes_linear_solve_matches_oracle(mode):
 	out = c.linear_solve(ul)
 	assert relerr(out, ref) < TOL_U, relerr(out, ref)
 	c.close()
+
+
+@pytest.mark.parametrize('name', ['rs_ismip_a_6x5x3', 'rs_marine_6x5x3'])
+def test_reduced_stokes_against_committed_golden_vectors(name):
+	"""the CUDA path against tests/golden/rs_*.npz (oracle outputs, see make_golden.py::main_rs)."""
+	import os
+	from cslvr_b200 import capi
+	from golden.make_golden import build
+	g = np.load(os.path.join(os.path.dirname(__file__), 'golden', name + '.npz'))
+	m = build(name[3:])
+	c = _rs_context(m, relative_tolerance=1e-9, maximum_iterations=50, relaxation_parameter=0.8, krylov_rtol=1e-13)
+	c.set_field(capi.FIELD_UZ, g['uz'])
+	c.set_field(capi.FIELD_B_RING, g['B_ring'])
+	F, J = c.assemble(g['u'], want_F=True, want_J=True)
+	assert relerr(F, g['F']) < TOL_ASM and relerr(J, g['J']) < TOL_ASM
+	u, uz = np.zeros(g['u'].size), np.zeros(g['uz'].size)
+	st = c.rs_newton_solve(u, uz, atol=1e-6, callback=True)
+	assert st['converged'] and st['iterations'] == int(g['newton_iterations'])
+	assert relerr(st['residuals'], g['residuals']) < 1e-6
+	assert relerr(u, g['u_newton']) < TOL_U and relerr(uz, g['uz_newton']) < 1e-7
+	c.close()

@@ -235,3 +235,20 @@ def test_golden_vectors_reproduce(name):
 	assert relerr(P.jacobian(g['u']), g['J']) < 1e-13
 	un, info = P.newton(rtol=1e-11, relax=float(g['relax']), maxit=80)
 	assert relerr(un, g['u_newton']) < 1e-9
+
+
+@pytest.mark.parametrize('name', ['rs_ismip_a_6x5x3', 'rs_marine_6x5x3'])
+def test_reduced_stokes_golden_vectors_reproduce(name):
+	"""tests/golden/rs_*.npz (make_golden.py::main_rs, oracle outputs): residual / Jacobian with a
+	frozen random u_z and B_ring, and the home-rolled Newton solution with the u_z callback."""
+	from cases import rs_problem
+	from golden.make_golden import build
+	g = np.load(os.path.join(GOLD, name + '.npz'))
+	P = rs_problem(build(name[3:]), B_ring=g['B_ring'])
+	P.set_uz(g['uz'])
+	assert relerr(P.residual(g['u']), g['F']) < 1e-13
+	assert relerr(P.jacobian(g['u']), g['J']) < 1e-13
+	P.set_uz(np.zeros_like(g['uz']))
+	un, info = P.newton_rs()
+	assert info['iterations'] == int(g['newton_iterations']) and relerr(un, g['u_newton']) < 1e-9
+	assert relerr(P.uz, g['uz_newton']) < 1e-8
