@@ -54,10 +54,13 @@ def quiet_stdout():
 
 def emit(text):
 	sys.stdout.flush()
-	if _JSON_FD is None:
+	fd = _JSON_FD
+	if fd is None:                 # imported as a module by bench_multi while the script itself runs as __main__
+		fd = getattr(sys.modules.get('__main__'), '_JSON_FD', None)
+	if fd is None:
 		print(text, flush=True)
 	else:
-		os.write(_JSON_FD, (text + "\n").encode())
+		os.write(fd, (text + "\n").encode())
 
 
 METRIC = "BP residual+Jacobian assembly throughput"
