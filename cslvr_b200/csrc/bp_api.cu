@@ -125,8 +125,10 @@ static int group_pc_prepare(bp_ctx** cs, int n)
 		if (!(lmax > 0.0) || !std::isfinite(lmax)) return bp_fail(cs[0], BP_ERR_STATE, "Chebyshev: eigenvalue bound failed (%g)", lmax);
 		for (int r = 0; r < n; ++r) cs[r]->cheb_lmax = lmax;
 	}
-	if (cs[0]->prm.pc == BP_PC_MG)
-		for (int r = 0; r < n; ++r) if ((rc = bp_mg_prepare(cs[r]))) { if (r) cs[0]->err = cs[r]->err; return rc; }
+	if (cs[0]->prm.pc == BP_PC_MG) {
+		if (bp_mg_use_coupled(cs, n)) { if ((rc = bp_mg_prepare_group(cs, n))) return rc; }
+		else for (int r = 0; r < n; ++r) if ((rc = bp_mg_prepare(cs[r]))) { if (r) cs[0]->err = cs[r]->err; return rc; }
+	}
 	if (cs[0]->prm.pc == BP_PC_COLUMN)
 		for (int r = 0; r < n; ++r) if (cs[r]->max_layers > 64)
 			return bp_fail(cs[0], BP_ERR_ARG, "column preconditioner supports at most 64 nodes per ice column (mesh has %d)", cs[r]->max_layers);
@@ -142,6 +144,7 @@ static int group_pc_apply(bp_ctx** cs, int n)
 		return BP_OK;
 	}
 	if (cs[0]->prm.pc == BP_PC_MG) {
+		if (bp_mg_use_coupled(cs, n)) return bp_mg_apply_group(cs, n);
 		for (int r = 0; r < n; ++r) if ((rc = bp_mg_apply(cs[r]))) return rc;
 		return BP_OK;
 	}

@@ -13,6 +13,7 @@
 #include "bp_internal.h"
 #include <dlfcn.h>
 #include <cstring>
+#include <algorithm>
 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
@@ -151,5 +152,36 @@ int bp_comm_allreduce_max(bp_ctx* c, int slot, int count)
 {
 	if (!c->comm || c->comm->n_ranks == 1) return BP_OK;
 	BP_NCCL(c, g_nccl.AllReduce(c->d_sc + slot, c->d_sc + slot, (size_t)count, ncclFloat64_, ncclMax_, c->comm->comm, c->stream));
+	return BP_OK;
+}
+
+int bp_comm_rank(const bp_ctx* c) { return c->comm ? c->comm->rank : 0; }
+int bp_comm_size(const bp_ctx* c) { return c->comm ? c->comm->n_ranks : 1; }
+
+struct BufPtrs { double* p[16]; };
+__global__ void k_allreduce_bufs(BufPtrs P, int n, size_t count, int op_max)
+{
+	for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+		double s = P.p[0][i];
+		for (int r = 1; r < n; ++r) { const double v = P.p[r][i]; s = op_max ? fmax(s, v) : s + v; }
+		for (int r = 0; r < n; ++r) P.p[r][i] = s;
+	}
+}
+
+int bp_comm_allreduce_buf(bp_ctx** ctxs, int n, double** bufs, size_t count, int op_max)
+{
+	if (count == 0) return BP_OK;
+	if (n == 1) {
+		bp_ctx* c = ctxs[0];
+		if (!c->comm || c->comm->n_ranks == 1) return BP_OK;
+		BP_NCCL(c, g_nccl.AllReduce(bufs[0], bufs[0], count, ncclFloat64_, op_max ? ncclMax_ : ncclSum_, c->comm->comm, c->stream));
+		return BP_OK;
+	}
+	if (n > 16) return bp_fail(ctxs[0], BP_ERR_ARG, "in-process groups are limited to 16 contexts");
+	BufPtrs P;
+	for (int r = 0; r < n; ++r) P.p[r] = bufs[r];
+	const int g = (int)std::min<size_t>((count + 255) / 256, 1184);
+	k_allreduce_bufs<<<g, 256, 0, ctxs[0]->stream>>>(P, n, count, op_max);
+	ctxs[0]->launches++;
 	return BP_OK;
 }

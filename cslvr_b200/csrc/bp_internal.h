@@ -112,6 +112,7 @@ struct bp_ctx {
 	std::vector<int32_t> nbr_rank;
 	std::vector<int64_t> send_ptr, recv_ptr;
 	int32_t* d_send_nodes = nullptr;
+	std::vector<int32_t> h_send_nodes;
 	double*  d_sendbuf = nullptr;
 	int64_t  n_send = 0;
 	bp_comm_state* comm = nullptr;
@@ -183,10 +184,19 @@ void bp_launch_lincomb(bp_ctx* c, double* out, double a, const double* x, double
 int  bp_mg_prepare(bp_ctx* c);      // numeric set-up for the current resident Jacobian
 int  bp_mg_apply(bp_ctx* c);        // d_z = M^-1 d_r
 void bp_mg_free(bp_ctx* c);
+// coupled hierarchy of a partitioned mesh: all ranks (or all contexts of an in-process group) in lock-step
+bool bp_mg_use_coupled(bp_ctx** cs, int n);
+int  bp_mg_prepare_group(bp_ctx** cs, int n);
+int  bp_mg_apply_group(bp_ctx** cs, int n);
 
 // comm (bp_comm.cu)
 int  bp_comm_halo(bp_ctx** ctxs, int n, int which_vec);   // 0:u 1:p
 int  bp_comm_allreduce(bp_ctx** ctxs, int n, int slot, int count);
 int  bp_comm_allreduce_max(bp_ctx* c, int slot, int count);
+// element-wise sum (or max) of one device buffer per context over all ranks: NCCL for a single context with a
+// communicator, a device kernel for an in-process group
+int  bp_comm_allreduce_buf(bp_ctx** ctxs, int n, double** bufs, size_t count, int op_max);
+int  bp_comm_rank(const bp_ctx* c);      // rank / number of ranks of the context's communicator (0 / 1 without one)
+int  bp_comm_size(const bp_ctx* c);
 void bp_comm_free(bp_ctx* c);
 double* bp_vec(bp_ctx* c, int which);

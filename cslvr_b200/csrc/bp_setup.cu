@@ -384,6 +384,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		for (int64_t k = 0; k < c->n_send; ++k)
 			if (m->send_nodes[k] < 0 || m->send_nodes[k] >= no)
 				return bp_fail(c, BP_ERR_ARG, "bp_mesh: send_nodes[%lld] is not an owned node", (long long)k);
+		c->h_send_nodes.assign(m->send_nodes, m->send_nodes + c->n_send);
 		UP(c->d_send_nodes, m->send_nodes, c->n_send);
 		UP(c->d_sendbuf, (const double*)nullptr, 2 * c->n_send);
 	} else if (nn != no) {
