@@ -14,8 +14,9 @@
 //   coarsest     : dense inverse computed on the host (<= 128 x 128), applied by one kernel.
 // All levels store 2x2 blocks in the same SELL-32 layout, so k_spmv / k_cheb_step / k_pc_setup
 // / k_gershgorin are reused unchanged through light-weight level contexts.
-// With several ranks the hierarchy is rank-local (ghost columns are ignored: block-Jacobi
-// over the slabs with a multigrid V-cycle inside) and needs no communication.
+// With several ranks the default is the COUPLED hierarchy further down (mgc_*: ghost nodes and a halo
+// exchange on every level, global dense coarsest solve); BP_MG_COUPLED=0 selects the rank-local one
+// (ghost columns ignored: block-Jacobi over the slabs with a V-cycle inside, no communication).
 #include "bp_internal.h"
 #include <algorithm>
 #include <cmath>

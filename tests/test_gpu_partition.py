@@ -40,3 +40,35 @@ def test_group_assembly_and_newton_match_single_context(builder, nr):
 		assert relerr(ul, local_vector(rm, ug)) < 1e-8
 	for c in ctxs + [single]:
 		c.close()
+
+
+def test_coupled_multigrid_keeps_the_single_context_iteration_count():
+	"""The multigrid hierarchy of a partitioned mesh keeps the couplings across the slab interfaces on
+	every level (ghost nodes + halo exchange per level, global dense coarsest solve): the CG iteration
+	count stays near the single-context one, where the rank-local hierarchy (BP_MG_COUPLED=0) needs
+	clearly more; the solution is the same either way."""
+	import os
+	m = ismip_model('C', L=20000.0, n=(64, 24, 4))
+	kw = dict(preconditioner='mg', relative_tolerance=1e-9, maximum_iterations=25, krylov_rtol=1e-8)
+	single = product_context(m, **kw)
+	u1 = np.full(2 * m.n_nodes, 3e-16)
+	s1 = single.newton_solve(u1)
+	single.close()
+	res = {}
+	for mode in ('1', '0'):
+		os.environ['BP_MG_COUPLED'] = mode
+		try:
+			rms = partition_model(m, 4)
+			ctxs = [rank_context(m, rm, **kw) for rm in rms]
+			us = [np.full(2 * rm.n_nodes, 3e-16) for rm in rms]
+			sg = capi.newton_solve_group(ctxs, us)
+			ug = gather_owned(rms, us, m.n_nodes)
+			for c in ctxs:
+				c.close()
+		finally:
+			os.environ.pop('BP_MG_COUPLED', None)
+		assert sg['converged'] and abs(sg['iterations'] - s1['iterations']) <= 1
+		assert relerr(ug, u1) < 1e-7
+		res[mode] = sg['krylov_iterations']
+	assert res['1'] <= 1.35 * s1['krylov_iterations'] + 8, (res, s1['krylov_iterations'])
+	assert res['0'] >= res['1'], (res, s1['krylov_iterations'])
