@@ -89,6 +89,7 @@ struct bp_ctx {
 	std::vector<int32_t> h_sell_ptr;
 	int32_t* d_col = nullptr;
 	int32_t* d_diag = nullptr;           // slot of the diagonal block of each owned row
+	int32_t* d_mirror = nullptr;         // [n_slots] slot of the transposed block (row j, column i) of block (i, j), j > i owned; else -1
 	double*  d_val = nullptr;            // [n_slots*4] 2x2 blocks {a00 a01 a10 a11}, SELL-32 slot order
 	float*   d_valf = nullptr;           // FP32 copy of d_val for the multigrid smoother (allocated on first use)
 	int32_t* d_csr_src = nullptr;        // CSR export gather map

@@ -303,14 +303,14 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
        const double* __restrict__ soa, size_t nv,
        const double2* __restrict__ u /* per VERTEX */, const double* __restrict__ Av,
        const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen,
-       double* __restrict__ F, double* __restrict__ val, AsmParams P, const double* __restrict__ uzv, int blk0)
+       double* __restrict__ F, double* __restrict__ val, AsmParams P, const double* __restrict__ uzv, int blk0,
+       const int32_t* __restrict__ mirror)
 {
-	extern __shared__ double acc[];                  // [4*(max_row-1)][RTPB]: off-diagonal blocks, strip slot = row position minus (position > diagonal's)
+	extern __shared__ double acc[];                  // [4*(max_row-1)][RTPB]: the blocks right of the diagonal, strip slot = row position - diagonal's - 1
 	const int tid = threadIdx.x;
 	const int i = (blockIdx.x + blk0) * RTPB + tid;
 	const bool active = i < nrows;
 	const int len = active ? rowlen[i] : 0;
-	if (WANT_J) for (int k = 0; k < 4 * (len - 1); ++k) acc[k * RTPB + tid] = 0.0;
 	double Fx = 0.0, Fy = 0.0;
 	double dg0 = 0.0, dg1 = 0.0, dg2 = 0.0, dg3 = 0.0;    // diagonal block
 	int kdiag = 1 << 30;
@@ -349,6 +349,9 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 		ai = Av[code >> 2];
 	}
 	int own = vid[0];                                // vertex whose data sits in p[0] / uu[0]
+	// J is symmetric: this thread accumulates the diagonal block and the blocks right of it; their
+	// transposes go to the rows of the column nodes at the end (mirror slots)
+	if (WANT_J && code >= 0) for (int k = 0; k < 4 * (len - 1 - kdiag); ++k) acc[k * RTPB + tid] = 0.0;
 	while (code >= 0) {
 		const uint32_t pk_cur = pk;
 		e += 32;
@@ -432,6 +435,10 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 			const double Ea = gamma * dx0, Ga = gamma * dy0;
 			#pragma unroll
 			for (int b = 0; b < 4; ++b) {
+				// the vertices of an incidence are ordered "column node > row node first" (bp_setup.cu): the
+				// first block left of the diagonal ends the visit
+				const int pos = (int)((pk_cur >> (8 * b)) & 255);
+				if (b > 0 && pos < kdiag) break;
 				const double dxb = cxx * X[b] + sh * Y[b] + hz0 * Z[b];
 				const double dyb = cyy * Y[b] + sh * X[b] + hz1 * Z[b];
 				const double jxx = Pa * X[b] + Qa * Y[b] + Ra * Z[b] + Ea * dxb;
@@ -441,8 +448,7 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 				if (b == 0) {                             // the diagonal block gets a term from every tet: keep it in registers
 					dg0 += jxx; dg1 += jxy; dg2 += jyx; dg3 += jyy;
 				} else {
-					const int pos = (int)((pk_cur >> (8 * b)) & 255);
-					double* s4 = acc + (4 * (pos - (pos > kdiag))) * RTPB + tid;
+					double* s4 = acc + (4 * (pos - kdiag - 1)) * RTPB + tid;
 					s4[0] += jxx; s4[RTPB] += jxy; s4[2 * RTPB] += jyx; s4[3 * RTPB] += jyy;
 				}
 			}
@@ -452,15 +458,22 @@ k_rows(int nrows, const int32_t* __restrict__ inc_slice, const int32_t* __restri
 	if (!active) return;
 	if (WANT_F) { F[2 * i] = Fx; F[2 * i + 1] = Fy; }
 	if (WANT_J) {
-		// SELL-32: block k of the 32 rows of a slice is contiguous -> coalesced 1 KB stores
-		double2* out = (double2*)val + 2 * ((size_t)sell_ptr[slice] + lane);
-		for (int k = 0; k < len; ++k) {
-			const bool dgk = (k == kdiag);
-			const double* s4 = acc + (4 * (dgk ? 0 : k - (k > kdiag))) * RTPB + tid;
-			double2 lo = make_double2(dg0, dg1), hi = make_double2(dg2, dg3);
-			if (!dgk) { lo = make_double2(s4[0], s4[RTPB]); hi = make_double2(s4[2 * RTPB], s4[3 * RTPB]); }
-			out[64 * (size_t)k]     = lo;
-			out[64 * (size_t)k + 1] = hi;
+		// SELL-32: block k of the 32 rows of a slice is contiguous -> coalesced stores for the diagonal and the
+		// blocks right of it; the blocks left of the diagonal are written by the threads of their column nodes
+		const size_t base = (size_t)sell_ptr[slice] + lane;
+		double2* out = (double2*)val + 2 * base;
+		if (kdiag < len) { out[64 * (size_t)kdiag] = make_double2(dg0, dg1); out[64 * (size_t)kdiag + 1] = make_double2(dg2, dg3); }
+		for (int k = kdiag + 1; k < len; ++k) {
+			const double* s4 = acc + (4 * (k - kdiag - 1)) * RTPB + tid;
+			const double a00 = s4[0], a01 = s4[RTPB], a10 = s4[2 * RTPB], a11 = s4[3 * RTPB];
+			out[64 * (size_t)k]     = make_double2(a00, a01);
+			out[64 * (size_t)k + 1] = make_double2(a10, a11);
+			const int ms = mirror[base + 32 * (size_t)k];
+			if (ms >= 0) {
+				double2* mo = (double2*)val + 2 * (size_t)ms;
+				mo[0] = make_double2(a00, a10);
+				mo[1] = make_double2(a01, a11);
+			}
 		}
 	}
 }
@@ -801,8 +814,8 @@ void bp_launch_rows_chunk(bp_ctx* c, int what, int blk0, int nblk, int v0, int v
 		uvert = (const double2*)c->d_uvert;
 	}
 	if (nblk <= 0) return;
-	#define ROWSC(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<nblk, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, blk0); \
-		else k_rows<WF, WJ, false><<<nblk, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, blk0); } while (0)
+	#define ROWSC(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<nblk, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, blk0, c->d_mirror); \
+		else k_rows<WF, WJ, false><<<nblk, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, blk0, c->d_mirror); } while (0)
 	if (wf && wj) ROWSC(true, true, row_smem);
 	else if (wf)  ROWSC(true, false, 0);
 	else if (wj)  ROWSC(false, true, row_smem);
@@ -837,7 +850,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
 			cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			k_rows<true, true, false><<<(int)((c->nn_owned + RTPB - 1) / RTPB), RTPB, rs, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos,
-				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0);
+				c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, bp_vertex_u(c), c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0, c->d_mirror);
 		} else {
 			const int gc = (int)((c->nt + TPB - 1) / TPB);
 			k_cell<true, true><<<gc, TPB, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_geo, c->d_v2n, (const double2*)c->d_u, c->d_ainv, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_uz);
@@ -861,8 +874,8 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		}
 		const int gr = (int)((c->nn_owned + RTPB - 1) / RTPB);
 		const double2* uvert = bp_vertex_u(c);
-		#define ROWS(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0); \
-			else k_rows<WF, WJ, false><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0); } while (0)
+		#define ROWS(WF, WJ, SM) do { if (P.rs) k_rows<WF, WJ, true><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0, c->d_mirror); \
+			else k_rows<WF, WJ, false><<<gr, RTPB, SM, c->stream>>>((int)c->nn_owned, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, (size_t)c->n_inc_slots, c->d_soa, (size_t)c->nv, uvert, c->d_ainv, c->d_sell_ptr, c->d_rowlen, c->d_F, c->d_val, P, c->d_uz, 0, c->d_mirror); } while (0)
 		if (wf && wj) ROWS(true, true, row_smem);
 		else if (wf)  ROWS(true, false, 0);
 		else if (wj)  ROWS(false, true, row_smem);

@@ -227,24 +227,63 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		std::vector<uint32_t> pos(sl_ptr[nsl], 0u);
 		const size_t nslot = (size_t)sl_ptr[nsl];
 		std::vector<int32_t> incv(4 * nslot, 0);
-		std::vector<int32_t> fill(no, 0);
+		// The Jacobian is symmetric: the thread of row i computes only the blocks (i, j) with j > i (and
+		// the diagonal) and writes their transposes into the rows j (d_mirror).  So that the lanes of a
+		// warp agree on how many blocks a visit computes, the other three vertices of an incidence are
+		// ordered "upper first" (column node > i) and the incidences of a row by descending number of
+		// upper vertices.
+		std::vector<int32_t> start(4 * (size_t)no, 0);          // [class 3 | 2 | 1 | 0] running offsets per row
+		auto n_upper_of = [&](int64_t t, int a, int32_t i) {
+			int nu = 0;
+			for (int j = 1; j < 4; ++j) if (cn[t * 4 + ((a + j) & 3)] > i) ++nu;
+			return nu;
+		};
+		for (int64_t t = 0; t < nt; ++t)
+			for (int a = 0; a < 4; ++a) {
+				const int32_t i = cn[t * 4 + a];
+				if (i < no) start[4 * (size_t)i + (3 - n_upper_of(t, a, i))]++;
+			}
+		for (int64_t i = 0; i < no; ++i) {
+			int32_t run = 0;
+			for (int q = 0; q < 4; ++q) { const int32_t cq = start[4 * i + q]; start[4 * i + q] = run; run += cq; }
+		}
 		for (int64_t t = 0; t < nt; ++t)
 			for (int a = 0; a < 4; ++a) {
 				const int32_t i = cn[t * 4 + a];
 				if (i >= no) continue;
-				const int64_t at = (int64_t)sl_ptr[i / 32] + 32 * (int64_t)(fill[i]++) + (i % 32);
+				const int nu = n_upper_of(t, a, i);
+				const int64_t at = (int64_t)sl_ptr[i / 32] + 32 * (int64_t)(start[4 * (size_t)i + (3 - nu)]++) + (i % 32);
 				code[at] = (int32_t)(t * 4 + a);
-				uint32_t pk = 0;
 				const int32_t* lo = c->h_col.data() + c->h_rowptr[i];
 				const int32_t* hi = c->h_col.data() + c->h_rowptr[i + 1];
+				int ord[4] = { a, 0, 0, 0 }, nu_seen = 0, nl_seen = 0;
+				for (int j = 1; j < 4; ++j) {                    // upper vertices first, the others after them
+					const int lv = (a + j) & 3;
+					if (cn[t * 4 + lv] > i) ord[1 + nu_seen++] = lv; else ord[1 + nu + nl_seen++] = lv;
+				}
+				uint32_t pk = 0;
 				for (int j = 0; j < 4; ++j) {
-					const uint32_t k = (uint32_t)(std::lower_bound(lo, hi, cn[t * 4 + ((a + j) & 3)]) - lo);
+					const uint32_t k = (uint32_t)(std::lower_bound(lo, hi, cn[t * 4 + ord[j]]) - lo);
 					if (k > 255) return bp_fail(c, BP_ERR_ARG, "bp_mesh: a Jacobian row has more than 255 node blocks");
 					pk |= k << (8 * j);
-					incv[(size_t)j * nslot + at] = m->cells[t * 4 + ((a + j) & 3)];
+					incv[(size_t)j * nslot + at] = m->cells[t * 4 + ord[j]];
 				}
 				pos[at] = pk;
 			}
+		{	// slot of the transposed block: (row j, column i) for every block (i, j) with j > i owned
+			std::vector<int32_t> mirror((size_t)std::max<int64_t>(c->n_slots, 1), -1);
+			#pragma omp parallel for schedule(static)
+			for (int64_t i = 0; i < no; ++i)
+				for (int32_t k = c->h_rowptr[i]; k < c->h_rowptr[i + 1]; ++k) {
+					const int32_t j = c->h_col[k];
+					if (j <= i || j >= no) continue;
+					const int32_t* lo = c->h_col.data() + c->h_rowptr[j];
+					const int32_t* hi = c->h_col.data() + c->h_rowptr[j + 1];
+					const int32_t kj = (int32_t)(std::lower_bound(lo, hi, (int32_t)i) - lo);
+					mirror[(size_t)sell_ptr[i >> 5] + 32 * (size_t)(k - c->h_rowptr[i]) + (i & 31)] = sell_ptr[j >> 5] + 32 * kj + (int32_t)(j & 31);
+				}
+			UP(c->d_mirror, mirror.data(), mirror.size());
+		}
 		{	// what the pipelined host-buffer bp_assemble needs per CTA of the row-gather kernel
 			const int64_t nblk = (no + BP_ROWS_PER_CTA - 1) / BP_ROWS_PER_CTA;
 			std::vector<int32_t> mxv(nblk, -1);
