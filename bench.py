@@ -321,10 +321,10 @@ def main():
 	        "gpu_launches": int(launches),
 	        "roofline": {"kernel": "k_rows<F,J> (cell assembly, row gather)", "bound": "hbm", "achieved": b_cell / (t_cell * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
 	                     "frac": b_cell / (t_cell * 1e-3) / 1e9 / peak,
-	                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_rows<1,1> launch on this very workload,
-	                     # ncu --set full, profiles/r1_f_ncu_final_kernels.csv (235.2 + 140.0 MB); the excess over the
-	                     # algorithmic bytes is the incidence list (24 B per (tet, node) pair)
-	                     "traffic": 375.2e6 if nt == 2028000 else None,
+	                     # dram__bytes_read.sum + dram__bytes_write.sum of one k_rows<1,1,0> launch on this very workload,
+	                     # ncu --set full, profiles/r1_h_ncu_k_rows.csv (254.5 + 147.1 MB); the excess over the
+	                     # algorithmic bytes is the incidence list (24 B per (tet, node) pair) and the mirror slots
+	                     "traffic": 401.6e6 if nt == 2028000 else None,
 	                     "peak_source": "measured" if peaks else "fallback", "bytes_per_tet": b_cell / nt, "ms": t_cell,
 	                     "pass_ms": t_pass, "pass_frac": b_full / (t_pass * 1e-3) / 1e9 / peak},
 	        "roofline_spmv": {"kernel": "k_spmv", "bound": "hbm", "achieved": b_spmv / (t_spmv * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
