@@ -631,8 +631,9 @@ static int solve_pressure_impl(bp_ctx* c, const double* u, const double* u_model
 		return bp_fail(c, BP_ERR_STATE, "bp_solve_pressure with the energy-dependent rate factor is not available yet");
 	bp_ctx* cs[1] = { c };
 	if (u_model) {                        // viscosity state of the reduced-Stokes solve(): per-vertex copy in d_uvert2
-		if (c->comm || c->nn != c->nn_owned) return bp_fail(c, BP_ERR_STATE, "bp_rs_solve_pressure runs on unpartitioned contexts only");
+		if (c->nn != c->nn_owned && !c->comm) return bp_fail(c, BP_ERR_STATE, "bp_rs_solve_pressure on a partitioned context needs its communicator");
 		if ((rc = vec_in(c, u_model, on_device, c->d_u))) return rc;
+		if ((rc = bp_comm_halo(cs, 1, 0))) return rc;
 		bp_launch_expand_to_vertex(c, c->d_u, c->d_uvert2);
 	}
 	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
@@ -768,7 +769,7 @@ int bp_rs_newton_solve(bp_ctx* c, double* u, double* uz_vertex, int on_device, d
 	int rc = ready(c);
 	if (rc) return rc;
 	if (!c->prm.reduced_stokes) return bp_fail(c, BP_ERR_STATE, "bp_rs_newton_solve: bp_params.reduced_stokes is not set");
-	if (c->comm || c->nn != c->nn_owned) return bp_fail(c, BP_ERR_STATE, "bp_rs_newton_solve runs on unpartitioned contexts only");
+	if (c->nn != c->nn_owned && !c->comm) return bp_fail(c, BP_ERR_STATE, "bp_rs_newton_solve on a partitioned context needs its communicator (one rank per process; in-process groups are not served)");
 	if (run_callback && !c->have_B) return bp_fail(c, BP_ERR_STATE, "bp_rs_newton_solve: BP_FIELD_B (bed height) not set");
 	const bp_params& P = c->prm;
 	bp_stats s;

@@ -236,7 +236,8 @@ int  bp_solve_vert_velocity(bp_ctx* ctx, const double* u, double* uz_vertex, int
  * converged = r < atol or r/r0 < rtol; u += relax d; u_z = solve_vert_velocity(u) }.
  * Needs reduced_stokes != 0 and BP_FIELD_B.  uz_vertex_inout: the starting u_z (NULL = keep the
  * one set with BP_FIELD_UZ) and, on return, the u_z of the last callback (per mesh vertex).
- * run_callback = 0 leaves u_z frozen (cb_ftn = None).                                          */
+ * run_callback = 0 leaves u_z frozen (cb_ftn = None).  Partitioned contexts: one rank per process with a
+ * communicator (bp_comm_init); in-process groups are not served.                                 */
 int  bp_rs_newton_solve(bp_ctx* ctx, double* u_inout, double* uz_vertex_inout, int on_device,
                         double atol, int run_callback, bp_stats* stats);
 /* solve_pressure as that solve() reaches it (momentumstokes.py:478 runs BEFORE update_model_var):

@@ -15,6 +15,12 @@ sys.path.insert(0, os.path.dirname(HERE))
 os.environ.setdefault('CSLVR_B200_QUIET', '1')
 
 
+def _fresh_id(capi, dist, dev, rank):
+	ids = [capi.comm_unique_id() if rank == 0 else None]
+	dist.broadcast_object_list(ids, src=0, device=dev)
+	return ids[0]
+
+
 def main():
 	import torch
 	import torch.distributed as dist
@@ -51,6 +57,28 @@ def main():
 	if rank == 0:
 		print("multi-GPU check, %d ranks: newton its %d vs %d, |du| %.2e |dp| %.2e |du_z| %.2e" % (world, st['iterations'], sg['iterations'], *t.tolist()))
 		assert st['converged'] and abs(st['iterations'] - sg['iterations']) <= 1
+		assert t[0] < 1e-8 and t[1] < 1e-8 and t[2] < 1e-7, t.tolist()
+		print("OK")
+	c.close(); s.close()
+	# ---- the reduced-Stokes model over NCCL: home-rolled Newton with the u_z callback, then its pressure
+	kr = dict(relative_tolerance=1e-9, maximum_iterations=50, relaxation_parameter=0.8, krylov_rtol=1e-13, reduced_stokes=True)
+	c = rank_context(m, rm, device=local, **kr)
+	c.set_field(capi.FIELD_B, m.vertex_field(m.B)[rm.vertex_global])
+	c.comm_init(ids[0] if world == 1 else _fresh_id(capi, dist, dev, rank), rank, world)
+	ul, uzl = np.zeros(2 * rm.n_nodes), np.zeros(rm.coords.shape[0])
+	st = c.rs_newton_solve(ul, uzl, atol=1e-6, callback=True)
+	pl = c.rs_solve_pressure(ul, np.zeros(2 * rm.n_nodes))
+	s = product_context(m, device=local, **kr)
+	s.set_field(capi.FIELD_B, m.vertex_field(m.B))
+	ug, uzg = np.zeros(2 * m.n_nodes), np.zeros(m.num_vertices)
+	sg = s.rs_newton_solve(ug, uzg, atol=1e-6, callback=True)
+	pg = s.rs_solve_pressure(ug, np.zeros(2 * m.n_nodes))
+	e = [relerr(ul[own], local_vector(rm, ug)[own]), relerr(pl, pg[rm.vertex_global]), relerr(uzl, uzg[rm.vertex_global])]
+	t = torch.tensor(e, device=dev, dtype=torch.float64)
+	dist.all_reduce(t, op=dist.ReduceOp.MAX)
+	if rank == 0:
+		print("reduced-Stokes, %d ranks: newton its %d vs %d, |du| %.2e |dp| %.2e |du_z| %.2e" % (world, st['iterations'], sg['iterations'], *t.tolist()))
+		assert st['converged'] and st['iterations'] == sg['iterations']
 		assert t[0] < 1e-8 and t[1] < 1e-8 and t[2] < 1e-7, t.tolist()
 		print("OK")
 	c.close(); s.close()
