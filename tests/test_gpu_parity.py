@@ -578,3 +578,34 @@ def test_reduced_stokes_against_committed_golden_vectors(name):
 	assert relerr(st['residuals'], g['residuals']) < 1e-6
 	assert relerr(u, g['u_newton']) < TOL_U and relerr(uz, g['uz_newton']) < 1e-7
 	c.close()
+
+
+def test_reduced_stokes_entry_points_refuse_misuse():
+	"""bp_rs_newton_solve / bp_rs_solve_pressure: the model flag and the bed field are required; an
+	in-process partition is refused (one rank per process serves partitioned contexts)."""
+	from cslvr_b200 import capi
+	from cslvr_b200.capi import BPError
+	from cslvr_b200.partition import partition_model, rank_context
+	m = ismip_model('A', n=(6, 5, 3))
+	c = product_context(m)                               # Blatter-Pattyn context: flag not set
+	u, uz = np.zeros(2 * m.n_nodes), np.zeros(m.num_vertices)
+	with pytest.raises(BPError) as e:
+		c.rs_newton_solve(u, uz)
+	assert e.value.code == capi.BP_ERR_STATE and 'reduced_stokes' in str(e.value)
+	with pytest.raises(BPError):
+		c.rs_solve_pressure(u, u)
+	c.set_params(reduced_stokes=True)
+	with pytest.raises(BPError) as e:                    # solve_vert_velocity callback needs B
+		c.rs_newton_solve(u, uz)
+	assert 'BP_FIELD_B' in str(e.value)
+	st = c.rs_newton_solve(u, uz, callback=False)        # cb_ftn = None works without it
+	assert st['converged'] and np.all(uz == 0.0)
+	with pytest.raises(ValueError):
+		c.rs_newton_solve(u.astype(np.float32), uz)
+	c.close()
+	rm = partition_model(m, 2, 0)
+	cp = rank_context(m, rm, reduced_stokes=True)
+	with pytest.raises(BPError) as e:
+		cp.rs_newton_solve(np.zeros(2 * rm.n_nodes), np.zeros(rm.coords.shape[0]), callback=False)
+	assert 'communicator' in str(e.value)
+	cp.close()

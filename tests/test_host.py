@@ -61,6 +61,22 @@ def test_default_solve_params_match_reference():
 		assert p['solve_vert_velocity'] and p['solve_pressure'] and p['vert_solve_method'] == 'mumps'
 
 
+def test_reduced_stokes_defaults_match_reference():
+	"""cslvr/momentumstokes.py:420-447 (relaxation 0.8, 50 iterations) and :396-404 (get_velocity)."""
+	from cslvr_b200 import MomentumDukowiczStokesReduced, MomentumBPBase
+	m = ismip_model('A', n=(3, 3, 2))
+	mom = MomentumDukowiczStokesReduced(m)               # construction needs no device
+	assert isinstance(mom, MomentumBPBase) and mom._reduced_stokes and mom.get_residual() == 'rs-dukowicz'
+	ns = mom.solve_params['solver']['newton_solver']
+	assert ns['relaxation_parameter'] == 0.8 and ns['maximum_iterations'] == 50 and ns['relative_tolerance'] == 1e-9
+	assert ns['linear_solver'] == 'cg' and ns['preconditioner'] == 'hypre_amg' and ns['error_on_nonconvergence'] is False
+	assert mom.solve_params['solve_vert_velocity'] and mom.solve_params['solve_pressure']
+	ux, uy, uz = mom.get_velocity()
+	assert ux.size == uy.size == uz.size == m.n_nodes and uz is mom.u_z.values
+	with pytest.raises(NotImplementedError):             # an external solver cannot tape
+		mom.solve(annotate=True)
+
+
 def test_misuse_errors_like_the_reference():
 	from cslvr_b200 import MomentumDukowiczBP, D3Model, BoxMesh, Point
 	with pytest.raises(SystemExit):                      # cslvr/momentumbp.py:30-33
