@@ -82,6 +82,9 @@ struct bp_ctx {
 	int32_t* d_fac_cell = nullptr;       // [nf]
 	int32_t* d_fac_info = nullptr;       // [nf] local facet | basal<<8 | pressure<<9 | grounded<<10
 	int32_t* d_ext_dof = nullptr;        // nullptr when identity
+	// facet row gather: owned nodes touched by an integrating facet, CSR of their (facet * 4 + local vertex) pairs
+	int64_t  n_fnodes = 0;
+	int32_t *d_fn_node = nullptr, *d_fn_ptr = nullptr, *d_fn_inc = nullptr;
 	// device: resident Jacobian, BSR 2x2, owned rows
 	int32_t* d_sell_ptr = nullptr;       // [slices+1] first slot of every 32-row slice
 	int32_t* d_rowlen = nullptr;         // [nn_owned] blocks in the row

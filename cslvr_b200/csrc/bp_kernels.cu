@@ -8,6 +8,7 @@
 // cell-constant, so the only quadrature is  wbar = |T| sum_q w_q A(x_q)^(-1/n).
 #include "bp_internal.h"
 #include <algorithm>
+#include <cstdlib>
 
 __constant__ double c_qw[BP_MAX_QUAD];
 __constant__ double c_ql[BP_MAX_QUAD * 4];
@@ -710,6 +711,94 @@ k_facet(int nf, int nt, const int32_t* __restrict__ fcell, const int32_t* __rest
 	}
 }
 
+// ---------------------------------------------------------------- facet kernel, row gather
+// The same integrals as k_facet without atomics: one thread per owned node that an integrating facet
+// touches.  It walks the node's (facet, local vertex) pairs, rebuilds the facet's area / normal / mass
+// integrals and adds ITS rows -- the two residual entries in registers, the Jacobian blocks by plain
+// read-modify-write of the slots of its own block row, which no other thread of this kernel touches
+// and which k_rows finished writing earlier in the stream.  Assembly is then free of atomics, so
+// F and J are bitwise reproducible.
+template <bool WANT_F, bool WANT_J>
+__global__ void __launch_bounds__(TPB)
+k_facet_rows(int nfn, const int32_t* __restrict__ fn_node, const int32_t* __restrict__ fn_ptr, const int32_t* __restrict__ fn_inc,
+             int nt, const int32_t* __restrict__ fcell, const int32_t* __restrict__ finfo,
+             const int4* __restrict__ tets, const double4* __restrict__ geo,
+             const int32_t* __restrict__ v2n, const double2* __restrict__ u,
+             const double* __restrict__ beta, const int32_t* __restrict__ tet_blk,
+             double* __restrict__ F, double* __restrict__ val, AsmParams P, const double* __restrict__ Bring)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nfn) return;
+	const int i = fn_node[r];
+	double Fx = 0.0, Fy = 0.0;
+	for (int q = fn_ptr[r]; q < fn_ptr[r + 1]; ++q) {
+		const int inc = fn_inc[q], f = inc >> 2, a = inc & 3;          // a: my position among the facet's three vertices
+		const int cell = fcell[f], info = finfo[f];
+		const int lf = info & 0xff;
+		const bool basal = P.rs ? ((info >> 10) & 1) : ((info >> 8) & 1), press = (info >> 9) & 1;
+		const int4 tv = tets[cell];
+		const int vid[4] = { tv.x, tv.y, tv.z, tv.w };
+		int la[3], k = 0;
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) if (j != lf) la[k++] = j;
+		double4 p[3];
+		double2 uu[3];
+		double bt[3], br[3] = { 0.0, 0.0, 0.0 };
+		#pragma unroll
+		for (int j = 0; j < 3; ++j) {
+			const int v = vid[la[j]];
+			p[j] = geo[v]; uu[j] = u[v2n ? v2n[v] : v]; bt[j] = beta[v];
+			if (P.rs) br[j] = Bring[v];
+		}
+		const double4 po = geo[vid[lf]];
+		const double ax = p[1].x - p[0].x, ay = p[1].y - p[0].y, az = p[1].z - p[0].z;
+		const double bx = p[2].x - p[0].x, by = p[2].y - p[0].y, bz = p[2].z - p[0].z;
+		double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+		const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
+		const double area = 0.5 * nrm;
+		const double side = nx * (po.x - p[0].x) + ny * (po.y - p[0].y) + nz * (po.z - p[0].z);
+		const double sgn = (side > 0.0 ? -1.0 : 1.0) / nrm;
+		nx *= sgn; ny *= sgn; nz *= sgn;
+		if (basal) {
+			const double bs = bt[0] + bt[1] + bt[2];
+			const double cx = P.rs ? nx / nz : 0.0, cy = P.rs ? ny / nz : 0.0, inz = P.rs ? 1.0 / nz : 0.0;
+			#pragma unroll
+			for (int b = 0; b < 3; ++b) {
+				// K[a][b] = |f| sum_d beta_d int(l_a l_b l_d),  int = {1/10, 1/30, 1/60}
+				double bta = 0.0, btb = bt[b];
+				#pragma unroll
+				for (int j = 0; j < 3; ++j) if (j == a) bta = bt[j];
+				const double Kab = (a == b) ? area * (bta * (1.0 / 10.0) + (bs - bta) * (1.0 / 30.0))
+				                            : area * ((bta + btb) * (1.0 / 30.0) + (bs - bta - btb) * (1.0 / 60.0));
+				const double t = P.rs ? br[b] * inz + (P.picard ? 0.0 : cx * uu[b].x + cy * uu[b].y) : 0.0;
+				if (!P.picard) { Fx += Kab * uu[b].x; Fy += Kab * uu[b].y; }
+				if (P.rs) { Fx += Kab * cx * t; Fy += Kab * cy * t; }
+				if (WANT_J) {
+					int lva = 0;
+					#pragma unroll
+					for (int j = 0; j < 3; ++j) if (j == a) lva = la[j];
+					const int slot = tet_blk[(lva * 4 + la[b]) * nt + cell];
+					if (slot >= 0) {
+						double2* v2 = (double2*)val + 2 * (size_t)slot;
+						double2 lo = v2[0], hi = v2[1];
+						lo.x += Kab * (1.0 + cx * cx); hi.y += Kab * (1.0 + cy * cy);
+						if (P.rs) { lo.y += Kab * cx * cy; hi.x += Kab * cx * cy; }
+						v2[0] = lo; v2[1] = hi;
+					}
+				}
+			}
+		}
+		if (press && WANT_F) {
+			double fw[3], fwa = 0.0;
+			#pragma unroll
+			for (int j = 0; j < 3; ++j) { fw[j] = P.rho_g * (p[j].w - p[j].z) - P.rho_sw_g * (-fmin(0.0, p[j].z)); if (j == a) fwa = fw[j]; }
+			const double mm = area * (fw[0] + fw[1] + fw[2] + fwa) * (1.0 / 12.0);
+			Fx -= nx * mm; Fy -= ny * mm;
+		}
+	}
+	if (WANT_F) { F[2 * i] += Fx; F[2 * i + 1] += Fy; }
+}
+
 static AsmParams make_params(const bp_ctx* c)
 {
 	AsmParams P;
@@ -828,8 +917,11 @@ void bp_launch_facets(bp_ctx* c, int what)
 	AsmParams P = make_params(c);
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
 	const int gf = (int)((c->nf + TPB - 1) / TPB);
+	const int gfr = (int)((c->n_fnodes + TPB - 1) / TPB);
+	const bool use_fr = c->n_fnodes > 0 && getenv("BP_FACET_ROWS");
 	const double2* u2 = (const double2*)c->d_u;
-	#define FACETC(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring)
+	#define FACETC(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)c->n_fnodes, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
+		else k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring); } while (0)
 	if (wf && wj) FACETC(true, true);
 	else if (wf)  FACETC(true, false);
 	else if (wj)  FACETC(false, true);
@@ -860,10 +952,14 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		return;
 	}
 	const int gf = (int)((c->nf + TPB - 1) / TPB);
+	const int gfr = (int)((c->n_fnodes + TPB - 1) / TPB);
 	const double2* u2 = (const double2*)c->d_u;
 	const size_t row_smem = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);   // the diagonal block lives in registers
 	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
-	#define FACET(WF, WJ) k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring)
+	// BP_FACET_ROWS=1: the atomic-free facet kernel (bitwise reproducible F and J; ~6 us slower at 2 M tets)
+	const bool use_fr = gather && c->n_fnodes > 0 && getenv("BP_FACET_ROWS");
+	#define FACET(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)c->n_fnodes, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
+		else k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring); } while (0)
 	if (gather) {
 		if (!c->smem_attr_set) {                     // function attributes are per device
 			cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -327,6 +327,26 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		finfo.push_back(lf | (basal << 8) | (press << 9) | ((mk == 3) << 10));   // bit 10: dGamma_bg (grounded bed), the reduced-Stokes sliding set
 	}
 	c->nf = (int64_t)fcell.size();
+	{	// facet row gather: every owned node touched by an integrating facet, with its (facet, local vertex) pairs
+		static const int LOCG[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
+		std::vector<int32_t> cntn(no, 0);
+		for (size_t f = 0; f < fcell.size(); ++f)
+			for (int k = 0; k < 3; ++k) { const int32_t nd_ = cn[(int64_t)fcell[f] * 4 + LOCG[finfo[f] & 0xff][k]]; if (nd_ < no) cntn[nd_]++; }
+		std::vector<int32_t> fn_node, fn_ptr(1, 0), slot_of_node(no, -1);
+		for (int64_t i = 0; i < no; ++i) if (cntn[i]) { slot_of_node[i] = (int32_t)fn_node.size(); fn_node.push_back((int32_t)i); fn_ptr.push_back(fn_ptr.back() + cntn[i]); }
+		std::vector<int32_t> fn_inc((size_t)std::max<int32_t>(fn_ptr.back(), 1), 0), fillf(fn_node.size(), 0);
+		for (size_t f = 0; f < fcell.size(); ++f)
+			for (int k = 0; k < 3; ++k) {
+				const int32_t nd_ = cn[(int64_t)fcell[f] * 4 + LOCG[finfo[f] & 0xff][k]];
+				if (nd_ >= no) continue;
+				const int32_t r = slot_of_node[nd_];
+				fn_inc[fn_ptr[r] + fillf[r]++] = (int32_t)(f * 4 + k);
+			}
+		c->n_fnodes = (int64_t)fn_node.size();
+		UP(c->d_fn_node, fn_node.data(), fn_node.size());
+		UP(c->d_fn_ptr, fn_ptr.data(), fn_ptr.size());
+		UP(c->d_fn_inc, fn_inc.data(), fn_inc.size());
+	}
 	{	// CTAs of the row-gather kernel with a row that a facet integral adds to
 		static const int LOCF[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
 		c->h_blk_facet.assign((size_t)((no + BP_ROWS_PER_CTA - 1) / BP_ROWS_PER_CTA), 0);

@@ -609,3 +609,19 @@ def test_reduced_stokes_entry_points_refuse_misuse():
 		cp.rs_newton_solve(np.zeros(2 * rm.n_nodes), np.zeros(rm.coords.shape[0]), callback=False)
 	assert 'communicator' in str(e.value)
 	cp.close()
+
+
+def test_atomic_free_facet_kernel_is_bitwise_reproducible(monkeypatch):
+	"""BP_FACET_ROWS=1: the facet integrals by row gather (one thread per touched node, plain
+	read-modify-write of its own rows after k_rows) -- same numbers as the atomic facet kernel to
+	rounding, and F and J identical bit for bit from run to run."""
+	m = marine_model()
+	P = oracle_problem(m)
+	u = state(P.n_dofs, 5)
+	monkeypatch.setenv('BP_FACET_ROWS', '1')
+	c = product_context(m, assembly='gather')
+	F1, J1 = c.assemble(u, want_F=True, want_J=True)
+	F2, J2 = c.assemble(u, want_F=True, want_J=True)
+	assert np.array_equal(F1, F2) and np.array_equal(J1, J2)
+	assert relerr(F1, P.residual(u)) < TOL_ASM and relerr(J1, P.jacobian(u)) < TOL_ASM
+	c.close()
