@@ -49,11 +49,35 @@ def main(out):
 	mom.solve_params['solve_vert_velocity'] = False
 	mom.solve_params['solve_pressure'] = False
 	mom.solve()
+	extra = dump_reduced_stokes(model, u0)
 	np.savez_compressed(out, coords=mesh.coordinates(), cells=mesh.cells(), cell_dofs=cell_dofs,
 	                    facet_cell=fcell, facet_local=flocal, facet_marker=ff[idx].astype(np.int32),
 	                    S=model.S.compute_vertex_values(mesh), A=model.A.compute_vertex_values(mesh),
-	                    beta=model.beta.compute_vertex_values(mesh),
-	                    u=u0, F=F, indptr=ip, indices=ix, J=jv, u_newton=u.vector().get_local(), relax=1.0)
+	                    beta=model.beta.compute_vertex_values(mesh), B=model.B.compute_vertex_values(mesh),
+	                    u=u0, F=F, indptr=ip, indices=ix, J=jv, u_newton=u.vector().get_local(), relax=1.0, **extra)
+
+
+def dump_reduced_stokes(model, u0):
+	"""the same for MomentumDukowiczStokesReduced (cslvr/momentumstokes.py:300-507): F and J at u0 with a
+	random frozen u_z, then the class's own solve() (home-rolled Newton with the u_z callback); keys match
+	tests/golden/make_golden.py::main_rs (rs_F, rs_J, rs_uz, rs_u_newton, rs_uz_newton, rs_newton_iterations)."""
+	from cslvr import MomentumDukowiczStokesReduced
+	from dolfin import assemble, as_backend_type
+	mom = MomentumDukowiczStokesReduced(model)
+	mesh = model.mesh
+	rng = np.random.default_rng(7)
+	uz0 = rng.normal(size=model.Q.dim()) * 3.0
+	mom.u_z.vector().set_local(uz0); mom.u_z.vector().apply('insert')
+	u = mom.get_unknown()
+	u.vector().set_local(u0); u.vector().apply('insert')
+	F = assemble(mom.get_residual()).get_local()
+	ip, ix, jv = as_backend_type(assemble(mom.get_jacobian())).mat().getValuesCSR()
+	uz_vertex = mom.u_z.compute_vertex_values(mesh)
+	u.vector().zero(); mom.u_z.vector().zero()
+	mom.solve_params['solve_pressure'] = False
+	mom.solve()
+	return dict(rs_F=F, rs_J=jv, rs_uz=uz_vertex, rs_u_newton=u.vector().get_local(),
+	            rs_uz_newton=mom.u_z.compute_vertex_values(mesh))
 
 
 if __name__ == '__main__':
