@@ -952,10 +952,8 @@ static int mgc_smooth(bp_ctx** cs, int n, int l, int deg, double ratio, double**
 		}
 		return BP_OK;
 	}
-	const char* eml = getenv("BP_MG_COUPLED_LEVELS");
-	const bool exch = !eml || l < atoi(eml);      // levels that exchange their ghosts (experiments: the deeper ones can stay rank-local)
 	auto step = [&](double c1, double c2) -> int {
-		if (exch && (rc = bp_comm_halo(Ls, n, zid[0]))) return rc;
+		if ((rc = bp_comm_halo(Ls, n, zid[0]))) return rc;
 		for (int r = 0; r < n; ++r) {
 			bp_ctx* M = Ls[r];
 			double* zo = (zid[r] == 2) ? M->d_z : M->d_z2;
@@ -1005,11 +1003,9 @@ static int mgc_vcycle(bp_ctx** cs, int n, int l, double** rhs, int deg, double r
 		return BP_OK;
 	}
 	if ((rc = mgc_smooth(cs, n, l, deg, ratio, rhs, zid, true))) return rc;
-	// residual (needs the ghosts of the iterate), restriction
-	{
-		const char* eml = getenv("BP_MG_COUPLED_LEVELS");
-		if ((!eml || l < atoi(eml)) && (rc = bp_comm_halo(Ls, n, zid[0]))) return rc;
-	}
+	// residual (needs the ghosts of the iterate), restriction.  Every level exchanges: an operator whose ghost
+	// columns see stale zeros is no longer symmetric positive definite as a whole and CG breaks down (tried).
+	if ((rc = bp_comm_halo(Ls, n, zid[0]))) return rc;
 	double* crhs[16];
 	for (int r = 0; r < n; ++r) {
 		bp_ctx* M = Ls[r];
