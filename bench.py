@@ -66,6 +66,8 @@ def emit(text):
 METRIC = "BP residual+Jacobian assembly throughput"
 UNIT = "Mtets/s"
 NX, NY, NZ, L = 260, 260, 5, 20000.0
+if os.environ.get('BENCH_NXY'):                 # tests only: a small mesh for the JSON-contract check
+	NX = NY = int(os.environ['BENCH_NXY'])
 
 
 def build_model(n_slabs=1):

@@ -117,3 +117,24 @@ def test_product_does_not_import_the_oracle():
 		if f.endswith(('.py', '.cu', '.h')):
 			src = open(f).read()
 			assert 'import oracle' not in src and 'from oracle' not in src and 'bp_oracle' not in src, f
+
+
+def test_bench_reference_arm_prints_one_json_line():
+	"""bench.py --impl reference (the reference's CPU path, oracle port): exactly one JSON line on stdout
+	with the keys of the bench contract; a small mesh through BENCH_NXY keeps it to seconds."""
+	import json
+	import subprocess
+	import sys
+	env = dict(os.environ, BENCH_NXY='20', CSLVR_B200_QUIET='1')
+	r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+	                   capture_output=True, text=True, env=env, timeout=600)
+	assert r.returncode == 0, r.stderr[-2000:]
+	lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+	assert len(lines) == 1, r.stdout
+	d = json.loads(lines[0])
+	for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+	          'vs_baseline', 'dtype', 'data', 'config', 'impl', 'cpu_baseline', 'e2e'):
+		assert k in d, k
+	assert d['impl'] == 'reference' and d['unit'] == 'Mtets/s' and d['value'] > 0 and d['vs_baseline'] is None
+	assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and 'workload' in d['config']
+	assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
