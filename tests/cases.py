@@ -48,13 +48,13 @@ def marine_model(n=(8, 7, 4), L=40000.0, variable_A=True):
 	return model
 
 
-def rs_problem(model, use_pressure_bc=True, quad_degree=None, B_ring=None):
+def rs_problem(model, use_pressure_bc=True, quad_degree=None, B_ring=None, energy=None):
 	"""the oracle's MomentumDukowiczStokesReduced problem on the model's arrays."""
 	from oracle.rs_oracle import RSProblem
 	return RSProblem(model.mesh.coordinates(), model.mesh.cells(), model.cell_dofs, 2 * model.n_nodes,
 	                 model.facet_cell, model.facet_local, model.ff,
 	                 model.vertex_field(model.S), model.vertex_field(model.A), model.vertex_field(model.beta),
-	                 periodic=model.use_periodic, use_pressure_bc=use_pressure_bc, quad_degree=quad_degree,
+	                 periodic=model.use_periodic, use_pressure_bc=use_pressure_bc, quad_degree=quad_degree, energy=energy,
 	                 consts=dict(n=model.n, eps_reg=model.eps_reg, rho_i=model.rho_i, rhosw=model.rhosw, g=model.g),
 	                 B=model.vertex_field(model.B), B_ring=B_ring)
 

@@ -625,3 +625,26 @@ def test_atomic_free_facet_kernel_is_bitwise_reproducible(monkeypatch):
 	assert np.array_equal(F1, F2) and np.array_equal(J1, J2)
 	assert relerr(F1, P.residual(u)) < TOL_ASM and relerr(J1, P.jacobian(u)) < TOL_ASM
 	c.close()
+
+
+def test_reduced_stokes_with_the_energy_dependent_rate_factor():
+	"""the two model switches together: A(T', W, E) at the quadrature points (cslvr/model.py:1815-1859)
+	inside the reduced-Stokes forms (cslvr/momentumstokes.py:300-400), generic Glen exponent included."""
+	from cases import rs_problem
+	from cslvr_b200 import capi
+	m = marine_model(n=(6, 5, 3))
+	X = m.mesh.coordinates()
+	Tp = 250.0 + 20.0 * (1.0 - (X[:, 2] + 500.0) / 1100.0) + 4.0 * np.sin(5 * X[:, 0] / 40000.0)
+	W = np.clip(0.02 * (Tp - 262.0) / 8.0, 0.0, 0.03)
+	E = 1.0 + 0.5 * np.cos(3 * X[:, 1] / 40000.0)
+	rng = np.random.default_rng(81)
+	uz = rng.normal(size=m.n_nodes)[m.vertex_to_node] * 3.0
+	P = rs_problem(m, energy=dict(Tp=Tp, W=W, E=E), quad_degree=4)
+	P.set_uz(uz)
+	c = _rs_context(m, energy_dependent_rate_factor=True, quadrature_degree=4)
+	for f, v in ((capi.FIELD_TP, Tp), (capi.FIELD_W, W), (capi.FIELD_E, E), (capi.FIELD_UZ, uz)):
+		c.set_field(f, v)
+	u = state(P.n_dofs, 62)
+	F, J = c.assemble(u, want_F=True, want_J=True)
+	assert relerr(F, P.residual(u)) < TOL_ASM and relerr(J, P.jacobian(u)) < TOL_ASM
+	c.close()
