@@ -47,7 +47,8 @@ class bp_params(C.Structure):
 	            ('energy_dependent', C.c_int32), ('a_T_l', C.c_double), ('a_T_u', C.c_double),
 	            ('Q_T_l', C.c_double), ('Q_T_u', C.c_double), ('R_gas', C.c_double),
 	            ('krylov_norm_preconditioned', C.c_int32), ('mg_smoother', C.c_int32),
-	            ('reduced_stokes', C.c_int32), ('mg_coarse_scale', C.c_double)]
+	            ('reduced_stokes', C.c_int32), ('mg_coarse_scale', C.c_double),
+	            ('krylov_error_on_nonconvergence', C.c_int32)]
 
 
 class bp_stats(C.Structure):
@@ -56,7 +57,8 @@ class bp_stats(C.Structure):
 	            ('residual_norm0', C.c_double), ('residual_norm', C.c_double),
 	            ('t_assemble_ms', C.c_double), ('t_krylov_ms', C.c_double),
 	            ('t_total_ms', C.c_double), ('n_assemblies', C.c_int32),
-	            ('gpu_launches', C.c_int32), ('residual_history', C.c_double * 64)]
+	            ('gpu_launches', C.c_int32), ('residual_history', C.c_double * 64),
+	            ('krylov_unconverged', C.c_int32), ('krylov_last_relres', C.c_double)]
 
 	def as_dict(self):
 		n = min(self.newton_iterations + 1, 64)
@@ -66,7 +68,8 @@ class bp_stats(C.Structure):
 		            residuals=[self.residual_history[i] for i in range(n)],
 		            t_assemble_ms=self.t_assemble_ms, t_krylov_ms=self.t_krylov_ms,
 		            t_total_ms=self.t_total_ms, n_assemblies=int(self.n_assemblies),
-		            gpu_launches=int(self.gpu_launches))
+		            gpu_launches=int(self.gpu_launches),
+		            krylov_unconverged=int(self.krylov_unconverged), krylov_last_relres=self.krylov_last_relres)
 
 
 # every symbol include/cslvr_b200.h declares (tests check the library exports them all)
@@ -139,14 +142,25 @@ def _is_torch(x):
 	return hasattr(x, 'data_ptr') and hasattr(x, 'is_cuda')
 
 
-def _ptr(x, dtype=np.float64):
-	"""(void*, on_device, keepalive) of a numpy array or a torch tensor."""
+def _ptr(x, dtype=np.float64, out=False):
+	"""(void*, on_device, keepalive) of a numpy array or a torch tensor.
+
+	Stream contract (include/cslvr_b200.h): the library reads and writes device buffers on the
+	context's stream.  A torch CUDA tensor produced on another stream is ordered by
+	synchronising that torch stream first (BPContext._order); every C-ABI call returns with
+	its outputs complete.  ``out=True``: the buffer is written by the library, so an array that
+	numpy would have to copy (wrong dtype, non-contiguous) is rejected instead of silently lost."""
 	if x is None:
 		return None, 0, None
 	if _is_torch(x):
+		import torch
+		if x.dtype != torch.float64:
+			raise ValueError("tensors passed to the C-ABI must be float64, got %s" % x.dtype)
 		if not x.is_contiguous():
 			raise ValueError("device tensors passed to the C-ABI must be contiguous")
 		return C.c_void_p(x.data_ptr()), int(x.is_cuda), x
+	if out and not (isinstance(x, np.ndarray) and x.dtype == dtype and x.flags.c_contiguous and x.flags.writeable):
+		raise ValueError("output buffers must be writeable C-contiguous %s numpy arrays (a copy would lose the result)" % np.dtype(dtype).name)
 	a = np.ascontiguousarray(x, dtype=dtype)
 	return a.ctypes.data_as(C.c_void_p), 0, a
 
@@ -263,6 +277,7 @@ class BPContext(object):
 		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
 		p.reduced_stokes = int(bool(d.get('reduced_stokes', False)))
 		p.mg_coarse_scale = float(d.get('mg_coarse_scale', 0.0))
+		p.krylov_error_on_nonconvergence = int(bool(d.get('krylov_error_on_nonconvergence', True)))
 		self._last_params = p
 		return p
 
@@ -284,8 +299,21 @@ class BPContext(object):
 		self._check(self.lib.bp_set_params(self.h, C.byref(p)))
 
 	def use_torch_stream(self):
+		"""run the library on torch's current stream of this device (no cross-stream ordering needed any more,
+		torch.cuda.Event sees the kernels, and the stream can be captured into CUDA graphs)."""
 		import torch
-		self._check(self.lib.bp_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+		h = torch.cuda.current_stream(self.device).cuda_stream
+		self._check(self.lib.bp_set_stream(self.h, C.c_void_p(h)))
+		self._stream_handle = h
+
+	def _order(self, x):
+		"""the library works on its own stream unless use_torch_stream() adopted torch's: a CUDA tensor
+		handed in may still be in flight on torch's current stream, so that stream is drained first."""
+		if _is_torch(x) and x.is_cuda:
+			import torch
+			s = torch.cuda.current_stream(x.device)
+			if s.cuda_stream != getattr(self, '_stream_handle', None):
+				s.synchronize()
 
 	def close(self):
 		if getattr(self, 'h', None):
@@ -303,6 +331,7 @@ class BPContext(object):
 		if np.isscalar(values):
 			values = np.full(self.n_vertices, float(values))
 		p, dev, keep = _ptr(values)
+		self._order(keep)
 		n = keep.numel() if _is_torch(keep) else keep.size
 		self._check(self.lib.bp_set_field(self.h, int(field), p, n, dev))
 
@@ -318,6 +347,7 @@ class BPContext(object):
 		"""assemble(F) and/or assemble(J) at u; numpy in -> numpy out, torch cuda in -> torch out."""
 		what = (ASSEMBLE_F if want_F else 0) | (ASSEMBLE_J if want_J else 0)
 		pu, dev, ku = _ptr(u)
+		self._order(ku)
 		if dev:
 			import torch
 			if want_F and F is None:
@@ -331,8 +361,8 @@ class BPContext(object):
 				J = np.empty(self.nnz_csr())
 		if J is False:
 			J = None
-		pF, _, kF = _ptr(F)
-		pJ, _, kJ = _ptr(J)
+		pF, _, kF = _ptr(F, out=True)
+		pJ, _, kJ = _ptr(J, out=True)
 		self._check(self.lib.bp_assemble(self.h, what, pu, pF, pJ, dev))
 		return F, J
 
@@ -345,25 +375,27 @@ class BPContext(object):
 
 	def spmv(self, x, y=None):
 		px, dev, kx = _ptr(x)
+		self._order(kx)
 		if y is None:
 			if dev:
 				import torch
 				y = torch.empty_like(kx)
 			else:
 				y = np.empty(self.n_dofs)
-		py, _, ky = _ptr(y)
+		py, _, ky = _ptr(y, out=True)
 		self._check(self.lib.bp_spmv(self.h, px, py, dev))
 		return y
 
 	def krylov_solve(self, b, x=None):
 		pb, dev, kb = _ptr(b)
+		self._order(kb)
 		if x is None:
 			if dev:
 				import torch
 				x = torch.empty_like(kb)
 			else:
 				x = np.empty(self.n_dofs)
-		px, _, kx = _ptr(x)
+		px, _, kx = _ptr(x, out=True)
 		it, rr = C.c_int32(), C.c_double()
 		self._check(self.lib.bp_krylov_solve(self.h, pb, px, dev, C.byref(it), C.byref(rr)))
 		return x, it.value, rr.value
@@ -373,6 +405,7 @@ class BPContext(object):
 		if not _is_torch(u) and not (isinstance(u, np.ndarray) and u.dtype == np.float64 and u.flags.c_contiguous):
 			raise ValueError("u must be a contiguous float64 numpy array or a torch tensor (updated in place)")
 		pu, dev, ku = _ptr(u)
+		self._order(ku)
 		st = bp_stats()
 		rc = self._check(self.lib.bp_newton_solve(self.h, pu, dev, C.byref(st)), allow=(BP_ERR_NONCONV,))
 		d = st.as_dict()
@@ -383,13 +416,14 @@ class BPContext(object):
 	def linear_solve(self, u_lin, u_out=None):
 		"""one linear solve with the viscosity frozen at eta(u_lin) (``linear=True``)."""
 		pl, dev, kl = _ptr(u_lin)
+		self._order(kl)
 		if u_out is None:
 			if dev:
 				import torch
 				u_out = torch.empty_like(kl)
 			else:
 				u_out = np.empty(self.n_dofs)
-		po, _, ko = _ptr(u_out)
+		po, _, ko = _ptr(u_out, out=True)
 		it = C.c_int32()
 		self._check(self.lib.bp_linear_solve(self.h, pl, po, dev, C.byref(it)))
 		self.last_linear_iterations = it.value
@@ -398,13 +432,14 @@ class BPContext(object):
 	def solve_pressure(self, u, p=None):
 		"""BP pressure (one value per mesh vertex) from the velocity dofs ``u``."""
 		pu, dev, ku = _ptr(u)
+		self._order(ku)
 		if p is None:
 			if dev:
 				import torch
 				p = torch.empty(self.n_vertices, dtype=torch.float64, device=ku.device)
 			else:
 				p = np.empty(self.n_vertices)
-		pp, _, kp = _ptr(p)
+		pp, _, kp = _ptr(p, out=True)
 		it = C.c_int32()
 		self._check(self.lib.bp_solve_pressure(self.h, pu, pp, dev, C.byref(it)))
 		self.last_projection_iterations = it.value
@@ -413,13 +448,14 @@ class BPContext(object):
 	def solve_vert_velocity(self, u, uz=None):
 		"""u_z (one value per mesh vertex) from continuity; needs FIELD_B."""
 		pu, dev, ku = _ptr(u)
+		self._order(ku)
 		if uz is None:
 			if dev:
 				import torch
 				uz = torch.empty(self.n_vertices, dtype=torch.float64, device=ku.device)
 			else:
 				uz = np.empty(self.n_vertices)
-		pz, _, kz = _ptr(uz)
+		pz, _, kz = _ptr(uz, out=True)
 		it = C.c_int32()
 		self._check(self.lib.bp_solve_vert_velocity(self.h, pu, pz, dev, C.byref(it)))
 		self.last_vert_iterations = it.value
@@ -434,7 +470,8 @@ class BPContext(object):
 		if uz is not None and not _is_torch(uz) and not (isinstance(uz, np.ndarray) and uz.dtype == np.float64 and uz.flags.c_contiguous):
 			raise ValueError("uz must be a contiguous float64 numpy array or a torch tensor (updated in place)")
 		pu, dev, ku = _ptr(u)
-		pz, _, kz = _ptr(uz)
+		self._order(ku)
+		pz, _, kz = _ptr(uz, out=True)
 		st = bp_stats()
 		rc = self._check(self.lib.bp_rs_newton_solve(self.h, pu, pz, dev, float(atol), int(bool(callback)), C.byref(st)),
 		                 allow=(BP_ERR_NONCONV,))
@@ -447,6 +484,7 @@ class BPContext(object):
 	def rs_solve_pressure(self, u, u_model, p=None):
 		"""pressure with the viscosity of ``u_model`` (+ the context's u_z) and the divergence of ``u``."""
 		pu, dev, ku = _ptr(u)
+		self._order(ku)
 		pm, _, km = _ptr(u_model)
 		if p is None:
 			if dev:
@@ -454,7 +492,7 @@ class BPContext(object):
 				p = torch.empty(self.n_vertices, dtype=torch.float64, device=ku.device)
 			else:
 				p = np.empty(self.n_vertices)
-		pp, _, kp = _ptr(p)
+		pp, _, kp = _ptr(p, out=True)
 		it = C.c_int32()
 		self._check(self.lib.bp_rs_solve_pressure(self.h, pu, pm, pp, dev, C.byref(it)))
 		self.last_projection_iterations = it.value
@@ -475,6 +513,23 @@ class BPContext(object):
 
 	def comm_init(self, unique_id, rank, n_ranks):
 		self._check(self.lib.bp_comm_init(self.h, nccl_library_path().encode(), unique_id, rank, n_ranks))
+
+
+def context_from_model(model, use_pressure_bc=True, cell_dofs=None, device=0, **params):
+	"""a :class:`BPContext` holding the mesh, markers and coefficient Functions (S, A, beta) of a
+	:class:`cslvr_b200.D3Model` -- what ``MomentumBPBase`` builds behind ``solve()``, for callers that
+	drive the C-ABI directly (bench.py, the parity tests).  ``params`` go to ``bp_params``."""
+	p = dict(n=model.n, eps_reg=model.eps_reg, rho_i=model.rho_i, rhosw=model.rhosw, g=model.g,
+	         periodic=model.use_periodic, use_pressure_bc=use_pressure_bc)
+	p.update(params)
+	c = BPContext(model.mesh.coordinates(), model.mesh.cells(), 2 * model.n_nodes,
+	              (model.facet_cell, model.facet_local, model.ff), p,
+	              cell_dofs=cell_dofs, device=device,
+	              vertex_to_node=(model.vertex_to_node if (model.use_periodic and cell_dofs is None) else None))
+	c.set_field(FIELD_S, model.vertex_field(model.S))
+	c.set_field(FIELD_A, model.vertex_field(model.A))
+	c.set_field(FIELD_BETA, model.vertex_field(model.beta))
+	return c
 
 
 def comm_unique_id():

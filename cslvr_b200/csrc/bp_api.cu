@@ -17,6 +17,26 @@
 std::string g_bp_create_error;
 void bp_upload_quadrature(bp_ctx* c);
 
+void bp_env_read(bp_env* e)
+{
+	auto geti = [](const char* k, int d) { const char* v = getenv(k); return v ? atoi(v) : d; };
+	auto getd = [](const char* k, double d) { const char* v = getenv(k); return v ? atof(v) : d; };
+	e->pipe_k = geti("BP_PIPE_K", 4);
+	e->no_pipeline = getenv("BP_NO_PIPELINE") != nullptr;
+	e->facet_atomic = geti("BP_FACET_ATOMIC", 0) != 0;
+	e->has_horizontal_first = getenv("BP_MG_HORIZONTAL_FIRST") != nullptr;
+	e->mg_horizontal_first = getd("BP_MG_HORIZONTAL_FIRST", 1.0);
+	e->mg_fp32 = geti("BP_MG_FP32", 1) != 0;
+	e->has_alpha0 = getenv("BP_MG_ALPHA0") != nullptr; e->mg_alpha0 = getd("BP_MG_ALPHA0", 0.0);
+	e->has_alpha = getenv("BP_MG_ALPHA") != nullptr;   e->mg_alpha = getd("BP_MG_ALPHA", 0.0);
+	e->mg_coupled = geti("BP_MG_COUPLED", 1) != 0;
+	e->mg_coupled_graph = geti("BP_MG_COUPLED_GRAPH", 1) != 0;
+	e->mg_gamma = geti("BP_MG_GAMMA", 0);
+	e->mg_tail = geti("BP_MG_TAIL", 4096);
+	e->asm_tiled = geti("BP_ASM_TILED", -1);
+	e->cg_graph = geti("BP_CG_GRAPH", 1) != 0;
+}
+
 // ------------------------------------------------------------------ helpers
 static int check_params(bp_ctx* c, const bp_params* p)
 {
@@ -206,9 +226,18 @@ static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 		done = cs[0]->h_sc[SC_DONE] != 0.0;
 	}
 	if (iters) *iters = (int)cs[0]->h_sc[SC_ITERS];
-	if (relres) *relres = cs[0]->h_sc[SC_NORM0] > 0 ? cs[0]->h_sc[SC_NORM] / cs[0]->h_sc[SC_NORM0] : 0.0;
+	const double rr = cs[0]->h_sc[SC_NORM0] > 0 ? cs[0]->h_sc[SC_NORM] / cs[0]->h_sc[SC_NORM0] : 0.0;
+	if (relres) *relres = rr;
+	cs[0]->krylov_last_relres = rr;
 	if (cs[0]->h_sc[SC_BREAKDOWN] != 0.0)
 		return bp_fail(cs[0], BP_ERR_STATE, "CG breakdown: p.Ap <= 0 (Jacobian not positive definite or NaN)");
+	if (!done) {
+		// PETSc KSP_DIVERGED_ITS: dolfin raises unless the krylov_solver's error_on_nonconvergence is off
+		cs[0]->krylov_unconverged++;
+		if (cs[0]->prm.krylov_error_on_nonconvergence)
+			return bp_fail(cs[0], BP_ERR_NONCONV, "Krylov solver did not converge in %d iterations (relative residual %.3e, rtol %.3e)",
+			               (int)cs[0]->h_sc[SC_ITERS], rr, cs[0]->prm.krylov_rtol);
+	}
 	return BP_OK;
 }
 
@@ -220,6 +249,7 @@ static int group_newton(bp_ctx** cs, int n, bp_stats* st)
 	memset(&s, 0, sizeof(s));
 	int rc;
 	int64_t l0 = 0;
+	const int unconv0 = c0->krylov_unconverged;
 	for (int r = 0; r < n; ++r) { if ((rc = ready(cs[r]))) { if (r) c0->err = cs[r]->err; return rc; } l0 += cs[r]->launches; }
 	cudaEvent_t eA, eB, eT0, eT1;
 	cudaEventCreate(&eA); cudaEventCreate(&eB); cudaEventCreate(&eT0); cudaEventCreate(&eT1);
@@ -272,6 +302,8 @@ out:
 	int64_t l1 = 0;
 	for (int r = 0; r < n; ++r) l1 += cs[r]->launches;
 	s.gpu_launches = (int32_t)(l1 - l0);
+	s.krylov_unconverged = c0->krylov_unconverged - unconv0;
+	s.krylov_last_relres = c0->krylov_last_relres;
 	if (st) *st = s;
 	return rc;
 }
@@ -292,6 +324,7 @@ int bp_create(bp_ctx** out, const bp_mesh* mesh, const bp_params* params, int de
 	if (device < 0 || device >= ndev) return bp_fail(nullptr, BP_ERR_ARG, "bp_create: device %d of %d", device, ndev);
 	bp_ctx* c = new bp_ctx();
 	c->device = device;
+	bp_env_read(&c->env);
 	int rc = check_params(c, params);
 	if (!rc) {
 		store_params(c, params);
@@ -314,7 +347,7 @@ void bp_destroy(bp_ctx* c)
 	bp_mg_free(c);
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, c->d_ext_dof,
-		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_mirror, c->d_val, c->d_valf, c->d_csr_src, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
+		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_mirror, c->d_val, c->d_valf, c->d_csr_src, c->d_csr_out, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
 		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
@@ -428,8 +461,7 @@ static int assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
 {
 	const int64_t no = c->nn_owned, nn = c->nn;
 	const int nblk = (int)((no + BP_ROWS_PER_CTA - 1) / BP_ROWS_PER_CTA);
-	const char* evk = getenv("BP_PIPE_K");
-	const int K = std::max(1, std::min(evk ? atoi(evk) : 4, std::min(8, nblk / 64)));
+	const int K = std::max(1, std::min(c->env.pipe_k, std::min(8, nblk / 64)));
 	if (!c->s_h2d) {
 		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
 		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
@@ -493,7 +525,7 @@ int bp_assemble(bp_ctx* c, int what, const double* u, double* F, double* Jv, int
 	if (rc) return rc;
 	if (Jv && (rc = bp_build_csr_export(c))) return rc;
 	if (!on_device && !Jv && c->identity_dofs && !c->comm && c->nn == c->nn_owned && c->nd_ext == 2 * c->nn && bp_rows_gather_mode(c)
-	    && !(what & ~(BP_ASSEMBLE_F | BP_ASSEMBLE_J)) && !getenv("BP_NO_PIPELINE"))
+	    && !(what & ~(BP_ASSEMBLE_F | BP_ASSEMBLE_J)) && !c->env.no_pipeline)
 		return assemble_pipelined(c, what, u, F);
 	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
 	bp_ctx* cs[1] = { c };
@@ -503,13 +535,11 @@ int bp_assemble(bp_ctx* c, int what, const double* u, double* F, double* Jv, int
 		const int64_t nnz = c->csr_indptr.back();
 		if (on_device) bp_launch_csr_export(c, Jv);
 		else {
-			double* tmp = nullptr;
-			BP_CUDA(c, cudaMalloc((void**)&tmp, std::max<int64_t>(nnz, 1) * sizeof(double)));
-			bp_launch_csr_export(c, tmp);
-			cudaError_t e = cudaMemcpyAsync(Jv, tmp, nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-			if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-			cudaFree(tmp);
-			BP_CUDA(c, e);
+			// the export buffer is allocated once and kept (a caller who asks for J on the host does so every Newton step)
+			if (!c->d_csr_out) BP_CUDA(c, cudaMalloc((void**)&c->d_csr_out, std::max<int64_t>(nnz, 1) * sizeof(double)));
+			bp_launch_csr_export(c, c->d_csr_out);
+			BP_CUDA(c, cudaMemcpyAsync(Jv, c->d_csr_out, nnz * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+			BP_CUDA(c, cudaStreamSynchronize(c->stream));
 		}
 	}
 	BP_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -643,6 +673,7 @@ static int solve_pressure_impl(bp_ctx* c, const double* u, const double* u_model
 	// mass-matrix solve: block-Jacobi PCG to 1e-13 (dolfin's project() uses a direct solver)
 	const bp_params saved = c->prm;
 	c->prm.pc = BP_PC_BLOCK_JACOBI; c->prm.krylov_rtol = 1e-13; c->prm.krylov_atol = 0.0; c->prm.krylov_maxit = 2000;
+	c->prm.krylov_error_on_nonconvergence = 1;       // dolfin's project() is a direct solve: an unconverged p is an error
 	int it = 0;
 	rc = group_pcg(cs, 1, &it, nullptr);
 	c->prm = saved;
@@ -685,6 +716,7 @@ static int vert_velocity_core(bp_ctx* c, int32_t* iterations)
 	{
 		const bp_params saved = c->prm;
 		c->prm.pc = BP_PC_BLOCK_JACOBI; c->prm.krylov_rtol = 1e-13; c->prm.krylov_atol = 0.0; c->prm.krylov_maxit = 2000;
+		c->prm.krylov_error_on_nonconvergence = 1;   // project() is a direct solve in the reference
 		rc = group_pcg(cs, 1, nullptr, nullptr);
 		c->prm = saved;
 		if (rc) return rc;
@@ -775,6 +807,7 @@ int bp_rs_newton_solve(bp_ctx* c, double* u, double* uz_vertex, int on_device, d
 	bp_stats s;
 	memset(&s, 0, sizeof(s));
 	const int64_t l0 = c->launches;
+	const int unconv0 = c->krylov_unconverged;
 	if (uz_vertex)
 		BP_CUDA(c, cudaMemcpyAsync(c->d_uz, uz_vertex, (size_t)c->nv * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
 	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;
@@ -825,6 +858,8 @@ int bp_rs_newton_solve(bp_ctx* c, double* u, double* uz_vertex, int on_device, d
 	s.t_total_ms = ms;
 	cudaEventDestroy(eA); cudaEventDestroy(eB); cudaEventDestroy(eT0); cudaEventDestroy(eT1);
 	s.gpu_launches = (int32_t)(c->launches - l0);
+	s.krylov_unconverged = c->krylov_unconverged - unconv0;
+	s.krylov_last_relres = c->krylov_last_relres;
 	if (st) *st = s;
 	if (rc && rc != BP_ERR_NONCONV) return rc;
 	int rc2 = vec_out(c, c->d_u, u, on_device);

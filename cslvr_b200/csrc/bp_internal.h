@@ -28,6 +28,24 @@ enum {
 	SC_COUNT = 16
 };
 
+// run-time switches, read from the environment ONCE per context at bp_create -- never per launch
+struct bp_env {
+	int    pipe_k = 4;              // BP_PIPE_K
+	bool   no_pipeline = false;     // BP_NO_PIPELINE
+	bool   facet_atomic = false;    // BP_FACET_ATOMIC=1: the atomic facet kernel (default: row gather, reproducible)
+	bool   has_horizontal_first = false;
+	double mg_horizontal_first = 1.0;                       // BP_MG_HORIZONTAL_FIRST
+	bool   mg_fp32 = true;          // BP_MG_FP32
+	bool   has_alpha0 = false, has_alpha = false;
+	double mg_alpha0 = 0.0, mg_alpha = 0.0;                 // BP_MG_ALPHA0 / BP_MG_ALPHA
+	bool   mg_coupled = true, mg_coupled_graph = true;      // BP_MG_COUPLED / BP_MG_COUPLED_GRAPH
+	int    mg_gamma = 0;            // BP_MG_GAMMA (0 = the hierarchy's default)
+	int    mg_tail = 4096;          // BP_MG_TAIL
+	int    asm_tiled = -1;          // BP_ASM_TILED: 1 / 0 force / forbid the tiled cell kernel (-1 = automatic)
+	bool   cg_graph = true;         // BP_CG_GRAPH=0: launch the CG iteration directly instead of replaying its graph
+};
+void bp_env_read(bp_env* e);
+
 struct bp_comm_state;   // NCCL binding (bp_comm.cu)
 struct bp_mg;           // multigrid hierarchy (bp_mg.cu)
 
@@ -37,6 +55,7 @@ struct bp_ctx {
 	bool         own_stream = false;
 	std::string  err;
 	bp_params    prm{};
+	bp_env       env;
 	std::vector<double> quad_pts, quad_wts, quad_pts_aux, quad_wts_aux;
 
 	// sizes
@@ -96,6 +115,7 @@ struct bp_ctx {
 	double*  d_val = nullptr;            // [n_slots*4] 2x2 blocks {a00 a01 a10 a11}, SELL-32 slot order
 	float*   d_valf = nullptr;           // FP32 copy of d_val for the multigrid smoother (allocated on first use)
 	int32_t* d_csr_src = nullptr;        // CSR export gather map
+	double*  d_csr_out = nullptr;        // CSR values staged for a host-side J_values (allocated on first use)
 	// device: vectors in internal layout [2*node + c], length 2*nn
 	double *d_u = nullptr, *d_F = nullptr, *d_dx = nullptr, *d_r = nullptr, *d_z = nullptr,
 	       *d_p = nullptr, *d_Ap = nullptr, *d_io = nullptr, *d_io2 = nullptr;
@@ -126,6 +146,8 @@ struct bp_ctx {
 
 	bool have_S = false, have_A = false, have_beta = false, have_J = false, have_B = false;
 	int64_t launches = 0;
+	int     krylov_unconverged = 0;      // linear solves that stopped at krylov_maxit (bp_stats)
+	double  krylov_last_relres = 0.0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	// host-buffer bp_assemble, pipelined: per CTA of the row-gather kernel, the vertex / node prefix its
 	// incidences reference (prefix maxima) and whether a facet integral touches one of its rows

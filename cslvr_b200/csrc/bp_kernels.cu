@@ -918,7 +918,7 @@ void bp_launch_facets(bp_ctx* c, int what)
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
 	const int gf = (int)((c->nf + TPB - 1) / TPB);
 	const int gfr = (int)((c->n_fnodes + TPB - 1) / TPB);
-	const bool use_fr = c->n_fnodes > 0 && getenv("BP_FACET_ROWS");
+	const bool use_fr = c->n_fnodes > 0 && !c->env.facet_atomic;
 	const double2* u2 = (const double2*)c->d_u;
 	#define FACETC(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)c->n_fnodes, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
 		else k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring); } while (0)
@@ -956,8 +956,8 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	const double2* u2 = (const double2*)c->d_u;
 	const size_t row_smem = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);   // the diagonal block lives in registers
 	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
-	// BP_FACET_ROWS=1: the atomic-free facet kernel (bitwise reproducible F and J; ~6 us slower at 2 M tets)
-	const bool use_fr = gather && c->n_fnodes > 0 && getenv("BP_FACET_ROWS");
+	// default: the atomic-free facet kernel (bitwise reproducible F and J); BP_FACET_ATOMIC=1 gives the atomic one back
+	const bool use_fr = gather && c->n_fnodes > 0 && !c->env.facet_atomic;
 	#define FACET(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)c->n_fnodes, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
 		else k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring); } while (0)
 	if (gather) {

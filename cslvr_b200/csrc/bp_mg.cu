@@ -314,7 +314,7 @@ static int make_level_ctx(bp_ctx* c, bp_mg_level& L, const std::vector<int32_t>&
 {
 	bp_ctx* M = new bp_ctx();
 	L.M = M;
-	M->device = c->device; M->stream = c->stream; M->prm = c->prm;
+	M->device = c->device; M->stream = c->stream; M->prm = c->prm; M->env = c->env;
 	M->prm.pc = BP_PC_BLOCK_JACOBI;
 	M->nn_owned = L.n;
 	M->nn = L.n + L.n_ghost;
@@ -450,11 +450,10 @@ static int mg_symbolic(bp_ctx* c)
 		for (int32_t j = c->h_colptr[cc]; j < c->h_colptr[cc + 1]; ++j) { col_of[c->h_colnode[j]] = (int32_t)cc; lay_of[c->h_colnode[j]] = j - c->h_colptr[cc]; }
 	}
 	double aspect = c->aspect;
-	const char* ev_h = getenv("BP_MG_HORIZONTAL_FIRST");
 	// slabs of a partitioned mesh keep the plain order: with the ghost columns ignored the layer-wise
 	// levels and the over-relaxation both cost iterations there (measured on 4 and 8 slabs)
 	const bool partitioned = c->nn > c->nn_owned;
-	const double aspect_switch = ev_h ? atof(ev_h) : (partitioned ? 0.0 : 1.0);
+	const double aspect_switch = c->env.has_horizontal_first ? c->env.mg_horizontal_first : (partitioned ? 0.0 : 1.0);
 	std::vector<int32_t> agg;
 	int32_t na = 0;
 	auto next_aggregation = [&](const bp_mg_level& F) {
@@ -657,8 +656,7 @@ static int mgc_symbolic(bp_ctx** cs, int n)
 		uniform = (v[0][0] == -v[0][1]) && v[0][2] == 0.0;
 		aspect = -v[0][3];
 	}
-	const char* ev_h = getenv("BP_MG_HORIZONTAL_FIRST");
-	const double aspect_switch = ev_h ? atof(ev_h) : 1.0;
+	const double aspect_switch = cs[0]->env.mg_horizontal_first;
 	for (int guard = 0; guard < 24; ++guard) {
 		const int l = (int)cs[0]->mg->lv.size() - 1;
 		// ---- A: aggregates of the owned nodes, rank by rank; the KIND of step is the same on every rank:
@@ -844,8 +842,7 @@ static int mgc_prepare(bp_ctx** cs, int n)
 			c->launches++;
 		}
 		{
-			const char* e32 = getenv("BP_MG_FP32");
-			mg->f32 = e32 ? atoi(e32) != 0 : true;
+			mg->f32 = cs[0]->env.mg_fp32;
 		}
 		for (int l = 0; l < nl; ++l) {
 			bp_ctx* M = mg->lv[l].M;
@@ -1022,9 +1019,9 @@ static int mgc_vcycle(bp_ctx** cs, int n, int l, double** rhs, int deg, double r
 		bp_ctx* M = Ls[r];
 		bp_mg_level& L = cs[r]->mg->lv[l];
 		bp_ctx* C = cs[r]->mg->lv[l + 1].M;
-		const char* ev = getenv(l == 0 ? "BP_MG_ALPHA0" : "BP_MG_ALPHA");
 		const double alpha_def = (cs[r]->prm.mg_coarse_scale > 0.0 && cs[r]->prm.mg_coarse_scale <= 2.0) ? cs[r]->prm.mg_coarse_scale : 1.8;
-		const double alpha = ev ? atof(ev) : alpha_def;
+		const bp_env& E = cs[r]->env;
+		const double alpha = (l == 0 ? E.has_alpha0 : E.has_alpha) ? (l == 0 ? E.mg_alpha0 : E.mg_alpha) : alpha_def;
 		k_mg_prolong_add<<<blocks(L.n, 256), 256, 0, cs[r]->stream>>>((int)L.n, L.d_agg, (const double2*)((czid[r] == 2) ? C->d_z : C->d_z2),
 			(double2*)((zid[r] == 2) ? M->d_z : M->d_z2), alpha);
 		cs[r]->launches++;
@@ -1056,8 +1053,7 @@ static int mgc_apply(bp_ctx** cs, int n)
 	bp_mg* mg = cs[0]->mg;                  // the graph of an in-process group lives in its first context
 	const int deg = std::max(cs[0]->prm.pc_degree, 1);
 	const double ratio = std::max(cs[0]->prm.pc_eig_ratio, 1.5);
-	const char* eg = getenv("BP_MG_COUPLED_GRAPH");
-	const bool want_graph = !(eg && atoi(eg) == 0) && !mg->no_graph;
+	const bool want_graph = cs[0]->env.mg_coupled_graph && !mg->no_graph;
 	if (mg->graph && (mg->g_r != cs[0]->d_r || mg->g_z != cs[0]->d_z || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_alpha != cs[0]->prm.mg_coarse_scale || mg->g_f32 != mg->f32)) {
 		cudaGraphExecDestroy(mg->graph);
 		mg->graph = nullptr;
@@ -1096,8 +1092,7 @@ static int mgc_apply(bp_ctx** cs, int n)
 // entry points for the partitioned path (bp_api.cu): coupled hierarchy unless BP_MG_COUPLED=0
 bool bp_mg_use_coupled(bp_ctx** cs, int n)
 {
-	const char* e = getenv("BP_MG_COUPLED");
-	if (e && atoi(e) == 0) return false;
+	if (!cs[0]->env.mg_coupled) return false;
 	if (cs[0]->mg) return cs[0]->mg->coupled;
 	const bool partitioned = (n > 1) || cs[0]->n_nbr > 0;
 	if (!partitioned) return false;
@@ -1130,8 +1125,7 @@ int bp_mg_prepare(bp_ctx* c)
 		c->launches++;
 	}
 	{
-		const char* e32 = getenv("BP_MG_FP32");
-		mg->f32 = e32 ? atoi(e32) != 0 : true;
+		mg->f32 = c->env.mg_fp32;
 	}
 	for (int l = 0; l < nl; ++l) {
 		bp_ctx* M = mg->lv[l].M;
@@ -1245,17 +1239,14 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 		return M->d_z;
 	}
 	{
-		const char* evg0 = getenv("BP_MG_GAMMA");
-		const char* evt = getenv("BP_MG_TAIL");
-		const int tail_nodes = evt ? atoi(evt) : 4096;
-		const bool v_only = std::max(1, evg0 ? atoi(evg0) : mg->gamma) == 1;
+		const int tail_nodes = c->env.mg_tail;
+		const bool v_only = std::max(1, c->env.mg_gamma ? c->env.mg_gamma : mg->gamma) == 1;
 		if (l > 0 && v_only && L.n <= tail_nodes && nl - l <= MG_TAIL_MAX && rhs == M->d_F) {
 			// this level and everything below it: one launch
 			TailArgs A;
 			memset(&A, 0, sizeof(A));
 			A.nl = nl - l; A.deg = deg; A.ratio = ratio;
-			const char* eva = getenv("BP_MG_ALPHA");
-			A.alpha = eva ? atof(eva) : ((c->prm.mg_coarse_scale > 0.0 && c->prm.mg_coarse_scale <= 2.0) ? c->prm.mg_coarse_scale : (c->nn > c->nn_owned ? 1.0 : 1.8));
+			A.alpha = c->env.has_alpha ? c->env.mg_alpha : ((c->prm.mg_coarse_scale > 0.0 && c->prm.mg_coarse_scale <= 2.0) ? c->prm.mg_coarse_scale : (c->nn > c->nn_owned ? 1.0 : 1.8));
 			A.dense = mg->d_dense; A.ndense = mg->nc;
 			for (int k = l; k < nl; ++k) {
 				bp_mg_level& Lk = mg->lv[k];
@@ -1281,11 +1272,11 @@ static double* vcycle(bp_ctx* c, bp_mg* mg, int l, const double* rhs, int deg, d
 	bp_ctx* C = mg->lv[l + 1].M;
 	// gamma coarse-grid visits per level below the finest (1 = V-cycle, 2 = W-cycle): plain
 	// aggregation has a stiff coarse operator, a second visit of the (tiny) coarser levels is cheap
-	const char* evg = getenv("BP_MG_GAMMA");
-	const int gamma = (l == 0) ? 1 : std::max(1, evg ? atoi(evg) : mg->gamma);
-	const char* ev = getenv(l == 0 ? "BP_MG_ALPHA0" : "BP_MG_ALPHA");
+	const int gamma = (l == 0) ? 1 : std::max(1, c->env.mg_gamma ? c->env.mg_gamma : mg->gamma);
+	const bool has_ev = (l == 0) ? c->env.has_alpha0 : c->env.has_alpha;
+	const double ev_alpha = (l == 0) ? c->env.mg_alpha0 : c->env.mg_alpha;
 	const double alpha_def = (c->prm.mg_coarse_scale > 0.0 && c->prm.mg_coarse_scale <= 2.0) ? c->prm.mg_coarse_scale : (c->nn > c->nn_owned ? 1.0 : 1.8);
-	const double alpha = ev ? atof(ev) : alpha_def;
+	const double alpha = has_ev ? ev_alpha : alpha_def;
 	for (int g = 0; g < gamma; ++g) {
 		double* other = (z == M->d_z) ? M->d_z2 : M->d_z;
 		if (line) {

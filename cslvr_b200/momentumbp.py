@@ -85,8 +85,26 @@ class MomentumBPBase(Momentum):
 	def _context(self):
 		m = self.model
 		X = m.mesh.coordinates()
-		key = (id(m.mesh), float(X[:, 2].sum()), float(np.abs(X[:, 2]).sum()), int(m.ff.sum()),
-		       bool(self.use_pressure_bc), bool(m.energy_dependent_rate_factor))
+		# everything bp_create digests: coordinates, connectivity, periodic map, markers, constants.  The
+		# connectivity of a mesh object is hashed once (stored on the mesh), coordinates and markers every time.
+		import hashlib
+		topo = getattr(m.mesh, '_b200_topology_hash', None)
+		if topo is None or topo[0] != (m.mesh.cells().shape, bool(m.use_periodic)):
+			ht = hashlib.blake2b(digest_size=16)
+			for a in (m.mesh.cells(), m.vertex_to_node if m.use_periodic else np.zeros(0), m.facet_cell, m.facet_local):
+				ht.update(np.ascontiguousarray(a).view(np.uint8))
+			topo = ((m.mesh.cells().shape, bool(m.use_periodic)), ht.hexdigest())
+			try:
+				m.mesh._b200_topology_hash = topo
+			except AttributeError:
+				pass
+		h = hashlib.blake2b(digest_size=16)
+		h.update(topo[1].encode())
+		for a in (X, m.ff):
+			h.update(np.ascontiguousarray(a).view(np.uint8))
+		key = (h.hexdigest(), float(m.n), float(m.eps_reg), float(m.rho_i), float(m.rhosw), float(m.g),
+		       bool(m.use_periodic), bool(self.use_pressure_bc), bool(m.energy_dependent_rate_factor),
+		       bool(self._reduced_stokes), self.device)
 		if self._ctx is None or key != self._ctx_key:
 			if self._ctx is not None:
 				self._ctx.close()
@@ -140,8 +158,15 @@ class MomentumBPBase(Momentum):
 		          krylov_maxit=ks.get('maximum_iterations', 10000),
 		          preconditioner=self._PC_MAP.get(pc, 'mg'),
 		          verbose=ks.get('monitor_convergence', False) or ns.get('report', False),
-		          quadrature_degree=self.solve_params.get('quadrature_degree', 9 if self.model.energy_dependent_rate_factor else 5))
+		          krylov_error_on_nonconvergence=ks.get('error_on_nonconvergence', True),
+		          quadrature_degree=self._quadrature_degree())
 		return kw
+
+	def _quadrature_degree(self):
+		"""UFL's estimate for the cell integrals (SURVEY A-Q): 5 with a P1 rate factor, 9 with the
+		energy-dependent expression at the quadrature points; ``solve_params['quadrature_degree']``
+		overrides, as ``parameters['form_compiler']['quadrature_degree']`` does in the reference."""
+		return self.solve_params.get('quadrature_degree', 9 if self.model.energy_dependent_rate_factor else 5)
 
 	def _newton_solve(self, ns):
 		c = self._context()
@@ -161,7 +186,7 @@ class MomentumBPBase(Momentum):
 		ks = inner.get('krylov_solver', {})
 		c.set_params(krylov_rtol=ks.get('relative_tolerance', 1e-5), krylov_atol=ks.get('absolute_tolerance', 1e-50),
 		             krylov_maxit=ks.get('maximum_iterations', 10000), preconditioner=self._PC_MAP.get(pc, 'mg'),
-		             quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		             quadrature_degree=self._quadrature_degree())
 		ul = np.empty(self.Q.dim())
 		ul[0::2], ul[1::2] = self.model.u.values[0::3], self.model.u.values[1::3]
 		self.get_unknown().values[:] = c.linear_solve(ul)
@@ -170,14 +195,14 @@ class MomentumBPBase(Momentum):
 	# ---- assemble(residual) / assemble(jacobian) ------------------------------
 	def assemble_residual(self, u=None):
 		c = self._context()
-		c.set_params(quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		c.set_params(quadrature_degree=self._quadrature_degree())
 		F, _ = c.assemble(self.get_unknown().values if u is None else u, want_F=True, want_J=False)
 		return F
 
 	def assemble_jacobian(self, u=None):
 		"""(indptr, indices, values) of the CSR Jacobian in the QM2 dof numbering."""
 		c = self._context()
-		c.set_params(quadrature_degree=self.solve_params.get('quadrature_degree', 5))
+		c.set_params(quadrature_degree=self._quadrature_degree())
 		_, J = c.assemble(self.get_unknown().values if u is None else u, want_F=False, want_J=True)
 		ip, ix = c.csr_pattern()
 		return ip, ix, J

@@ -26,7 +26,8 @@ extern "C" {
 #define BP_ERR_CUDA        2   /* CUDA runtime error (no GPU, OOM, launch fail) */
 #define BP_ERR_STATE       3   /* call out of order (field not set, no J yet)   */
 #define BP_ERR_COMM        4   /* NCCL could not be loaded / collective failed  */
-#define BP_ERR_NONCONV     5   /* Newton did not converge and error_on_nonconvergence != 0 */
+#define BP_ERR_NONCONV     5   /* Newton (or a Krylov solve) did not converge and the matching
+                                   error_on_nonconvergence flag is set                       */
 
 /* field ids for bp_set_field.  All coefficient fields are VERTEX-indexed
  * (n = n_vertices): a P1 Function f on a dolfin space with dofmap dm is passed
@@ -156,6 +157,11 @@ typedef struct {
 	 * prolongation gives a coarse operator that is too stiff, so the plain correction under-shoots;
 	 * any factor in (0, 2] keeps the V-cycle symmetric positive definite.                          */
 	double  mg_coarse_scale;
+	/* dolfin's PETScKrylovSolver raises when KSP stops without converging ('error_on_nonconvergence'
+	 * of the krylov_solver parameter set, default True; cslvr/momentumbp.py:190 leaves it alone):
+	 * != 0 -> a linear solve that reaches krylov_maxit returns BP_ERR_NONCONV; 0 -> the step is taken
+	 * anyway and counted in bp_stats.krylov_unconverged                                            */
+	int32_t krylov_error_on_nonconvergence;
 } bp_params;
 
 typedef struct {
@@ -170,6 +176,8 @@ typedef struct {
 	int32_t n_assemblies;
 	int32_t gpu_launches;            /* kernels launched by this call             */
 	double  residual_history[64];
+	int32_t krylov_unconverged;      /* linear solves that stopped at krylov_maxit            */
+	double  krylov_last_relres;      /* relative residual of the last linear solve            */
 } bp_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */
@@ -177,6 +185,12 @@ int  bp_create(bp_ctx** out, const bp_mesh* mesh, const bp_params* params, int d
 void bp_destroy(bp_ctx* ctx);
 const char* bp_last_error(const bp_ctx* ctx);      /* ctx may be NULL: last create error */
 int  bp_set_params(bp_ctx* ctx, const bp_params* params);
+/* Stream contract.  bp_create gives the context its own non-blocking stream; every kernel and copy
+ * of the library runs there, and every entry point returns only after its outputs are complete
+ * (it synchronises that stream).  Device buffers handed in (on_device != 0) are READ on the context's
+ * stream: work that produces them on another stream must have completed (or been ordered by the
+ * caller) before the call.  bp_set_stream adopts the caller's stream instead (e.g. torch's current
+ * stream), which makes that ordering automatic and lets the caller time / graph-capture the work.  */
 int  bp_set_stream(bp_ctx* ctx, void* cuda_stream); /* run on the caller's stream        */
 
 /* coefficient Functions: model.init_beta / init_A / init_S,

@@ -41,6 +41,17 @@ static inline void atomic_add(double* p, double v)
 	*p += v;
 }
 
+/* torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: the CPU baseline asks for its
+ * thread count explicitly (bench.py) instead of inheriting that */
+void bpo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#else
+	(void)n;
+#endif
+}
+
 int bpo_num_threads(void)
 {
 #ifdef _OPENMP

@@ -31,8 +31,12 @@ def _p(a):
 
 
 class COracle(object):
-	def __init__(self, prob):
+	def __init__(self, prob, threads=None):
+		"""``threads``: OpenMP threads of the C twin (default: what the OpenMP runtime picks; under
+		torch.distributed.run that is 1 unless asked for explicitly)."""
 		self.lib = _lib()
+		if threads:
+			self.lib.bpo_set_num_threads(C.c_int(int(threads)))
 		self.prob = prob
 		self.coords = np.ascontiguousarray(prob.coords, dtype=np.float64)
 		self.cells = np.ascontiguousarray(prob.cells, dtype=np.int32)

@@ -71,19 +71,10 @@ def oracle_problem(model, use_pressure_bc=True, quad_degree=None, cell_dofs=None
 	                                rhosw=model.rhosw, g=model.g))
 
 
-def product_context(model, use_pressure_bc=True, cell_dofs=None, device=0, **params):
+def product_context(model, **kw):
+	"""the product's device context for a model (lives in the package: cslvr_b200.capi.context_from_model)."""
 	from cslvr_b200 import capi
-	p = dict(n=model.n, eps_reg=model.eps_reg, rho_i=model.rho_i, rhosw=model.rhosw, g=model.g,
-	         periodic=model.use_periodic, use_pressure_bc=use_pressure_bc)
-	p.update(params)
-	c = capi.BPContext(model.mesh.coordinates(), model.mesh.cells(), 2 * model.n_nodes,
-	                   (model.facet_cell, model.facet_local, model.ff), p,
-	                   cell_dofs=cell_dofs, device=device,
-	                   vertex_to_node=(model.vertex_to_node if (model.use_periodic and cell_dofs is None) else None))
-	c.set_field(capi.FIELD_S, model.vertex_field(model.S))
-	c.set_field(capi.FIELD_A, model.vertex_field(model.A))
-	c.set_field(capi.FIELD_BETA, model.vertex_field(model.beta))
-	return c
+	return capi.context_from_model(model, **kw)
 
 
 def state(n_dofs, seed=1234, scale=30.0):
@@ -92,6 +83,14 @@ def state(n_dofs, seed=1234, scale=30.0):
 
 def relerr(a, b):
 	return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+def relerr_entrywise(a, b, floor=1e-10):
+	"""largest |a - b| / |b| over the entries with |b| > floor * max|b|: relerr() is a max-norm measure and
+	never looks at a small entry by itself; this one does."""
+	a, b = np.asarray(a), np.asarray(b)
+	m = np.abs(b) > floor * np.abs(b).max()
+	return float((np.abs(a - b)[m] / np.abs(b)[m]).max()) if m.any() else 0.0
 
 
 def delaunay_extruded_model(n_pts=60, n_layers=4, seed=3, L=30000.0):

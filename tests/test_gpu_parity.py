@@ -611,19 +611,25 @@ def test_reduced_stokes_entry_points_refuse_misuse():
 	cp.close()
 
 
-def test_atomic_free_facet_kernel_is_bitwise_reproducible(monkeypatch):
-	"""BP_FACET_ROWS=1: the facet integrals by row gather (one thread per touched node, plain
-	read-modify-write of its own rows after k_rows) -- same numbers as the atomic facet kernel to
-	rounding, and F and J identical bit for bit from run to run."""
+def test_default_assembly_is_atomic_free_and_bitwise_reproducible(monkeypatch):
+	"""the default path has no atomics anywhere: cell integrals by row gather (or the tiled cell kernel),
+	facet integrals by row gather (one thread per touched node, plain read-modify-write of its own rows
+	after the cell kernel) -- F and J identical bit for bit from run to run, with no environment switch;
+	BP_FACET_ATOMIC=1 gives the atomic facet kernel back (same numbers to rounding)."""
 	m = marine_model()
 	P = oracle_problem(m)
 	u = state(P.n_dofs, 5)
-	monkeypatch.setenv('BP_FACET_ROWS', '1')
-	c = product_context(m, assembly='gather')
+	monkeypatch.delenv('BP_FACET_ATOMIC', raising=False)
+	c = product_context(m)
 	F1, J1 = c.assemble(u, want_F=True, want_J=True)
 	F2, J2 = c.assemble(u, want_F=True, want_J=True)
 	assert np.array_equal(F1, F2) and np.array_equal(J1, J2)
 	assert relerr(F1, P.residual(u)) < TOL_ASM and relerr(J1, P.jacobian(u)) < TOL_ASM
+	c.close()
+	monkeypatch.setenv('BP_FACET_ATOMIC', '1')
+	c = product_context(m)
+	F3, J3 = c.assemble(u, want_F=True, want_J=True)
+	assert relerr(F3, F1) < TOL_ASM and relerr(J3, J1) < TOL_ASM
 	c.close()
 
 

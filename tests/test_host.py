@@ -125,7 +125,7 @@ def test_bench_reference_arm_prints_one_json_line():
 	import json
 	import subprocess
 	import sys
-	env = dict(os.environ, BENCH_NXY='20', CSLVR_B200_QUIET='1')
+	env = dict(os.environ, BENCH_NXY='20', BENCH_NEWTON_NXY='15', CSLVR_B200_QUIET='1', OMP_NUM_THREADS='1')   # as under torch.distributed.run
 	r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
 	                   capture_output=True, text=True, env=env, timeout=600)
 	assert r.returncode == 0, r.stderr[-2000:]
@@ -138,3 +138,8 @@ def test_bench_reference_arm_prints_one_json_line():
 	assert d['impl'] == 'reference' and d['unit'] == 'Mtets/s' and d['value'] > 0 and d['vs_baseline'] is None
 	assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and 'workload' in d['config']
 	assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+	assert 'ISMIP-HOM A' in d['config']['workload']
+	# all host cores even though the launcher exported OMP_NUM_THREADS=1
+	assert d['cpu_baseline']['cores'] == len(os.sched_getaffinity(0))
+	nb = d['cpu_baseline_newton']
+	assert nb[0]['converged'] and nb[0]['newton_iterations'] > 3 and nb[0]['solve_s'] > 0
