@@ -49,7 +49,10 @@ def test_full_size_parity_with_the_c_twin(big):
 	F, J = c.assemble(u, want_F=True, want_J=True)
 	c.close()
 	assert relerr(F, Fo) < 1e-12 and relerr(J, Jo) < 1e-12
-	assert relerr_entrywise(J, Jo) < 1e-9 and relerr_entrywise(F, Fo, floor=1e-8) < 1e-9
+	# entry by entry: an entry is a sum of up to 24 element contributions of the size of the largest entries, so
+	# its own relative error is eps * max|J| / |entry|: 1e-11 above 1e-4 max|J|, 1e-5 down to 1e-10 max|J|
+	assert relerr_entrywise(J, Jo, floor=1e-4) < 1e-11 and relerr_entrywise(J, Jo, floor=1e-10) < 1e-5
+	assert relerr_entrywise(F, Fo, floor=1e-4) < 1e-10
 
 
 def test_gather_and_scatter_assembly_agree_at_full_size(big):
