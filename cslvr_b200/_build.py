@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, 'csrc', f) for f in
-       ('bp_setup.cu', 'bp_kernels.cu', 'bp_mg.cu', 'bp_comm.cu', 'bp_api.cu')]
+       ('bp_setup.cu', 'bp_kernels.cu', 'bp_tiles.cu', 'bp_mg.cu', 'bp_comm.cu', 'bp_api.cu')]
 HDR = [os.path.join(HERE, 'csrc', 'bp_internal.h'), os.path.join(ROOT, 'include', 'cslvr_b200.h')]
 LIB = os.environ.get('BP_LIB_PATH') or os.path.join(HERE, 'lib', 'libcslvr_b200.so')
 

@@ -78,7 +78,8 @@ SYMBOLS = ['bp_create', 'bp_destroy', 'bp_last_error', 'bp_set_params', 'bp_set_
            'bp_krylov_solve', 'bp_newton_solve', 'bp_time_assemble', 'bp_time_spmv',
            'bp_launch_count', 'bp_comm_unique_id', 'bp_comm_init',
            'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity', 'bp_linear_solve',
-           'bp_rs_newton_solve', 'bp_rs_solve_pressure']
+           'bp_rs_newton_solve', 'bp_rs_solve_pressure',
+           'bp_debug_create_host', 'bp_debug_bsr_pattern', 'bp_debug_tiles_emulate', 'bp_debug_tiles_info', 'bp_debug_tiles_why']
 
 _lib = None
 
@@ -274,7 +275,7 @@ class BPContext(object):
 		p.verbose = int(bool(d.get('verbose', False)))
 		p.krylov_norm_preconditioned = int(d.get('krylov_norm', 'unpreconditioned') == 'preconditioned')
 		p.mg_smoother = {'auto': -1, 'block': 0, 'column': 1}[d.get('mg_smoother', 'auto')]
-		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2}[d.get('assembly', 'auto')]
+		p.assembly = {'auto': 0, 'scatter': 1, 'gather': 2, 'tiled': 3}[d.get('assembly', 'auto')]
 		p.reduced_stokes = int(bool(d.get('reduced_stokes', False)))
 		p.mg_coarse_scale = float(d.get('mg_coarse_scale', 0.0))
 		p.krylov_error_on_nonconvergence = int(bool(d.get('krylov_error_on_nonconvergence', True)))
@@ -530,6 +531,99 @@ def context_from_model(model, use_pressure_bc=True, cell_dofs=None, device=0, **
 	c.set_field(FIELD_A, model.vertex_field(model.A))
 	c.set_field(FIELD_BETA, model.vertex_field(model.beta))
 	return c
+
+
+class HostTileContext(object):
+	"""DEBUG / CPU tests: a ``bp_ctx`` without a device (``bp_debug_create_host``).  It only holds the index
+	tables of the tiled cell kernel, which :meth:`emulate` walks on the host exactly as the kernel does; no
+	product path goes through here (include/cslvr_b200.h, "debug hooks")."""
+
+	def __init__(self, coords, cells, n_dofs, facets, params, vertex_to_node=None, partition=None):
+		self.lib = load_library()
+		self.lib.bp_debug_create_host.argtypes = [C.POINTER(C.c_void_p), C.POINTER(bp_mesh), C.POINTER(bp_params)]
+		self.lib.bp_debug_bsr_pattern.argtypes = [C.c_void_p, c_i64p, C.POINTER(c_i32p), C.POINTER(c_i32p)]
+		self.lib.bp_debug_tiles_emulate.argtypes = [C.c_void_p, c_f64p, c_f64p, c_f64p, C.c_int, c_f64p, c_f64p]
+		self.lib.bp_debug_tiles_info.argtypes = [C.c_void_p] + [c_i64p] * 5
+		self.lib.bp_debug_tiles_why.argtypes = [C.c_void_p]
+		self.lib.bp_debug_tiles_why.restype = C.c_char_p
+		self._keep = []
+		m = bp_mesh()
+		coords = np.ascontiguousarray(coords, dtype=np.float64)
+		cells = np.ascontiguousarray(cells, dtype=np.int32)
+		m.n_vertices, m.n_cells, m.n_dofs = coords.shape[0], cells.shape[0], int(n_dofs)
+		m.coords, m.cells = coords.ctypes.data_as(c_f64p), cells.ctypes.data_as(c_i32p)
+		self._keep += [coords, cells]
+
+		def i32(a):
+			a = np.ascontiguousarray(a, dtype=np.int32)
+			self._keep.append(a)
+			return a.ctypes.data_as(c_i32p)
+
+		def i64(a):
+			a = np.ascontiguousarray(a, dtype=np.int64)
+			self._keep.append(a)
+			return a.ctypes.data_as(c_i64p)
+		if vertex_to_node is not None:
+			m.vertex_to_node = i32(vertex_to_node)
+		fc, fl, fm = facets
+		m.n_facets = len(fc)
+		m.facet_cell, m.facet_local, m.facet_marker = i32(fc), i32(fl), i32(fm)
+		if partition is None:
+			m.n_owned_nodes, m.n_neighbors = -1, 0
+		else:
+			m.n_owned_nodes, m.n_neighbors = int(partition['n_owned_nodes']), len(partition['neighbor_rank'])
+			m.neighbor_rank, m.send_ptr = i32(partition['neighbor_rank']), i64(partition['send_ptr'])
+			m.send_nodes, m.recv_ptr = i32(partition['send_nodes']), i64(partition['recv_ptr'])
+		self._bpc = BPContext.__new__(BPContext)
+		p = BPContext._make_params(self._bpc, dict(params))
+		h = C.c_void_p()
+		rc = self.lib.bp_debug_create_host(C.byref(h), C.byref(m), C.byref(p))
+		if rc != BP_OK:
+			raise BPError(rc, self.lib.bp_last_error(None).decode())
+		self.h = h
+		self.coords, self.n_dofs = coords, int(n_dofs)
+
+	def why_not(self):
+		return self.lib.bp_debug_tiles_why(self.h).decode()
+
+	def info(self):
+		v = [C.c_int64() for _ in range(5)]
+		if self.lib.bp_debug_tiles_info(self.h, *[C.byref(x) for x in v]) != BP_OK:
+			return None
+		return dict(zip(('n_tiles', 'n_prism_columns', 'n_threads_used', 'n_entries', 'n_contributions'), [x.value for x in v]))
+
+	def bsr_pattern(self):
+		n = C.c_int64()
+		rp, ci = c_i32p(), c_i32p()
+		self.lib.bp_debug_bsr_pattern(self.h, C.byref(n), C.byref(rp), C.byref(ci))
+		rowptr = np.ctypeslib.as_array(rp, shape=(n.value + 1,)).copy()
+		col = np.ctypeslib.as_array(ci, shape=(max(int(rowptr[-1]), 1),))[:rowptr[-1]].copy()
+		return rowptr, col
+
+	def emulate(self, S_vertex, u_nodes, ainv_cells, picard=False):
+		"""(F[2*n_owned], J blocks [nnzb, 2, 2] in BSR row order) of the CELL integrals at ``u_nodes`` ([2*node + c])."""
+		xyzS = np.ascontiguousarray(np.column_stack([self.coords, np.asarray(S_vertex, dtype=np.float64)]))
+		u = np.ascontiguousarray(u_nodes, dtype=np.float64)
+		a = np.ascontiguousarray(ainv_cells, dtype=np.float64)
+		rowptr, col = self.bsr_pattern()
+		F = np.zeros(2 * (rowptr.size - 1))
+		J = np.zeros(4 * int(rowptr[-1]))
+		rc = self.lib.bp_debug_tiles_emulate(self.h, xyzS.ctypes.data_as(c_f64p), u.ctypes.data_as(c_f64p), a.ctypes.data_as(c_f64p),
+		                                     int(bool(picard)), F.ctypes.data_as(c_f64p), J.ctypes.data_as(c_f64p))
+		if rc != BP_OK:
+			raise BPError(rc, self.lib.bp_last_error(self.h).decode())
+		return F, J.reshape(-1, 2, 2), rowptr, col
+
+	def close(self):
+		if getattr(self, 'h', None):
+			self.lib.bp_destroy(self.h)
+			self.h = None
+
+	def __del__(self):
+		try:
+			self.close()
+		except Exception:
+			pass
 
 
 def comm_unique_id():

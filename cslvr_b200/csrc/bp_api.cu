@@ -49,7 +49,7 @@ static int check_params(bp_ctx* c, const bp_params* p)
 	for (int q = 0; q < p->n_quad; ++q) s += p->quad_weights[q];
 	if (std::fabs(s - 1.0) > 1e-12) return bp_fail(c, BP_ERR_ARG, "bp_params: quadrature weights sum to %.17g, not 1", s);
 	if (p->n_quad_aux < 0 || p->n_quad_aux > BP_MAX_QUAD) return bp_fail(c, BP_ERR_ARG, "bp_params: n_quad_aux must be in [0,%d]", BP_MAX_QUAD);
-	if (p->assembly < BP_ASM_AUTO || p->assembly > BP_ASM_GATHER) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown assembly mode %d", p->assembly);
+	if (p->assembly < BP_ASM_AUTO || p->assembly > BP_ASM_TILED) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown assembly mode %d", p->assembly);
 	if (p->pc < BP_PC_NONE || p->pc > BP_PC_MG) return bp_fail(c, BP_ERR_ARG, "bp_params: unknown preconditioner %d", p->pc);
 	return BP_OK;
 }
@@ -343,7 +343,9 @@ int bp_create(bp_ctx** out, const bp_mesh* mesh, const bp_params* params, int de
 void bp_destroy(bp_ctx* c)
 {
 	if (!c) return;
+	if (c->host_only) { bp_tiles_free(c); delete c; return; }
 	cudaSetDevice(c->device);
+	bp_tiles_free(c);
 	bp_mg_free(c);
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, c->d_ext_dof,
@@ -360,6 +362,34 @@ void bp_destroy(bp_ctx* c)
 	delete c;
 }
 
+/* ---- debug: a context WITHOUT a device.  It digests the mesh like bp_create and keeps the index tables of
+ * the tiled cell kernel on the host, so the CPU test suite can run them through bp_debug_tiles_emulate.
+ * Nothing else works on such a context: every compute entry point needs the GPU.                        */
+int bp_debug_create_host(bp_ctx** out, const bp_mesh* mesh, const bp_params* params)
+{
+	if (!out || !mesh) return bp_fail(nullptr, BP_ERR_ARG, "bp_debug_create_host: NULL argument");
+	*out = nullptr;
+	bp_ctx* c = new bp_ctx();
+	c->host_only = true;
+	bp_env_read(&c->env);
+	int rc = check_params(c, params);
+	if (!rc) { store_params(c, params); rc = bp_setup_topology(c, mesh); }
+	if (rc) { g_bp_create_error = c->err; bp_destroy(c); return rc; }
+	*out = c;
+	return BP_OK;
+}
+
+int bp_debug_bsr_pattern(const bp_ctx* c, int64_t* n_rows, const int32_t** rowptr, const int32_t** col)
+{
+	if (!c) return BP_ERR_ARG;
+	if (n_rows) *n_rows = c->nn_owned;
+	if (rowptr) *rowptr = c->h_rowptr.data();
+	if (col) *col = c->h_col.data();
+	return BP_OK;
+}
+
+const char* bp_debug_tiles_why(const bp_ctx* c) { return c ? c->tiles_why.c_str() : ""; }
+
 int bp_set_params(bp_ctx* c, const bp_params* p)
 {
 	if (!c) return BP_ERR_ARG;
@@ -367,6 +397,8 @@ int bp_set_params(bp_ctx* c, const bp_params* p)
 	if (rc) return rc;
 	if ((p->periodic != c->prm.periodic) || (p->use_pressure_bc != c->prm.use_pressure_bc))
 		return bp_fail(c, BP_ERR_ARG, "bp_set_params: periodic / use_pressure_bc select the facet sets at bp_create and cannot change");
+	if (p->assembly == BP_ASM_TILED && !c->tiles)
+		return bp_fail(c, BP_ERR_ARG, "bp_set_params: assembly = BP_ASM_TILED but the tiled cell kernel cannot serve this mesh: %s", c->tiles_why.c_str());
 	store_params(c, p);
 	c->ainv_dirty = true;
 	cudaSetDevice(c->device);

@@ -46,6 +46,16 @@ struct bp_env {
 };
 void bp_env_read(bp_env* e);
 
+// constants of the element kernels (built from bp_params per launch)
+struct AsmParams {
+	double n, eps_reg, rho_g, rho_sw_g;
+	int    n_quad;
+	int    n_is_3;
+	int    picard;      // linear=True: viscosity frozen at the given state, no eta' term, F = u-independent part
+	int    rs;          // MomentumDukowiczStokesReduced: u_z in the strain rate, u_z_b in the sliding term
+};
+struct bp_tiles;        // tiled cell assembly (bp_tiles.cu)
+
 struct bp_comm_state;   // NCCL binding (bp_comm.cu)
 struct bp_mg;           // multigrid hierarchy (bp_mg.cu)
 
@@ -141,6 +151,9 @@ struct bp_ctx {
 	int64_t  n_send = 0;
 	bp_comm_state* comm = nullptr;
 	bp_mg*   mg = nullptr;
+	bp_tiles* tiles = nullptr;           // tiled cell assembly: nullptr when the mesh is not an extruded prism mesh (k_rows serves it)
+	std::string tiles_why;               // why not
+	bool     host_only = false;          // debug contexts without a device (index-table emulation in the CPU test suite)
 	std::vector<int32_t> h_colptr, h_colnode;      // ice columns on the host (first multigrid aggregation)
 	int      grid_spmv0 = 0, grid_spmv1 = 0, grid_cheb = 0;   // one-wave launch grids, per context
 
@@ -205,6 +218,15 @@ void bp_launch_expand_to_vertex(bp_ctx* c, const double* node_vec2, double* vert
 void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out);
 void bp_launch_col_gtsv(bp_ctx* c, const double* r, double* z);   // scalar pivoted tridiagonal solve per column
 void bp_launch_lincomb(bp_ctx* c, double* out, double a, const double* x, double b, const double* y, double cc, const double* z);        // upper bound of lmax(D^-1 J) -> d_sc[slot]
+
+AsmParams bp_asm_params(const bp_ctx* c);
+
+// tiled cell assembly (bp_tiles.cu)
+int  bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n);
+bool bp_tiles_serve(const bp_ctx* c, int what);           // the tiled kernel serves this assembly request
+void bp_launch_tiles(bp_ctx* c, int what);                // d_u -> d_F / d_val (cell integrals)
+void bp_tiles_update_ainv(bp_ctx* c);                     // d_ainv -> tile order (after k_tet_ainv)
+void bp_tiles_free(bp_ctx* c);
 
 // multigrid (bp_mg.cu)
 int  bp_mg_prepare(bp_ctx* c);      // numeric set-up for the current resident Jacobian

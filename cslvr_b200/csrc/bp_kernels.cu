@@ -15,15 +15,7 @@ __constant__ double c_ql[BP_MAX_QUAD * 4];
 __constant__ double c_qw2[BP_MAX_QUAD];          // projection right-hand sides (degree 6)
 __constant__ double c_ql2[BP_MAX_QUAD * 4];
 
-struct AsmParams;
 static AsmParams make_params_fwd(const bp_ctx* c);
-struct AsmParams {
-	double n, eps_reg, rho_g, rho_sw_g;
-	int    n_quad;
-	int    n_is_3;
-	int    picard;      // linear=True: viscosity frozen at the given state, no eta' term, F = u-independent part
-	int    rs;          // MomentumDukowiczStokesReduced: u_z in the strain rate, u_z_b in the sliding term
-};
 
 #define TPB 128
 
@@ -812,6 +804,7 @@ static AsmParams make_params(const bp_ctx* c)
 }
 
 static AsmParams make_params_fwd(const bp_ctx* c) { return make_params(c); }
+AsmParams bp_asm_params(const bp_ctx* c) { return make_params(c); }
 
 void bp_upload_quadrature(bp_ctx* c)
 {
@@ -871,6 +864,7 @@ void bp_update_ainv(bp_ctx* c)
 	else k_tet_ainv<false><<<g, 128, 0, c->stream>>>((int)c->nt, c->d_tets, c->d_A, c->d_Tp, c->d_W, c->d_E, L, P, c->d_ainv);
 	c->launches++;
 	c->ainv_dirty = false;
+	bp_tiles_update_ainv(c);
 }
 
 __global__ void k_expand_u_range(int v0, int v1, const int32_t* __restrict__ v2n, const double2* __restrict__ u, double2* __restrict__ uv)
@@ -937,6 +931,7 @@ void bp_launch_assemble(bp_ctx* c, int what)
 #ifdef BP_EXPERIMENTS
 	if (what & 8) { bp_launch_proxy(c); return; }
 #endif
+	if ((what & BP_TIME_CELL_ONLY) && bp_tiles_serve(c, what)) { bp_launch_tiles(c, what); c->have_J = false; return; }
 	if (what & BP_TIME_CELL_ONLY) {        // timing aid: the dominant kernel alone (accumulates into stale values)
 		const size_t rs = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);
 		if (c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && rs <= 200 * 1024)) {
@@ -957,10 +952,14 @@ void bp_launch_assemble(bp_ctx* c, int what)
 	const size_t row_smem = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);   // the diagonal block lives in registers
 	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
 	// default: the atomic-free facet kernel (bitwise reproducible F and J); BP_FACET_ATOMIC=1 gives the atomic one back
-	const bool use_fr = gather && c->n_fnodes > 0 && !c->env.facet_atomic;
+	const bool use_fr = (gather || bp_tiles_serve(c, what)) && c->n_fnodes > 0 && !c->env.facet_atomic;
 	#define FACET(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)c->n_fnodes, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
 		else k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring); } while (0)
-	if (gather) {
+	const bool tiled = bp_tiles_serve(c, what);
+	if (tiled) {
+		bp_launch_tiles(c, what);
+		c->launches--;                               // counted below
+	} else if (gather) {
 		if (!c->smem_attr_set) {                     // function attributes are per device
 			cudaFuncSetAttribute(k_rows<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 			cudaFuncSetAttribute(k_rows<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

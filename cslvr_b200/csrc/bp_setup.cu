@@ -27,6 +27,7 @@ template <class T>
 static int upload(bp_ctx* c, T** dst, const T* src, size_t n)
 {
 	*dst = nullptr;
+	if (c->host_only) return BP_OK;            // debug contexts without a device keep the host tables only
 	if (n == 0) n = 1;
 	BP_CUDA(c, cudaMalloc((void**)dst, n * sizeof(T)));
 	if (src) BP_CUDA(c, cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
@@ -464,14 +465,14 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	UP(c->d_beta, (const double*)nullptr, nv);
 	UP(c->d_Tp, (const double*)nullptr, nv);
 	UP(c->d_W, (const double*)nullptr, nv);
-	BP_CUDA(c, cudaMemset(c->d_W, 0, (size_t)nv * sizeof(double)));
+	if (!c->host_only) BP_CUDA(c, cudaMemset(c->d_W, 0, (size_t)nv * sizeof(double)));
 	{ std::vector<double> ones(nv, 1.0); UP(c->d_E, ones.data(), nv); }
 	UP(c->d_ainv, (const double*)nullptr, nt);
 	UP(c->d_Bv, (const double*)nullptr, nv);
 	UP(c->d_Bring, (const double*)nullptr, nv);
-	BP_CUDA(c, cudaMemset(c->d_Bring, 0, (size_t)nv * sizeof(double)));
+	if (!c->host_only) BP_CUDA(c, cudaMemset(c->d_Bring, 0, (size_t)nv * sizeof(double)));
 	UP(c->d_uz, (const double*)nullptr, nv);
-	BP_CUDA(c, cudaMemset(c->d_uz, 0, (size_t)nv * sizeof(double)));
+	if (!c->host_only) BP_CUDA(c, cudaMemset(c->d_uz, 0, (size_t)nv * sizeof(double)));
 	UP(c->d_uvert2, (const double*)nullptr, 2 * nv);
 	UP(c->d_tets, (const int4*)m->cells, nt);
 	if (!c->identity_v2n) { UP(c->d_v2n, v2n.data(), nv); UP(c->d_uvert, (const double*)nullptr, (size_t)2 * nv); }
@@ -489,17 +490,20 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	for (double** v : vecs) {
 		size_t len = std::max<size_t>((size_t)2 * nn, (size_t)std::max<int64_t>(std::max<int64_t>(c->nd_ext, nv), 1));
 		UP(*v, (const double*)nullptr, len);
-		BP_CUDA(c, cudaMemset(*v, 0, len * sizeof(double)));
+		if (!c->host_only) BP_CUDA(c, cudaMemset(*v, 0, len * sizeof(double)));
 	}
 	UP(c->d_dinv, (const double*)nullptr, (size_t)no * 4);
 	UP(c->d_sc, (const double*)nullptr, SC_COUNT);
-	BP_CUDA(c, cudaMemset(c->d_sc, 0, SC_COUNT * sizeof(double)));
+	if (!c->host_only) BP_CUDA(c, cudaMemset(c->d_sc, 0, SC_COUNT * sizeof(double)));
 	UP(c->d_part, (const double*)nullptr, 4 * 4096);
 	UP(c->d_counter, (const unsigned*)nullptr, 16);
-	BP_CUDA(c, cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned)));
-	BP_CUDA(c, cudaMallocHost((void**)&c->h_sc, SC_COUNT * sizeof(double)));
-	BP_CUDA(c, cudaMemset(c->d_val, 0, (size_t)std::max<int64_t>(c->n_slots, 1) * 4 * sizeof(double)));
-	return BP_OK;
+	if (!c->host_only) {
+		BP_CUDA(c, cudaMemset(c->d_counter, 0, 16 * sizeof(unsigned)));
+		BP_CUDA(c, cudaMallocHost((void**)&c->h_sc, SC_COUNT * sizeof(double)));
+		BP_CUDA(c, cudaMemset(c->d_val, 0, (size_t)std::max<int64_t>(c->n_slots, 1) * 4 * sizeof(double)));
+	}
+	// tiled cell assembly for extruded prism meshes (bp_tiles.cu); other meshes are served by the row gather
+	return bp_setup_tiles(c, m, v2n);
 }
 
 // Scalar CSR in the caller's numbering: row = caller's dof, columns ascending,

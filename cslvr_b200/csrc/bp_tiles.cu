@@ -1,0 +1,807 @@
+// bp_tiles.cu -- compute-once cell assembly for extruded prism meshes (the D3Model mesh family).
+//
+// Replaces FFC tabulate_tensor + dolfin Assembler for the cell integrals of the BP residual and
+// Jacobian (cslvr/momentumbp.py:481-500, cslvr/physics.py:75-77) on meshes that D3Model produces:
+// a footprint triangulation extruded into layers, every prism split into three tetrahedra the
+// same way along a column (BoxMesh, and the gmsh-extruded meshes of cslvr/meshing.py:771-860).
+//
+// k_rows (bp_kernels.cu) rebuilds every tetrahedron's cell-constant data once per node: 4x the
+// FP64 work.  Here every tetrahedron is evaluated ONCE:
+//   * a CTA owns a tile of ice columns (compact footprint patch) and all their layers;
+//   * one THREAD per prism column (footprint triangle), marching bottom -> top.  With the column's
+//     canonical vertex order (c0, c1, c2) the three tets of a prism are always
+//         (b0 b1 b2 t2)  (b0 b1 t1 t2)  (b0 t0 t1 t2),        b = layer k, t = layer k + 1,
+//     so the code is straight-line and the warp never diverges;
+//   * contributions of consecutive prisms to the nodes of their shared interface are merged in
+//     registers; per layer the thread stages 51 doubles in shared memory ([slot][thread]: bank =
+//     thread, conflict-free): the interface blocks 3 x D (symmetric 2x2), 3 x E, 3 x F and the six
+//     blocks between the two layers;
+//   * after one barrier the CTA's threads turn to the block rows of the tile's own columns: a
+//     table (layer-independent) lists for every Jacobian block the (thread, staged slot) pairs to
+//     add -- fixed order, no atomics, bitwise reproducible -- and the SELL-32 slot it goes to.
+//     Rows are complete inside the tile: prism columns that touch a tile column but belong to a
+//     neighbouring tile are recomputed (halo factor ~1.2).
+// Staging is double-buffered, so summing layer k overlaps computing layer k + 1 with ONE barrier
+// per layer.  Every J block and F entry is written exactly once (checked at set-up).
+//
+// The index tables are also run by a host emulator (bp_debug_tiles_emulate): the CPU test suite
+// checks tables + element math against the oracle without a GPU.  It is not reachable from
+// bp_assemble.
+#include "bp_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#define TILE_T      256        // threads per CTA = prism columns per tile (incl. halo)
+#define TILE_NSLOT  51         // staged doubles per thread and layer
+#define TILE_MAXC   120        // ice columns owned by one tile
+
+// staged slots:   0..8  D(b0) D(b1) D(b2): xx xy yy      9..20 E(b0b1) E(b0b2) E(b1b2): xx xy yx yy (row first, col second)
+//                21..26 F(b0) F(b1) F(b2): x y           27..50 C00 C01 C02 C11 C12 C22: block (row b_i, col t_j)
+// contribution codes (5 bits):
+//   0-2 D(b_i)   3-5 E direct   6-8 E transposed   9-14 C direct   15-20 C transposed   21-23 F(b_i)
+enum { CT_D = 0, CT_E = 1, CT_ET = 2, CT_F = 3 };
+static const uint8_t H_CODE_BASE[24] = { 0, 3, 6,  9, 13, 17,  9, 13, 17,  27, 31, 35, 39, 43, 47,  27, 31, 35, 39, 43, 47,  21, 23, 25 };
+static const uint8_t H_CODE_TYPE[24] = { CT_D, CT_D, CT_D,  CT_E, CT_E, CT_E,  CT_ET, CT_ET, CT_ET,  CT_E, CT_E, CT_E, CT_E, CT_E, CT_E,
+                                         CT_ET, CT_ET, CT_ET, CT_ET, CT_ET, CT_ET,  CT_F, CT_F, CT_F };
+__constant__ uint8_t c_code_base[24];
+__constant__ uint8_t c_code_type[24];
+
+static inline int pair_E(int i, int j) { return (i == 0) ? (j - 1) : 2; }                 // (0,1) (0,2) (1,2) -> 0 1 2
+static inline int pair_C(int i, int j) { return (i == 0) ? j : (i == 1 ? 2 + j : 5); }   // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2) -> 0..5
+
+struct bp_tiles {
+	int     n_tiles = 0, NL = 0;
+	int64_t n_ent = 0, n_contrib = 0, n_prism_cols = 0, n_threads_used = 0;
+	int32_t *d_vert = nullptr, *d_node = nullptr, *d_tet = nullptr, *d_nthr = nullptr, *d_ent0 = nullptr, *d_out = nullptr;
+	uint32_t *d_eptr = nullptr;
+	uint16_t *d_contrib = nullptr;
+	double  *d_ainv = nullptr;
+	bool     attr_set = false;
+	// host copies (kept by host-only debug contexts for the emulator)
+	std::vector<int32_t> h_vert, h_node, h_tet, h_nthr, h_ent0, h_out;
+	std::vector<uint32_t> h_eptr;
+	std::vector<uint16_t> h_contrib;
+};
+
+// ------------------------------------------------------------------------------------------------
+// element math: one tetrahedron, evaluated once.  Closed form of SURVEY.md §8a (the strain rate of a
+// P1 velocity is cell-constant; the quadrature of A^(-1/n) arrives as ai = sum_q w_q A_q^(-1/n)).
+// F[2a + c]; D[3a + {xx, xy, yy}] (diagonal blocks are symmetric); E[4 pair + {xx, xy, yx, yy}] for the
+// pairs (0,1) (0,2) (0,3) (1,2) (1,3) (2,3), block (row a, col b).
+struct TetOut { double F[8]; double D[12]; double E[24]; };
+
+__host__ __device__ __forceinline__ void tet_eval(const double4 p0, const double4 p1, const double4 p2, const double4 p3,
+                                                   const double2 u0, const double2 u1, const double2 u2, const double2 u3,
+                                                   const double ai, const AsmParams& P, TetOut& o)
+{
+	const double e1x = p1.x - p0.x, e1y = p1.y - p0.y, e1z = p1.z - p0.z;
+	const double e2x = p2.x - p0.x, e2y = p2.y - p0.y, e2z = p2.z - p0.z;
+	const double e3x = p3.x - p0.x, e3y = p3.y - p0.y, e3z = p3.z - p0.z;
+	double X[4], Y[4], Z[4];
+	X[1] = e2y * e3z - e2z * e3y; Y[1] = e2z * e3x - e2x * e3z; Z[1] = e2x * e3y - e2y * e3x;
+	X[2] = e3y * e1z - e3z * e1y; Y[2] = e3z * e1x - e3x * e1z; Z[2] = e3x * e1y - e3y * e1x;
+	X[3] = e1y * e2z - e1z * e2y; Y[3] = e1z * e2x - e1x * e2z; Z[3] = e1x * e2y - e1y * e2x;
+	const double det = e1x * X[1] + e1y * Y[1] + e1z * Z[1];
+#ifdef __CUDA_ARCH__
+	const double idet = __drcp_rn(det);
+#else
+	const double idet = 1.0 / det;
+#endif
+	#pragma unroll
+	for (int a = 1; a < 4; ++a) { X[a] *= idet; Y[a] *= idet; Z[a] *= idet; }
+	X[0] = -(X[1] + X[2] + X[3]); Y[0] = -(Y[1] + Y[2] + Y[3]); Z[0] = -(Z[1] + Z[2] + Z[3]);
+	const double vol = fabs(det) * (1.0 / 6.0);
+	const double wbar = vol * ai;
+	const double ux[4] = { u0.x, u1.x, u2.x, u3.x }, uy[4] = { u0.y, u1.y, u2.y, u3.y }, S[4] = { p0.w, p1.w, p2.w, p3.w };
+	double g00 = 0, g01 = 0, g02 = 0, g10 = 0, g11 = 0, g12 = 0, sx = 0, sy = 0;
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		g00 += ux[a] * X[a]; g01 += ux[a] * Y[a]; g02 += ux[a] * Z[a];
+		g10 += uy[a] * X[a]; g11 += uy[a] * Y[a]; g12 += uy[a] * Z[a];
+		sx += S[a] * X[a]; sy += S[a] * Y[a];
+	}
+	const double sh = 0.5 * (g01 + g10);
+	const double ed = g00 * g00 + g11 * g11 + g00 * g11 + sh * sh + 0.25 * (g02 * g02 + g12 * g12) + P.eps_reg;
+	// 2 eta = ed^((1-n)/(2n)),  2 eta' = (1-n)/(2n) ed^((1-n)/(2n) - 1)
+	double two_eta, two_eta_p;
+	if (P.n_is_3) {
+#ifdef __CUDA_ARCH__
+		two_eta = rcbrt(ed);
+#else
+		two_eta = 1.0 / cbrt(ed);
+#endif
+		two_eta_p = (-1.0 / 3.0) * (two_eta * two_eta) * (two_eta * two_eta);           // ed^(-4/3)
+	} else {
+		const double ex = (1.0 - P.n) / (2.0 * P.n);
+		two_eta = pow(ed, ex);
+		two_eta_p = ex * two_eta / ed;
+	}
+	const double alpha = wbar * two_eta, gamma = P.picard ? 0.0 : wbar * two_eta_p;
+	const double cxx = 2.0 * g00 + g11, cyy = 2.0 * g11 + g00, hz0 = 0.5 * g02, hz1 = 0.5 * g12;
+	double dx[4], dy[4];
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		dx[a] = cxx * X[a] + sh * Y[a] + hz0 * Z[a];
+		dy[a] = cyy * Y[a] + sh * X[a] + hz1 * Z[a];
+	}
+	const double gx = P.rho_g * vol * 0.25 * sx, gy = P.rho_g * vol * 0.25 * sy;
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		// linear=True keeps the u-independent part only (gravity)
+		o.F[2 * a]     = (P.picard ? 0.0 : alpha * dx[a]) + gx;
+		o.F[2 * a + 1] = (P.picard ? 0.0 : alpha * dy[a]) + gy;
+	}
+	#pragma unroll
+	for (int a = 0; a < 4; ++a) {
+		const double Pa = 2.0 * alpha * X[a], Qa = 0.5 * alpha * Y[a], Ra = 0.5 * alpha * Z[a];
+		const double Sa = 2.0 * alpha * Y[a], Ta = 0.5 * alpha * X[a];
+		const double Ua = alpha * X[a], Wa = alpha * Y[a];
+		const double Ea = gamma * dx[a], Ga = gamma * dy[a];
+		o.D[3 * a]     = Pa * X[a] + Qa * Y[a] + Ra * Z[a] + Ea * dx[a];
+		o.D[3 * a + 1] = Ua * Y[a] + Qa * X[a] + Ea * dy[a];
+		o.D[3 * a + 2] = Sa * Y[a] + Ta * X[a] + Ra * Z[a] + Ga * dy[a];
+		#pragma unroll
+		for (int b = a + 1; b < 4; ++b) {
+			const int pr = (a == 0) ? (b - 1) : (a == 1 ? b + 1 : 5);
+			o.E[4 * pr]     = Pa * X[b] + Qa * Y[b] + Ra * Z[b] + Ea * dx[b];
+			o.E[4 * pr + 1] = Ua * Y[b] + Qa * X[b] + Ea * dy[b];
+			o.E[4 * pr + 2] = Wa * X[b] + Ta * Y[b] + Ga * dx[b];
+			o.E[4 * pr + 3] = Sa * Y[b] + Ta * X[b] + Ra * Z[b] + Ga * dy[b];
+		}
+	}
+}
+
+// per-thread state of the march: the accumulators of the bottom interface (layer k), the ones being built
+// for the top interface (layer k + 1), the six blocks between the layers
+struct Iface { double D[9]; double E[12]; double F[6]; };
+
+__host__ __device__ __forceinline__ void iface_zero(Iface& a)
+{
+	#pragma unroll
+	for (int i = 0; i < 9; ++i) a.D[i] = 0.0;
+	#pragma unroll
+	for (int i = 0; i < 12; ++i) a.E[i] = 0.0;
+	#pragma unroll
+	for (int i = 0; i < 6; ++i) a.F[i] = 0.0;
+}
+
+// one prism = three tets; bot gets the bottom-interface parts added, top is SET to the top-interface parts,
+// C (24 doubles: C00 C01 C02 C11 C12 C22) is SET to the blocks between the layers
+__host__ __device__ __forceinline__ void prism_eval(const double4* pb, const double2* ub, const double4* pt, const double2* ut,
+                                                     const double a0, const double a1, const double a2, const AsmParams& P,
+                                                     Iface& bot, Iface& top, double* C)
+{
+	TetOut o;
+	// ---- tet A = (b0 b1 b2 t2): local 0 1 2 3
+	tet_eval(pb[0], pb[1], pb[2], pt[2], ub[0], ub[1], ub[2], ut[2], a0, P, o);
+	#pragma unroll
+	for (int i = 0; i < 9; ++i) bot.D[i] += o.D[i];                      // D(b0) D(b1) D(b2)
+	#pragma unroll
+	for (int i = 0; i < 6; ++i) bot.F[i] += o.F[i];
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		bot.E[i] += o.E[i];               // (0,1) -> E(b0b1)
+		bot.E[4 + i] += o.E[4 + i];       // (0,2) -> E(b0b2)
+		bot.E[8 + i] += o.E[12 + i];      // (1,2) -> E(b1b2)
+		C[8 + i]  = o.E[8 + i];           // (0,3) -> C02
+		C[16 + i] = o.E[16 + i];          // (1,3) -> C12
+		C[20 + i] = o.E[20 + i];          // (2,3) -> C22
+	}
+	top.D[6] = o.D[9]; top.D[7] = o.D[10]; top.D[8] = o.D[11];           // D(t2)
+	top.F[4] = o.F[6]; top.F[5] = o.F[7];
+	// ---- tet B = (b0 b1 t1 t2)
+	tet_eval(pb[0], pb[1], pt[1], pt[2], ub[0], ub[1], ut[1], ut[2], a1, P, o);
+	#pragma unroll
+	for (int i = 0; i < 6; ++i) bot.D[i] += o.D[i];                      // D(b0) D(b1)
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) bot.F[i] += o.F[i];
+	top.D[3] = o.D[6]; top.D[4] = o.D[7]; top.D[5] = o.D[8];             // D(t1)
+	top.D[6] += o.D[9]; top.D[7] += o.D[10]; top.D[8] += o.D[11];        // D(t2)
+	top.F[2] = o.F[4]; top.F[3] = o.F[5]; top.F[4] += o.F[6]; top.F[5] += o.F[7];
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		bot.E[i] += o.E[i];               // (0,1) -> E(b0b1)
+		C[4 + i]  = o.E[4 + i];           // (0,2) -> C01
+		C[8 + i] += o.E[8 + i];           // (0,3) -> C02
+		C[12 + i] = o.E[12 + i];          // (1,2) -> C11
+		C[16 + i] += o.E[16 + i];         // (1,3) -> C12
+		top.E[8 + i] = o.E[20 + i];       // (2,3) -> E(t1t2)
+	}
+	// ---- tet C = (b0 t0 t1 t2)
+	tet_eval(pb[0], pt[0], pt[1], pt[2], ub[0], ut[0], ut[1], ut[2], a2, P, o);
+	bot.D[0] += o.D[0]; bot.D[1] += o.D[1]; bot.D[2] += o.D[2];          // D(b0)
+	bot.F[0] += o.F[0]; bot.F[1] += o.F[1];
+	top.D[0] = o.D[3]; top.D[1] = o.D[4]; top.D[2] = o.D[5];             // D(t0)
+	top.D[3] += o.D[6]; top.D[4] += o.D[7]; top.D[5] += o.D[8];          // D(t1)
+	top.D[6] += o.D[9]; top.D[7] += o.D[10]; top.D[8] += o.D[11];        // D(t2)
+	top.F[0] = o.F[2]; top.F[1] = o.F[3]; top.F[2] += o.F[4]; top.F[3] += o.F[5]; top.F[4] += o.F[6]; top.F[5] += o.F[7];
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		C[i]      = o.E[i];               // (0,1) -> C00
+		C[4 + i] += o.E[4 + i];           // (0,2) -> C01
+		C[8 + i] += o.E[8 + i];           // (0,3) -> C02
+		top.E[i]      = o.E[12 + i];      // (1,2) -> E(t0t1)
+		top.E[4 + i]  = o.E[16 + i];      // (1,3) -> E(t0t2)
+		top.E[8 + i] += o.E[20 + i];      // (2,3) -> E(t1t2)
+	}
+}
+
+// add the contributions of one table entry (fixed order) from the staged buffer
+__host__ __device__ __forceinline__ void entry_sum(const double* st, int stride, const uint16_t* ct, uint32_t c0, uint32_t c1,
+                                                    const uint8_t* code_base, const uint8_t* code_type, double& a0, double& a1, double& a2, double& a3)
+{
+	a0 = a1 = a2 = a3 = 0.0;
+	for (uint32_t q = c0; q < c1; ++q) {
+		const uint32_t w = ct[q];
+		const int t = w & 511, code = w >> 9;
+		const double* b = st + (size_t)code_base[code] * stride + t;
+		const int ty = code_type[code];
+		if (ty == CT_D) { const double xy = b[stride]; a0 += b[0]; a1 += xy; a2 += xy; a3 += b[2 * stride]; }
+		else if (ty == CT_E) { a0 += b[0]; a1 += b[stride]; a2 += b[2 * stride]; a3 += b[3 * stride]; }
+		else if (ty == CT_ET) { a0 += b[0]; a1 += b[2 * stride]; a2 += b[stride]; a3 += b[3 * stride]; }
+		else { a0 += b[0]; a1 += b[stride]; }
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+__global__ void __launch_bounds__(TILE_T, 1)
+k_tile(const int NL, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
+       const int32_t* __restrict__ nthr, const int32_t* __restrict__ ent0, const uint32_t* __restrict__ eptr,
+       const uint16_t* __restrict__ contrib, const int32_t* __restrict__ out, const int64_t n_ent,
+       const double4* __restrict__ geo, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
+{
+	extern __shared__ double stage[];                       // [2][TILE_NSLOT][TILE_T]
+	const int t = threadIdx.x, tile = blockIdx.x;
+	const bool act = t < nthr[tile];
+	const int NZ = NL - 1;
+	const int32_t* tv = tvert + (size_t)tile * NL * 3 * TILE_T + t;
+	const int32_t* tn = tnode + (size_t)tile * NL * 3 * TILE_T + t;
+	const double*  ta = tainv + (size_t)tile * NZ * 3 * TILE_T + t;
+	const int e_lo = ent0[tile], e_hi = ent0[tile + 1];
+	double4 pb[3], pt[3];
+	double2 ub[3], ut[3];
+	Iface bot, top;
+	double C[24];
+	iface_zero(bot);
+	if (act) {
+		#pragma unroll
+		for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }
+	}
+	for (int k = 0; k <= NZ; ++k) {
+		double* sb = stage + (size_t)(k & 1) * TILE_NSLOT * TILE_T + t;
+		if (act) {
+			if (k < NZ) {
+				#pragma unroll
+				for (int i = 0; i < 3; ++i) { pt[i] = geo[tv[((k + 1) * 3 + i) * TILE_T]]; ut[i] = u[tn[((k + 1) * 3 + i) * TILE_T]]; }
+				const double a0 = ta[(k * 3) * TILE_T], a1 = ta[(k * 3 + 1) * TILE_T], a2 = ta[(k * 3 + 2) * TILE_T];
+				prism_eval(pb, ub, pt, ut, a0, a1, a2, P, bot, top, C);
+				#pragma unroll
+				for (int i = 0; i < 24; ++i) sb[(27 + i) * TILE_T] = C[i];
+			}
+			#pragma unroll
+			for (int i = 0; i < 9; ++i) sb[i * TILE_T] = bot.D[i];
+			#pragma unroll
+			for (int i = 0; i < 12; ++i) sb[(9 + i) * TILE_T] = bot.E[i];
+			#pragma unroll
+			for (int i = 0; i < 6; ++i) sb[(21 + i) * TILE_T] = bot.F[i];
+			if (k < NZ) {
+				bot = top;
+				#pragma unroll
+				for (int i = 0; i < 3; ++i) { pb[i] = pt[i]; ub[i] = ut[i]; }
+			}
+		}
+		__syncthreads();
+		// ---- block rows of the tile's own columns at this step: fixed-order sums, every block written once
+		const double* st = stage + (size_t)(k & 1) * TILE_NSLOT * TILE_T;
+		const int32_t* ok = out + (size_t)k * n_ent;
+		for (int e = e_lo + t; e < e_hi; e += TILE_T) {
+			const int o = ok[e];
+			if (o == -1) continue;
+			double a0, a1, a2, a3;
+			entry_sum(st, TILE_T, contrib, eptr[e], eptr[e + 1], c_code_base, c_code_type, a0, a1, a2, a3);
+			if (o >= 0) {
+				double2* dst = (double2*)val + 2 * (size_t)o;
+				dst[0] = make_double2(a0, a1);
+				dst[1] = make_double2(a2, a3);
+			} else {
+				*(double2*)(F + 2 * (size_t)(-o - 2)) = make_double2(a0, a1);
+			}
+		}
+		// the buffer written next (k + 1) was last read at step k - 1: every thread passed this step's barrier
+		// only after finishing those reads, so one barrier per layer is enough
+	}
+}
+
+// d_ainv (per tet, mesh order) -> tile order [tile][layer][3][thread]
+__global__ void k_tile_ainv(int64_t n, const int32_t* __restrict__ ttet, const double* __restrict__ ainv, double* __restrict__ out)
+{
+	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+		const int tt = ttet[i];
+		out[i] = tt >= 0 ? ainv[tt] : 0.0;
+	}
+}
+
+void bp_tiles_update_ainv(bp_ctx* c)
+{
+	if (!c->tiles || c->host_only) return;
+	bp_tiles* T = c->tiles;
+	const int64_t n = (int64_t)T->n_tiles * (T->NL - 1) * 3 * TILE_T;
+	k_tile_ainv<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, c->stream>>>(n, T->d_tet, c->d_ainv, T->d_ainv);
+	c->launches++;
+}
+
+bool bp_tiles_serve(const bp_ctx* c, int what)
+{
+	if (!c->tiles || c->prm.reduced_stokes) return false;
+	if ((what & (BP_ASSEMBLE_F | BP_ASSEMBLE_J)) != (BP_ASSEMBLE_F | BP_ASSEMBLE_J)) return false;
+	if (c->prm.assembly == BP_ASM_SCATTER || c->prm.assembly == BP_ASM_GATHER) return false;
+	return c->env.asm_tiled != 0;
+}
+
+void bp_launch_tiles(bp_ctx* c, int what)
+{
+	bp_tiles* T = c->tiles;
+	AsmParams P = bp_asm_params(c);
+	P.picard = (what & 16) ? 1 : 0;
+	const size_t sm = (size_t)2 * TILE_NSLOT * TILE_T * sizeof(double);
+	if (!T->attr_set) {
+		cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+		cudaMemcpyToSymbol(c_code_base, H_CODE_BASE, sizeof(H_CODE_BASE));
+		cudaMemcpyToSymbol(c_code_type, H_CODE_TYPE, sizeof(H_CODE_TYPE));
+		T->attr_set = true;
+	}
+	k_tile<<<T->n_tiles, TILE_T, sm, c->stream>>>(T->NL, T->d_vert, T->d_node, T->d_ainv, T->d_nthr, T->d_ent0, T->d_eptr, T->d_contrib, T->d_out,
+	                                                T->n_ent, c->d_geo, (const double2*)c->d_u, c->d_F, c->d_val, P);
+	c->launches++;
+}
+
+void bp_tiles_free(bp_ctx* c)
+{
+	if (!c->tiles) return;
+	bp_tiles* T = c->tiles;
+	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_eptr, T->d_contrib, T->d_ainv };
+	for (void* p : ptrs) if (p) cudaFree(p);
+	delete T;
+	c->tiles = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// set-up (host)
+template <class V>
+static int up(bp_ctx* c, V** dst, const std::vector<V>& src)
+{
+	*dst = nullptr;
+	if (c->host_only) return BP_OK;
+	const size_t n = std::max<size_t>(src.size(), 1);
+	BP_CUDA(c, cudaMalloc((void**)dst, n * sizeof(V)));
+	if (!src.empty()) BP_CUDA(c, cudaMemcpy(*dst, src.data(), src.size() * sizeof(V), cudaMemcpyHostToDevice));
+	return BP_OK;
+}
+
+static int no_tiles(bp_ctx* c, const char* why)
+{
+	c->tiles_why = why;
+	if (c->prm.assembly == BP_ASM_TILED) return bp_fail(c, BP_ERR_ARG, "assembly = BP_ASM_TILED but the tiled cell kernel cannot serve this mesh: %s", why);
+	if (c->env.asm_tiled == 1) return bp_fail(c, BP_ERR_ARG, "BP_ASM_TILED=1 but the tiled cell kernel cannot serve this mesh: %s", why);
+	return BP_OK;
+}
+
+int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
+{
+	c->tiles = nullptr;
+	if (c->env.asm_tiled == 0) { c->tiles_why = "disabled (BP_ASM_TILED=0)"; return BP_OK; }
+	const int64_t nv = c->nv, nt = c->nt, nn = c->nn, no = c->nn_owned;
+	if (no == 0) return no_tiles(c, "no owned nodes");
+
+	// ---- 1. vertex columns: vertices with equal (x, y), bottom -> top --------------------------
+	double lo[2] = { 1e300, 1e300 }, hi[2] = { -1e300, -1e300 };
+	for (int64_t v = 0; v < nv; ++v) for (int d = 0; d < 2; ++d) { lo[d] = std::min(lo[d], m->coords[3 * v + d]); hi[d] = std::max(hi[d], m->coords[3 * v + d]); }
+	const double sx_ = (hi[0] > lo[0]) ? 1048576.0 / (hi[0] - lo[0]) : 0.0, sy_ = (hi[1] > lo[1]) ? 1048576.0 / (hi[1] - lo[1]) : 0.0;
+	std::vector<int64_t> key(nv);
+	for (int64_t v = 0; v < nv; ++v)
+		key[v] = ((int64_t)std::llround((m->coords[3 * v] - lo[0]) * sx_) << 22) | (int64_t)std::llround((m->coords[3 * v + 1] - lo[1]) * sy_);
+	std::vector<int32_t> ord(nv);
+	std::iota(ord.begin(), ord.end(), 0);
+	std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return key[a] != key[b] ? key[a] < key[b] : (m->coords[3 * a + 2] != m->coords[3 * b + 2] ? m->coords[3 * a + 2] < m->coords[3 * b + 2] : a < b); });
+	int NL = 1;
+	while (NL < nv && key[ord[NL]] == key[ord[0]]) ++NL;
+	if (NL < 2 || nv % NL) return no_tiles(c, "vertices do not form columns of equal length");
+	const int NZ = NL - 1;
+	const int64_t nvc = nv / NL;
+	std::vector<int32_t> vcol(nv), vlay(nv);
+	for (int64_t q = 0; q < nvc; ++q)
+		for (int k = 0; k < NL; ++k) {
+			const int32_t v = ord[q * NL + k];
+			if (key[v] != key[ord[q * NL]] || (k && !(m->coords[3 * v + 2] > m->coords[3 * (int64_t)ord[q * NL + k - 1] + 2])))
+				return no_tiles(c, "vertices do not form columns of equal length");
+			vcol[v] = (int32_t)q; vlay[v] = k;
+		}
+	if (nt % (3 * NZ)) return no_tiles(c, "cell count is not 3 x layers x triangles");
+
+	// ---- 2. node columns (periodic images of a vertex column share one node column) -------------
+	std::vector<int32_t> ncol(nn, -1), nlay(nn, -1), ncol_of_vcol(nvc), colnode;
+	int32_t n_ncol = 0;
+	for (int64_t q = 0; q < nvc; ++q) {
+		const int32_t n0 = v2n[ord[q * NL]];
+		if (ncol[n0] < 0) {
+			for (int k = 0; k < NL; ++k) {
+				const int32_t nk = v2n[ord[q * NL + k]];
+				if (ncol[nk] >= 0) return no_tiles(c, "a node belongs to two columns");
+				ncol[nk] = n_ncol; nlay[nk] = k;
+				colnode.push_back(nk);
+			}
+			++n_ncol;
+		} else {
+			for (int k = 0; k < NL; ++k) {
+				const int32_t nk = v2n[ord[q * NL + k]];
+				if (ncol[nk] != ncol[n0] || nlay[nk] != k) return no_tiles(c, "periodic images of a column disagree");
+			}
+		}
+		ncol_of_vcol[q] = ncol[n0];
+	}
+	for (int64_t i = 0; i < nn; ++i) if (ncol[i] < 0) return no_tiles(c, "a node is used by no vertex");
+	std::vector<uint8_t> col_owned(n_ncol);
+	for (int32_t q = 0; q < n_ncol; ++q) {
+		const bool ow = colnode[(size_t)q * NL] < no;
+		for (int k = 1; k < NL; ++k) if ((colnode[(size_t)q * NL + k] < no) != ow) return no_tiles(c, "an ice column is split between ranks");
+		col_owned[q] = ow;
+	}
+
+	// ---- 3. prism columns: every tet lies in one (triangle of vertex columns, layer); 3 tets per prism -------
+	struct Rec { int32_t a, b, cc, k, t; };
+	std::vector<Rec> rec(nt);
+	bool bad = false;
+	#pragma omp parallel for schedule(static)
+	for (int64_t t = 0; t < nt; ++t) {
+		int32_t q[4], kmin = INT32_MAX, kmax = -1;
+		for (int a = 0; a < 4; ++a) { const int32_t v = m->cells[t * 4 + a]; q[a] = vcol[v]; kmin = std::min(kmin, vlay[v]); kmax = std::max(kmax, vlay[v]); }
+		std::sort(q, q + 4);
+		int nu = 1;
+		int32_t uq[4] = { q[0], 0, 0, 0 };
+		for (int a = 1; a < 4; ++a) if (q[a] != q[a - 1]) uq[nu++] = q[a];
+		if (nu != 3 || kmax != kmin + 1) { bad = true; rec[t] = { 0, 0, 0, 0, (int32_t)t }; continue; }
+		rec[t] = { uq[0], uq[1], uq[2], kmin, (int32_t)t };
+	}
+	if (bad) return no_tiles(c, "a cell does not span three vertex columns and two adjacent layers");
+	std::sort(rec.begin(), rec.end(), [](const Rec& x, const Rec& y) {
+		if (x.a != y.a) return x.a < y.a; if (x.b != y.b) return x.b < y.b; if (x.cc != y.cc) return x.cc < y.cc; if (x.k != y.k) return x.k < y.k; return x.t < y.t; });
+	const int64_t ntri = nt / (3 * NZ);
+	std::vector<int32_t> tri_col(3 * ntri), tri_tet((size_t)ntri * NZ * 3);       // canonical vertex columns; tets (A, B, C) per layer
+	for (int64_t r = 0; r < ntri && !bad; ++r) {
+		const Rec& r0 = rec[r * 3 * NZ];
+		const int32_t s[3] = { r0.a, r0.b, r0.cc };
+		int perm[3] = { -1, -1, -1 };
+		for (int k = 0; k < NZ && !bad; ++k) {
+			int cb[3] = { 0, 0, 0 }, ct[3] = { 0, 0, 0 }, bm[3], tm[3];
+			for (int j = 0; j < 3; ++j) {
+				const Rec& rr = rec[(r * NZ + k) * 3 + j];
+				if (rr.a != s[0] || rr.b != s[1] || rr.cc != s[2] || rr.k != k) { bad = true; break; }
+				bm[j] = tm[j] = 0;
+				for (int a = 0; a < 4; ++a) {
+					const int32_t v = m->cells[(int64_t)rr.t * 4 + a];
+					const int i = (vcol[v] == s[0]) ? 0 : (vcol[v] == s[1] ? 1 : 2);
+					if (vlay[v] == k) { if (bm[j] >> i & 1) bad = true; bm[j] |= 1 << i; cb[i]++; } else { if (tm[j] >> i & 1) bad = true; tm[j] |= 1 << i; ct[i]++; }
+				}
+			}
+			if (bad) break;
+			int p[3] = { -1, -1, -1 };
+			for (int i = 0; i < 3; ++i) { if (cb[i] == 3 && ct[i] == 1) p[0] = i; else if (cb[i] == 2 && ct[i] == 2) p[1] = i; else if (cb[i] == 1 && ct[i] == 3) p[2] = i; }
+			if (p[0] < 0 || p[1] < 0 || p[2] < 0) { bad = true; break; }
+			if (k == 0) { perm[0] = p[0]; perm[1] = p[1]; perm[2] = p[2]; }
+			else if (p[0] != perm[0] || p[1] != perm[1] || p[2] != perm[2]) { bad = true; break; }
+			// the three tets as (b0 b1 b2 t2), (b0 b1 t1 t2), (b0 t0 t1 t2)
+			const int mA_b = 7, mA_t = 1 << p[2], mB_b = (1 << p[0]) | (1 << p[1]), mB_t = (1 << p[1]) | (1 << p[2]), mC_b = 1 << p[0], mC_t = 7;
+			int found[3] = { -1, -1, -1 };
+			for (int j = 0; j < 3; ++j) {
+				if (bm[j] == mA_b && tm[j] == mA_t) found[0] = j; else if (bm[j] == mB_b && tm[j] == mB_t) found[1] = j; else if (bm[j] == mC_b && tm[j] == mC_t) found[2] = j;
+			}
+			if (found[0] < 0 || found[1] < 0 || found[2] < 0) { bad = true; break; }
+			for (int j = 0; j < 3; ++j) tri_tet[((size_t)r * NZ + k) * 3 + j] = rec[(r * NZ + k) * 3 + found[j]].t;
+		}
+		for (int i = 0; i < 3 && !bad; ++i) tri_col[3 * r + i] = s[perm[i]];
+	}
+	if (bad) return no_tiles(c, "prisms are not split into three tets the same way along a column");
+	{ std::vector<Rec>().swap(rec); }
+
+	// ---- 4. tiles of owned ice columns: compact footprint patches, at most TILE_T prism columns touch one ----
+	std::vector<int64_t> ctp(n_ncol + 1, 0);                   // node column -> prism columns touching it
+	for (int64_t r = 0; r < ntri; ++r) {
+		int32_t q[3] = { ncol_of_vcol[tri_col[3 * r]], ncol_of_vcol[tri_col[3 * r + 1]], ncol_of_vcol[tri_col[3 * r + 2]] };
+		for (int i = 0; i < 3; ++i) { bool dup = false; for (int j = 0; j < i; ++j) dup |= q[j] == q[i]; if (!dup) ctp[q[i] + 1]++; }
+	}
+	for (int32_t q = 0; q < n_ncol; ++q) ctp[q + 1] += ctp[q];
+	std::vector<int32_t> ctl(ctp[n_ncol]);
+	{
+		std::vector<int64_t> fill(ctp.begin(), ctp.end() - 1);
+		for (int64_t r = 0; r < ntri; ++r) {
+			int32_t q[3] = { ncol_of_vcol[tri_col[3 * r]], ncol_of_vcol[tri_col[3 * r + 1]], ncol_of_vcol[tri_col[3 * r + 2]] };
+			for (int i = 0; i < 3; ++i) { bool dup = false; for (int j = 0; j < i; ++j) dup |= q[j] == q[i]; if (!dup) ctl[fill[q[i]]++] = (int32_t)r; }
+		}
+	}
+	for (int32_t q = 0; q < n_ncol; ++q) if (col_owned[q] && ctp[q + 1] - ctp[q] > TILE_T) return no_tiles(c, "an ice column is touched by more prism columns than a tile holds");
+	// position of a node column: its lowest vertex (the master of periodic images)
+	std::vector<int32_t> rep(nn, -1);
+	for (int64_t v = nv - 1; v >= 0; --v) rep[v2n[v]] = (int32_t)v;
+	std::vector<int32_t> own_cols;
+	double olo[2] = { 1e300, 1e300 }, ohi[2] = { -1e300, -1e300 };
+	std::vector<double> cx(n_ncol), cy(n_ncol);
+	for (int32_t q = 0; q < n_ncol; ++q) {
+		const int32_t v = rep[colnode[(size_t)q * NL]];
+		cx[q] = m->coords[3 * (int64_t)v]; cy[q] = m->coords[3 * (int64_t)v + 1];
+		if (!col_owned[q]) continue;
+		own_cols.push_back(q);
+		olo[0] = std::min(olo[0], cx[q]); ohi[0] = std::max(ohi[0], cx[q]); olo[1] = std::min(olo[1], cy[q]); ohi[1] = std::max(ohi[1], cy[q]);
+	}
+	const double area = std::max(ohi[0] - olo[0], 1e-300) * std::max(ohi[1] - olo[1], 1e-300);
+	const double rho = (double)own_cols.size() / area;
+	const double strip_h = 7.0 / std::sqrt(rho);                  // ~7 rows of columns per strip: (7 + 1) x (15 + 1) x 2 = 256 prism columns
+	std::vector<int64_t> ybin(n_ncol, 0);
+	for (int32_t q : own_cols) ybin[q] = (int64_t)std::floor((cy[q] - olo[1]) / strip_h + 1e-9);
+	std::sort(own_cols.begin(), own_cols.end(), [&](int32_t a, int32_t b) {
+		if (ybin[a] != ybin[b]) return ybin[a] < ybin[b]; if (cx[a] != cx[b]) return cx[a] < cx[b]; if (cy[a] != cy[b]) return cy[a] < cy[b]; return a < b; });
+	std::vector<int32_t> tile_c0(1, 0);                            // tile -> range of own_cols
+	{
+		std::vector<int32_t> stamp(ntri, -1);
+		int ntile = 0, ntr = 0, ncl = 0;
+		for (size_t i = 0; i < own_cols.size(); ++i) {
+			const int32_t q = own_cols[i];
+			int add = 0;
+			for (int64_t k = ctp[q]; k < ctp[q + 1]; ++k) if (stamp[ctl[k]] != ntile) ++add;
+			const bool new_strip = i > 0 && ybin[q] != ybin[own_cols[i - 1]];
+			if (ncl > 0 && (ntr + add > TILE_T || ncl + 1 > TILE_MAXC || new_strip)) {
+				tile_c0.push_back((int32_t)i); ++ntile; ntr = 0; ncl = 0;
+				add = (int)(ctp[q + 1] - ctp[q]);
+			}
+			for (int64_t k = ctp[q]; k < ctp[q + 1]; ++k) stamp[ctl[k]] = ntile;
+			ntr += add; ++ncl;
+		}
+		tile_c0.push_back((int32_t)own_cols.size());
+	}
+	const int n_tiles = (int)tile_c0.size() - 1;
+
+	// ---- 5 + 6. per tile: thread list (prism columns), vertex / node / tet tables, sum tables -----------------
+	bp_tiles* T = new bp_tiles();
+	T->n_tiles = n_tiles; T->NL = NL; T->n_prism_cols = ntri;
+	T->h_vert.assign((size_t)n_tiles * NL * 3 * TILE_T, 0);
+	T->h_node.assign((size_t)n_tiles * NL * 3 * TILE_T, 0);
+	T->h_tet.assign((size_t)n_tiles * NZ * 3 * TILE_T, -1);
+	T->h_nthr.assign(n_tiles, 0);
+	T->h_ent0.assign(n_tiles + 1, 0);
+	struct Con { int8_t kind; int64_t delta; int32_t p, q; int16_t t; uint8_t code; };
+	struct Ent { int8_t kind; int32_t p, q; };
+	std::vector<std::vector<Ent>> tile_ent(n_tiles);
+	std::vector<std::vector<uint32_t>> tile_eptr(n_tiles);
+	std::vector<std::vector<uint16_t>> tile_con(n_tiles);
+	std::vector<std::vector<int32_t>> tile_cols(n_tiles);
+	int fail = 0;
+	#pragma omp parallel
+	{
+		std::vector<int32_t> local(n_ncol, -1), tris;
+		std::vector<Con> cons;
+		#pragma omp for schedule(dynamic, 8)
+		for (int tl = 0; tl < n_tiles; ++tl) {
+			// the tile's columns, ordered by the id of their bottom node: consecutive rows -> consecutive SELL slots
+			std::vector<int32_t>& cols = tile_cols[tl];
+			cols.assign(own_cols.begin() + tile_c0[tl], own_cols.begin() + tile_c0[tl + 1]);
+			std::sort(cols.begin(), cols.end(), [&](int32_t a, int32_t b) { return colnode[(size_t)a * NL] < colnode[(size_t)b * NL]; });
+			for (size_t p = 0; p < cols.size(); ++p) local[cols[p]] = (int32_t)p;
+			tris.clear();
+			for (int32_t q : cols) for (int64_t k = ctp[q]; k < ctp[q + 1]; ++k) tris.push_back(ctl[k]);
+			std::sort(tris.begin(), tris.end());
+			tris.erase(std::unique(tris.begin(), tris.end()), tris.end());
+			if ((int)tris.size() > TILE_T) { fail = 1; for (int32_t q : cols) local[q] = -1; continue; }
+			// thread order: prism columns of one orientation class next to each other, then by position -- the lanes of a
+			// warp then read staged slots of neighbouring threads when they sum neighbouring rows
+			auto cls = [&](int32_t r) {
+				const int32_t a = tri_col[3 * r], b = tri_col[3 * r + 1], d = tri_col[3 * r + 2];
+				const double xa = m->coords[3 * (int64_t)ord[(int64_t)a * NL]], xb = m->coords[3 * (int64_t)ord[(int64_t)b * NL]], xd = m->coords[3 * (int64_t)ord[(int64_t)d * NL]];
+				const double ya = m->coords[3 * (int64_t)ord[(int64_t)a * NL] + 1], yb = m->coords[3 * (int64_t)ord[(int64_t)b * NL] + 1], yd = m->coords[3 * (int64_t)ord[(int64_t)d * NL] + 1];
+				return ((xb > xa) ? 1 : 0) | ((xd > xa) ? 2 : 0) | ((yb > ya) ? 4 : 0) | ((yd > ya) ? 8 : 0) | ((xd > xb) ? 16 : 0) | ((yd > yb) ? 32 : 0);
+			};
+			auto pos = [&](int32_t r, int d) { return m->coords[3 * (int64_t)ord[(int64_t)tri_col[3 * r] * NL] + d]; };
+			std::sort(tris.begin(), tris.end(), [&](int32_t a, int32_t b) {
+				const int ca = cls(a), cb2 = cls(b);
+				if (ca != cb2) return ca < cb2;
+				if (pos(a, 1) != pos(b, 1)) return pos(a, 1) < pos(b, 1);
+				if (pos(a, 0) != pos(b, 0)) return pos(a, 0) < pos(b, 0);
+				return a < b; });
+			T->h_nthr[tl] = (int32_t)tris.size();
+			cons.clear();
+			for (size_t t = 0; t < tris.size(); ++t) {
+				const int32_t r = tris[t];
+				int32_t nc[3];
+				for (int i = 0; i < 3; ++i) {
+					const int32_t vc = tri_col[3 * r + i];
+					nc[i] = ncol_of_vcol[vc];
+					for (int k = 0; k < NL; ++k) {
+						const int32_t v = ord[(int64_t)vc * NL + k];
+						T->h_vert[(((size_t)tl * NL + k) * 3 + i) * TILE_T + t] = v;
+						T->h_node[(((size_t)tl * NL + k) * 3 + i) * TILE_T + t] = v2n[v];
+					}
+				}
+				for (int k = 0; k < NZ; ++k) for (int j = 0; j < 3; ++j)
+					T->h_tet[(((size_t)tl * NZ + k) * 3 + j) * TILE_T + t] = tri_tet[((size_t)r * NZ + k) * 3 + j];
+				for (int i = 0; i < 3; ++i) {
+					const int32_t p = local[nc[i]];
+					if (p < 0) continue;                                   // not a column of this tile
+					auto dl = [&](int32_t q) { return (int64_t)colnode[(size_t)q * NL] - (int64_t)colnode[(size_t)nc[i] * NL]; };
+					cons.push_back({ 0, 0, p, nc[i], (int16_t)t, (uint8_t)i });                            // D(b_i)
+					cons.push_back({ 3, 0, p, nc[i], (int16_t)t, (uint8_t)(21 + i) });                     // F(b_i)
+					for (int j = 0; j < 3; ++j) {
+						if (j != i) cons.push_back({ 0, dl(nc[j]), p, nc[j], (int16_t)t, (uint8_t)(i < j ? 3 + pair_E(i, j) : 6 + pair_E(j, i)) });
+						if (j >= i) cons.push_back({ 1, dl(nc[j]), p, nc[j], (int16_t)t, (uint8_t)(9 + pair_C(i, j)) });      // row (p, k), col (q, k+1)
+						if (j <= i) cons.push_back({ 2, dl(nc[j]), p, nc[j], (int16_t)t, (uint8_t)(15 + pair_C(j, i)) });     // row (p, k+1), col (q, k)
+					}
+				}
+			}
+			std::sort(cons.begin(), cons.end(), [](const Con& a, const Con& b) {
+				if (a.kind != b.kind) return a.kind < b.kind; if (a.delta != b.delta) return a.delta < b.delta; if (a.p != b.p) return a.p < b.p;
+				if (a.q != b.q) return a.q < b.q; if (a.t != b.t) return a.t < b.t; return a.code < b.code; });
+			std::vector<Ent>& E = tile_ent[tl];
+			std::vector<uint32_t>& ep = tile_eptr[tl];
+			std::vector<uint16_t>& cc = tile_con[tl];
+			for (size_t i = 0; i < cons.size(); ++i) {
+				if (i == 0 || cons[i].kind != cons[i - 1].kind || cons[i].p != cons[i - 1].p || cons[i].q != cons[i - 1].q) { E.push_back({ cons[i].kind, cons[i].p, cons[i].q }); ep.push_back((uint32_t)cc.size()); }
+				cc.push_back((uint16_t)((uint16_t)cons[i].t | ((uint16_t)cons[i].code << 9)));
+			}
+			ep.push_back((uint32_t)cc.size());
+			for (int32_t q : cols) local[q] = -1;
+		}
+	}
+	if (fail) { delete T; return no_tiles(c, "a tile is touched by more prism columns than it holds"); }
+	int64_t ne = 0, ncn = 0;
+	for (int tl = 0; tl < n_tiles; ++tl) { T->h_ent0[tl] = (int32_t)ne; ne += (int64_t)tile_ent[tl].size(); ncn += (int64_t)tile_con[tl].size(); T->n_threads_used += T->h_nthr[tl]; }
+	T->h_ent0[n_tiles] = (int32_t)ne;
+	if (ne > INT32_MAX / 2 || ncn > (int64_t)UINT32_MAX / 2) { delete T; return no_tiles(c, "too many table entries for one rank"); }
+	T->n_ent = ne; T->n_contrib = ncn;
+	T->h_eptr.resize(ne + 1);
+	T->h_contrib.resize(ncn);
+	T->h_out.assign((size_t)NL * ne, -1);
+	{
+		int64_t co = 0;
+		for (int tl = 0; tl < n_tiles; ++tl) {
+			for (size_t e = 0; e < tile_ent[tl].size(); ++e) T->h_eptr[T->h_ent0[tl] + e] = (uint32_t)(co + tile_eptr[tl][e]);
+			std::copy(tile_con[tl].begin(), tile_con[tl].end(), T->h_contrib.begin() + co);
+			co += (int64_t)tile_con[tl].size();
+		}
+		T->h_eptr[ne] = (uint32_t)co;
+	}
+	// output slots per layer, and the exactly-once check
+	std::vector<uint8_t> hitJ((size_t)std::max<int64_t>(c->n_slots, 1), 0), hitF((size_t)no, 0);
+	int miss = 0;
+	#pragma omp parallel for schedule(dynamic, 8)
+	for (int tl = 0; tl < n_tiles; ++tl) {
+		const std::vector<int32_t>& cols = tile_cols[tl];
+		for (size_t e = 0; e < tile_ent[tl].size(); ++e) {
+			const Ent& en = tile_ent[tl][e];
+			const int32_t pc = cols[en.p];
+			for (int k = 0; k < NL; ++k) {
+				int32_t o = -1;
+				if (en.kind == 3) o = -(colnode[(size_t)pc * NL + k] + 2);
+				else {
+					if (en.kind != 0 && k == NL - 1) continue;
+					const int32_t i = colnode[(size_t)pc * NL + k + (en.kind == 2 ? 1 : 0)];
+					const int32_t j = colnode[(size_t)en.q * NL + k + (en.kind == 1 ? 1 : 0)];
+					const int32_t* lo_ = c->h_col.data() + c->h_rowptr[i];
+					const int32_t* hi_ = c->h_col.data() + c->h_rowptr[i + 1];
+					const int32_t* it = std::lower_bound(lo_, hi_, j);
+					if (it == hi_ || *it != j) { miss = 1; continue; }
+					o = c->h_sell_ptr[i >> 5] + 32 * (int32_t)(it - lo_) + (i & 31);
+				}
+				T->h_out[(size_t)k * ne + T->h_ent0[tl] + e] = o;
+				if (o >= 0) {
+					#pragma omp atomic
+					hitJ[o]++;
+				} else {
+					#pragma omp atomic
+					hitF[-o - 2]++;
+				}
+			}
+		}
+	}
+	if (!miss) {
+		for (int64_t i = 0; i < no && !miss; ++i) {
+			if (hitF[i] != 1) miss = 1;
+			for (int32_t k = 0; k < c->h_rowptr[i + 1] - c->h_rowptr[i]; ++k)
+				if (hitJ[(size_t)c->h_sell_ptr[i >> 5] + 32 * k + (i & 31)] != 1) { miss = 1; break; }
+		}
+	}
+	if (miss) { delete T; return no_tiles(c, "internal: the tile tables do not cover every Jacobian block exactly once"); }
+
+	int rc = up(c, &T->d_vert, T->h_vert);
+	if (!rc) rc = up(c, &T->d_node, T->h_node);
+	if (!rc) rc = up(c, &T->d_tet, T->h_tet);
+	if (!rc) rc = up(c, &T->d_nthr, T->h_nthr);
+	if (!rc) rc = up(c, &T->d_ent0, T->h_ent0);
+	if (!rc) rc = up(c, &T->d_out, T->h_out);
+	if (!rc) rc = up(c, &T->d_eptr, T->h_eptr);
+	if (!rc) rc = up(c, &T->d_contrib, T->h_contrib);
+	if (!rc && !c->host_only) {
+		cudaError_t e = cudaMalloc((void**)&T->d_ainv, (size_t)n_tiles * NZ * 3 * TILE_T * sizeof(double));
+		if (e != cudaSuccess) rc = bp_fail(c, BP_ERR_CUDA, "cudaMalloc(tile ainv) failed: %s", cudaGetErrorString(e));
+	}
+	c->tiles = T;
+	if (rc) { bp_tiles_free(c); return rc; }
+	if (!c->host_only) {                       // the emulator of a host-only context keeps the tables
+		std::vector<int32_t>().swap(T->h_vert); std::vector<int32_t>().swap(T->h_node); std::vector<int32_t>().swap(T->h_tet);
+		std::vector<int32_t>().swap(T->h_out); std::vector<uint32_t>().swap(T->h_eptr); std::vector<uint16_t>().swap(T->h_contrib);
+	}
+	if (c->prm.verbose)
+		fprintf(stderr, "[cslvr_b200] tiled cell assembly: %d tiles, %lld prism columns x %d layers, halo factor %.3f, %lld table entries\n",
+		        n_tiles, (long long)ntri, NZ, (double)T->n_threads_used / (double)ntri, (long long)ne);
+	return BP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host emulation of k_tile: same tables, same element math, same order of additions.  Debug / CPU tests only.
+extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const double* u, const double* ainv, int picard,
+                                      double* F, double* Jblocks)
+{
+	if (!c || !c->tiles) return bp_fail(c, BP_ERR_STATE, "no tile tables: %s", c ? c->tiles_why.c_str() : "");
+	bp_tiles* T = c->tiles;
+	if (T->h_vert.empty()) return bp_fail(c, BP_ERR_STATE, "tile tables were released after the upload (host-only contexts keep them)");
+	AsmParams P = bp_asm_params(c);
+	P.picard = picard;
+	const int NL = T->NL, NZ = NL - 1;
+	const double4* geo = (const double4*)vert_xyzS;
+	const double2* u2 = (const double2*)u;
+	std::vector<double> val((size_t)c->n_slots * 4, 0.0);
+	#pragma omp parallel
+	{
+		std::vector<double> stage((size_t)TILE_NSLOT * TILE_T);
+		std::vector<Iface> bot(TILE_T), top(TILE_T);
+		#pragma omp for schedule(dynamic, 4)
+		for (int tile = 0; tile < T->n_tiles; ++tile) {
+			const int nthr = T->h_nthr[tile];
+			for (int t = 0; t < nthr; ++t) iface_zero(bot[t]);
+			for (int k = 0; k <= NZ; ++k) {
+				for (int t = 0; t < nthr; ++t) {
+					double* sb = stage.data() + t;
+					if (k < NZ) {
+						double4 pb[3], pt[3]; double2 ub[3], ut[3]; double C[24];
+						for (int i = 0; i < 3; ++i) {
+							pb[i] = geo[T->h_vert[(((size_t)tile * NL + k) * 3 + i) * TILE_T + t]];
+							ub[i] = u2[T->h_node[(((size_t)tile * NL + k) * 3 + i) * TILE_T + t]];
+							pt[i] = geo[T->h_vert[(((size_t)tile * NL + k + 1) * 3 + i) * TILE_T + t]];
+							ut[i] = u2[T->h_node[(((size_t)tile * NL + k + 1) * 3 + i) * TILE_T + t]];
+						}
+						double a[3];
+						for (int j = 0; j < 3; ++j) a[j] = ainv[T->h_tet[(((size_t)tile * NZ + k) * 3 + j) * TILE_T + t]];
+						prism_eval(pb, ub, pt, ut, a[0], a[1], a[2], P, bot[t], top[t], C);
+						for (int i = 0; i < 24; ++i) sb[(27 + i) * TILE_T] = C[i];
+					}
+					for (int i = 0; i < 9; ++i) sb[i * TILE_T] = bot[t].D[i];
+					for (int i = 0; i < 12; ++i) sb[(9 + i) * TILE_T] = bot[t].E[i];
+					for (int i = 0; i < 6; ++i) sb[(21 + i) * TILE_T] = bot[t].F[i];
+					if (k < NZ) bot[t] = top[t];
+				}
+				for (int e = T->h_ent0[tile]; e < T->h_ent0[tile + 1]; ++e) {
+					const int o = T->h_out[(size_t)k * T->n_ent + e];
+					if (o == -1) continue;
+					double a0, a1, a2, a3;
+					entry_sum(stage.data(), TILE_T, T->h_contrib.data(), T->h_eptr[e], T->h_eptr[e + 1], H_CODE_BASE, H_CODE_TYPE, a0, a1, a2, a3);
+					if (o >= 0) { double* d = val.data() + 4 * (size_t)o; d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3; }
+					else { F[2 * (size_t)(-o - 2)] = a0; F[2 * (size_t)(-o - 2) + 1] = a1; }
+				}
+			}
+		}
+	}
+	for (int64_t i = 0; i < c->nn_owned; ++i)
+		for (int32_t k = 0; k < c->h_rowptr[i + 1] - c->h_rowptr[i]; ++k)
+			memcpy(Jblocks + 4 * ((size_t)c->h_rowptr[i] + k), val.data() + 4 * ((size_t)c->h_sell_ptr[i >> 5] + 32 * k + (i & 31)), 4 * sizeof(double));
+	return BP_OK;
+}
+
+extern "C" int bp_debug_tiles_info(const bp_ctx* c, int64_t* n_tiles, int64_t* n_prism_cols, int64_t* n_threads_used, int64_t* n_entries, int64_t* n_contrib)
+{
+	if (!c || !c->tiles) return BP_ERR_STATE;
+	if (n_tiles) *n_tiles = c->tiles->n_tiles;
+	if (n_prism_cols) *n_prism_cols = c->tiles->n_prism_cols;
+	if (n_threads_used) *n_threads_used = c->tiles->n_threads_used;
+	if (n_entries) *n_entries = c->tiles->n_ent;
+	if (n_contrib) *n_contrib = c->tiles->n_contrib;
+	return BP_OK;
+}

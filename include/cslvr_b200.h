@@ -60,9 +60,14 @@ extern "C" {
                                    coupling inside every ice column (extruded meshes)          */
 
 /* how the element tensors reach the resident Jacobian */
-#define BP_ASM_AUTO     0   /* row gather unless a block row is too long for shared memory     */
+#define BP_ASM_AUTO     0   /* tiled on extruded prism meshes, else row gather unless a block row
+                               is too long for shared memory                                    */
 #define BP_ASM_SCATTER  1   /* one thread per tetrahedron, FP64 atomics into F and J           */
 #define BP_ASM_GATHER   2   /* one thread per Jacobian block row, no atomics, deterministic    */
+#define BP_ASM_TILED    3   /* extruded prism meshes: one thread per prism column, every tetrahedron
+                               evaluated once, tile-local sums in shared memory, no atomics,
+                               deterministic (what AUTO picks when the mesh qualifies; asking for
+                               it on a mesh that does not is an error)                          */
 
 #define BP_PC_MG            5   /* aggregation multigrid V-cycle: ice columns -> footprint nodes ->
                                    greedy 2-D aggregates, Chebyshev smoothing (pc_degree, pc_eig_ratio),
@@ -275,6 +280,20 @@ int  bp_comm_init(bp_ctx* ctx, const char* nccl_library_path, const char id[128]
  * reductions by device copies.                                                     */
 int  bp_newton_solve_group(bp_ctx** ctxs, int n, double** u_inout, int on_device, bp_stats* stats);
 int  bp_assemble_group(bp_ctx** ctxs, int n, int what, const double** u, double** F, int on_device);
+
+/* ---- debug hooks of the tiled cell kernel (BP_ASM_TILED) -- used by the CPU test suite, never by the
+ * product path.  bp_debug_create_host digests a mesh WITHOUT a device (no compute entry point works on
+ * such a context) and keeps the tile tables on the host; bp_debug_tiles_emulate walks them exactly as the
+ * kernel does (same element math, same order of additions) and returns F (internal node order) and the
+ * 2x2 blocks of J in BSR row order (bp_debug_bsr_pattern).  vert_xyzS: [n_vertices*4] x, y, z, S;
+ * u: [2*n_nodes] in node order; ainv: [n_cells] sum_q w_q A_q^(-1/n).                                  */
+int  bp_debug_create_host(bp_ctx** out, const bp_mesh* mesh, const bp_params* params);
+int  bp_debug_bsr_pattern(const bp_ctx* ctx, int64_t* n_rows, const int32_t** rowptr, const int32_t** col);
+int  bp_debug_tiles_emulate(bp_ctx* ctx, const double* vert_xyzS, const double* u, const double* ainv,
+                            int picard, double* F, double* J_blocks);
+int  bp_debug_tiles_info(const bp_ctx* ctx, int64_t* n_tiles, int64_t* n_prism_columns,
+                         int64_t* n_threads_used, int64_t* n_entries, int64_t* n_contributions);
+const char* bp_debug_tiles_why(const bp_ctx* ctx);   /* why the mesh is not served by the tiled kernel ("" if it is) */
 
 #ifdef __cplusplus
 }

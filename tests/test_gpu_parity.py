@@ -611,6 +611,27 @@ def test_reduced_stokes_entry_points_refuse_misuse():
 	cp.close()
 
 
+@pytest.mark.parametrize('case', ['ismip', 'marine', 'delaunay'])
+def test_tiled_cell_kernel_matches_oracle_and_row_gather(case):
+	"""assembly='tiled' (one thread per prism column, every tet evaluated once; the default on extruded meshes)
+	against the oracle to 1e-12 and against the row gather, bit-for-bit reproducible from run to run."""
+	from cases import delaunay_extruded_model
+	m = {'ismip': lambda: ismip_model('A', n=(40, 33, 4)), 'marine': lambda: marine_model(n=(21, 17, 5)),
+	     'delaunay': lambda: delaunay_extruded_model(n_pts=300, n_layers=5)}[case]()
+	P = oracle_problem(m)
+	u = state(P.n_dofs, 7)
+	c = product_context(m, assembly='tiled')
+	F1, J1 = c.assemble(u, want_F=True, want_J=True)
+	F2, J2 = c.assemble(u, want_F=True, want_J=True)
+	c.close()
+	assert np.array_equal(F1, F2) and np.array_equal(J1, J2)
+	assert relerr(F1, P.residual(u)) < TOL_ASM and relerr(J1, P.jacobian(u)) < TOL_ASM
+	c = product_context(m, assembly='gather')
+	F3, J3 = c.assemble(u, want_F=True, want_J=True)
+	c.close()
+	assert relerr(F1, F3) < TOL_ASM and relerr(J1, J3) < TOL_ASM
+
+
 def test_default_assembly_is_atomic_free_and_bitwise_reproducible(monkeypatch):
 	"""the default path has no atomics anywhere: cell integrals by row gather (or the tiled cell kernel),
 	facet integrals by row gather (one thread per touched node, plain read-modify-write of its own rows
