@@ -33,36 +33,39 @@
 #include <cstring>
 #include <numeric>
 
-#define TILE_T      256        // threads per CTA = prism columns per tile (incl. halo)
-#define TILE_NSLOT  51         // staged doubles per thread and layer
+#define TILE_T      256        // compute threads per CTA = prism columns per tile (incl. halo)
+#define TILE_S      128        // summing threads per CTA (one warpgroup)
+#define TILE_NSLOT  51         // staged doubles per compute thread and layer
 #define TILE_MAXC   120        // ice columns owned by one tile
+#define TILE_TABW   16384      // contribution words (uint16) of one tile's table in shared memory
+#define TILE_MAXE   (16 * TILE_S)   // table entries per tile: at most 16 per summing thread
 
 // staged slots:   0..8  D(b0) D(b1) D(b2): xx xy yy      9..20 E(b0b1) E(b0b2) E(b1b2): xx xy yx yy (row first, col second)
 //                21..26 F(b0) F(b1) F(b2): x y           27..50 C00 C01 C02 C11 C12 C22: block (row b_i, col t_j)
-// contribution codes (5 bits):
-//   0-2 D(b_i)   3-5 E direct   6-8 E transposed   9-14 C direct   15-20 C transposed   21-23 F(b_i)
+// a contribution word: thread (bits 0-7) | first slot (bits 8-13) | type (bits 14-15); 0xffff = none
 enum { CT_D = 0, CT_E = 1, CT_ET = 2, CT_F = 3 };
+#define CW(t, slot, ty) ((uint16_t)((t) | ((slot) << 8) | ((ty) << 14)))
+#define CW_NONE 0xffffu
+
+// old-style contribution codes used while the tables are built: 0-2 D(b_i), 3-5 E direct, 6-8 E transposed,
+// 9-14 C direct, 15-20 C transposed, 21-23 F(b_i) -> (first slot, type)
 static const uint8_t H_CODE_BASE[24] = { 0, 3, 6,  9, 13, 17,  9, 13, 17,  27, 31, 35, 39, 43, 47,  27, 31, 35, 39, 43, 47,  21, 23, 25 };
 static const uint8_t H_CODE_TYPE[24] = { CT_D, CT_D, CT_D,  CT_E, CT_E, CT_E,  CT_ET, CT_ET, CT_ET,  CT_E, CT_E, CT_E, CT_E, CT_E, CT_E,
                                          CT_ET, CT_ET, CT_ET, CT_ET, CT_ET, CT_ET,  CT_F, CT_F, CT_F };
-__constant__ uint8_t c_code_base[24];
-__constant__ uint8_t c_code_type[24];
 
 static inline int pair_E(int i, int j) { return (i == 0) ? (j - 1) : 2; }                 // (0,1) (0,2) (1,2) -> 0 1 2
 static inline int pair_C(int i, int j) { return (i == 0) ? j : (i == 1 ? 2 + j : 5); }   // (0,0) (0,1) (0,2) (1,1) (1,2) (2,2) -> 0..5
 
 struct bp_tiles {
-	int     n_tiles = 0, NL = 0;
+	int     n_tiles = 0, NL = 0, W = 8;       // W: contribution words per table entry (8 or 16)
 	int64_t n_ent = 0, n_contrib = 0, n_prism_cols = 0, n_threads_used = 0;
 	int32_t *d_vert = nullptr, *d_node = nullptr, *d_tet = nullptr, *d_nthr = nullptr, *d_ent0 = nullptr, *d_out = nullptr;
-	uint32_t *d_eptr = nullptr;
-	uint16_t *d_contrib = nullptr;
+	uint16_t *d_tab = nullptr;                // [n_ent][W]
 	double  *d_ainv = nullptr;
 	bool     attr_set = false;
 	// host copies (kept by host-only debug contexts for the emulator)
 	std::vector<int32_t> h_vert, h_node, h_tet, h_nthr, h_ent0, h_out;
-	std::vector<uint32_t> h_eptr;
-	std::vector<uint16_t> h_contrib;
+	std::vector<uint16_t> h_tab;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -153,8 +156,7 @@ __host__ __device__ __forceinline__ void tet_eval(const double4 p0, const double
 	}
 }
 
-// per-thread state of the march: the accumulators of the bottom interface (layer k), the ones being built
-// for the top interface (layer k + 1), the six blocks between the layers
+// per-thread state of the march: the accumulators of the interface between two prisms
 struct Iface { double D[9]; double E[12]; double F[6]; };
 
 __host__ __device__ __forceinline__ void iface_zero(Iface& a)
@@ -167,151 +169,240 @@ __host__ __device__ __forceinline__ void iface_zero(Iface& a)
 	for (int i = 0; i < 6; ++i) a.F[i] = 0.0;
 }
 
-// one prism = three tets; bot gets the bottom-interface parts added, top is SET to the top-interface parts,
-// C (24 doubles: C00 C01 C02 C11 C12 C22) is SET to the blocks between the layers
-__host__ __device__ __forceinline__ void prism_eval(const double4* pb, const double2* ub, const double4* pt, const double2* ut,
-                                                     const double a0, const double a1, const double a2, const AsmParams& P,
-                                                     Iface& bot, Iface& top, double* C)
+// One prism = three tets (b0 b1 b2 t2) (b0 b1 t1 t2) (b0 t0 t1 t2).  bot holds what the prism below added to the nodes
+// of the bottom interface; every staged value goes out as soon as it is final (after the tet that touches it last), so
+// few accumulators stay live; top is SET to this prism's part of the top interface.  st.gate() is called once, before
+// the first store (the kernel waits there until the summing warps have released the staging buffer).
+template <class ST>
+__host__ __device__ __forceinline__ void prism_steps(const double4* pb, const double2* ub, const double4* pt, const double2* ut,
+                                                      const double a0, const double a1, const double a2, const AsmParams& P,
+                                                      Iface& bot, Iface& top, ST& st)
 {
 	TetOut o;
-	// ---- tet A = (b0 b1 b2 t2): local 0 1 2 3
+	double C01[4], C02[4], C12[4];
+	// ---- tet A = (b0 b1 b2 t2): local 0 1 2 3.  Final afterwards: everything of b2, C22
 	tet_eval(pb[0], pb[1], pb[2], pt[2], ub[0], ub[1], ub[2], ut[2], a0, P, o);
+	st.gate();
 	#pragma unroll
-	for (int i = 0; i < 9; ++i) bot.D[i] += o.D[i];                      // D(b0) D(b1) D(b2)
-	#pragma unroll
-	for (int i = 0; i < 6; ++i) bot.F[i] += o.F[i];
+	for (int i = 0; i < 3; ++i) st.put(6 + i, bot.D[6 + i] + o.D[6 + i]);                 // D(b2)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		bot.E[i] += o.E[i];               // (0,1) -> E(b0b1)
-		bot.E[4 + i] += o.E[4 + i];       // (0,2) -> E(b0b2)
-		bot.E[8 + i] += o.E[12 + i];      // (1,2) -> E(b1b2)
-		C[8 + i]  = o.E[8 + i];           // (0,3) -> C02
-		C[16 + i] = o.E[16 + i];          // (1,3) -> C12
-		C[20 + i] = o.E[20 + i];          // (2,3) -> C22
+		st.put(13 + i, bot.E[4 + i] + o.E[4 + i]);                                         // (0,2) -> E(b0b2)
+		st.put(17 + i, bot.E[8 + i] + o.E[12 + i]);                                        // (1,2) -> E(b1b2)
+		st.put(47 + i, o.E[20 + i]);                                                       // (2,3) -> C22
+		bot.E[i] += o.E[i];                                                                // (0,1) -> E(b0b1)
+		C02[i] = o.E[8 + i];                                                               // (0,3) -> C02
+		C12[i] = o.E[16 + i];                                                              // (1,3) -> C12
 	}
-	top.D[6] = o.D[9]; top.D[7] = o.D[10]; top.D[8] = o.D[11];           // D(t2)
-	top.F[4] = o.F[6]; top.F[5] = o.F[7];
-	// ---- tet B = (b0 b1 t1 t2)
-	tet_eval(pb[0], pb[1], pt[1], pt[2], ub[0], ub[1], ut[1], ut[2], a1, P, o);
+	st.put(25, bot.F[4] + o.F[4]); st.put(26, bot.F[5] + o.F[5]);                          // F(b2)
 	#pragma unroll
-	for (int i = 0; i < 6; ++i) bot.D[i] += o.D[i];                      // D(b0) D(b1)
+	for (int i = 0; i < 6; ++i) bot.D[i] += o.D[i];                                        // D(b0) D(b1)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) bot.F[i] += o.F[i];
-	top.D[3] = o.D[6]; top.D[4] = o.D[7]; top.D[5] = o.D[8];             // D(t1)
-	top.D[6] += o.D[9]; top.D[7] += o.D[10]; top.D[8] += o.D[11];        // D(t2)
-	top.F[2] = o.F[4]; top.F[3] = o.F[5]; top.F[4] += o.F[6]; top.F[5] += o.F[7];
+	top.D[6] = o.D[9]; top.D[7] = o.D[10]; top.D[8] = o.D[11];                             // D(t2)
+	top.F[4] = o.F[6]; top.F[5] = o.F[7];
+	// ---- tet B = (b0 b1 t1 t2).  Final afterwards: everything of b1, C11, C12
+	tet_eval(pb[0], pb[1], pt[1], pt[2], ub[0], ub[1], ut[1], ut[2], a1, P, o);
+	#pragma unroll
+	for (int i = 0; i < 3; ++i) st.put(3 + i, bot.D[3 + i] + o.D[3 + i]);                 // D(b1)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		bot.E[i] += o.E[i];               // (0,1) -> E(b0b1)
-		C[4 + i]  = o.E[4 + i];           // (0,2) -> C01
-		C[8 + i] += o.E[8 + i];           // (0,3) -> C02
-		C[12 + i] = o.E[12 + i];          // (1,2) -> C11
-		C[16 + i] += o.E[16 + i];         // (1,3) -> C12
-		top.E[8 + i] = o.E[20 + i];       // (2,3) -> E(t1t2)
+		st.put(9 + i, bot.E[i] + o.E[i]);                                                  // (0,1) -> E(b0b1)
+		st.put(39 + i, o.E[12 + i]);                                                       // (1,2) -> C11
+		st.put(43 + i, C12[i] + o.E[16 + i]);                                              // (1,3) -> C12
+		C01[i] = o.E[4 + i];                                                               // (0,2) -> C01
+		C02[i] += o.E[8 + i];                                                              // (0,3) -> C02
+		top.E[8 + i] = o.E[20 + i];                                                        // (2,3) -> E(t1t2)
 	}
-	// ---- tet C = (b0 t0 t1 t2)
-	tet_eval(pb[0], pt[0], pt[1], pt[2], ub[0], ut[0], ut[1], ut[2], a2, P, o);
-	bot.D[0] += o.D[0]; bot.D[1] += o.D[1]; bot.D[2] += o.D[2];          // D(b0)
+	st.put(23, bot.F[2] + o.F[2]); st.put(24, bot.F[3] + o.F[3]);                          // F(b1)
+	bot.D[0] += o.D[0]; bot.D[1] += o.D[1]; bot.D[2] += o.D[2];
 	bot.F[0] += o.F[0]; bot.F[1] += o.F[1];
-	top.D[0] = o.D[3]; top.D[1] = o.D[4]; top.D[2] = o.D[5];             // D(t0)
-	top.D[3] += o.D[6]; top.D[4] += o.D[7]; top.D[5] += o.D[8];          // D(t1)
-	top.D[6] += o.D[9]; top.D[7] += o.D[10]; top.D[8] += o.D[11];        // D(t2)
-	top.F[0] = o.F[2]; top.F[1] = o.F[3]; top.F[2] += o.F[4]; top.F[3] += o.F[5]; top.F[4] += o.F[6]; top.F[5] += o.F[7];
+	top.D[3] = o.D[6]; top.D[4] = o.D[7]; top.D[5] = o.D[8];                               // D(t1)
+	top.D[6] += o.D[9]; top.D[7] += o.D[10]; top.D[8] += o.D[11];                          // D(t2)
+	top.F[2] = o.F[4]; top.F[3] = o.F[5]; top.F[4] += o.F[6]; top.F[5] += o.F[7];
+	// ---- tet C = (b0 t0 t1 t2).  Final afterwards: everything of b0, C00, C01, C02
+	tet_eval(pb[0], pt[0], pt[1], pt[2], ub[0], ut[0], ut[1], ut[2], a2, P, o);
+	#pragma unroll
+	for (int i = 0; i < 3; ++i) st.put(i, bot.D[i] + o.D[i]);                             // D(b0)
+	st.put(21, bot.F[0] + o.F[0]); st.put(22, bot.F[1] + o.F[1]);                          // F(b0)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		C[i]      = o.E[i];               // (0,1) -> C00
-		C[4 + i] += o.E[4 + i];           // (0,2) -> C01
-		C[8 + i] += o.E[8 + i];           // (0,3) -> C02
-		top.E[i]      = o.E[12 + i];      // (1,2) -> E(t0t1)
-		top.E[4 + i]  = o.E[16 + i];      // (1,3) -> E(t0t2)
-		top.E[8 + i] += o.E[20 + i];      // (2,3) -> E(t1t2)
+		st.put(27 + i, o.E[i]);                                                            // (0,1) -> C00
+		st.put(31 + i, C01[i] + o.E[4 + i]);                                               // (0,2) -> C01
+		st.put(35 + i, C02[i] + o.E[8 + i]);                                               // (0,3) -> C02
+		top.E[i]      = o.E[12 + i];                                                       // (1,2) -> E(t0t1)
+		top.E[4 + i]  = o.E[16 + i];                                                       // (1,3) -> E(t0t2)
+		top.E[8 + i] += o.E[20 + i];                                                       // (2,3) -> E(t1t2)
 	}
+	top.D[0] = o.D[3]; top.D[1] = o.D[4]; top.D[2] = o.D[5];                               // D(t0)
+	top.D[3] += o.D[6]; top.D[4] += o.D[7]; top.D[5] += o.D[8];                            // D(t1)
+	top.D[6] += o.D[9]; top.D[7] += o.D[10]; top.D[8] += o.D[11];                          // D(t2)
+	top.F[0] = o.F[2]; top.F[1] = o.F[3]; top.F[2] += o.F[4]; top.F[3] += o.F[5]; top.F[4] += o.F[6]; top.F[5] += o.F[7];
 }
 
-// add the contributions of one table entry (fixed order) from the staged buffer
-__host__ __device__ __forceinline__ void entry_sum(const double* st, int stride, const uint16_t* ct, uint32_t c0, uint32_t c1,
-                                                    const uint8_t* code_base, const uint8_t* code_type, double& a0, double& a1, double& a2, double& a3)
+template <class ST>
+__host__ __device__ __forceinline__ void iface_stage(const Iface& bot, ST& st)       // the top interface of the last prism
 {
-	a0 = a1 = a2 = a3 = 0.0;
-	for (uint32_t q = c0; q < c1; ++q) {
-		const uint32_t w = ct[q];
-		const int t = w & 511, code = w >> 9;
-		const double* b = st + (size_t)code_base[code] * stride + t;
-		const int ty = code_type[code];
-		if (ty == CT_D) { const double xy = b[stride]; a0 += b[0]; a1 += xy; a2 += xy; a3 += b[2 * stride]; }
-		else if (ty == CT_E) { a0 += b[0]; a1 += b[stride]; a2 += b[2 * stride]; a3 += b[3 * stride]; }
-		else if (ty == CT_ET) { a0 += b[0]; a1 += b[2 * stride]; a2 += b[stride]; a3 += b[3 * stride]; }
-		else { a0 += b[0]; a1 += b[stride]; }
-	}
+	st.gate();
+	#pragma unroll
+	for (int i = 0; i < 9; ++i) st.put(i, bot.D[i]);
+	#pragma unroll
+	for (int i = 0; i < 12; ++i) st.put(9 + i, bot.E[i]);
+	#pragma unroll
+	for (int i = 0; i < 6; ++i) st.put(21 + i, bot.F[i]);
+}
+
+// add the contributions of one table entry (fixed order) from the staged buffer st[slot][TILE_T]
+__host__ __device__ __forceinline__ void entry_add(const double* st, const uint32_t x, double& a0, double& a1, double& a2, double& a3)
+{
+	const int t = x & 255, slot = (x >> 8) & 63, ty = x >> 14;
+	const double* b = st + slot * TILE_T + t;
+	const int o1 = (ty == CT_ET) ? 2 : 1, o2 = (ty == CT_E) ? 2 : 1, o3 = (ty == CT_D) ? 2 : (ty == CT_F ? 1 : 3);
+	a0 += b[0]; a1 += b[o1 * TILE_T]; a2 += b[o2 * TILE_T]; a3 += b[o3 * TILE_T];
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel
-__global__ void __launch_bounds__(TILE_T, 1)
-k_tile(const int NL, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
-       const int32_t* __restrict__ nthr, const int32_t* __restrict__ ent0, const uint32_t* __restrict__ eptr,
-       const uint16_t* __restrict__ contrib, const int32_t* __restrict__ out, const int64_t n_ent,
+// the kernel: 8 compute warps (one thread per prism column) + 4 summing warps, registers re-balanced with
+// setmaxnreg (224 / 56: the CTA's register pool is conserved), hand-over through two named barriers:
+//   FULL   compute warps arrive after staging layer k, summing warps wait
+//   EMPTY  summing warps arrive after reading layer k, compute warps wait before they stage layer k + 1
+// so the sums of layer k overlap the element math of layer k + 1.  The vertex data of the next layer arrives by
+// cp.async (LDGSTS) into a per-thread shared-memory slot while the current prism is computed; the tile's table of
+// (thread, slot) contributions is copied to shared memory once per CTA.
+#define BAR_FULL  1
+#define BAR_EMPTY 2
+#define BAR_SUM   3
+__device__ __forceinline__ void bar_sync(const int id, const int n)   { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+struct DevStage {
+	double* sb; bool wait;
+	__device__ __forceinline__ void gate() { if (wait) bar_sync(BAR_EMPTY, TILE_T + TILE_S); }
+	__device__ __forceinline__ void put(const int slot, const double v) { sb[slot * TILE_T] = v; }
+};
+
+__global__ void __launch_bounds__(TILE_T + TILE_S, 1)
+k_tile(const int NL, const int W, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
+       const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const int32_t* __restrict__ out, const int64_t n_ent,
        const double4* __restrict__ geo, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
 {
-	extern __shared__ double stage[];                       // [2][TILE_NSLOT][TILE_T]
-	const int t = threadIdx.x, tile = blockIdx.x;
-	const bool act = t < nthr[tile];
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	double* stage = (double*)smem_raw;                                              // [TILE_NSLOT][TILE_T]
+	uint4*  vbuf  = (uint4*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8);           // [2][9][TILE_T] 16-byte chunks
+	uint16_t* stab = (uint16_t*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 9 * TILE_T * 16);   // [entries][W]
+	const int tile = blockIdx.x;
 	const int NZ = NL - 1;
-	const int32_t* tv = tvert + (size_t)tile * NL * 3 * TILE_T + t;
-	const int32_t* tn = tnode + (size_t)tile * NL * 3 * TILE_T + t;
-	const double*  ta = tainv + (size_t)tile * NZ * 3 * TILE_T + t;
-	const int e_lo = ent0[tile], e_hi = ent0[tile + 1];
-	double4 pb[3], pt[3];
-	double2 ub[3], ut[3];
-	Iface bot, top;
-	double C[24];
-	iface_zero(bot);
-	if (act) {
+	if (threadIdx.x < TILE_T) {
+		// ================================================================= compute warps
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");     // ... which is exactly what 256 x 56 more take out of it
+		const int t = threadIdx.x;
+		const int32_t* tv = tvert + (size_t)tile * NL * 3 * TILE_T + t;
+		const int32_t* tn = tnode + (size_t)tile * NL * 3 * TILE_T + t;
+		const double*  ta = tainv + (size_t)tile * NZ * 3 * TILE_T + t;
+		double4 pb[3], pt[3];
+		double2 ub[3], ut[3];
+		Iface bot, top;
+		iface_zero(bot);
+		int iv[3], in[3];                       // vertex / node ids of the layer fetched next
 		#pragma unroll
-		for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }
-	}
-	for (int k = 0; k <= NZ; ++k) {
-		double* sb = stage + (size_t)(k & 1) * TILE_NSLOT * TILE_T + t;
-		if (act) {
-			if (k < NZ) {
-				#pragma unroll
-				for (int i = 0; i < 3; ++i) { pt[i] = geo[tv[((k + 1) * 3 + i) * TILE_T]]; ut[i] = u[tn[((k + 1) * 3 + i) * TILE_T]]; }
-				const double a0 = ta[(k * 3) * TILE_T], a1 = ta[(k * 3 + 1) * TILE_T], a2 = ta[(k * 3 + 2) * TILE_T];
-				prism_eval(pb, ub, pt, ut, a0, a1, a2, P, bot, top, C);
-				#pragma unroll
-				for (int i = 0; i < 24; ++i) sb[(27 + i) * TILE_T] = C[i];
+		for (int i = 0; i < 3; ++i) { iv[i] = tv[(3 + i) * TILE_T]; in[i] = tn[(3 + i) * TILE_T]; }        // layer 1
+		#pragma unroll
+		for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }            // layer 0: straight into registers
+		{	// layer 1 -> vbuf[0]
+			uint4* vb = vbuf + t;
+			#pragma unroll
+			for (int i = 0; i < 3; ++i) {
+				cp_async16(vb + (3 * i) * TILE_T, &geo[iv[i]]);
+				cp_async16(vb + (3 * i + 1) * TILE_T, (const char*)&geo[iv[i]] + 16);
+				cp_async16(vb + (3 * i + 2) * TILE_T, &u[in[i]]);
 			}
-			#pragma unroll
-			for (int i = 0; i < 9; ++i) sb[i * TILE_T] = bot.D[i];
-			#pragma unroll
-			for (int i = 0; i < 12; ++i) sb[(9 + i) * TILE_T] = bot.E[i];
-			#pragma unroll
-			for (int i = 0; i < 6; ++i) sb[(21 + i) * TILE_T] = bot.F[i];
-			if (k < NZ) {
-				bot = top;
-				#pragma unroll
-				for (int i = 0; i < 3; ++i) { pb[i] = pt[i]; ub[i] = ut[i]; }
-			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
-		__syncthreads();
-		// ---- block rows of the tile's own columns at this step: fixed-order sums, every block written once
-		const double* st = stage + (size_t)(k & 1) * TILE_NSLOT * TILE_T;
-		const int32_t* ok = out + (size_t)k * n_ent;
-		for (int e = e_lo + t; e < e_hi; e += TILE_T) {
-			const int o = ok[e];
-			if (o == -1) continue;
-			double a0, a1, a2, a3;
-			entry_sum(st, TILE_T, contrib, eptr[e], eptr[e + 1], c_code_base, c_code_type, a0, a1, a2, a3);
-			if (o >= 0) {
-				double2* dst = (double2*)val + 2 * (size_t)o;
-				dst[0] = make_double2(a0, a1);
-				dst[1] = make_double2(a2, a3);
-			} else {
-				*(double2*)(F + 2 * (size_t)(-o - 2)) = make_double2(a0, a1);
-			}
+		if (NZ >= 2) {
+			#pragma unroll
+			for (int i = 0; i < 3; ++i) { iv[i] = tv[(6 + i) * TILE_T]; in[i] = tn[(6 + i) * TILE_T]; }    // layer 2
 		}
-		// the buffer written next (k + 1) was last read at step k - 1: every thread passed this step's barrier
-		// only after finishing those reads, so one barrier per layer is enough
+		for (int k = 0; k < NZ; ++k) {
+			const double a0 = ta[(k * 3) * TILE_T], a1 = ta[(k * 3 + 1) * TILE_T], a2 = ta[(k * 3 + 2) * TILE_T];
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			{	// the top layer of this prism
+				const uint4* vb = vbuf + (size_t)(k & 1) * 9 * TILE_T + t;
+				#pragma unroll
+				for (int i = 0; i < 3; ++i) {
+					const uint4 q0 = vb[(3 * i) * TILE_T], q1 = vb[(3 * i + 1) * TILE_T], q2 = vb[(3 * i + 2) * TILE_T];
+					pt[i] = make_double4(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x), __hiloint2double(q1.w, q1.z));
+					ut[i] = make_double2(__hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z));
+				}
+			}
+			if (k + 2 <= NZ) {                  // layer k + 2 -> the other buffer, while this prism is computed
+				uint4* vb = vbuf + (size_t)((k + 1) & 1) * 9 * TILE_T + t;
+				#pragma unroll
+				for (int i = 0; i < 3; ++i) {
+					cp_async16(vb + (3 * i) * TILE_T, &geo[iv[i]]);
+					cp_async16(vb + (3 * i + 1) * TILE_T, (const char*)&geo[iv[i]] + 16);
+					cp_async16(vb + (3 * i + 2) * TILE_T, &u[in[i]]);
+				}
+				asm volatile("cp.async.commit_group;" ::: "memory");
+				if (k + 3 <= NZ) {
+					#pragma unroll
+					for (int i = 0; i < 3; ++i) { iv[i] = tv[((k + 3) * 3 + i) * TILE_T]; in[i] = tn[((k + 3) * 3 + i) * TILE_T]; }
+				}
+			}
+			DevStage st = { stage + t, k > 0 };
+			prism_steps(pb, ub, pt, ut, a0, a1, a2, P, bot, top, st);
+			__threadfence_block();
+			bar_arrive(BAR_FULL, TILE_T + TILE_S);
+			bot = top;
+			#pragma unroll
+			for (int i = 0; i < 3; ++i) { pb[i] = pt[i]; ub[i] = ut[i]; }
+		}
+		DevStage st = { stage + t, NZ > 0 };
+		iface_stage(bot, st);
+		__threadfence_block();
+		bar_arrive(BAR_FULL, TILE_T + TILE_S);
+	} else {
+		// ================================================================= summing warps
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // releases 128 x 112 registers into the CTA pool ...
+		const int sidx = threadIdx.x - TILE_T;
+		const int e_lo = ent0[tile], ne = ent0[tile + 1] - e_lo;
+		{	// the tile's table -> shared memory (16-byte pieces)
+			const uint4* src = (const uint4*)(tab + (size_t)e_lo * W);
+			uint4* dst = (uint4*)stab;
+			const int n16 = ne * W / 8;
+			for (int i = sidx; i < n16; i += TILE_S) dst[i] = src[i];
+		}
+		bar_sync(BAR_SUM, TILE_S);
+		for (int k = 0; k <= NZ; ++k) {
+			int o[16];
+			const int32_t* ok = out + (size_t)k * n_ent + e_lo;
+			#pragma unroll
+			for (int i = 0; i < 16; ++i) { const int e = sidx + i * TILE_S; o[i] = (e < ne) ? ok[e] : -1; }
+			bar_sync(BAR_FULL, TILE_T + TILE_S);
+			#pragma unroll
+			for (int i = 0; i < 16; ++i) {
+				if (o[i] == -1) continue;
+				const int e = sidx + i * TILE_S;
+				double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+				for (int w8 = 0; w8 < W; w8 += 8) {
+					const uint4 q = *(const uint4*)(stab + (size_t)e * W + w8);
+					const uint32_t x[8] = { q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16 };
+					#pragma unroll
+					for (int c = 0; c < 8; ++c) if (x[c] != CW_NONE) entry_add(stage, x[c], a0, a1, a2, a3);
+				}
+				if (o[i] >= 0) {
+					double2* dst = (double2*)val + 2 * (size_t)o[i];
+					dst[0] = make_double2(a0, a1);
+					dst[1] = make_double2(a2, a3);
+				} else {
+					*(double2*)(F + 2 * (size_t)(-o[i] - 2)) = make_double2(a0, a1);
+				}
+			}
+			if (k < NZ) bar_arrive(BAR_EMPTY, TILE_T + TILE_S);
+		}
 	}
 }
 
@@ -341,20 +432,20 @@ bool bp_tiles_serve(const bp_ctx* c, int what)
 	return c->env.asm_tiled != 0;
 }
 
+static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 9 * TILE_T * 16 + (size_t)TILE_TABW * 2; }
+
 void bp_launch_tiles(bp_ctx* c, int what)
 {
 	bp_tiles* T = c->tiles;
 	AsmParams P = bp_asm_params(c);
 	P.picard = (what & 16) ? 1 : 0;
-	const size_t sm = (size_t)2 * TILE_NSLOT * TILE_T * sizeof(double);
+	const size_t sm = tile_smem_bytes();
 	if (!T->attr_set) {
 		cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-		cudaMemcpyToSymbol(c_code_base, H_CODE_BASE, sizeof(H_CODE_BASE));
-		cudaMemcpyToSymbol(c_code_type, H_CODE_TYPE, sizeof(H_CODE_TYPE));
 		T->attr_set = true;
 	}
-	k_tile<<<T->n_tiles, TILE_T, sm, c->stream>>>(T->NL, T->d_vert, T->d_node, T->d_ainv, T->d_nthr, T->d_ent0, T->d_eptr, T->d_contrib, T->d_out,
-	                                                T->n_ent, c->d_geo, (const double2*)c->d_u, c->d_F, c->d_val, P);
+	k_tile<<<T->n_tiles, TILE_T + TILE_S, sm, c->stream>>>(T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_out,
+	                                                         T->n_ent, c->d_geo, (const double2*)c->d_u, c->d_F, c->d_val, P);
 	c->launches++;
 }
 
@@ -362,7 +453,7 @@ void bp_tiles_free(bp_ctx* c)
 {
 	if (!c->tiles) return;
 	bp_tiles* T = c->tiles;
-	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_eptr, T->d_contrib, T->d_ainv };
+	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_tab, T->d_ainv };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	delete T;
 	c->tiles = nullptr;
@@ -522,6 +613,32 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		}
 	}
 	for (int32_t q = 0; q < n_ncol; ++q) if (col_owned[q] && ctp[q + 1] - ctp[q] > TILE_T) return no_tiles(c, "an ice column is touched by more prism columns than a tile holds");
+	// table entries a column brings into its tile: one per (kind, neighbour column) + one for F; and the largest
+	// number of prism columns around a column (= contributions of its diagonal / vertical blocks)
+	std::vector<int32_t> col_ent(n_ncol, 1);
+	int max_val = 0;
+	{
+		struct PK { int32_t p, q; int8_t kind; };
+		std::vector<PK> pk;
+		pk.reserve((size_t)ntri * 21);
+		for (int64_t r = 0; r < ntri; ++r) {
+			int32_t q[3] = { ncol_of_vcol[tri_col[3 * r]], ncol_of_vcol[tri_col[3 * r + 1]], ncol_of_vcol[tri_col[3 * r + 2]] };
+			for (int i = 0; i < 3; ++i) {
+				if (!col_owned[q[i]]) continue;
+				for (int j = 0; j < 3; ++j) {
+					pk.push_back({ q[i], q[j], 0 });
+					if (j >= i) pk.push_back({ q[i], q[j], 1 });
+					if (j <= i) pk.push_back({ q[i], q[j], 2 });
+				}
+			}
+		}
+		std::sort(pk.begin(), pk.end(), [](const PK& a, const PK& b) { if (a.p != b.p) return a.p < b.p; if (a.kind != b.kind) return a.kind < b.kind; return a.q < b.q; });
+		for (size_t i = 0; i < pk.size(); ++i)
+			if (i == 0 || pk[i].p != pk[i - 1].p || pk[i].kind != pk[i - 1].kind || pk[i].q != pk[i - 1].q) col_ent[pk[i].p]++;
+		for (int32_t q = 0; q < n_ncol; ++q) if (col_owned[q]) max_val = std::max(max_val, (int)(ctp[q + 1] - ctp[q]));
+	}
+	int W = (max_val <= 8) ? 8 : 16;
+	const int max_ent = std::min<int>(TILE_MAXE, TILE_TABW / W);
 	// position of a node column: its lowest vertex (the master of periodic images)
 	std::vector<int32_t> rep(nn, -1);
 	for (int64_t v = nv - 1; v >= 0; --v) rep[v2n[v]] = (int32_t)v;
@@ -545,18 +662,19 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	std::vector<int32_t> tile_c0(1, 0);                            // tile -> range of own_cols
 	{
 		std::vector<int32_t> stamp(ntri, -1);
-		int ntile = 0, ntr = 0, ncl = 0;
+		int ntile = 0, ntr = 0, ncl = 0, nen = 0;
 		for (size_t i = 0; i < own_cols.size(); ++i) {
 			const int32_t q = own_cols[i];
 			int add = 0;
 			for (int64_t k = ctp[q]; k < ctp[q + 1]; ++k) if (stamp[ctl[k]] != ntile) ++add;
 			const bool new_strip = i > 0 && ybin[q] != ybin[own_cols[i - 1]];
-			if (ncl > 0 && (ntr + add > TILE_T || ncl + 1 > TILE_MAXC || new_strip)) {
-				tile_c0.push_back((int32_t)i); ++ntile; ntr = 0; ncl = 0;
+			if (col_ent[q] > max_ent) return no_tiles(c, "an ice column has more Jacobian blocks than a tile's table holds");
+			if (ncl > 0 && (ntr + add > TILE_T || ncl + 1 > TILE_MAXC || nen + col_ent[q] > max_ent || new_strip)) {
+				tile_c0.push_back((int32_t)i); ++ntile; ntr = 0; ncl = 0; nen = 0;
 				add = (int)(ctp[q + 1] - ctp[q]);
 			}
 			for (int64_t k = ctp[q]; k < ctp[q + 1]; ++k) stamp[ctl[k]] = ntile;
-			ntr += add; ++ncl;
+			ntr += add; ++ncl; nen += col_ent[q];
 		}
 		tile_c0.push_back((int32_t)own_cols.size());
 	}
@@ -564,7 +682,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 
 	// ---- 5 + 6. per tile: thread list (prism columns), vertex / node / tet tables, sum tables -----------------
 	bp_tiles* T = new bp_tiles();
-	T->n_tiles = n_tiles; T->NL = NL; T->n_prism_cols = ntri;
+	T->n_tiles = n_tiles; T->NL = NL; T->n_prism_cols = ntri; T->W = W;
 	T->h_vert.assign((size_t)n_tiles * NL * 3 * TILE_T, 0);
 	T->h_node.assign((size_t)n_tiles * NL * 3 * TILE_T, 0);
 	T->h_tet.assign((size_t)n_tiles * NZ * 3 * TILE_T, -1);
@@ -655,19 +773,26 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	int64_t ne = 0, ncn = 0;
 	for (int tl = 0; tl < n_tiles; ++tl) { T->h_ent0[tl] = (int32_t)ne; ne += (int64_t)tile_ent[tl].size(); ncn += (int64_t)tile_con[tl].size(); T->n_threads_used += T->h_nthr[tl]; }
 	T->h_ent0[n_tiles] = (int32_t)ne;
-	if (ne > INT32_MAX / 2 || ncn > (int64_t)UINT32_MAX / 2) { delete T; return no_tiles(c, "too many table entries for one rank"); }
+	if (ne > INT32_MAX / 32) { delete T; return no_tiles(c, "too many table entries for one rank"); }
 	T->n_ent = ne; T->n_contrib = ncn;
-	T->h_eptr.resize(ne + 1);
-	T->h_contrib.resize(ncn);
 	T->h_out.assign((size_t)NL * ne, -1);
-	{
-		int64_t co = 0;
-		for (int tl = 0; tl < n_tiles; ++tl) {
-			for (size_t e = 0; e < tile_ent[tl].size(); ++e) T->h_eptr[T->h_ent0[tl] + e] = (uint32_t)(co + tile_eptr[tl][e]);
-			std::copy(tile_con[tl].begin(), tile_con[tl].end(), T->h_contrib.begin() + co);
-			co += (int64_t)tile_con[tl].size();
-		}
-		T->h_eptr[ne] = (uint32_t)co;
+	{	// the packed table: W words per entry, contributions in ascending thread order, padded with CW_NONE
+		int maxc = 0;
+		for (int tl = 0; tl < n_tiles; ++tl)
+			for (size_t e = 0; e < tile_ent[tl].size(); ++e) maxc = std::max(maxc, (int)(tile_eptr[tl][e + 1] - tile_eptr[tl][e]));
+		bool fits = maxc <= W;
+		for (int tl = 0; tl < n_tiles && fits; ++tl) fits = (int64_t)tile_ent[tl].size() <= std::min<int64_t>(TILE_MAXE, TILE_TABW / W);
+		if (!fits) { delete T; return no_tiles(c, "a Jacobian block gets more contributions than a table entry holds"); }
+		T->h_tab.assign((size_t)ne * W, (uint16_t)CW_NONE);
+		for (int tl = 0; tl < n_tiles; ++tl)
+			for (size_t e = 0; e < tile_ent[tl].size(); ++e) {
+				uint16_t* dst = T->h_tab.data() + ((size_t)T->h_ent0[tl] + e) * W;
+				for (uint32_t q = tile_eptr[tl][e]; q < tile_eptr[tl][e + 1]; ++q) {
+					const uint16_t w = tile_con[tl][q];
+					const int t = w & 511, code = w >> 9;
+					*dst++ = CW(t, H_CODE_BASE[code], H_CODE_TYPE[code]);
+				}
+			}
 	}
 	// output slots per layer, and the exactly-once check
 	std::vector<uint8_t> hitJ((size_t)std::max<int64_t>(c->n_slots, 1), 0), hitF((size_t)no, 0);
@@ -717,8 +842,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (!rc) rc = up(c, &T->d_nthr, T->h_nthr);
 	if (!rc) rc = up(c, &T->d_ent0, T->h_ent0);
 	if (!rc) rc = up(c, &T->d_out, T->h_out);
-	if (!rc) rc = up(c, &T->d_eptr, T->h_eptr);
-	if (!rc) rc = up(c, &T->d_contrib, T->h_contrib);
+	if (!rc) rc = up(c, &T->d_tab, T->h_tab);
 	if (!rc && !c->host_only) {
 		cudaError_t e = cudaMalloc((void**)&T->d_ainv, (size_t)n_tiles * NZ * 3 * TILE_T * sizeof(double));
 		if (e != cudaSuccess) rc = bp_fail(c, BP_ERR_CUDA, "cudaMalloc(tile ainv) failed: %s", cudaGetErrorString(e));
@@ -727,7 +851,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (rc) { bp_tiles_free(c); return rc; }
 	if (!c->host_only) {                       // the emulator of a host-only context keeps the tables
 		std::vector<int32_t>().swap(T->h_vert); std::vector<int32_t>().swap(T->h_node); std::vector<int32_t>().swap(T->h_tet);
-		std::vector<int32_t>().swap(T->h_out); std::vector<uint32_t>().swap(T->h_eptr); std::vector<uint16_t>().swap(T->h_contrib);
+		std::vector<int32_t>().swap(T->h_out); std::vector<uint16_t>().swap(T->h_tab);
 	}
 	if (c->prm.verbose)
 		fprintf(stderr, "[cslvr_b200] tiled cell assembly: %d tiles, %lld prism columns x %d layers, halo factor %.3f, %lld table entries\n",
@@ -749,19 +873,24 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 	const double4* geo = (const double4*)vert_xyzS;
 	const double2* u2 = (const double2*)u;
 	std::vector<double> val((size_t)c->n_slots * 4, 0.0);
+	struct HostStage {
+		double* sb;
+		void gate() {}
+		void put(int slot, double v) { sb[(size_t)slot * TILE_T] = v; }
+	};
+	const int W = T->W;
 	#pragma omp parallel
 	{
 		std::vector<double> stage((size_t)TILE_NSLOT * TILE_T);
 		std::vector<Iface> bot(TILE_T), top(TILE_T);
 		#pragma omp for schedule(dynamic, 4)
 		for (int tile = 0; tile < T->n_tiles; ++tile) {
-			const int nthr = T->h_nthr[tile];
-			for (int t = 0; t < nthr; ++t) iface_zero(bot[t]);
+			for (int t = 0; t < TILE_T; ++t) iface_zero(bot[t]);
 			for (int k = 0; k <= NZ; ++k) {
-				for (int t = 0; t < nthr; ++t) {
-					double* sb = stage.data() + t;
+				for (int t = 0; t < TILE_T; ++t) {           // every compute thread, padding threads (vertex 0, ainv 0) included
+					HostStage st = { stage.data() + t };
 					if (k < NZ) {
-						double4 pb[3], pt[3]; double2 ub[3], ut[3]; double C[24];
+						double4 pb[3], pt[3]; double2 ub[3], ut[3];
 						for (int i = 0; i < 3; ++i) {
 							pb[i] = geo[T->h_vert[(((size_t)tile * NL + k) * 3 + i) * TILE_T + t]];
 							ub[i] = u2[T->h_node[(((size_t)tile * NL + k) * 3 + i) * TILE_T + t]];
@@ -769,20 +898,16 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 							ut[i] = u2[T->h_node[(((size_t)tile * NL + k + 1) * 3 + i) * TILE_T + t]];
 						}
 						double a[3];
-						for (int j = 0; j < 3; ++j) a[j] = ainv[T->h_tet[(((size_t)tile * NZ + k) * 3 + j) * TILE_T + t]];
-						prism_eval(pb, ub, pt, ut, a[0], a[1], a[2], P, bot[t], top[t], C);
-						for (int i = 0; i < 24; ++i) sb[(27 + i) * TILE_T] = C[i];
-					}
-					for (int i = 0; i < 9; ++i) sb[i * TILE_T] = bot[t].D[i];
-					for (int i = 0; i < 12; ++i) sb[(9 + i) * TILE_T] = bot[t].E[i];
-					for (int i = 0; i < 6; ++i) sb[(21 + i) * TILE_T] = bot[t].F[i];
-					if (k < NZ) bot[t] = top[t];
+						for (int j = 0; j < 3; ++j) { const int32_t tt = T->h_tet[(((size_t)tile * NZ + k) * 3 + j) * TILE_T + t]; a[j] = tt >= 0 ? ainv[tt] : 0.0; }
+						prism_steps(pb, ub, pt, ut, a[0], a[1], a[2], P, bot[t], top[t], st);
+						bot[t] = top[t];
+					} else iface_stage(bot[t], st);
 				}
 				for (int e = T->h_ent0[tile]; e < T->h_ent0[tile + 1]; ++e) {
 					const int o = T->h_out[(size_t)k * T->n_ent + e];
 					if (o == -1) continue;
-					double a0, a1, a2, a3;
-					entry_sum(stage.data(), TILE_T, T->h_contrib.data(), T->h_eptr[e], T->h_eptr[e + 1], H_CODE_BASE, H_CODE_TYPE, a0, a1, a2, a3);
+					double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+					for (int q = 0; q < W; ++q) { const uint32_t x = T->h_tab[(size_t)e * W + q]; if (x != CW_NONE) entry_add(stage.data(), x, a0, a1, a2, a3); }
 					if (o >= 0) { double* d = val.data() + 4 * (size_t)o; d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3; }
 					else { F[2 * (size_t)(-o - 2)] = a0; F[2 * (size_t)(-o - 2) + 1] = a1; }
 				}
