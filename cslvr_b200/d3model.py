@@ -17,6 +17,8 @@ sets (:556-602), mesh deformation (:629-667), the P1 coefficient Functions
 ``Expression`` objects are replaced by callables ``f(x, y, z)`` on numpy arrays.
 Everything is numpy: this is one-off set-up, the hot path is in the CUDA library.
 """
+import sys
+
 import numpy as np
 
 from .mesh import Mesh, facet_geometry
@@ -295,9 +297,19 @@ class D3Model(object):
 		mask at the facet midpoint and the midpoint elevation; cell markers from the
 		mask at the cell midpoint."""
 		print_text("::: calculating boundaries :::", cls=self)
-		if mark_divide or contour is not None:
-			raise NotImplementedError("mark_divide/contour (basin divides) are outside the B200 hot path")
 		self.mark_divide = mark_divide
+		if (contour is None and mark_divide) or (contour is not None and not mark_divide):
+			print_text(">>> IF PARAMETER <mark_divide> OF calculate_boundaries() IS "
+			           "TRUE, PARAMETER <contour> MUST BE A NUMPY ARRAY OF COORDINATES "
+			           "OF THE ICE-SHEET EXTERIOR BOUNDARY <<<", 'red', 1)
+			sys.exit(1)
+		tree = None
+		if contour is not None and mark_divide:
+			# cslvr/d3model.py:360-364: lateral facets further than 1 km from the ice-sheet contour are basin divides
+			print_text("    - marking the interior facets for incomplete meshes -", cls=self)
+			from scipy.spatial import cKDTree
+			tree = cKDTree(np.asarray(contour, dtype=np.float64)[:, 0:2])
+			self.contour_tree = tree
 		self.init_mask(1.0 if mask is None else mask)
 		X = self.mesh.coordinates()
 		cells = self.mesh.cells()
@@ -326,6 +338,9 @@ class D3Model(object):
 		ff[dn & ~flt]   = self.GAMMA_B_GND
 		ff[side & (mid[:, 2] > 0)]  = self.GAMMA_L_OVR
 		ff[side & ~(mid[:, 2] > 0)] = self.GAMMA_L_UDR
+		if tree is not None:                         # cslvr/d3model.py:441-448
+			far = ~(tree.query(mid[:, 0:2])[0] < 1000)
+			ff[side & far] = self.GAMMA_L_DVD
 		self.facet_cell, self.facet_local, self.ff = fc, fl, ff
 		print_text("    - iterating through %i cells - " % self.num_cells, cls=self)
 		self.cf = np.where(m_c > 1, self.OMEGA_FLT, self.OMEGA_GND).astype(np.int32)

@@ -128,7 +128,7 @@ def facet_geometry(coords, cells, fc, fl):
 	return fv, area, nrm, p.mean(axis=1)
 
 
-def mark_facets(coords, cells, fc, fl, mask=None):
+def mark_facets(coords, cells, fc, fl, mask=None, contour=None):
 	"""facet markers of ``D3Model.calculate_boundaries``, d3model.py:399-455.
 
 	``mask`` is an optional callable (x, y, z) -> value evaluated at the facet
@@ -149,6 +149,13 @@ def mark_facets(coords, cells, fc, fl, mask=None):
 	ff[dn & ~(m > 1)] = GAMMA_B_GND
 	ff[sd & (mid[:, 2] > 0)] = GAMMA_L_OVR
 	ff[sd & ~(mid[:, 2] > 0)] = GAMMA_L_UDR
+	if contour is not None:
+		# mark_divide=True (d3model.py:441-448): lateral facets whose midpoint is not within 1000 m of a point
+		# of the ice-sheet contour are basin divides (brute-force nearest point; the reference uses a cKDTree)
+		c2 = np.asarray(contour, dtype=np.float64)[:, 0:2]
+		for i in np.flatnonzero(sd):
+			if not (np.sqrt(((c2 - mid[i, 0:2]) ** 2).sum(axis=1)).min() < 1000):
+				ff[i] = GAMMA_L_DVD
 	return ff
 
 

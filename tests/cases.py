@@ -38,6 +38,7 @@ def marine_model(n=(8, 7, 4), L=40000.0, variable_A=True):
 	model.deform_mesh_to_geometry(S, B)
 	mask = lambda x, y, z: np.where(x > 0.6 * L, 2.0, 1.0)
 	model.calculate_boundaries(mask=mask)
+	model.mask_callable = mask                  # for the marker tests: oracle.mark_facets(mask) vs model.ff
 	model.init_beta(lambda x, y, z: 200.0 + 150.0 * np.sin(7 * x / L) * np.cos(3 * y / L))
 	if variable_A:
 		Tp = lambda x, y, z: 250.0 + 18.0 * (1.0 - (z + 500.0) / 1100.0) + 3.0 * np.sin(5 * x / L)
@@ -128,7 +129,8 @@ def delaunay_extruded_model(n_pts=60, n_layers=4, seed=3, L=30000.0):
 	B = lambda x, y, z: -150.0 - 250.0 * x / L + 60.0 * np.cos(6 * x / L) * np.sin(5 * y / L)
 	model.calculate_boundaries()
 	model.deform_mesh_to_geometry(S, B)
-	model.calculate_boundaries(mask=lambda x, y, z: np.where(x > 0.65 * L, 2.0, 1.0))
+	model.mask_callable = lambda x, y, z: np.where(x > 0.65 * L, 2.0, 1.0)
+	model.calculate_boundaries(mask=model.mask_callable)
 	model.init_beta(lambda x, y, z: 300.0 + 200.0 * np.sin(6 * x / L) * np.cos(4 * y / L))
 	X = model.mesh.coordinates()
 	model.init_A(model.rate_factor(252.0 + 15.0 * (1.0 - (X[:, 2] + 400.0) / 900.0)))

@@ -143,3 +143,39 @@ def test_bench_reference_arm_prints_one_json_line():
 	assert d['cpu_baseline']['cores'] == len(os.sched_getaffinity(0))
 	nb = d['cpu_baseline_newton']
 	assert nb[0]['converged'] and nb[0]['newton_iterations'] > 3 and nb[0]['solve_s'] > 0
+
+
+@pytest.mark.parametrize('case', ['ismip', 'marine', 'delaunay', 'eismint', 'greenland'])
+def test_facet_markers_of_the_mirror_equal_the_oracles(case):
+	"""a13: ``D3Model.calculate_boundaries`` (cslvr/d3model.py:337-475) of the host mirror against the oracle's own
+	exterior-facet search and marker rules on every mesh family of the test suite, shelf masks included -- the
+	oracle is NOT handed the product's markers here."""
+	from cases import delaunay_extruded_model, eismint_dome_model, greenland_like_model
+	m = {'ismip': lambda: ismip_model('A', n=(6, 5, 3)), 'marine': marine_model, 'delaunay': delaunay_extruded_model,
+	     'eismint': eismint_dome_model, 'greenland': greenland_like_model}[case]()
+	X, cells = m.mesh.coordinates(), m.mesh.cells()
+	fc, fl = bo.exterior_facets(cells)
+	ff = bo.mark_facets(X, cells, fc, fl, mask=getattr(m, 'mask_callable', None))
+	mine = {(int(c), int(l)): int(k) for c, l, k in zip(m.facet_cell, m.facet_local, m.ff)}
+	theirs = {(int(c), int(l)): int(k) for c, l, k in zip(fc, fl, ff)}
+	assert mine == theirs
+	if case in ('marine', 'delaunay'):
+		assert 5 in mine.values() and 3 in mine.values() and 10 in mine.values()       # floating bed, grounded bed, under-water sides
+
+
+def test_basin_divide_markers():
+	"""mark_divide=True with the ice-sheet contour (cslvr/d3model.py:352-364, 441-448): lateral facets further than 1 km
+	from the contour become GAMMA_L_DVD = 7; without the contour the reference exits."""
+	m = marine_model()
+	X, cells = m.mesh.coordinates(), m.mesh.cells()
+	L = X[:, 0].max()
+	# the "true" ice-sheet margin: only the x = L side; the other three sides are cut through the ice (divides)
+	contour = np.column_stack([np.full(200, L), np.linspace(X[:, 1].min(), X[:, 1].max(), 200)])
+	m.calculate_boundaries(mask=m.mask_callable, mark_divide=True, contour=contour)
+	assert m.N_GAMMA_L_DVD > 0 and m.N_GAMMA_L_OVR + m.N_GAMMA_L_UDR > 0
+	fc, fl = bo.exterior_facets(cells)
+	ff = bo.mark_facets(X, cells, fc, fl, mask=m.mask_callable, contour=contour)
+	assert {(int(c), int(l)): int(k) for c, l, k in zip(m.facet_cell, m.facet_local, m.ff)} == \
+	       {(int(c), int(l)): int(k) for c, l, k in zip(fc, fl, ff)}
+	with pytest.raises(SystemExit):
+		m.calculate_boundaries(mark_divide=True)
