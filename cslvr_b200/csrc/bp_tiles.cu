@@ -37,14 +37,15 @@
 #define TILE_S      128        // summing threads per CTA (one warpgroup)
 #define TILE_NSLOT  51         // staged doubles per compute thread and layer
 #define TILE_MAXC   120        // ice columns owned by one tile
-#define TILE_TABW   16384      // contribution words (uint16) of one tile's table in shared memory
-#define TILE_MAXE   (16 * TILE_S)   // table entries per tile: at most 16 per summing thread
+#define TILE_EPT     9          // table entries per summing thread
+#define TILE_MAXE   (TILE_EPT * TILE_S)   // table entries per tile
+#define TILE_TABW   (8 * TILE_MAXE)       // contribution words (uint16) of one tile's table in shared memory
 
 // staged slots:   0..8  D(b0) D(b1) D(b2): xx xy yy      9..20 E(b0b1) E(b0b2) E(b1b2): xx xy yx yy (row first, col second)
 //                21..26 F(b0) F(b1) F(b2): x y           27..50 C00 C01 C02 C11 C12 C22: block (row b_i, col t_j)
-// a contribution word: thread (bits 0-7) | first slot (bits 8-13) | type (bits 14-15); 0xffff = none
+// a contribution word: offset slot * TILE_T + thread into the staged buffer (bits 0-13) | type (bits 14-15); 0xffff = none
 enum { CT_D = 0, CT_E = 1, CT_ET = 2, CT_F = 3 };
-#define CW(t, slot, ty) ((uint16_t)((t) | ((slot) << 8) | ((ty) << 14)))
+#define CW(t, slot, ty) ((uint16_t)(((slot) * TILE_T + (t)) | ((ty) << 14)))
 #define CW_NONE 0xffffu
 
 // old-style contribution codes used while the tables are built: 0-2 D(b_i), 3-5 E direct, 6-8 E transposed,
@@ -59,12 +60,12 @@ static inline int pair_C(int i, int j) { return (i == 0) ? j : (i == 1 ? 2 + j :
 struct bp_tiles {
 	int     n_tiles = 0, NL = 0, W = 8;       // W: contribution words per table entry (8 or 16)
 	int64_t n_ent = 0, n_contrib = 0, n_prism_cols = 0, n_threads_used = 0;
-	int32_t *d_vert = nullptr, *d_node = nullptr, *d_tet = nullptr, *d_nthr = nullptr, *d_ent0 = nullptr, *d_out = nullptr;
+	int32_t *d_vert = nullptr, *d_node = nullptr, *d_tet = nullptr, *d_nthr = nullptr, *d_ent0 = nullptr, *d_out = nullptr, *d_out2 = nullptr;
 	uint16_t *d_tab = nullptr;                // [n_ent][W]
 	double  *d_ainv = nullptr;
 	bool     attr_set = false;
 	// host copies (kept by host-only debug contexts for the emulator)
-	std::vector<int32_t> h_vert, h_node, h_tet, h_nthr, h_ent0, h_out;
+	std::vector<int32_t> h_vert, h_node, h_tet, h_nthr, h_ent0, h_out, h_out2;   // out2: slot of the transposed block (same sum, second output)
 	std::vector<uint16_t> h_tab;
 };
 
@@ -252,11 +253,11 @@ __host__ __device__ __forceinline__ void iface_stage(const Iface& bot, ST& st)  
 	for (int i = 0; i < 6; ++i) st.put(21 + i, bot.F[i]);
 }
 
-// add the contributions of one table entry (fixed order) from the staged buffer st[slot][TILE_T]
+// add one contribution (a table word) from the staged buffer st[slot][TILE_T]
 __host__ __device__ __forceinline__ void entry_add(const double* st, const uint32_t x, double& a0, double& a1, double& a2, double& a3)
 {
-	const int t = x & 255, slot = (x >> 8) & 63, ty = x >> 14;
-	const double* b = st + slot * TILE_T + t;
+	const int ty = x >> 14;
+	const double* b = st + (x & 0x3fffu);
 	const int o1 = (ty == CT_ET) ? 2 : 1, o2 = (ty == CT_E) ? 2 : 1, o3 = (ty == CT_D) ? 2 : (ty == CT_F ? 1 : 3);
 	a0 += b[0]; a1 += b[o1 * TILE_T]; a2 += b[o2 * TILE_T]; a3 += b[o3 * TILE_T];
 }
@@ -287,7 +288,7 @@ struct DevStage {
 
 __global__ void __launch_bounds__(TILE_T + TILE_S, 1)
 k_tile(const int NL, const int W, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
-       const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const int32_t* __restrict__ out, const int64_t n_ent,
+       const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const int32_t* __restrict__ out, const int32_t* __restrict__ out2, const int64_t n_ent,
        const double4* __restrict__ geo, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -377,26 +378,32 @@ k_tile(const int NL, const int W, const int32_t* __restrict__ tvert, const int32
 		}
 		bar_sync(BAR_SUM, TILE_S);
 		for (int k = 0; k <= NZ; ++k) {
-			int o[16];
+			int o[TILE_EPT], o2[TILE_EPT];
 			const int32_t* ok = out + (size_t)k * n_ent + e_lo;
+			const int32_t* ok2 = out2 + (size_t)k * n_ent + e_lo;
 			#pragma unroll
-			for (int i = 0; i < 16; ++i) { const int e = sidx + i * TILE_S; o[i] = (e < ne) ? ok[e] : -1; }
+			for (int i = 0; i < TILE_EPT; ++i) { const int e = sidx + i * TILE_S; o[i] = (e < ne) ? ok[e] : -1; o2[i] = (e < ne) ? ok2[e] : -1; }
 			bar_sync(BAR_FULL, TILE_T + TILE_S);
 			#pragma unroll
-			for (int i = 0; i < 16; ++i) {
+			for (int i = 0; i < TILE_EPT; ++i) {
 				if (o[i] == -1) continue;
 				const int e = sidx + i * TILE_S;
 				double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-				for (int w8 = 0; w8 < W; w8 += 8) {
-					const uint4 q = *(const uint4*)(stab + (size_t)e * W + w8);
-					const uint32_t x[8] = { q.x & 0xffffu, q.x >> 16, q.y & 0xffffu, q.y >> 16, q.z & 0xffffu, q.z >> 16, q.w & 0xffffu, q.w >> 16 };
-					#pragma unroll
-					for (int c = 0; c < 8; ++c) if (x[c] != CW_NONE) entry_add(stage, x[c], a0, a1, a2, a3);
+				const uint16_t* w = stab + (size_t)e * W;
+				for (int c = 0; c < W; ++c) {
+					const uint32_t x = w[c];
+					if (x == CW_NONE) break;
+					entry_add(stage, x, a0, a1, a2, a3);
 				}
 				if (o[i] >= 0) {
 					double2* dst = (double2*)val + 2 * (size_t)o[i];
 					dst[0] = make_double2(a0, a1);
 					dst[1] = make_double2(a2, a3);
+					if (o2[i] >= 0) {                      // J is symmetric: the transposed block of the partner row, same sum
+						double2* dt = (double2*)val + 2 * (size_t)o2[i];
+						dt[0] = make_double2(a0, a2);
+						dt[1] = make_double2(a1, a3);
+					}
 				} else {
 					*(double2*)(F + 2 * (size_t)(-o[i] - 2)) = make_double2(a0, a1);
 				}
@@ -444,7 +451,7 @@ void bp_launch_tiles(bp_ctx* c, int what)
 		cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
 		T->attr_set = true;
 	}
-	k_tile<<<T->n_tiles, TILE_T + TILE_S, sm, c->stream>>>(T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_out,
+	k_tile<<<T->n_tiles, TILE_T + TILE_S, sm, c->stream>>>(T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_out, T->d_out2,
 	                                                         T->n_ent, c->d_geo, (const double2*)c->d_u, c->d_F, c->d_val, P);
 	c->launches++;
 }
@@ -453,7 +460,7 @@ void bp_tiles_free(bp_ctx* c)
 {
 	if (!c->tiles) return;
 	bp_tiles* T = c->tiles;
-	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_tab, T->d_ainv };
+	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_out2, T->d_tab, T->d_ainv };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	delete T;
 	c->tiles = nullptr;
@@ -613,28 +620,30 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		}
 	}
 	for (int32_t q = 0; q < n_ncol; ++q) if (col_owned[q] && ctp[q + 1] - ctp[q] > TILE_T) return no_tiles(c, "an ice column is touched by more prism columns than a tile holds");
-	// table entries a column brings into its tile: one per (kind, neighbour column) + one for F; and the largest
-	// number of prism columns around a column (= contributions of its diagonal / vertical blocks)
-	std::vector<int32_t> col_ent(n_ncol, 1);
+	// relations of every owned column: (kind, neighbour column) pairs, kind 0 same layer / 1 layer above / 2 layer below.
+	// A tile's table has one entry per diagonal block and per F row of its columns, one per relation that leaves the tile,
+	// and ONE per pair of relations inside the tile (J is symmetric: same sum, two outputs).
+	struct PK { int32_t p, q; int8_t kind; };
+	std::vector<PK> pk;
+	std::vector<int64_t> pkp(n_ncol + 1, 0);
 	int max_val = 0;
 	{
-		struct PK { int32_t p, q; int8_t kind; };
-		std::vector<PK> pk;
 		pk.reserve((size_t)ntri * 21);
 		for (int64_t r = 0; r < ntri; ++r) {
 			int32_t q[3] = { ncol_of_vcol[tri_col[3 * r]], ncol_of_vcol[tri_col[3 * r + 1]], ncol_of_vcol[tri_col[3 * r + 2]] };
 			for (int i = 0; i < 3; ++i) {
 				if (!col_owned[q[i]]) continue;
 				for (int j = 0; j < 3; ++j) {
-					pk.push_back({ q[i], q[j], 0 });
+					if (q[j] != q[i]) pk.push_back({ q[i], q[j], 0 });
 					if (j >= i) pk.push_back({ q[i], q[j], 1 });
 					if (j <= i) pk.push_back({ q[i], q[j], 2 });
 				}
 			}
 		}
 		std::sort(pk.begin(), pk.end(), [](const PK& a, const PK& b) { if (a.p != b.p) return a.p < b.p; if (a.kind != b.kind) return a.kind < b.kind; return a.q < b.q; });
-		for (size_t i = 0; i < pk.size(); ++i)
-			if (i == 0 || pk[i].p != pk[i - 1].p || pk[i].kind != pk[i - 1].kind || pk[i].q != pk[i - 1].q) col_ent[pk[i].p]++;
+		pk.erase(std::unique(pk.begin(), pk.end(), [](const PK& a, const PK& b) { return a.p == b.p && a.kind == b.kind && a.q == b.q; }), pk.end());
+		for (const PK& e : pk) pkp[e.p + 1]++;
+		for (int32_t q = 0; q < n_ncol; ++q) pkp[q + 1] += pkp[q];
 		for (int32_t q = 0; q < n_ncol; ++q) if (col_owned[q]) max_val = std::max(max_val, (int)(ctp[q + 1] - ctp[q]));
 	}
 	int W = (max_val <= 8) ? 8 : 16;
@@ -661,20 +670,37 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		if (ybin[a] != ybin[b]) return ybin[a] < ybin[b]; if (cx[a] != cx[b]) return cx[a] < cx[b]; if (cy[a] != cy[b]) return cy[a] < cy[b]; return a < b; });
 	std::vector<int32_t> tile_c0(1, 0);                            // tile -> range of own_cols
 	{
-		std::vector<int32_t> stamp(ntri, -1);
+		std::vector<int32_t> stamp(ntri, -1), in_tile(n_ncol, -1);
 		int ntile = 0, ntr = 0, ncl = 0, nen = 0;
+		// entries the tile's table grows by when column q joins it (see above)
+		auto grow = [&](int32_t q) {
+			int d = 2;
+			for (int64_t k = pkp[q]; k < pkp[q + 1]; ++k) {
+				const bool inside = in_tile[pk[k].q] == ntile || pk[k].q == q;
+				if (pk[k].kind == 0) d += inside ? 0 : 1;              // the pair entry was counted when the partner joined (as its relation leaving the tile)
+				else if (pk[k].kind == 1) d += 1;                      // own "above" relations: always one entry
+				else d += inside ? 0 : 1;                              // "below" relations inside the tile ride on the partner's "above" entry
+			}
+			// relations of columns already inside that pointed below at q were counted as leaving the tile: now they ride on q's "above" entries
+			for (int64_t k = pkp[q]; k < pkp[q + 1]; ++k)
+				if (pk[k].kind == 1 && pk[k].q != q && in_tile[pk[k].q] == ntile) d -= 1;
+			return d;
+		};
 		for (size_t i = 0; i < own_cols.size(); ++i) {
 			const int32_t q = own_cols[i];
 			int add = 0;
 			for (int64_t k = ctp[q]; k < ctp[q + 1]; ++k) if (stamp[ctl[k]] != ntile) ++add;
 			const bool new_strip = i > 0 && ybin[q] != ybin[own_cols[i - 1]];
-			if (col_ent[q] > max_ent) return no_tiles(c, "an ice column has more Jacobian blocks than a tile's table holds");
-			if (ncl > 0 && (ntr + add > TILE_T || ncl + 1 > TILE_MAXC || nen + col_ent[q] > max_ent || new_strip)) {
+			int de = grow(q);
+			if (pkp[q + 1] - pkp[q] + 2 > max_ent) return no_tiles(c, "an ice column has more Jacobian blocks than a tile's table holds");
+			if (ncl > 0 && (ntr + add > TILE_T || ncl + 1 > TILE_MAXC || nen + de > max_ent || new_strip)) {
 				tile_c0.push_back((int32_t)i); ++ntile; ntr = 0; ncl = 0; nen = 0;
 				add = (int)(ctp[q + 1] - ctp[q]);
+				de = grow(q);
 			}
 			for (int64_t k = ctp[q]; k < ctp[q + 1]; ++k) stamp[ctl[k]] = ntile;
-			ntr += add; ++ncl; nen += col_ent[q];
+			in_tile[q] = ntile;
+			ntr += add; ++ncl; nen += de;
 		}
 		tile_c0.push_back((int32_t)own_cols.size());
 	}
@@ -689,7 +715,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	T->h_nthr.assign(n_tiles, 0);
 	T->h_ent0.assign(n_tiles + 1, 0);
 	struct Con { int8_t kind; int64_t delta; int32_t p, q; int16_t t; uint8_t code; };
-	struct Ent { int8_t kind; int32_t p, q; };
+	struct Ent { int8_t kind, mirror; int32_t p, q; };       // mirror: -1 none, 0 / 2 the transposed block is the partner's same-layer / below block
 	std::vector<std::vector<Ent>> tile_ent(n_tiles);
 	std::vector<std::vector<uint32_t>> tile_eptr(n_tiles);
 	std::vector<std::vector<uint16_t>> tile_con(n_tiles);
@@ -761,9 +787,19 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 			std::vector<Ent>& E = tile_ent[tl];
 			std::vector<uint32_t>& ep = tile_eptr[tl];
 			std::vector<uint16_t>& cc = tile_con[tl];
+			bool keep = false;
 			for (size_t i = 0; i < cons.size(); ++i) {
-				if (i == 0 || cons[i].kind != cons[i - 1].kind || cons[i].p != cons[i - 1].p || cons[i].q != cons[i - 1].q) { E.push_back({ cons[i].kind, cons[i].p, cons[i].q }); ep.push_back((uint32_t)cc.size()); }
-				cc.push_back((uint16_t)((uint16_t)cons[i].t | ((uint16_t)cons[i].code << 9)));
+				if (i == 0 || cons[i].kind != cons[i - 1].kind || cons[i].p != cons[i - 1].p || cons[i].q != cons[i - 1].q) {
+					const int8_t kind = cons[i].kind;
+					const int32_t lq = local[cons[i].q];
+					int8_t mirror = -1;
+					keep = true;
+					if (kind == 0 && cons[i].q != cols[cons[i].p] && lq >= 0) { if (cons[i].p < lq) mirror = 0; else keep = false; }
+					else if (kind == 1 && lq >= 0) mirror = 2;
+					else if (kind == 2 && lq >= 0) keep = false;
+					if (keep) { E.push_back({ kind, mirror, cons[i].p, cons[i].q }); ep.push_back((uint32_t)cc.size()); }
+				}
+				if (keep) cc.push_back((uint16_t)((uint16_t)cons[i].t | ((uint16_t)cons[i].code << 9)));
 			}
 			ep.push_back((uint32_t)cc.size());
 			for (int32_t q : cols) local[q] = -1;
@@ -776,6 +812,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (ne > INT32_MAX / 32) { delete T; return no_tiles(c, "too many table entries for one rank"); }
 	T->n_ent = ne; T->n_contrib = ncn;
 	T->h_out.assign((size_t)NL * ne, -1);
+	T->h_out2.assign((size_t)NL * ne, -1);
 	{	// the packed table: W words per entry, contributions in ascending thread order, padded with CW_NONE
 		int maxc = 0;
 		for (int tl = 0; tl < n_tiles; ++tl)
@@ -824,6 +861,18 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 					#pragma omp atomic
 					hitF[-o - 2]++;
 				}
+				if (en.mirror >= 0 && o >= 0) {             // the transposed block: row = the partner's node, column = this column's node
+					const int32_t i2 = colnode[(size_t)en.q * NL + k + (en.mirror == 2 ? 1 : 0)];
+					const int32_t j2 = colnode[(size_t)pc * NL + k];
+					const int32_t* lo2 = c->h_col.data() + c->h_rowptr[i2];
+					const int32_t* hi2 = c->h_col.data() + c->h_rowptr[i2 + 1];
+					const int32_t* it2 = std::lower_bound(lo2, hi2, j2);
+					if (i2 >= no || it2 == hi2 || *it2 != j2) { miss = 1; continue; }
+					const int32_t om = c->h_sell_ptr[i2 >> 5] + 32 * (int32_t)(it2 - lo2) + (i2 & 31);
+					T->h_out2[(size_t)k * ne + T->h_ent0[tl] + e] = om;
+					#pragma omp atomic
+					hitJ[om]++;
+				}
 			}
 		}
 	}
@@ -842,6 +891,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (!rc) rc = up(c, &T->d_nthr, T->h_nthr);
 	if (!rc) rc = up(c, &T->d_ent0, T->h_ent0);
 	if (!rc) rc = up(c, &T->d_out, T->h_out);
+	if (!rc) rc = up(c, &T->d_out2, T->h_out2);
 	if (!rc) rc = up(c, &T->d_tab, T->h_tab);
 	if (!rc && !c->host_only) {
 		cudaError_t e = cudaMalloc((void**)&T->d_ainv, (size_t)n_tiles * NZ * 3 * TILE_T * sizeof(double));
@@ -851,7 +901,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (rc) { bp_tiles_free(c); return rc; }
 	if (!c->host_only) {                       // the emulator of a host-only context keeps the tables
 		std::vector<int32_t>().swap(T->h_vert); std::vector<int32_t>().swap(T->h_node); std::vector<int32_t>().swap(T->h_tet);
-		std::vector<int32_t>().swap(T->h_out); std::vector<uint16_t>().swap(T->h_tab);
+		std::vector<int32_t>().swap(T->h_out); std::vector<int32_t>().swap(T->h_out2); std::vector<uint16_t>().swap(T->h_tab);
 	}
 	if (c->prm.verbose)
 		fprintf(stderr, "[cslvr_b200] tiled cell assembly: %d tiles, %lld prism columns x %d layers, halo factor %.3f, %lld table entries\n",
@@ -907,9 +957,12 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 					const int o = T->h_out[(size_t)k * T->n_ent + e];
 					if (o == -1) continue;
 					double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-					for (int q = 0; q < W; ++q) { const uint32_t x = T->h_tab[(size_t)e * W + q]; if (x != CW_NONE) entry_add(stage.data(), x, a0, a1, a2, a3); }
-					if (o >= 0) { double* d = val.data() + 4 * (size_t)o; d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3; }
-					else { F[2 * (size_t)(-o - 2)] = a0; F[2 * (size_t)(-o - 2) + 1] = a1; }
+					for (int q = 0; q < W; ++q) { const uint32_t x = T->h_tab[(size_t)e * W + q]; if (x == CW_NONE) break; entry_add(stage.data(), x, a0, a1, a2, a3); }
+					if (o >= 0) {
+						double* d = val.data() + 4 * (size_t)o; d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
+						const int om = T->h_out2[(size_t)k * T->n_ent + e];
+						if (om >= 0) { double* dt = val.data() + 4 * (size_t)om; dt[0] = a0; dt[1] = a2; dt[2] = a1; dt[3] = a3; }
+					} else { F[2 * (size_t)(-o - 2)] = a0; F[2 * (size_t)(-o - 2) + 1] = a1; }
 				}
 			}
 		}
