@@ -556,7 +556,9 @@ int bp_assemble(bp_ctx* c, int what, const double* u, double* F, double* Jv, int
 	int rc = ready(c);
 	if (rc) return rc;
 	if (Jv && (rc = bp_build_csr_export(c))) return rc;
-	if (!on_device && !Jv && c->identity_dofs && !c->comm && c->nn == c->nn_owned && c->nd_ext == 2 * c->nn && bp_rows_gather_mode(c)
+	if (!on_device && !Jv && bp_tiles_pipeline_ready(c, what))
+		return bp_tiles_assemble_pipelined(c, what, u, F);
+	if (!on_device && !Jv && !bp_tiles_serve(c, what) && c->identity_dofs && !c->comm && c->nn == c->nn_owned && c->nd_ext == 2 * c->nn && bp_rows_gather_mode(c)
 	    && !(what & ~(BP_ASSEMBLE_F | BP_ASSEMBLE_J)) && !c->env.no_pipeline)
 		return assemble_pipelined(c, what, u, F);
 	if ((rc = vec_in(c, u, on_device, c->d_u))) return rc;

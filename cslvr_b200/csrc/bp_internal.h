@@ -166,6 +166,7 @@ struct bp_ctx {
 	// incidences reference (prefix maxima) and whether a facet integral touches one of its rows
 	std::vector<int32_t> h_blk_need_vert, h_blk_need_node;
 	std::vector<uint8_t> h_blk_facet;
+	std::vector<uint8_t> h_facet_node;   // owned node gets a facet integral (its F row is final after the facet kernel only)
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
 	std::vector<cudaEvent_t> pipe_ev;
 };
@@ -227,6 +228,8 @@ bool bp_tiles_serve(const bp_ctx* c, int what);           // the tiled kernel se
 void bp_launch_tiles(bp_ctx* c, int what);                // d_u -> d_F / d_val (cell integrals)
 void bp_tiles_update_ainv(bp_ctx* c);                     // d_ainv -> tile order (after k_tet_ainv)
 void bp_tiles_free(bp_ctx* c);
+bool bp_tiles_pipeline_ready(const bp_ctx* c, int what);  // host-buffer bp_assemble can run the tiled kernel pipelined
+int  bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F);
 
 // multigrid (bp_mg.cu)
 int  bp_mg_prepare(bp_ctx* c);      // numeric set-up for the current resident Jacobian

@@ -344,6 +344,8 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 				fn_inc[fn_ptr[r] + fillf[r]++] = (int32_t)(f * 4 + k);
 			}
 		c->n_fnodes = (int64_t)fn_node.size();
+		c->h_facet_node.assign((size_t)std::max<int64_t>(no, 1), 0);
+		for (int32_t nd_ : fn_node) c->h_facet_node[nd_] = 1;
 		UP(c->d_fn_node, fn_node.data(), fn_node.size());
 		UP(c->d_fn_ptr, fn_ptr.data(), fn_ptr.size());
 		UP(c->d_fn_inc, fn_inc.data(), fn_inc.size());

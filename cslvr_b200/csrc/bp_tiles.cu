@@ -67,6 +67,10 @@ struct bp_tiles {
 	// host copies (kept by host-only debug contexts for the emulator)
 	std::vector<int32_t> h_vert, h_node, h_tet, h_nthr, h_ent0, h_out, h_out2;   // out2: slot of the transposed block (same sum, second output)
 	std::vector<uint16_t> h_tab;
+	// host-buffer bp_assemble, pipelined: groups of consecutive tiles with the node ranges of u they need (beyond what the
+	// groups before them brought in) and the ranges of F rows they complete (those a facet integral adds to leave later)
+	struct Chunk { int tile0 = 0, ntile = 0; std::vector<std::pair<int32_t, int32_t>> in, out_plain, out_facet; };
+	std::vector<Chunk> chunks;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -287,7 +291,7 @@ struct DevStage {
 };
 
 __global__ void __launch_bounds__(TILE_T + TILE_S, 1)
-k_tile(const int NL, const int W, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
+k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
        const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const int32_t* __restrict__ out, const int32_t* __restrict__ out2, const int64_t n_ent,
        const double4* __restrict__ geo, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
 {
@@ -295,7 +299,7 @@ k_tile(const int NL, const int W, const int32_t* __restrict__ tvert, const int32
 	double* stage = (double*)smem_raw;                                              // [TILE_NSLOT][TILE_T]
 	uint4*  vbuf  = (uint4*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8);           // [2][9][TILE_T] 16-byte chunks
 	uint16_t* stab = (uint16_t*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 9 * TILE_T * 16);   // [entries][W]
-	const int tile = blockIdx.x;
+	const int tile = tile0 + blockIdx.x;
 	const int NZ = NL - 1;
 	if (threadIdx.x < TILE_T) {
 		// ================================================================= compute warps
@@ -441,7 +445,7 @@ bool bp_tiles_serve(const bp_ctx* c, int what)
 
 static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 9 * TILE_T * 16 + (size_t)TILE_TABW * 2; }
 
-void bp_launch_tiles(bp_ctx* c, int what)
+static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile)
 {
 	bp_tiles* T = c->tiles;
 	AsmParams P = bp_asm_params(c);
@@ -451,9 +455,69 @@ void bp_launch_tiles(bp_ctx* c, int what)
 		cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
 		T->attr_set = true;
 	}
-	k_tile<<<T->n_tiles, TILE_T + TILE_S, sm, c->stream>>>(T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_out, T->d_out2,
-	                                                         T->n_ent, c->d_geo, (const double2*)c->d_u, c->d_F, c->d_val, P);
+	if (ntile <= 0) return;
+	k_tile<<<ntile, TILE_T + TILE_S, sm, c->stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_out, T->d_out2,
+	                                                   T->n_ent, c->d_geo, (const double2*)c->d_u, c->d_F, c->d_val, P);
 	c->launches++;
+}
+
+void bp_launch_tiles(bp_ctx* c, int what) { launch_tiles_range(c, what, 0, c->tiles->n_tiles); }
+
+// Host-buffer assembly through the tiled kernel, pipelined over three streams (copies in, kernels, copies out; PCIe is
+// full duplex): u travels in the node ranges each group of tiles needs, the group's kernel starts as soon as its
+// ranges have arrived, and the F rows it completes start back right after it -- the rows a facet integral adds to
+// after the facet kernel.  Needs the caller's numbering to be the internal one (no ghosts, identity dof map).
+bool bp_tiles_pipeline_ready(const bp_ctx* c, int what)
+{
+	return bp_tiles_serve(c, what) && !(what & ~(BP_ASSEMBLE_F | BP_ASSEMBLE_J)) && !c->tiles->chunks.empty() && c->identity_dofs && !c->comm &&
+	       c->nn == c->nn_owned && c->nd_ext == 2 * c->nn && !c->env.no_pipeline;
+}
+
+int bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
+{
+	bp_tiles* T = c->tiles;
+	const int K = (int)T->chunks.size();
+	if (!c->s_h2d) {
+		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+		c->pipe_ev.resize(2 * 8 + 2);
+		for (auto& e : c->pipe_ev) BP_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	cudaEvent_t* e_h = c->pipe_ev.data();
+	cudaEvent_t* e_c = c->pipe_ev.data() + 8;
+	cudaEvent_t e_f = c->pipe_ev[16], e_0 = c->pipe_ev[17];
+	bp_update_ainv(c);
+	BP_CUDA(c, cudaEventRecord(e_0, c->stream));
+	BP_CUDA(c, cudaStreamWaitEvent(c->s_h2d, e_0, 0));
+	BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_0, 0));
+	for (int k = 0; k < K; ++k) {
+		for (const auto& r : T->chunks[k].in)
+			BP_CUDA(c, cudaMemcpyAsync(c->d_u + 2 * (size_t)r.first, u + 2 * (size_t)r.first, (size_t)(r.second - r.first) * 2 * sizeof(double), cudaMemcpyHostToDevice, c->s_h2d));
+		BP_CUDA(c, cudaEventRecord(e_h[k], c->s_h2d));
+	}
+	for (int k = 0; k < K; ++k) {
+		BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_h[k], 0));
+		launch_tiles_range(c, what, T->chunks[k].tile0, T->chunks[k].ntile);
+		BP_CUDA(c, cudaEventRecord(e_c[k], c->stream));
+	}
+	bp_launch_facets(c, what);
+	BP_CUDA(c, cudaEventRecord(e_f, c->stream));
+	if (what & BP_ASSEMBLE_J) c->have_J = true;
+	if (F) {
+		for (int k = 0; k < K; ++k) {
+			BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_c[k], 0));
+			for (const auto& r : T->chunks[k].out_plain)
+				BP_CUDA(c, cudaMemcpyAsync(F + 2 * (size_t)r.first, c->d_F + 2 * (size_t)r.first, (size_t)(r.second - r.first) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
+		}
+		BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_f, 0));
+		for (int k = 0; k < K; ++k)
+			for (const auto& r : T->chunks[k].out_facet)
+				BP_CUDA(c, cudaMemcpyAsync(F + 2 * (size_t)r.first, c->d_F + 2 * (size_t)r.first, (size_t)(r.second - r.first) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
+		BP_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+	}
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	BP_CUDA(c, cudaGetLastError());
+	return BP_OK;
 }
 
 void bp_tiles_free(bp_ctx* c)
@@ -884,6 +948,43 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		}
 	}
 	if (miss) { delete T; return no_tiles(c, "internal: the tile tables do not cover every Jacobian block exactly once"); }
+
+	// ---- groups of tiles for the pipelined host-buffer path
+	if (!c->host_only && c->identity_dofs && nn == no) {
+		const int K = std::max(1, std::min(c->env.pipe_k, std::min(8, n_tiles / 148)));
+		std::vector<uint8_t> have(nn, 0), mark(nn, 0);
+		const int GAP = 128;                                  // ranges closer than this are copied as one (the nodes between are needed later anyway)
+		T->chunks.resize(K);
+		for (int k = 0; k < K; ++k) {
+			bp_tiles::Chunk& ch = T->chunks[k];
+			ch.tile0 = (int)((int64_t)k * n_tiles / K);
+			ch.ntile = (int)((int64_t)(k + 1) * n_tiles / K) - ch.tile0;
+			std::fill(mark.begin(), mark.end(), 0);
+			for (size_t i = (size_t)ch.tile0 * NL * 3 * TILE_T; i < (size_t)(ch.tile0 + ch.ntile) * NL * 3 * TILE_T; ++i) mark[T->h_node[i]] = 1;
+			for (int64_t i = 0; i < nn; ) {
+				if (!mark[i] || have[i]) { ++i; continue; }
+				int64_t j = i, last = i;                          // extend over needed or not-yet-present nodes, never over present ones
+				while (j < nn && !have[j] && j - last <= GAP) { if (mark[j]) last = j; ++j; }
+				ch.in.push_back({ (int32_t)i, (int32_t)(last + 1) });
+				for (int64_t q = i; q <= last; ++q) have[q] = 1;
+				i = last + 1;
+			}
+			std::fill(mark.begin(), mark.end(), 0);
+			for (int tl = ch.tile0; tl < ch.tile0 + ch.ntile; ++tl)
+				for (int32_t q : tile_cols[tl]) for (int kk = 0; kk < NL; ++kk) mark[colnode[(size_t)q * NL + kk]] = 1;
+			for (int64_t i = 0; i < nn; ) {
+				if (!mark[i]) { ++i; continue; }
+				int64_t j = i;
+				bool facet = false;
+				while (j < nn && mark[j]) { facet |= (!c->h_facet_node.empty() && c->h_facet_node[j]); ++j; }
+				(facet ? ch.out_facet : ch.out_plain).push_back({ (int32_t)i, (int32_t)j });
+				i = j;
+			}
+		}
+		size_t nr = 0;
+		for (auto& ch : T->chunks) nr += ch.in.size() + ch.out_plain.size() + ch.out_facet.size();
+		if (nr > 600) T->chunks.clear();                      // a numbering without locality: too many small copies, the plain path serves it
+	}
 
 	int rc = up(c, &T->d_vert, T->h_vert);
 	if (!rc) rc = up(c, &T->d_node, T->h_node);
