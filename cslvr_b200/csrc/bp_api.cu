@@ -348,7 +348,7 @@ void bp_destroy(bp_ctx* c)
 	bp_tiles_free(c);
 	bp_mg_free(c);
 	bp_comm_free(c);
-	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, c->d_ext_dof,
+	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_zS, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_mirror, c->d_val, c->d_valf, c->d_csr_src, c->d_csr_out, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
 		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);

@@ -107,6 +107,7 @@ struct bp_ctx {
 	int64_t  n_inc_slots = 0;
 	double*  d_uvert = nullptr;          // [2*nv] u per vertex (only when vertices != nodes)
 	double*  d_soa = nullptr;            // [4][nv] x | y | z | S (struct-of-arrays copy of d_geo)
+	double2* d_zS = nullptr;             // per vertex {z, S}: what changes along an ice column (tiled cell kernel)
 	int32_t  max_row = 0;                // longest block row
 	int32_t* d_fac_cell = nullptr;       // [nf]
 	int32_t* d_fac_info = nullptr;       // [nf] local facet | basal<<8 | pressure<<9 | grounded<<10

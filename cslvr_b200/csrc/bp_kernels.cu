@@ -1169,13 +1169,13 @@ void bp_launch_csr_export(bp_ctx* c, double* out)
 	c->launches++;
 }
 
-__global__ void k_set_S(int nv, const double* __restrict__ S, double4* geo, double* soa_S)
+__global__ void k_set_S(int nv, const double* __restrict__ S, double4* geo, double* soa_S, double2* zS)
 {
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) { geo[i].w = S[i]; soa_S[i] = S[i]; }
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += gridDim.x * blockDim.x) { geo[i].w = S[i]; soa_S[i] = S[i]; zS[i].y = S[i]; }
 }
 void bp_launch_set_S(bp_ctx* c, const double* S_dev)
 {
-	k_set_S<<<red_blocks(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, S_dev, c->d_geo, c->d_soa + 3 * (size_t)c->nv);
+	k_set_S<<<red_blocks(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, S_dev, c->d_geo, c->d_soa + 3 * (size_t)c->nv, c->d_zS);
 	c->launches++;
 }
 

@@ -462,6 +462,9 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		std::vector<double> soa((size_t)4 * nv, 0.0);        // x | y | z | S, for the row-gather kernel
 		for (int64_t v = 0; v < nv; ++v) for (int d = 0; d < 3; ++d) soa[(size_t)d * nv + v] = m->coords[3 * v + d];
 		UP(c->d_soa, soa.data(), (size_t)4 * nv);
+		std::vector<double2> zs(nv);
+		for (int64_t v = 0; v < nv; ++v) zs[v] = make_double2(m->coords[3 * v + 2], 0.0);
+		UP(c->d_zS, zs.data(), nv);
 	}
 	UP(c->d_A, (const double*)nullptr, nv);
 	UP(c->d_beta, (const double*)nullptr, nv);

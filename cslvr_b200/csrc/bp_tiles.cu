@@ -33,11 +33,26 @@
 #include <cstring>
 #include <numeric>
 
-#define TILE_T      256        // compute threads per CTA = prism columns per tile (incl. halo)
+// Two shapes (compile time): 256 compute + 128 summing threads, one CTA per SM (registers 224 / 56 after setmaxnreg), or
+// -DTILE_SMALL: 128 + 128 threads, two CTAs per SM (216 / 40) -- smaller tiles recompute more halo prisms but two
+// independent CTAs keep the FP64 pipe busier.
+#ifdef TILE_SMALL
+#define TILE_T      128        // compute threads per CTA = prism columns per tile (incl. halo)
 #define TILE_S      128        // summing threads per CTA (one warpgroup)
+#define TILE_CTAS   2
+#define TILE_REG_C  "216"
+#define TILE_REG_S  "40"
+#define TILE_EPT    5          // table entries per summing thread
+#else
+#define TILE_T      256
+#define TILE_S      128
+#define TILE_CTAS   1
+#define TILE_REG_C  "224"      // 256 x 56 more registers for the compute warps = ...
+#define TILE_REG_S  "56"       // ... the 128 x 112 the summing warps release into the CTA's pool
+#define TILE_EPT    9
+#endif
 #define TILE_NSLOT  51         // staged doubles per compute thread and layer
 #define TILE_MAXC   120        // ice columns owned by one tile
-#define TILE_EPT     9          // table entries per summing thread
 #define TILE_MAXE   (TILE_EPT * TILE_S)   // table entries per tile
 #define TILE_TABW   (8 * TILE_MAXE)       // contribution words (uint16) of one tile's table in shared memory
 
@@ -62,11 +77,14 @@ struct bp_tiles {
 	int64_t n_ent = 0, n_contrib = 0, n_prism_cols = 0, n_threads_used = 0;
 	int32_t *d_vert = nullptr, *d_node = nullptr, *d_tet = nullptr, *d_nthr = nullptr, *d_ent0 = nullptr, *d_out = nullptr, *d_out2 = nullptr;
 	uint16_t *d_tab = nullptr;                // [n_ent][W]
+	uint16_t *d_tflag = nullptr;              // [n_tiles][TILE_T] which staged blocks a compute thread writes transposed
+	uint8_t  *d_einfo = nullptr;              // [n_ent] contributions (bits 0-4) | mixed types (bit 5) | kind (bits 6-7: 0 block, 1 diagonal, 2 F)
 	double  *d_ainv = nullptr;
 	bool     attr_set = false;
 	// host copies (kept by host-only debug contexts for the emulator)
 	std::vector<int32_t> h_vert, h_node, h_tet, h_nthr, h_ent0, h_out, h_out2;   // out2: slot of the transposed block (same sum, second output)
-	std::vector<uint16_t> h_tab;
+	std::vector<uint16_t> h_tab, h_tflag;
+	std::vector<uint8_t> h_einfo;
 	// host-buffer bp_assemble, pipelined: groups of consecutive tiles with the node ranges of u they need (beyond what the
 	// groups before them brought in) and the ranges of F rows they complete (those a facet integral adds to leave later)
 	struct Chunk { int tile0 = 0, ntile = 0; std::vector<std::pair<int32_t, int32_t>> in, out_plain, out_facet; };
@@ -178,6 +196,16 @@ __host__ __device__ __forceinline__ void iface_zero(Iface& a)
 // of the bottom interface; every staged value goes out as soon as it is final (after the tet that touches it last), so
 // few accumulators stay live; top is SET to this prism's part of the top interface.  st.gate() is called once, before
 // the first store (the kernel waits there until the summing warps have released the staging buffer).
+// stage a 2x2 block (xx xy yx yy) in the orientation its (single) consumer wants: block b of this thread is read
+// transposed iff bit b of the thread's flag word is set (E01 E02 E12 C00 C01 C02 C11 C12 C22 = bits 0..8), so the summing
+// warps never have to look at the type of a contribution
+template <class ST>
+__host__ __device__ __forceinline__ void put_blk(ST& st, const int slot, const int blk, const double xx, const double xy, const double yx, const double yy)
+{
+	const bool f = (st.flags >> blk) & 1u;
+	st.put(slot, xx); st.put(slot + 1, f ? yx : xy); st.put(slot + 2, f ? xy : yx); st.put(slot + 3, yy);
+}
+
 template <class ST>
 __host__ __device__ __forceinline__ void prism_steps(const double4* pb, const double2* ub, const double4* pt, const double2* ut,
                                                       const double a0, const double a1, const double a2, const AsmParams& P,
@@ -190,11 +218,11 @@ __host__ __device__ __forceinline__ void prism_steps(const double4* pb, const do
 	st.gate();
 	#pragma unroll
 	for (int i = 0; i < 3; ++i) st.put(6 + i, bot.D[6 + i] + o.D[6 + i]);                 // D(b2)
+	put_blk(st, 13, 1, bot.E[4] + o.E[4], bot.E[5] + o.E[5], bot.E[6] + o.E[6], bot.E[7] + o.E[7]);           // (0,2) -> E(b0b2)
+	put_blk(st, 17, 2, bot.E[8] + o.E[12], bot.E[9] + o.E[13], bot.E[10] + o.E[14], bot.E[11] + o.E[15]);     // (1,2) -> E(b1b2)
+	put_blk(st, 47, 8, o.E[20], o.E[21], o.E[22], o.E[23]);                                                   // (2,3) -> C22
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		st.put(13 + i, bot.E[4 + i] + o.E[4 + i]);                                         // (0,2) -> E(b0b2)
-		st.put(17 + i, bot.E[8 + i] + o.E[12 + i]);                                        // (1,2) -> E(b1b2)
-		st.put(47 + i, o.E[20 + i]);                                                       // (2,3) -> C22
 		bot.E[i] += o.E[i];                                                                // (0,1) -> E(b0b1)
 		C02[i] = o.E[8 + i];                                                               // (0,3) -> C02
 		C12[i] = o.E[16 + i];                                                              // (1,3) -> C12
@@ -210,11 +238,11 @@ __host__ __device__ __forceinline__ void prism_steps(const double4* pb, const do
 	tet_eval(pb[0], pb[1], pt[1], pt[2], ub[0], ub[1], ut[1], ut[2], a1, P, o);
 	#pragma unroll
 	for (int i = 0; i < 3; ++i) st.put(3 + i, bot.D[3 + i] + o.D[3 + i]);                 // D(b1)
+	put_blk(st, 9, 0, bot.E[0] + o.E[0], bot.E[1] + o.E[1], bot.E[2] + o.E[2], bot.E[3] + o.E[3]);            // (0,1) -> E(b0b1)
+	put_blk(st, 39, 6, o.E[12], o.E[13], o.E[14], o.E[15]);                                                   // (1,2) -> C11
+	put_blk(st, 43, 7, C12[0] + o.E[16], C12[1] + o.E[17], C12[2] + o.E[18], C12[3] + o.E[19]);               // (1,3) -> C12
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		st.put(9 + i, bot.E[i] + o.E[i]);                                                  // (0,1) -> E(b0b1)
-		st.put(39 + i, o.E[12 + i]);                                                       // (1,2) -> C11
-		st.put(43 + i, C12[i] + o.E[16 + i]);                                              // (1,3) -> C12
 		C01[i] = o.E[4 + i];                                                               // (0,2) -> C01
 		C02[i] += o.E[8 + i];                                                              // (0,3) -> C02
 		top.E[8 + i] = o.E[20 + i];                                                        // (2,3) -> E(t1t2)
@@ -230,11 +258,11 @@ __host__ __device__ __forceinline__ void prism_steps(const double4* pb, const do
 	#pragma unroll
 	for (int i = 0; i < 3; ++i) st.put(i, bot.D[i] + o.D[i]);                             // D(b0)
 	st.put(21, bot.F[0] + o.F[0]); st.put(22, bot.F[1] + o.F[1]);                          // F(b0)
+	put_blk(st, 27, 3, o.E[0], o.E[1], o.E[2], o.E[3]);                                                       // (0,1) -> C00
+	put_blk(st, 31, 4, C01[0] + o.E[4], C01[1] + o.E[5], C01[2] + o.E[6], C01[3] + o.E[7]);                   // (0,2) -> C01
+	put_blk(st, 35, 5, C02[0] + o.E[8], C02[1] + o.E[9], C02[2] + o.E[10], C02[3] + o.E[11]);                 // (0,3) -> C02
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		st.put(27 + i, o.E[i]);                                                            // (0,1) -> C00
-		st.put(31 + i, C01[i] + o.E[4 + i]);                                               // (0,2) -> C01
-		st.put(35 + i, C02[i] + o.E[8 + i]);                                               // (0,3) -> C02
 		top.E[i]      = o.E[12 + i];                                                       // (1,2) -> E(t0t1)
 		top.E[4 + i]  = o.E[16 + i];                                                       // (1,3) -> E(t0t2)
 		top.E[8 + i] += o.E[20 + i];                                                       // (2,3) -> E(t1t2)
@@ -252,7 +280,7 @@ __host__ __device__ __forceinline__ void iface_stage(const Iface& bot, ST& st)  
 	#pragma unroll
 	for (int i = 0; i < 9; ++i) st.put(i, bot.D[i]);
 	#pragma unroll
-	for (int i = 0; i < 12; ++i) st.put(9 + i, bot.E[i]);
+	for (int b = 0; b < 3; ++b) put_blk(st, 9 + 4 * b, b, bot.E[4 * b], bot.E[4 * b + 1], bot.E[4 * b + 2], bot.E[4 * b + 3]);
 	#pragma unroll
 	for (int i = 0; i < 6; ++i) st.put(21 + i, bot.F[i]);
 }
@@ -266,9 +294,34 @@ __host__ __device__ __forceinline__ void entry_add(const double* st, const uint3
 	a0 += b[0]; a1 += b[o1 * TILE_T]; a2 += b[o2 * TILE_T]; a3 += b[o3 * TILE_T];
 }
 
+// the sum of one table entry: its contributions in table order
+__host__ __device__ __forceinline__ void entry_total(const double* stage, const uint16_t* w, const uint32_t info, double& a0, double& a1, double& a2, double& a3)
+{
+	const int cnt = info & 31, kind = info >> 6;
+	if (info & 32) {                                   // contributions of different types (rare: columns that meet themselves)
+		for (int c = 0; c < cnt; ++c) entry_add(stage, w[c], a0, a1, a2, a3);
+	} else if (kind == 0) {                            // 2x2 blocks, staged in the orientation this entry wants
+		for (int c = 0; c < cnt; ++c) {
+			const double* b = stage + (w[c] & 0x3fffu);
+			a0 += b[0]; a1 += b[TILE_T]; a2 += b[2 * TILE_T]; a3 += b[3 * TILE_T];
+		}
+	} else if (kind == 1) {                            // diagonal blocks: symmetric, three numbers staged
+		for (int c = 0; c < cnt; ++c) {
+			const double* b = stage + (w[c] & 0x3fffu);
+			const double xy = b[TILE_T];
+			a0 += b[0]; a1 += xy; a2 += xy; a3 += b[2 * TILE_T];
+		}
+	} else {                                           // F rows
+		for (int c = 0; c < cnt; ++c) {
+			const double* b = stage + (w[c] & 0x3fffu);
+			a0 += b[0]; a1 += b[TILE_T];
+		}
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // the kernel: 8 compute warps (one thread per prism column) + 4 summing warps, registers re-balanced with
-// setmaxnreg (224 / 56: the CTA's register pool is conserved), hand-over through two named barriers:
+// setmaxnreg (TILE_REG_C / TILE_REG_S: the CTA's register pool is conserved), hand-over through two named barriers:
 //   FULL   compute warps arrive after staging layer k, summing warps wait
 //   EMPTY  summing warps arrive after reading layer k, compute warps wait before they stage layer k + 1
 // so the sums of layer k overlap the element math of layer k + 1.  The vertex data of the next layer arrives by
@@ -285,26 +338,29 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 }
 
 struct DevStage {
-	double* sb; bool wait;
+	double* sb; bool wait; uint32_t flags;
 	__device__ __forceinline__ void gate() { if (wait) bar_sync(BAR_EMPTY, TILE_T + TILE_S); }
 	__device__ __forceinline__ void put(const int slot, const double v) { sb[slot * TILE_T] = v; }
 };
 
-__global__ void __launch_bounds__(TILE_T + TILE_S, 1)
+__global__ void __launch_bounds__(TILE_T + TILE_S, TILE_CTAS)
 k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
-       const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const int32_t* __restrict__ out, const int32_t* __restrict__ out2, const int64_t n_ent,
-       const double4* __restrict__ geo, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
+       const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const uint8_t* __restrict__ einfo, const uint16_t* __restrict__ tflag,
+       const int32_t* __restrict__ out, const int32_t* __restrict__ out2, const int64_t n_ent,
+       const double4* __restrict__ geo, const double2* __restrict__ zS, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	double* stage = (double*)smem_raw;                                              // [TILE_NSLOT][TILE_T]
-	uint4*  vbuf  = (uint4*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8);           // [2][9][TILE_T] 16-byte chunks
-	uint16_t* stab = (uint16_t*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 9 * TILE_T * 16);   // [entries][W]
+	double2* vbuf = (double2*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8);         // [2][6][TILE_T]: {z, S} and {u_x, u_y} of three vertices
+	uint16_t* stab = (uint16_t*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 6 * TILE_T * 16);   // [entries][W]
+	uint8_t* sinfo = (uint8_t*)(stab + TILE_TABW);                                  // [entries]
 	const int tile = tile0 + blockIdx.x;
 	const int NZ = NL - 1;
 	if (threadIdx.x < TILE_T) {
 		// ================================================================= compute warps
-		asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");     // ... which is exactly what 256 x 56 more take out of it
+		asm volatile("setmaxnreg.inc.sync.aligned.u32 " TILE_REG_C ";");
 		const int t = threadIdx.x;
+		const uint32_t tflags = tflag[(size_t)tile * TILE_T + t];
 		const int32_t* tv = tvert + (size_t)tile * NL * 3 * TILE_T + t;
 		const int32_t* tn = tnode + (size_t)tile * NL * 3 * TILE_T + t;
 		const double*  ta = tainv + (size_t)tile * NZ * 3 * TILE_T + t;
@@ -317,14 +373,10 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		for (int i = 0; i < 3; ++i) { iv[i] = tv[(3 + i) * TILE_T]; in[i] = tn[(3 + i) * TILE_T]; }        // layer 1
 		#pragma unroll
 		for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }            // layer 0: straight into registers
-		{	// layer 1 -> vbuf[0]
-			uint4* vb = vbuf + t;
+		{	// layer 1 -> vbuf[0]: only z, S and u change along a column
+			double2* vb = vbuf + t;
 			#pragma unroll
-			for (int i = 0; i < 3; ++i) {
-				cp_async16(vb + (3 * i) * TILE_T, &geo[iv[i]]);
-				cp_async16(vb + (3 * i + 1) * TILE_T, (const char*)&geo[iv[i]] + 16);
-				cp_async16(vb + (3 * i + 2) * TILE_T, &u[in[i]]);
-			}
+			for (int i = 0; i < 3; ++i) { cp_async16(vb + (2 * i) * TILE_T, &zS[iv[i]]); cp_async16(vb + (2 * i + 1) * TILE_T, &u[in[i]]); }
 			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
 		if (NZ >= 2) {
@@ -335,29 +387,25 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			const double a0 = ta[(k * 3) * TILE_T], a1 = ta[(k * 3 + 1) * TILE_T], a2 = ta[(k * 3 + 2) * TILE_T];
 			asm volatile("cp.async.wait_group 0;" ::: "memory");
 			{	// the top layer of this prism
-				const uint4* vb = vbuf + (size_t)(k & 1) * 9 * TILE_T + t;
+				const double2* vb = vbuf + (size_t)(k & 1) * 6 * TILE_T + t;
 				#pragma unroll
 				for (int i = 0; i < 3; ++i) {
-					const uint4 q0 = vb[(3 * i) * TILE_T], q1 = vb[(3 * i + 1) * TILE_T], q2 = vb[(3 * i + 2) * TILE_T];
-					pt[i] = make_double4(__hiloint2double(q0.y, q0.x), __hiloint2double(q0.w, q0.z), __hiloint2double(q1.y, q1.x), __hiloint2double(q1.w, q1.z));
-					ut[i] = make_double2(__hiloint2double(q2.y, q2.x), __hiloint2double(q2.w, q2.z));
+					const double2 q0 = vb[(2 * i) * TILE_T];
+					pt[i] = make_double4(pb[i].x, pb[i].y, q0.x, q0.y);
+					ut[i] = vb[(2 * i + 1) * TILE_T];
 				}
 			}
 			if (k + 2 <= NZ) {                  // layer k + 2 -> the other buffer, while this prism is computed
-				uint4* vb = vbuf + (size_t)((k + 1) & 1) * 9 * TILE_T + t;
+				double2* vb = vbuf + (size_t)((k + 1) & 1) * 6 * TILE_T + t;
 				#pragma unroll
-				for (int i = 0; i < 3; ++i) {
-					cp_async16(vb + (3 * i) * TILE_T, &geo[iv[i]]);
-					cp_async16(vb + (3 * i + 1) * TILE_T, (const char*)&geo[iv[i]] + 16);
-					cp_async16(vb + (3 * i + 2) * TILE_T, &u[in[i]]);
-				}
+				for (int i = 0; i < 3; ++i) { cp_async16(vb + (2 * i) * TILE_T, &zS[iv[i]]); cp_async16(vb + (2 * i + 1) * TILE_T, &u[in[i]]); }
 				asm volatile("cp.async.commit_group;" ::: "memory");
 				if (k + 3 <= NZ) {
 					#pragma unroll
 					for (int i = 0; i < 3; ++i) { iv[i] = tv[((k + 3) * 3 + i) * TILE_T]; in[i] = tn[((k + 3) * 3 + i) * TILE_T]; }
 				}
 			}
-			DevStage st = { stage + t, k > 0 };
+			DevStage st = { stage + t, k > 0, tflags };
 			prism_steps(pb, ub, pt, ut, a0, a1, a2, P, bot, top, st);
 			__threadfence_block();
 			bar_arrive(BAR_FULL, TILE_T + TILE_S);
@@ -365,13 +413,13 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			#pragma unroll
 			for (int i = 0; i < 3; ++i) { pb[i] = pt[i]; ub[i] = ut[i]; }
 		}
-		DevStage st = { stage + t, NZ > 0 };
+		DevStage st = { stage + t, NZ > 0, tflags };
 		iface_stage(bot, st);
 		__threadfence_block();
 		bar_arrive(BAR_FULL, TILE_T + TILE_S);
 	} else {
 		// ================================================================= summing warps
-		asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");      // releases 128 x 112 registers into the CTA pool ...
+		asm volatile("setmaxnreg.dec.sync.aligned.u32 " TILE_REG_S ";");
 		const int sidx = threadIdx.x - TILE_T;
 		const int e_lo = ent0[tile], ne = ent0[tile + 1] - e_lo;
 		{	// the tile's table -> shared memory (16-byte pieces)
@@ -379,6 +427,7 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			uint4* dst = (uint4*)stab;
 			const int n16 = ne * W / 8;
 			for (int i = sidx; i < n16; i += TILE_S) dst[i] = src[i];
+			for (int i = sidx; i < ne; i += TILE_S) sinfo[i] = einfo[e_lo + i];
 		}
 		bar_sync(BAR_SUM, TILE_S);
 		for (int k = 0; k <= NZ; ++k) {
@@ -394,11 +443,7 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 				const int e = sidx + i * TILE_S;
 				double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 				const uint16_t* w = stab + (size_t)e * W;
-				for (int c = 0; c < W; ++c) {
-					const uint32_t x = w[c];
-					if (x == CW_NONE) break;
-					entry_add(stage, x, a0, a1, a2, a3);
-				}
+				entry_total(stage, w, sinfo[e], a0, a1, a2, a3);
 				if (o[i] >= 0) {
 					double2* dst = (double2*)val + 2 * (size_t)o[i];
 					dst[0] = make_double2(a0, a1);
@@ -443,7 +488,7 @@ bool bp_tiles_serve(const bp_ctx* c, int what)
 	return c->env.asm_tiled != 0;
 }
 
-static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 9 * TILE_T * 16 + (size_t)TILE_TABW * 2; }
+static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 6 * TILE_T * 16 + (size_t)TILE_TABW * 2 + TILE_MAXE; }
 
 static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile)
 {
@@ -456,8 +501,8 @@ static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile)
 		T->attr_set = true;
 	}
 	if (ntile <= 0) return;
-	k_tile<<<ntile, TILE_T + TILE_S, sm, c->stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_out, T->d_out2,
-	                                                   T->n_ent, c->d_geo, (const double2*)c->d_u, c->d_F, c->d_val, P);
+	k_tile<<<ntile, TILE_T + TILE_S, sm, c->stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_einfo, T->d_tflag, T->d_out, T->d_out2,
+	                                                   T->n_ent, c->d_geo, c->d_zS, (const double2*)c->d_u, c->d_F, c->d_val, P);
 	c->launches++;
 }
 
@@ -524,7 +569,7 @@ void bp_tiles_free(bp_ctx* c)
 {
 	if (!c->tiles) return;
 	bp_tiles* T = c->tiles;
-	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_out2, T->d_tab, T->d_ainv };
+	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_out2, T->d_tab, T->d_tflag, T->d_einfo, T->d_ainv };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	delete T;
 	c->tiles = nullptr;
@@ -579,6 +624,9 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 			const int32_t v = ord[q * NL + k];
 			if (key[v] != key[ord[q * NL]] || (k && !(m->coords[3 * v + 2] > m->coords[3 * (int64_t)ord[q * NL + k - 1] + 2])))
 				return no_tiles(c, "vertices do not form columns of equal length");
+			// the kernel carries x, y once per column: they must be the same numbers on every layer
+			if (m->coords[3 * (int64_t)v] != m->coords[3 * (int64_t)ord[q * NL]] || m->coords[3 * (int64_t)v + 1] != m->coords[3 * (int64_t)ord[q * NL] + 1])
+				return no_tiles(c, "x, y are not bitwise equal along a vertex column");
 			vcol[v] = (int32_t)q; vlay[v] = k;
 		}
 	if (nt % (3 * NZ)) return no_tiles(c, "cell count is not 3 x layers x triangles");
@@ -727,7 +775,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	}
 	const double area = std::max(ohi[0] - olo[0], 1e-300) * std::max(ohi[1] - olo[1], 1e-300);
 	const double rho = (double)own_cols.size() / area;
-	const double strip_h = 7.0 / std::sqrt(rho);                  // ~7 rows of columns per strip: (7 + 1) x (15 + 1) x 2 = 256 prism columns
+	const double strip_h = 7.0 / std::sqrt(rho);                  // ~7 rows of columns per strip: (7 + 1) x (15 + 1) x 2 = 256 prism columns (x 8 for 128)
 	std::vector<int64_t> ybin(n_ncol, 0);
 	for (int32_t q : own_cols) ybin[q] = (int64_t)std::floor((cy[q] - olo[1]) / strip_h + 1e-9);
 	std::sort(own_cols.begin(), own_cols.end(), [&](int32_t a, int32_t b) {
@@ -885,15 +933,34 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		for (int tl = 0; tl < n_tiles && fits; ++tl) fits = (int64_t)tile_ent[tl].size() <= std::min<int64_t>(TILE_MAXE, TILE_TABW / W);
 		if (!fits) { delete T; return no_tiles(c, "a Jacobian block gets more contributions than a table entry holds"); }
 		T->h_tab.assign((size_t)ne * W, (uint16_t)CW_NONE);
-		for (int tl = 0; tl < n_tiles; ++tl)
+		T->h_einfo.assign((size_t)ne, 0);
+		T->h_tflag.assign((size_t)n_tiles * TILE_T, 0);
+		std::vector<uint16_t> seen((size_t)TILE_T);
+		for (int tl = 0; tl < n_tiles; ++tl) {
+			std::fill(seen.begin(), seen.end(), 0);
+			uint16_t* flg = T->h_tflag.data() + (size_t)tl * TILE_T;
 			for (size_t e = 0; e < tile_ent[tl].size(); ++e) {
 				uint16_t* dst = T->h_tab.data() + ((size_t)T->h_ent0[tl] + e) * W;
+				const int cnt = (int)(tile_eptr[tl][e + 1] - tile_eptr[tl][e]);
+				int types = 0;
 				for (uint32_t q = tile_eptr[tl][e]; q < tile_eptr[tl][e + 1]; ++q) {
 					const uint16_t w = tile_con[tl][q];
 					const int t = w & 511, code = w >> 9;
-					*dst++ = CW(t, H_CODE_BASE[code], H_CODE_TYPE[code]);
+					int ty = H_CODE_TYPE[code];
+					if (ty == CT_E || ty == CT_ET) {
+						// the staged block: E01 E02 E12 = 0..2, C00..C22 = 3..8; its first consumer decides how the thread stages it
+						const int blk = (code < 9) ? (code - 3) % 3 : 3 + (code - 9) % 6;
+						const bool want_t = (ty == CT_ET);
+						if (!((seen[t] >> blk) & 1)) { seen[t] |= (uint16_t)(1u << blk); if (want_t) flg[t] |= (uint16_t)(1u << blk); }
+						ty = (want_t == (bool)((flg[t] >> blk) & 1)) ? CT_E : CT_ET;
+					}
+					types |= 1 << ty;
+					*dst++ = CW(t, H_CODE_BASE[code], ty);
 				}
+				const int kind = (types == (1 << CT_E)) ? 0 : (types == (1 << CT_D)) ? 1 : (types == (1 << CT_F)) ? 2 : 3;
+				T->h_einfo[(size_t)T->h_ent0[tl] + e] = (uint8_t)(cnt | (kind == 3 ? 32 : 0) | ((kind & 3) << 6));
 			}
+		}
 	}
 	// output slots per layer, and the exactly-once check
 	std::vector<uint8_t> hitJ((size_t)std::max<int64_t>(c->n_slots, 1), 0), hitF((size_t)no, 0);
@@ -994,6 +1061,8 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (!rc) rc = up(c, &T->d_out, T->h_out);
 	if (!rc) rc = up(c, &T->d_out2, T->h_out2);
 	if (!rc) rc = up(c, &T->d_tab, T->h_tab);
+	if (!rc) rc = up(c, &T->d_tflag, T->h_tflag);
+	if (!rc) rc = up(c, &T->d_einfo, T->h_einfo);
 	if (!rc && !c->host_only) {
 		cudaError_t e = cudaMalloc((void**)&T->d_ainv, (size_t)n_tiles * NZ * 3 * TILE_T * sizeof(double));
 		if (e != cudaSuccess) rc = bp_fail(c, BP_ERR_CUDA, "cudaMalloc(tile ainv) failed: %s", cudaGetErrorString(e));
@@ -1002,7 +1071,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (rc) { bp_tiles_free(c); return rc; }
 	if (!c->host_only) {                       // the emulator of a host-only context keeps the tables
 		std::vector<int32_t>().swap(T->h_vert); std::vector<int32_t>().swap(T->h_node); std::vector<int32_t>().swap(T->h_tet);
-		std::vector<int32_t>().swap(T->h_out); std::vector<int32_t>().swap(T->h_out2); std::vector<uint16_t>().swap(T->h_tab);
+		std::vector<int32_t>().swap(T->h_out); std::vector<int32_t>().swap(T->h_out2); std::vector<uint16_t>().swap(T->h_tab); std::vector<uint8_t>().swap(T->h_einfo);
 	}
 	if (c->prm.verbose)
 		fprintf(stderr, "[cslvr_b200] tiled cell assembly: %d tiles, %lld prism columns x %d layers, halo factor %.3f, %lld table entries\n",
@@ -1025,7 +1094,7 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 	const double2* u2 = (const double2*)u;
 	std::vector<double> val((size_t)c->n_slots * 4, 0.0);
 	struct HostStage {
-		double* sb;
+		double* sb; uint32_t flags;
 		void gate() {}
 		void put(int slot, double v) { sb[(size_t)slot * TILE_T] = v; }
 	};
@@ -1039,7 +1108,7 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 			for (int t = 0; t < TILE_T; ++t) iface_zero(bot[t]);
 			for (int k = 0; k <= NZ; ++k) {
 				for (int t = 0; t < TILE_T; ++t) {           // every compute thread, padding threads (vertex 0, ainv 0) included
-					HostStage st = { stage.data() + t };
+					HostStage st = { stage.data() + t, T->h_tflag[(size_t)tile * TILE_T + t] };
 					if (k < NZ) {
 						double4 pb[3], pt[3]; double2 ub[3], ut[3];
 						for (int i = 0; i < 3; ++i) {
@@ -1058,7 +1127,7 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 					const int o = T->h_out[(size_t)k * T->n_ent + e];
 					if (o == -1) continue;
 					double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-					for (int q = 0; q < W; ++q) { const uint32_t x = T->h_tab[(size_t)e * W + q]; if (x == CW_NONE) break; entry_add(stage.data(), x, a0, a1, a2, a3); }
+					entry_total(stage.data(), T->h_tab.data() + (size_t)e * W, T->h_einfo[e], a0, a1, a2, a3);
 					if (o >= 0) {
 						double* d = val.data() + 4 * (size_t)o; d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
 						const int om = T->h_out2[(size_t)k * T->n_ent + e];
