@@ -43,13 +43,20 @@
 #define TILE_REG_C  "216"
 #define TILE_REG_S  "40"
 #define TILE_EPT    5          // table entries per summing thread
-#else
+#elif defined(TILE_S128)
 #define TILE_T      256
 #define TILE_S      128
 #define TILE_CTAS   1
 #define TILE_REG_C  "224"      // 256 x 56 more registers for the compute warps = ...
 #define TILE_REG_S  "56"       // ... the 128 x 112 the summing warps release into the CTA's pool
 #define TILE_EPT    9
+#else
+#define TILE_T      256        // 8 compute warps
+#define TILE_S      256        // 8 summing warps: two per scheduler, the sums of a layer take half as long
+#define TILE_CTAS   1
+#define TILE_REG_C  "216"      // launch bound 512 threads -> 128 registers each; 256 x 88 move from the summing to the compute warps
+#define TILE_REG_S  "40"
+#define TILE_EPT    5
 #endif
 #define TILE_NSLOT  51         // staged doubles per compute thread and layer
 #define TILE_MAXC   120        // ice columns owned by one tile
@@ -215,27 +222,47 @@ __host__ __device__ __forceinline__ void prism_steps(const double4* pb, const do
 	double C01[4], C02[4], C12[4];
 	// ---- tet A = (b0 b1 b2 t2): local 0 1 2 3.  Final afterwards: everything of b2, C22
 	tet_eval(pb[0], pb[1], pb[2], pt[2], ub[0], ub[1], ub[2], ut[2], a0, P, o);
-	st.gate();
+	// what tet A makes final is kept in registers until the gate after tet B: the summing warps then have two thirds of
+	// a prism's time to finish with the previous layer
+	double fin[17];
 	#pragma unroll
-	for (int i = 0; i < 3; ++i) st.put(6 + i, bot.D[6 + i] + o.D[6 + i]);                 // D(b2)
-	put_blk(st, 13, 1, bot.E[4] + o.E[4], bot.E[5] + o.E[5], bot.E[6] + o.E[6], bot.E[7] + o.E[7]);           // (0,2) -> E(b0b2)
-	put_blk(st, 17, 2, bot.E[8] + o.E[12], bot.E[9] + o.E[13], bot.E[10] + o.E[14], bot.E[11] + o.E[15]);     // (1,2) -> E(b1b2)
-	put_blk(st, 47, 8, o.E[20], o.E[21], o.E[22], o.E[23]);                                                   // (2,3) -> C22
+	for (int i = 0; i < 3; ++i) fin[i] = bot.D[6 + i] + o.D[6 + i];                        // D(b2)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
+		fin[3 + i] = bot.E[4 + i] + o.E[4 + i];                                            // (0,2) -> E(b0b2)
+		fin[7 + i] = bot.E[8 + i] + o.E[12 + i];                                           // (1,2) -> E(b1b2)
+		fin[11 + i] = o.E[20 + i];                                                         // (2,3) -> C22
 		bot.E[i] += o.E[i];                                                                // (0,1) -> E(b0b1)
 		C02[i] = o.E[8 + i];                                                               // (0,3) -> C02
 		C12[i] = o.E[16 + i];                                                              // (1,3) -> C12
 	}
-	st.put(25, bot.F[4] + o.F[4]); st.put(26, bot.F[5] + o.F[5]);                          // F(b2)
+	fin[15] = bot.F[4] + o.F[4]; fin[16] = bot.F[5] + o.F[5];                              // F(b2)
 	#pragma unroll
 	for (int i = 0; i < 6; ++i) bot.D[i] += o.D[i];                                        // D(b0) D(b1)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) bot.F[i] += o.F[i];
 	top.D[6] = o.D[9]; top.D[7] = o.D[10]; top.D[8] = o.D[11];                             // D(t2)
 	top.F[4] = o.F[6]; top.F[5] = o.F[7];
+#ifndef TILE_GATE_B
+	st.gate();
+	#pragma unroll
+	for (int i = 0; i < 3; ++i) st.put(6 + i, fin[i]);
+	put_blk(st, 13, 1, fin[3], fin[4], fin[5], fin[6]);
+	put_blk(st, 17, 2, fin[7], fin[8], fin[9], fin[10]);
+	put_blk(st, 47, 8, fin[11], fin[12], fin[13], fin[14]);
+	st.put(25, fin[15]); st.put(26, fin[16]);
+#endif
 	// ---- tet B = (b0 b1 t1 t2).  Final afterwards: everything of b1, C11, C12
 	tet_eval(pb[0], pb[1], pt[1], pt[2], ub[0], ub[1], ut[1], ut[2], a1, P, o);
+#ifdef TILE_GATE_B
+	st.gate();
+	#pragma unroll
+	for (int i = 0; i < 3; ++i) st.put(6 + i, fin[i]);
+	put_blk(st, 13, 1, fin[3], fin[4], fin[5], fin[6]);
+	put_blk(st, 17, 2, fin[7], fin[8], fin[9], fin[10]);
+	put_blk(st, 47, 8, fin[11], fin[12], fin[13], fin[14]);
+	st.put(25, fin[15]); st.put(26, fin[16]);
+#endif
 	#pragma unroll
 	for (int i = 0; i < 3; ++i) st.put(3 + i, bot.D[3 + i] + o.D[3 + i]);                 // D(b1)
 	put_blk(st, 9, 0, bot.E[0] + o.E[0], bot.E[1] + o.E[1], bot.E[2] + o.E[2], bot.E[3] + o.E[3]);            // (0,1) -> E(b0b1)
@@ -294,9 +321,11 @@ __host__ __device__ __forceinline__ void entry_add(const double* st, const uint3
 	a0 += b[0]; a1 += b[o1 * TILE_T]; a2 += b[o2 * TILE_T]; a3 += b[o3 * TILE_T];
 }
 
-// the sum of one table entry: its contributions in table order
-__host__ __device__ __forceinline__ void entry_total(const double* stage, const uint16_t* w, const uint32_t info, double& a0, double& a1, double& a2, double& a3)
+// the sum of one table entry: its contributions in table order.  Not inlined on the device: the summing warps call it
+// for every entry, inlining it five to nine times only fills the instruction cache
+__host__ __device__ __noinline__ double4 entry_total(const double* stage, const uint16_t* w, const uint32_t info)
 {
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 	const int cnt = info & 31, kind = info >> 6;
 	if (info & 32) {                                   // contributions of different types (rare: columns that meet themselves)
 		for (int c = 0; c < cnt; ++c) entry_add(stage, w[c], a0, a1, a2, a3);
@@ -317,6 +346,7 @@ __host__ __device__ __forceinline__ void entry_total(const double* stage, const 
 			a0 += b[0]; a1 += b[TILE_T];
 		}
 	}
+	return make_double4(a0, a1, a2, a3);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -330,6 +360,7 @@ __host__ __device__ __forceinline__ void entry_total(const double* stage, const 
 #define BAR_FULL  1
 #define BAR_EMPTY 2
 #define BAR_SUM   3
+#define BAR_VDATA 4
 __device__ __forceinline__ void bar_sync(const int id, const int n)   { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
@@ -351,62 +382,38 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	double* stage = (double*)smem_raw;                                              // [TILE_NSLOT][TILE_T]
-	double2* vbuf = (double2*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8);         // [2][6][TILE_T]: {z, S} and {u_x, u_y} of three vertices
-	uint16_t* stab = (uint16_t*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 6 * TILE_T * 16);   // [entries][W]
+	double2* vbuf = (double2*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8);         // [2][8][TILE_T]: per prism {z, S}, {u_x, u_y} of the three top vertices, ainv of the three tets
+	uint16_t* stab = (uint16_t*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 8 * TILE_T * 16);   // [entries][W]
 	uint8_t* sinfo = (uint8_t*)(stab + TILE_TABW);                                  // [entries]
 	const int tile = tile0 + blockIdx.x;
 	const int NZ = NL - 1;
 	if (threadIdx.x < TILE_T) {
-		// ================================================================= compute warps
+		// ================================================================= compute warps: no global loads inside the march
 		asm volatile("setmaxnreg.inc.sync.aligned.u32 " TILE_REG_C ";");
 		const int t = threadIdx.x;
 		const uint32_t tflags = tflag[(size_t)tile * TILE_T + t];
-		const int32_t* tv = tvert + (size_t)tile * NL * 3 * TILE_T + t;
-		const int32_t* tn = tnode + (size_t)tile * NL * 3 * TILE_T + t;
-		const double*  ta = tainv + (size_t)tile * NZ * 3 * TILE_T + t;
 		double4 pb[3], pt[3];
 		double2 ub[3], ut[3];
 		Iface bot, top;
 		iface_zero(bot);
-		int iv[3], in[3];                       // vertex / node ids of the layer fetched next
-		#pragma unroll
-		for (int i = 0; i < 3; ++i) { iv[i] = tv[(3 + i) * TILE_T]; in[i] = tn[(3 + i) * TILE_T]; }        // layer 1
-		#pragma unroll
-		for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }            // layer 0: straight into registers
-		{	// layer 1 -> vbuf[0]: only z, S and u change along a column
-			double2* vb = vbuf + t;
+		{
+			const int32_t* tv = tvert + (size_t)tile * NL * 3 * TILE_T + t;
+			const int32_t* tn = tnode + (size_t)tile * NL * 3 * TILE_T + t;
 			#pragma unroll
-			for (int i = 0; i < 3; ++i) { cp_async16(vb + (2 * i) * TILE_T, &zS[iv[i]]); cp_async16(vb + (2 * i + 1) * TILE_T, &u[in[i]]); }
-			asm volatile("cp.async.commit_group;" ::: "memory");
-		}
-		if (NZ >= 2) {
-			#pragma unroll
-			for (int i = 0; i < 3; ++i) { iv[i] = tv[(6 + i) * TILE_T]; in[i] = tn[(6 + i) * TILE_T]; }    // layer 2
+			for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }        // layer 0: straight into registers
 		}
 		for (int k = 0; k < NZ; ++k) {
-			const double a0 = ta[(k * 3) * TILE_T], a1 = ta[(k * 3 + 1) * TILE_T], a2 = ta[(k * 3 + 2) * TILE_T];
-			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			{	// the top layer of this prism
-				const double2* vb = vbuf + (size_t)(k & 1) * 6 * TILE_T + t;
-				#pragma unroll
-				for (int i = 0; i < 3; ++i) {
-					const double2 q0 = vb[(2 * i) * TILE_T];
-					pt[i] = make_double4(pb[i].x, pb[i].y, q0.x, q0.y);
-					ut[i] = vb[(2 * i + 1) * TILE_T];
-				}
+			bar_sync(BAR_VDATA, TILE_T + TILE_S);               // the summing warps have brought in this prism's package
+			const double2* vb = vbuf + (size_t)(k & 1) * 8 * TILE_T + t;
+			#pragma unroll
+			for (int i = 0; i < 3; ++i) {
+				const double2 q0 = vb[(2 * i) * TILE_T];
+				pt[i] = make_double4(pb[i].x, pb[i].y, q0.x, q0.y);  // x, y are the column's
+				ut[i] = vb[(2 * i + 1) * TILE_T];
 			}
-			if (k + 2 <= NZ) {                  // layer k + 2 -> the other buffer, while this prism is computed
-				double2* vb = vbuf + (size_t)((k + 1) & 1) * 6 * TILE_T + t;
-				#pragma unroll
-				for (int i = 0; i < 3; ++i) { cp_async16(vb + (2 * i) * TILE_T, &zS[iv[i]]); cp_async16(vb + (2 * i + 1) * TILE_T, &u[in[i]]); }
-				asm volatile("cp.async.commit_group;" ::: "memory");
-				if (k + 3 <= NZ) {
-					#pragma unroll
-					for (int i = 0; i < 3; ++i) { iv[i] = tv[((k + 3) * 3 + i) * TILE_T]; in[i] = tn[((k + 3) * 3 + i) * TILE_T]; }
-				}
-			}
+			const double2 a01 = vb[6 * TILE_T], a2x = vb[7 * TILE_T];
 			DevStage st = { stage + t, k > 0, tflags };
-			prism_steps(pb, ub, pt, ut, a0, a1, a2, P, bot, top, st);
+			prism_steps(pb, ub, pt, ut, a01.x, a01.y, a2x.x, P, bot, top, st);
 			__threadfence_block();
 			bar_arrive(BAR_FULL, TILE_T + TILE_S);
 			bot = top;
@@ -418,10 +425,25 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		__threadfence_block();
 		bar_arrive(BAR_FULL, TILE_T + TILE_S);
 	} else {
-		// ================================================================= summing warps
+		// ================================================================= summing warps (and feeders of the compute warps)
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 " TILE_REG_S ";");
 		const int sidx = threadIdx.x - TILE_T;
 		const int e_lo = ent0[tile], ne = ent0[tile + 1] - e_lo;
+		// package of prism j for compute thread c: {z, S} and u of the three vertices of layer j + 1, ainv of the three tets
+		auto feed = [&](const int j) {
+			for (int c = sidx; c < TILE_T; c += TILE_S) {
+				const int32_t* tv = tvert + ((size_t)tile * NL + j + 1) * 3 * TILE_T + c;
+				const int32_t* tn = tnode + ((size_t)tile * NL + j + 1) * 3 * TILE_T + c;
+				double2* vb = vbuf + (size_t)(j & 1) * 8 * TILE_T + c;
+				#pragma unroll
+				for (int i = 0; i < 3; ++i) { cp_async16(vb + (2 * i) * TILE_T, &zS[tv[i * TILE_T]]); cp_async16(vb + (2 * i + 1) * TILE_T, &u[tn[i * TILE_T]]); }
+				const double* ta = tainv + (((size_t)tile * NZ + j) * TILE_T + c) * 4;
+				cp_async16(vb + 6 * TILE_T, ta); cp_async16(vb + 7 * TILE_T, ta + 2);
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		};
+		if (NZ >= 1) feed(0);
+		if (NZ >= 2) feed(1);
 		{	// the tile's table -> shared memory (16-byte pieces)
 			const uint4* src = (const uint4*)(tab + (size_t)e_lo * W);
 			uint4* dst = (uint4*)stab;
@@ -430,6 +452,11 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			for (int i = sidx; i < ne; i += TILE_S) sinfo[i] = einfo[e_lo + i];
 		}
 		bar_sync(BAR_SUM, TILE_S);
+		if (NZ >= 1) {
+			if (NZ >= 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+			__threadfence_block();
+			bar_arrive(BAR_VDATA, TILE_T + TILE_S);             // package 0 is in
+		}
 		for (int k = 0; k <= NZ; ++k) {
 			int o[TILE_EPT], o2[TILE_EPT];
 			const int32_t* ok = out + (size_t)k * n_ent + e_lo;
@@ -437,13 +464,20 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			#pragma unroll
 			for (int i = 0; i < TILE_EPT; ++i) { const int e = sidx + i * TILE_S; o[i] = (e < ne) ? ok[e] : -1; o2[i] = (e < ne) ? ok2[e] : -1; }
 			bar_sync(BAR_FULL, TILE_T + TILE_S);
+			// the compute warps are done with prism k (they read its package at the start): release package k + 1, which
+			// was requested one prism ago, and request package k + 2 into the buffer that just became free
+			if (k + 1 < NZ) {
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
+				__threadfence_block();
+				bar_arrive(BAR_VDATA, TILE_T + TILE_S);
+			}
+			if (k + 2 < NZ) feed(k + 2);
 			#pragma unroll
 			for (int i = 0; i < TILE_EPT; ++i) {
 				if (o[i] == -1) continue;
 				const int e = sidx + i * TILE_S;
-				double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-				const uint16_t* w = stab + (size_t)e * W;
-				entry_total(stage, w, sinfo[e], a0, a1, a2, a3);
+				const double4 acc = entry_total(stage, stab + (size_t)e * W, sinfo[e]);
+				const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
 				if (o[i] >= 0) {
 					double2* dst = (double2*)val + 2 * (size_t)o[i];
 					dst[0] = make_double2(a0, a1);
@@ -462,11 +496,14 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 	}
 }
 
-// d_ainv (per tet, mesh order) -> tile order [tile][layer][3][thread]
+// d_ainv (per tet, mesh order) -> tile order [tile][layer][thread][4] (three tets + padding: two 16-byte pieces per thread)
 __global__ void k_tile_ainv(int64_t n, const int32_t* __restrict__ ttet, const double* __restrict__ ainv, double* __restrict__ out)
 {
 	for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-		const int tt = ttet[i];
+		const int j = (int)(i & 3);
+		const int64_t tk = i >> 2;                       // (tile * NZ + k) * TILE_T + t
+		const int64_t t = tk % TILE_T, lk = tk / TILE_T;
+		const int tt = (j < 3) ? ttet[(lk * 3 + j) * TILE_T + t] : -1;
 		out[i] = tt >= 0 ? ainv[tt] : 0.0;
 	}
 }
@@ -475,7 +512,7 @@ void bp_tiles_update_ainv(bp_ctx* c)
 {
 	if (!c->tiles || c->host_only) return;
 	bp_tiles* T = c->tiles;
-	const int64_t n = (int64_t)T->n_tiles * (T->NL - 1) * 3 * TILE_T;
+	const int64_t n = (int64_t)T->n_tiles * (T->NL - 1) * TILE_T * 4;
 	k_tile_ainv<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, c->stream>>>(n, T->d_tet, c->d_ainv, T->d_ainv);
 	c->launches++;
 }
@@ -488,7 +525,7 @@ bool bp_tiles_serve(const bp_ctx* c, int what)
 	return c->env.asm_tiled != 0;
 }
 
-static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 6 * TILE_T * 16 + (size_t)TILE_TABW * 2 + TILE_MAXE; }
+static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 8 * TILE_T * 16 + (size_t)TILE_TABW * 2 + TILE_MAXE; }
 
 static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile)
 {
@@ -1064,7 +1101,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (!rc) rc = up(c, &T->d_tflag, T->h_tflag);
 	if (!rc) rc = up(c, &T->d_einfo, T->h_einfo);
 	if (!rc && !c->host_only) {
-		cudaError_t e = cudaMalloc((void**)&T->d_ainv, (size_t)n_tiles * NZ * 3 * TILE_T * sizeof(double));
+		cudaError_t e = cudaMalloc((void**)&T->d_ainv, (size_t)n_tiles * NZ * 4 * TILE_T * sizeof(double));
 		if (e != cudaSuccess) rc = bp_fail(c, BP_ERR_CUDA, "cudaMalloc(tile ainv) failed: %s", cudaGetErrorString(e));
 	}
 	c->tiles = T;
@@ -1126,8 +1163,8 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 				for (int e = T->h_ent0[tile]; e < T->h_ent0[tile + 1]; ++e) {
 					const int o = T->h_out[(size_t)k * T->n_ent + e];
 					if (o == -1) continue;
-					double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-					entry_total(stage.data(), T->h_tab.data() + (size_t)e * W, T->h_einfo[e], a0, a1, a2, a3);
+					const double4 acc = entry_total(stage.data(), T->h_tab.data() + (size_t)e * W, T->h_einfo[e]);
+					const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
 					if (o >= 0) {
 						double* d = val.data() + 4 * (size_t)o; d[0] = a0; d[1] = a1; d[2] = a2; d[3] = a3;
 						const int om = T->h_out2[(size_t)k * T->n_ent + e];
