@@ -357,6 +357,7 @@ void bp_destroy(bp_ctx* c)
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
 	if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+	if (c->s_aux) cudaStreamDestroy(c->s_aux);
 	for (auto e : c->pipe_ev) if (e) cudaEventDestroy(e);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;

@@ -168,7 +168,7 @@ struct bp_ctx {
 	std::vector<int32_t> h_blk_need_vert, h_blk_need_node;
 	std::vector<uint8_t> h_blk_facet;
 	std::vector<uint8_t> h_facet_node;   // owned node gets a facet integral (its F row is final after the facet kernel only)
-	cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+	cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;
 	std::vector<cudaEvent_t> pipe_ev;
 };
 

@@ -368,10 +368,51 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
+// the summing warps' version of entry_total for entries of one type: the eight table words of an entry arrive with one
+// 16-byte load, two contributions are in flight at a time (eight independent loads), additions in table order
+__device__ __forceinline__ double4 entry_total_dev(const double* stage, const uint16_t* w, const uint32_t info, const int W)
+{
+	if (info & 32) return entry_total(stage, w, info);
+	const int cnt = info & 31, kind = info >> 6;
+	const int s2 = (kind == 0) ? 2 * TILE_T : TILE_T, s3 = (kind == 0) ? 3 * TILE_T : (kind == 1 ? 2 * TILE_T : TILE_T);
+	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+	for (int c0 = 0; c0 < cnt; c0 += 8) {
+		const uint4 q = *(const uint4*)(w + c0);
+		const uint32_t wd[8] = { q.x & 0x3fffu, (q.x >> 16) & 0x3fffu, q.y & 0x3fffu, (q.y >> 16) & 0x3fffu,
+		                         q.z & 0x3fffu, (q.z >> 16) & 0x3fffu, q.w & 0x3fffu, (q.w >> 16) & 0x3fffu };
+		#pragma unroll
+		for (int c = 0; c < 8; c += 2) {
+			if (c0 + c >= cnt) break;
+			const bool two = c0 + c + 1 < cnt;
+			const double* b0 = stage + wd[c];
+			const double* b1 = stage + (two ? wd[c + 1] : 0u);
+			const double x0 = b0[0], x1 = b0[TILE_T], x2 = b0[s2], x3 = b0[s3];
+			const double y0 = b1[0], y1 = b1[TILE_T], y2 = b1[s2], y3 = b1[s3];
+			a0 += x0; a1 += x1; a2 += x2; a3 += x3;
+			if (two) { a0 += y0; a1 += y1; a2 += y2; a3 += y3; }
+		}
+	}
+	return make_double4(a0, a1, a2, a3);
+}
+
 struct DevStage {
 	double* sb; bool wait; uint32_t flags;
+#ifdef TILE_GATE_END
+	// everything a prism stages is held back (registers, what does not fit: local memory) until the whole prism is
+	// computed: the summing warps then have a full prism's time for the previous layer
+	double v[TILE_NSLOT];
+	__device__ __forceinline__ void gate() {}
+	__device__ __forceinline__ void put(const int slot, const double x) { v[slot] = x; }
+	__device__ __forceinline__ void flush(const int n) {
+		if (wait) bar_sync(BAR_EMPTY, TILE_T + TILE_S);
+		#pragma unroll
+		for (int i = 0; i < TILE_NSLOT; ++i) if (i < n) sb[i * TILE_T] = v[i];
+	}
+#else
 	__device__ __forceinline__ void gate() { if (wait) bar_sync(BAR_EMPTY, TILE_T + TILE_S); }
 	__device__ __forceinline__ void put(const int slot, const double v) { sb[slot * TILE_T] = v; }
+	__device__ __forceinline__ void flush(const int) {}
+#endif
 };
 
 __global__ void __launch_bounds__(TILE_T + TILE_S, TILE_CTAS)
@@ -414,7 +455,8 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			const double2 a01 = vb[6 * TILE_T], a2x = vb[7 * TILE_T];
 			DevStage st = { stage + t, k > 0, tflags };
 			prism_steps(pb, ub, pt, ut, a01.x, a01.y, a2x.x, P, bot, top, st);
-			__threadfence_block();
+			st.flush(TILE_NSLOT);
+			asm volatile("fence.acq_rel.cta;" ::: "memory");
 			bar_arrive(BAR_FULL, TILE_T + TILE_S);
 			bot = top;
 			#pragma unroll
@@ -422,7 +464,8 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		}
 		DevStage st = { stage + t, NZ > 0, tflags };
 		iface_stage(bot, st);
-		__threadfence_block();
+		st.flush(27);
+		asm volatile("fence.acq_rel.cta;" ::: "memory");
 		bar_arrive(BAR_FULL, TILE_T + TILE_S);
 	} else {
 		// ================================================================= summing warps (and feeders of the compute warps)
@@ -454,7 +497,7 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		bar_sync(BAR_SUM, TILE_S);
 		if (NZ >= 1) {
 			if (NZ >= 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-			__threadfence_block();
+			asm volatile("fence.acq_rel.cta;" ::: "memory");
 			bar_arrive(BAR_VDATA, TILE_T + TILE_S);             // package 0 is in
 		}
 		for (int k = 0; k <= NZ; ++k) {
@@ -468,7 +511,7 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			// was requested one prism ago, and request package k + 2 into the buffer that just became free
 			if (k + 1 < NZ) {
 				asm volatile("cp.async.wait_group 0;" ::: "memory");
-				__threadfence_block();
+				asm volatile("fence.acq_rel.cta;" ::: "memory");
 				bar_arrive(BAR_VDATA, TILE_T + TILE_S);
 			}
 			if (k + 2 < NZ) feed(k + 2);
@@ -476,7 +519,7 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			for (int i = 0; i < TILE_EPT; ++i) {
 				if (o[i] == -1) continue;
 				const int e = sidx + i * TILE_S;
-				const double4 acc = entry_total(stage, stab + (size_t)e * W, sinfo[e]);
+				const double4 acc = entry_total_dev(stage, stab + (size_t)e * W, sinfo[e], W);
 				const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
 				if (o[i] >= 0) {
 					double2* dst = (double2*)val + 2 * (size_t)o[i];
@@ -527,8 +570,9 @@ bool bp_tiles_serve(const bp_ctx* c, int what)
 
 static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 8 * TILE_T * 16 + (size_t)TILE_TABW * 2 + TILE_MAXE; }
 
-static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile)
+static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile, cudaStream_t stream = nullptr)
 {
+	if (!stream) stream = c->stream;
 	bp_tiles* T = c->tiles;
 	AsmParams P = bp_asm_params(c);
 	P.picard = (what & 16) ? 1 : 0;
@@ -538,7 +582,7 @@ static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile)
 		T->attr_set = true;
 	}
 	if (ntile <= 0) return;
-	k_tile<<<ntile, TILE_T + TILE_S, sm, c->stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_einfo, T->d_tflag, T->d_out, T->d_out2,
+	k_tile<<<ntile, TILE_T + TILE_S, sm, stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_einfo, T->d_tflag, T->d_out, T->d_out2,
 	                                                   T->n_ent, c->d_geo, c->d_zS, (const double2*)c->d_u, c->d_F, c->d_val, P);
 	c->launches++;
 }
@@ -577,11 +621,16 @@ int bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
 			BP_CUDA(c, cudaMemcpyAsync(c->d_u + 2 * (size_t)r.first, u + 2 * (size_t)r.first, (size_t)(r.second - r.first) * 2 * sizeof(double), cudaMemcpyHostToDevice, c->s_h2d));
 		BP_CUDA(c, cudaEventRecord(e_h[k], c->s_h2d));
 	}
+	// the groups' kernels alternate between two streams: the partial last wave of one overlaps the first wave of the next
+	if (!c->s_aux) BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+	BP_CUDA(c, cudaStreamWaitEvent(c->s_aux, e_0, 0));
 	for (int k = 0; k < K; ++k) {
-		BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_h[k], 0));
-		launch_tiles_range(c, what, T->chunks[k].tile0, T->chunks[k].ntile);
-		BP_CUDA(c, cudaEventRecord(e_c[k], c->stream));
+		cudaStream_t sk = (k & 1) ? c->s_aux : c->stream;
+		BP_CUDA(c, cudaStreamWaitEvent(sk, e_h[k], 0));
+		launch_tiles_range(c, what, T->chunks[k].tile0, T->chunks[k].ntile, sk);
+		BP_CUDA(c, cudaEventRecord(e_c[k], sk));
 	}
+	for (int k = 1; k < K; k += 2) BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_c[k], 0));
 	bp_launch_facets(c, what);
 	BP_CUDA(c, cudaEventRecord(e_f, c->stream));
 	if (what & BP_ASSEMBLE_J) c->have_J = true;
@@ -1058,11 +1107,24 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		const int K = std::max(1, std::min(c->env.pipe_k, std::min(8, n_tiles / 148)));
 		std::vector<uint8_t> have(nn, 0), mark(nn, 0);
 		const int GAP = 128;                                  // ranges closer than this are copied as one (the nodes between are needed later anyway)
+		// group boundaries sit where a strip of tiles ends (tiles are ordered strip by strip): the node ranges of a group are
+		// then whole rows of columns per layer -- a handful of large copies instead of one per row of a cut strip
+		std::vector<int> bound(K + 1, 0);
+		bound[K] = n_tiles;
+		for (int k = 1; k < K; ++k) {
+			int b = (int)((int64_t)k * n_tiles / K);
+			int lo_b = b, hi_b = b;
+			auto strip_of = [&](int tl) { return ybin[own_cols[tile_c0[tl]]]; };
+			while (lo_b > bound[k - 1] + 1 && strip_of(lo_b) == strip_of(lo_b - 1)) --lo_b;
+			while (hi_b < n_tiles && strip_of(hi_b) == strip_of(hi_b - 1)) ++hi_b;
+			b = (b - lo_b <= hi_b - b && lo_b > bound[k - 1]) ? lo_b : hi_b;
+			bound[k] = std::min(std::max(b, bound[k - 1]), n_tiles);
+		}
 		T->chunks.resize(K);
 		for (int k = 0; k < K; ++k) {
 			bp_tiles::Chunk& ch = T->chunks[k];
-			ch.tile0 = (int)((int64_t)k * n_tiles / K);
-			ch.ntile = (int)((int64_t)(k + 1) * n_tiles / K) - ch.tile0;
+			ch.tile0 = bound[k];
+			ch.ntile = bound[k + 1] - bound[k];
 			std::fill(mark.begin(), mark.end(), 0);
 			for (size_t i = (size_t)ch.tile0 * NL * 3 * TILE_T; i < (size_t)(ch.tile0 + ch.ntile) * NL * 3 * TILE_T; ++i) mark[T->h_node[i]] = 1;
 			for (int64_t i = 0; i < nn; ) {
@@ -1087,6 +1149,16 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		}
 		size_t nr = 0;
 		for (auto& ch : T->chunks) nr += ch.in.size() + ch.out_plain.size() + ch.out_facet.size();
+		if (c->prm.verbose) {
+			for (auto& ch : T->chunks) {
+				int64_t ni = 0, no_ = 0;
+				for (auto& r : ch.in) ni += r.second - r.first;
+				for (auto& r : ch.out_plain) no_ += r.second - r.first;
+				for (auto& r : ch.out_facet) no_ += r.second - r.first;
+				fprintf(stderr, "[cslvr_b200] pipeline group: tiles %d+%d, in %zu ranges (%lld nodes), out %zu + %zu ranges (%lld nodes)\n", ch.tile0, ch.ntile,
+				        ch.in.size(), (long long)ni, ch.out_plain.size(), ch.out_facet.size(), (long long)no_);
+			}
+		}
 		if (nr > 600) T->chunks.clear();                      // a numbering without locality: too many small copies, the plain path serves it
 	}
 
