@@ -397,7 +397,7 @@ __device__ __forceinline__ double4 entry_total_dev(const double* stage, const ui
 
 struct DevStage {
 	double* sb; bool wait; uint32_t flags;
-#ifdef TILE_GATE_END
+#ifndef TILE_GATE_EARLY
 	// everything a prism stages is held back (registers, what does not fit: local memory) until the whole prism is
 	// computed: the summing warps then have a full prism's time for the previous layer
 	double v[TILE_NSLOT];
