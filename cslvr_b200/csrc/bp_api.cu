@@ -33,6 +33,7 @@ void bp_env_read(bp_env* e)
 	e->mg_coupled_graph = geti("BP_MG_COUPLED_GRAPH", 1) != 0;
 	e->mg_gamma = geti("BP_MG_GAMMA", 0);
 	e->mg_tail = geti("BP_MG_TAIL", 4096);
+	e->mg_lmax_scale = getd("BP_MG_LMAX_SCALE", 1.0);
 	e->asm_tiled = geti("BP_ASM_TILED", -1);
 	e->cg_graph = geti("BP_CG_GRAPH", 1) != 0;
 }

@@ -1699,7 +1699,7 @@ void bp_launch_cheb_step(bp_ctx* c, double c1, double c2, const double* r, const
 // that misses the top of the spectrum makes the preconditioner indefinite).
 __global__ void __launch_bounds__(256)
 k_gershgorin(int nrows, const int32_t* __restrict__ sell_ptr, const double2* __restrict__ val,
-             const double* __restrict__ dinv, double* part, unsigned* counter, double* out)
+             const double* __restrict__ dinv, double* part, unsigned* counter, double* out, double scale)
 {
 	__shared__ double sm[32];
 	__shared__ bool last;
@@ -1738,13 +1738,13 @@ k_gershgorin(int nrows, const int32_t* __restrict__ sell_ptr, const double2* __r
 		for (int b = lane; b < (int)gridDim.x; b += 32) mx = fmax(mx, ((volatile double*)part)[b]);
 		#pragma unroll
 		for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-		if (lane == 0) { *out = mx; *counter = 0u; }
+		if (lane == 0) { *out = mx * scale; *counter = 0u; }
 	}
 }
 void bp_launch_gershgorin(bp_ctx* c, int sc_slot)
 {
 	k_gershgorin<<<red_blocks(c->nn_owned, 256), 256, 0, c->stream>>>((int)c->nn_owned, c->d_sell_ptr, (const double2*)c->d_val, c->d_dinv,
-		c->d_part, c->d_counter, c->d_sc + sc_slot);
+		c->d_part, c->d_counter, c->d_sc + sc_slot, sc_slot == SC_LMAX ? c->env.mg_lmax_scale : 1.0);
 	c->launches++;
 }
 
