@@ -34,6 +34,7 @@ void bp_env_read(bp_env* e)
 	e->mg_gamma = geti("BP_MG_GAMMA", 0);
 	e->mg_tail = geti("BP_MG_TAIL", 4096);
 	e->mg_lmax_scale = getd("BP_MG_LMAX_SCALE", 1.0);
+	e->mg_repl = geti("BP_MG_REPL", 32768);
 	e->asm_tiled = geti("BP_ASM_TILED", -1);
 	e->cg_graph = geti("BP_CG_GRAPH", 1) != 0;
 }

@@ -41,6 +41,7 @@ struct bp_env {
 	bool   mg_coupled = true, mg_coupled_graph = true;      // BP_MG_COUPLED / BP_MG_COUPLED_GRAPH
 	int    mg_gamma = 0;            // BP_MG_GAMMA (0 = the hierarchy's default)
 	int    mg_tail = 4096;          // BP_MG_TAIL
+	int    mg_repl = 32768;         // BP_MG_REPL: coupled hierarchy: levels with at most this many nodes (globally) are replicated on every rank (0: only the dense coarsest level)
 	double mg_lmax_scale = 1.0;     // BP_MG_LMAX_SCALE: factor on the Gershgorin bound of lmax(D^-1 A) the multigrid smoothers use (experiments)
 	int    asm_tiled = -1;          // BP_ASM_TILED: 1 / 0 force / forbid the tiled cell kernel (-1 = automatic)
 	bool   cg_graph = true;         // BP_CG_GRAPH=0: launch the CG iteration directly instead of replaying its graph

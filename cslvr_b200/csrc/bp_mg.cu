@@ -56,6 +56,12 @@ struct bp_mg {
 	double *d_gmat = nullptr, *d_gvec = nullptr, *d_xs = nullptr;
 	int32_t* d_gcol = nullptr;               // global id of every local (owned + ghost) coarsest node
 	bool f32 = true;                     // the V-cycle reads FP32 copies of the level matrices (vectors and accumulation stay FP64)
+	// coupled hierarchy, replicated tail: below a few ten thousand nodes (globally) a level is all exchange latency, so from
+	// there down EVERY rank holds the whole operator (R: a context of its own with an ordinary single-rank hierarchy) and the
+	// ranks only all-reduce the right-hand side of that level -- one collective instead of ~8 halo exchanges per level
+	bp_ctx* R = nullptr;
+	bp_mg_level Rlevel;                  // owns R's host pattern
+	int32_t* d_rmap = nullptr;           // slot of the last coupled level -> slot of R
 };
 
 template <class T>
@@ -596,6 +602,111 @@ static int mgc_attach_halo(bp_ctx* c, bp_mg_level& L)
 	return BP_OK;
 }
 
+// ---- replicated tail (see bp_mg::R): the pattern of the last coupled level is gathered from all ranks (every rank adds its
+// rows, in global numbering, to a zero-padded table that is all-reduced), every rank builds the same SELL layout from it and
+// an ordinary single-rank hierarchy below it.
+static int mgc_build_replicated(bp_ctx** cs, int n)
+{
+	int rc;
+	const int NG = cs[0]->mg->NG;
+	// widest row, over all ranks
+	std::vector<std::vector<double>> wv(n, std::vector<double>(1, 0.0));
+	for (int r = 0; r < n; ++r) {
+		const bp_mg_level& Lc = cs[r]->mg->lv.back();
+		for (int64_t i = 0; i < Lc.n; ++i) wv[r][0] = std::max(wv[r][0], (double)(Lc.h_rowptr[i + 1] - Lc.h_rowptr[i]));
+	}
+	if ((rc = mgc_allreduce_host(cs, n, wv, 1, 1))) return rc;
+	const int maxw = (int)wv[0][0];
+	const size_t cnt = (size_t)NG * maxw;
+	// the table of global column ids (+1; 0 = none), one device buffer per context
+	double* bufs[16];
+	std::vector<double> tab(cnt);
+	for (int r = 0; r < n; ++r) {
+		bp_ctx* c = cs[r];
+		bp_mg* mg = c->mg;
+		const bp_mg_level& Lc = mg->lv.back();
+		std::vector<int32_t> gcol(Lc.n + Lc.n_ghost);
+		for (int64_t i = 0; i < Lc.n; ++i) gcol[i] = (int32_t)(mg->goff[mg->my_rank] + i);
+		for (int64_t g = 0; g < Lc.n_ghost; ++g) gcol[Lc.n + g] = (int32_t)(mg->goff[c->nbr_rank[Lc.ghost_nbr[g]]] + Lc.ghost_owner_id[g]);
+		std::fill(tab.begin(), tab.end(), 0.0);
+		for (int64_t i = 0; i < Lc.n; ++i) {
+			double* row = tab.data() + (size_t)(mg->goff[mg->my_rank] + i) * maxw;
+			for (int32_t k = Lc.h_rowptr[i]; k < Lc.h_rowptr[i + 1]; ++k) row[k - Lc.h_rowptr[i]] = (double)gcol[Lc.h_col[k]] + 1.0;
+		}
+		BP_CUDA(c, cudaMalloc((void**)&bufs[r], std::max<size_t>(cnt, 1) * sizeof(double)));
+		BP_CUDA(c, cudaMemcpyAsync(bufs[r], tab.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	if ((rc = bp_comm_allreduce_buf(cs, n, bufs, cnt, 0))) return rc;
+	for (int r = 0; r < n; ++r) {
+		bp_ctx* c = cs[r];
+		bp_mg* mg = c->mg;
+		BP_CUDA(c, cudaMemcpyAsync(tab.data(), bufs[r], cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		BP_CUDA(c, cudaStreamSynchronize(c->stream));
+		cudaFree(bufs[r]);
+		bp_mg_level& G = mg->Rlevel;
+		G.n = NG; G.n_ghost = 0;
+		G.h_rowptr.assign(NG + 1, 0);
+		G.h_col.clear();
+		for (int I = 0; I < NG; ++I) {
+			std::vector<int32_t> row;
+			for (int k = 0; k < maxw; ++k) { const double v = tab[(size_t)I * maxw + k]; if (v > 0.0) row.push_back((int32_t)(v - 1.0)); }
+			std::sort(row.begin(), row.end());
+			row.erase(std::unique(row.begin(), row.end()), row.end());
+			G.h_col.insert(G.h_col.end(), row.begin(), row.end());
+			G.h_rowptr[I + 1] = (int32_t)G.h_col.size();
+		}
+		const int64_t nsl = ((int64_t)NG + 31) / 32;
+		G.h_sell_ptr.assign(nsl + 1, 0);
+		for (int64_t sl = 0; sl < nsl; ++sl) {
+			int32_t w = 0;
+			for (int64_t I = sl * 32; I < std::min<int64_t>(NG, sl * 32 + 32); ++I) w = std::max(w, G.h_rowptr[I + 1] - G.h_rowptr[I]);
+			G.h_sell_ptr[sl + 1] = G.h_sell_ptr[sl] + 32 * w;
+		}
+		const int64_t nslots = G.h_sell_ptr[nsl];
+		auto slot_g = [&](int64_t I, int32_t k) -> int32_t { return G.h_sell_ptr[I >> 5] + 32 * k + (int32_t)(I & 31); };
+		std::vector<int32_t> sell_col((size_t)std::max<int64_t>(nslots, 1), 0), diag(NG, -1);
+		for (int64_t I = 0; I < nsl * 32; ++I) {
+			const int32_t w = (G.h_sell_ptr[(I >> 5) + 1] - G.h_sell_ptr[I >> 5]) >> 5;
+			const int32_t len = I < NG ? G.h_rowptr[I + 1] - G.h_rowptr[I] : 0;
+			for (int32_t k = 0; k < w; ++k) {
+				const int32_t cj = (k < len) ? G.h_col[G.h_rowptr[I] + k] : (I < NG ? (int32_t)I : 0);
+				sell_col[slot_g(I, k)] = cj;
+				if (k < len && cj == I) diag[I] = slot_g(I, k);
+			}
+		}
+		if ((rc = make_level_ctx(c, G, diag, sell_col, nslots))) return rc;
+		bp_ctx* R = G.M;
+		mg->R = R;
+		// R doubles as the "fine context" of a single-rank hierarchy of its own (bp_mg_prepare / bp_mg_apply)
+		R->nn = R->nn_owned = NG;
+		R->h_rowptr = G.h_rowptr; R->h_col = G.h_col; R->h_sell_ptr = G.h_sell_ptr;
+		R->n_cols = 0; R->max_layers = 0; R->aspect = 1.0; R->nnzb = G.h_rowptr[NG];
+		R->prm.pc = BP_PC_MG; R->prm.mg_smoother = 0;
+		R->h_colptr.assign(1, 0);
+		UPM(R->d_r, (const double*)nullptr, (size_t)2 * NG);
+		// slot of the last coupled level -> slot of R
+		const bp_mg_level& Lc = mg->lv.back();
+		std::vector<int32_t> gcol(Lc.n + Lc.n_ghost);
+		for (int64_t i = 0; i < Lc.n; ++i) gcol[i] = (int32_t)(mg->goff[mg->my_rank] + i);
+		for (int64_t g = 0; g < Lc.n_ghost; ++g) gcol[Lc.n + g] = (int32_t)(mg->goff[c->nbr_rank[Lc.ghost_nbr[g]]] + Lc.ghost_owner_id[g]);
+		std::vector<int32_t> rmap((size_t)std::max<int64_t>(Lc.h_sell_ptr.back(), 1), -1);
+		for (int64_t i = 0; i < Lc.n; ++i) {
+			const int64_t I = mg->goff[mg->my_rank] + i;
+			const int32_t* lo = G.h_col.data() + G.h_rowptr[I];
+			const int32_t* hi = G.h_col.data() + G.h_rowptr[I + 1];
+			for (int32_t k = Lc.h_rowptr[i]; k < Lc.h_rowptr[i + 1]; ++k) {
+				const int32_t kc = (int32_t)(std::lower_bound(lo, hi, gcol[Lc.h_col[k]]) - lo);
+				rmap[Lc.h_sell_ptr[i >> 5] + 32 * (k - Lc.h_rowptr[i]) + (i & 31)] = slot_g(I, kc);
+			}
+		}
+		UPM(mg->d_rmap, rmap.data(), rmap.size());
+		if (c->prm.verbose && mg->my_rank == 0)
+			printf("coupled multigrid: replicated tail from %d global nodes (%lld blocks) on every rank\n", NG, (long long)G.h_rowptr[NG]);
+	}
+	return BP_OK;
+}
+
 static int mgc_symbolic(bp_ctx** cs, int n)
 {
 	int rc;
@@ -757,7 +868,7 @@ static int mgc_symbolic(bp_ctx** cs, int n)
 			if ((rc = build_level(c, mg, aggfull, na[r], ncg, &H))) return rc;
 			if ((rc = mgc_attach_halo(c, mg->lv.back()))) return rc;
 		}
-		if (g_after <= 64.0) break;
+		if (g_after <= std::max(64.0, (double)cs[0]->env.mg_repl)) break;
 	}
 	// ---- the global coarsest system: rank r's nodes are [goff[r], goff[r+1])
 	{
@@ -771,16 +882,17 @@ static int mgc_symbolic(bp_ctx** cs, int n)
 			for (int q = 0; q < n_ranks; ++q) mg->goff[q + 1] = mg->goff[q] + (int64_t)v[r][q];
 			mg->NG = (int)mg->goff[n_ranks];
 			mg->nc = 2 * mg->NG;
-			if (mg->nc > 4096) return bp_fail(c, BP_ERR_STATE, "coupled multigrid: the global coarsest level has %d dofs (aggregation stalled)", mg->nc);
 			bp_mg_level& Lc = mg->lv.back();
 			std::vector<int32_t> gcol(Lc.n + Lc.n_ghost);
 			for (int64_t i = 0; i < Lc.n; ++i) gcol[i] = (int32_t)(mg->goff[mg->my_rank] + i);
 			for (int64_t g = 0; g < Lc.n_ghost; ++g) gcol[Lc.n + g] = (int32_t)(mg->goff[c->nbr_rank[Lc.ghost_nbr[g]]] + Lc.ghost_owner_id[g]);
 			UPM(mg->d_gcol, gcol.data(), gcol.size());
-			mg->h_dense.resize((size_t)mg->nc * mg->nc);
-			UPM(mg->d_dense, (const double*)nullptr, (size_t)mg->nc * mg->nc);
-			UPM(mg->d_gmat, (const double*)nullptr, (size_t)mg->nc * mg->nc);
 			UPM(mg->d_gvec, (const double*)nullptr, (size_t)mg->nc);
+			if (mg->NG <= 64) {                            // small enough for the dense inverse
+				mg->h_dense.resize((size_t)mg->nc * mg->nc);
+				UPM(mg->d_dense, (const double*)nullptr, (size_t)mg->nc * mg->nc);
+				UPM(mg->d_gmat, (const double*)nullptr, (size_t)mg->nc * mg->nc);
+			}
 			if (c->prm.verbose && mg->my_rank == 0) {
 				printf("coupled multigrid levels (rank 0, owned+ghost):");
 				for (auto& L : mg->lv) printf(" %lld+%lld", (long long)L.n, (long long)L.n_ghost);
@@ -788,6 +900,7 @@ static int mgc_symbolic(bp_ctx** cs, int n)
 			}
 		}
 	}
+	if (cs[0]->mg->NG > 64 && (rc = mgc_build_replicated(cs, n))) return rc;
 	return BP_OK;
 }
 
@@ -868,6 +981,32 @@ static int mgc_prepare(bp_ctx** cs, int n)
 				bp_ctx* M = cs[r]->mg->lv[l].M;
 				BP_CUDA(cs[r], cudaMemcpyAsync(M->d_sc + SC_LMAX, &cs[r]->mg->lv[l].lmax, sizeof(double), cudaMemcpyHostToDevice, cs[r]->stream));
 			}
+	}
+	if (cs[0]->mg->R) {
+		// replicated tail: every rank adds its rows of the last coupled level to R (zero elsewhere), all-reduce, then the
+		// ordinary single-rank numeric set-up below R -- the same numbers on every rank
+		double* rv[16];
+		for (int r = 0; r < n; ++r) {
+			bp_ctx* c = cs[r];
+			bp_mg* mg = c->mg;
+			bp_ctx* R = mg->R;
+			bp_mg_level& Lc = mg->lv.back();
+			R->stream = c->stream;
+			BP_CUDA(c, cudaMemsetAsync(R->d_val, 0, (size_t)R->n_slots * 4 * sizeof(double), c->stream));
+			const int64_t ns = Lc.h_sell_ptr.back();
+			if (ns) k_mg_galerkin<<<blocks(ns, 256), 256, 0, c->stream>>>(ns, mg->d_rmap, Lc.M->d_val, R->d_val);
+			c->launches++;
+			rv[r] = R->d_val;
+		}
+		if ((rc = bp_comm_allreduce_buf(cs, n, rv, (size_t)cs[0]->mg->R->n_slots * 4, 0))) return rc;
+		for (int r = 0; r < n; ++r) {
+			bp_ctx* R = cs[r]->mg->R;
+			{ const bp_params keep = cs[r]->prm; R->prm = keep; R->prm.pc = BP_PC_MG; R->prm.mg_smoother = 0; }
+			bp_launch_pc_setup(R);
+			if ((rc = bp_mg_prepare(R))) { cs[0]->err = R->err; return rc; }
+			R->mg->no_graph = true;                   // its launches are part of the coupled V-cycle's graph
+		}
+		return BP_OK;
 	}
 	// the global coarsest matrix: every rank adds its rows, all-reduce, dense inverse on every rank
 	double* gm[16];
@@ -978,6 +1117,32 @@ static int mgc_vcycle(bp_ctx** cs, int n, int l, double** rhs, int deg, double r
 	const int nl = (int)cs[0]->mg->lv.size();
 	bp_ctx* Ls[16];
 	mgc_level_ctxs(cs, n, l, Ls);
+	if (l == nl - 1 && cs[0]->mg->R) {
+		// replicated tail: all-reduce the right-hand side of this level, one V-cycle of R's hierarchy on every rank, own part back
+		double* gv[16];
+		for (int r = 0; r < n; ++r) {
+			bp_mg* mg = cs[r]->mg;
+			bp_ctx* R = mg->R;
+			const int64_t nloc = mg->lv[l].n;
+			BP_CUDA(cs[r], cudaMemsetAsync(R->d_r, 0, (size_t)mg->nc * sizeof(double), cs[r]->stream));
+			if (nloc) k_mgc_rhs_in<<<(int)((nloc + 127) / 128), 128, 0, cs[r]->stream>>>((int)nloc, (int)mg->goff[mg->my_rank], (const double2*)rhs[r], (double2*)R->d_r);
+			cs[r]->launches++;
+			gv[r] = R->d_r;
+		}
+		if ((rc = bp_comm_allreduce_buf(cs, n, gv, (size_t)cs[0]->mg->nc, 0))) return rc;
+		for (int r = 0; r < n; ++r) {
+			bp_mg* mg = cs[r]->mg;
+			bp_ctx* R = mg->R;
+			const int64_t nloc = mg->lv[l].n, l0 = R->launches;
+			R->stream = cs[r]->stream;
+			for (size_t q = 1; q < R->mg->lv.size(); ++q) R->mg->lv[q].M->stream = cs[r]->stream;
+			if ((rc = bp_mg_apply(R))) { cs[0]->err = R->err; return rc; }
+			cs[r]->launches += R->launches - l0;
+			if (nloc) BP_CUDA(cs[r], cudaMemcpyAsync(Ls[r]->d_z, R->d_z + 2 * mg->goff[mg->my_rank], (size_t)2 * nloc * sizeof(double), cudaMemcpyDeviceToDevice, cs[r]->stream));
+			zid[r] = 2;
+		}
+		return BP_OK;
+	}
 	if (l == nl - 1) {
 		// gather the right-hand side, apply the rows of the dense inverse that belong to this rank
 		double* gv[16];
@@ -1352,9 +1517,17 @@ void bp_mg_free(bp_ctx* c)
 			delete M;
 		}
 	}
+	if (c->mg->R) {                                   // the replicated tail: a context with a hierarchy of its own
+		bp_ctx* M = c->mg->R;
+		bp_mg_free(M);
+		void* ptrs[] = { M->d_sell_ptr, M->d_col, M->d_diag, M->d_val, M->d_valf, M->d_dinv, M->d_F, M->d_z, M->d_z2, M->d_cd, M->d_io, M->d_sc, M->d_part, M->d_counter, M->d_r };
+		for (void* p : ptrs) if (p) cudaFree(p);
+		if (M->h_sc) cudaFreeHost(M->h_sc);
+		delete M;
+	}
 	if (c->mg->graph) cudaGraphExecDestroy(c->mg->graph);
 	if (c->mg->d_dense) cudaFree(c->mg->d_dense);
-	{ void* t[] = { c->mg->d_gmat, c->mg->d_gvec, c->mg->d_xs, c->mg->d_gcol }; for (void* p : t) if (p) cudaFree(p); }
+	{ void* t[] = { c->mg->d_gmat, c->mg->d_gvec, c->mg->d_xs, c->mg->d_gcol, c->mg->d_rmap }; for (void* p : t) if (p) cudaFree(p); }
 	delete c->mg;
 	c->mg = nullptr;
 }
