@@ -33,34 +33,29 @@
 #include <cstring>
 #include <numeric>
 
-// Two shapes (compile time): 256 compute + 128 summing threads, one CTA per SM (registers 224 / 56 after setmaxnreg), or
-// -DTILE_SMALL: 128 + 128 threads, two CTAs per SM (216 / 40) -- smaller tiles recompute more halo prisms but two
-// independent CTAs keep the FP64 pipe busier.
-#ifdef TILE_SMALL
-#define TILE_T      128        // compute threads per CTA = prism columns per tile (incl. halo)
-#define TILE_S      128        // summing threads per CTA (one warpgroup)
-#define TILE_CTAS   2
-#define TILE_REG_C  "216"
-#define TILE_REG_S  "40"
-#define TILE_EPT    5          // table entries per summing thread
-#elif defined(TILE_S128)
-#define TILE_T      256
-#define TILE_S      128
-#define TILE_CTAS   1
-#define TILE_REG_C  "224"      // 256 x 56 more registers for the compute warps = ...
-#define TILE_REG_S  "56"       // ... the 128 x 112 the summing warps release into the CTA's pool
-#define TILE_EPT    9
-#else
-#define TILE_T      256        // 8 compute warps
-#define TILE_S      256        // 8 summing warps: two per scheduler, the sums of a layer take half as long
+// Shape (compile time).  Default: the staging buffer is DOUBLE-buffered, so the sums of layer k run while the compute warps
+// are already staging layer k + 1 (with one buffer the two kinds of warps take turns: measured 49 % of the compute warps'
+// time and 46 % of the summing warps' time spent at the hand-over barriers).  Two buffers of 51 doubles per thread only fit
+// into the 227 KB of an SM for 224 prism columns per tile: the 8 compute warps use 28 of their 32 lanes (the other four
+// lanes shadow lane 0 and store nothing), which keeps two compute warps on every scheduler and the register split of
+// setmaxnreg (a warpgroup = 4 warps must agree on it).  -DTILE_NBUF=1 -DTILE_LANES=32 is the single-buffered shape.
+#ifndef TILE_NBUF
+#define TILE_NBUF   2
+#endif
+#ifndef TILE_LANES
+#define TILE_LANES  (TILE_NBUF == 2 ? 28 : 32)   // active lanes per compute warp
+#endif
+#define TILE_CW     8                            // compute warps
+#define TILE_T      (TILE_CW * TILE_LANES)       // prism columns per tile (incl. halo) = compute threads that stage
+#define TILE_TW     (TILE_CW * 32)               // threads of the compute warps
+#define TILE_S      256                          // 8 summing warps: two per scheduler
 #define TILE_CTAS   1
 #define TILE_REG_C  "216"      // launch bound 512 threads -> 128 registers each; 256 x 88 move from the summing to the compute warps
 #define TILE_REG_S  "40"
-#define TILE_EPT    5
-#endif
+#define TILE_EPT    5          // table entries per summing thread (at most)
 #define TILE_NSLOT  51         // staged doubles per compute thread and layer
 #define TILE_MAXC   120        // ice columns owned by one tile
-#define TILE_MAXE   (TILE_EPT * TILE_S)   // table entries per tile
+#define TILE_MAXE   (TILE_NBUF == 2 ? 1152 : TILE_EPT * TILE_S)   // table entries per tile
 #define TILE_TABW   (8 * TILE_MAXE)       // contribution words (uint16) of one tile's table in shared memory
 
 // staged slots:   0..8  D(b0) D(b1) D(b2): xx xy yy      9..20 E(b0b1) E(b0b2) E(b1b2): xx xy yx yy (row first, col second)
@@ -209,8 +204,9 @@ __host__ __device__ __forceinline__ void iface_zero(Iface& a)
 template <class ST>
 __host__ __device__ __forceinline__ void put_blk(ST& st, const int slot, const int blk, const double xx, const double xy, const double yx, const double yy)
 {
-	const bool f = (st.flags >> blk) & 1u;
-	st.put(slot, xx); st.put(slot + 1, f ? yx : xy); st.put(slot + 2, f ? xy : yx); st.put(slot + 3, yy);
+	// transposed = the two off-diagonal values change places: an address offset, no select on the values
+	const int f = (st.flags >> blk) & 1u;
+	st.put(slot, xx); st.put_off(slot + 1, f, xy); st.put_off(slot + 2, -f, yx); st.put(slot + 3, yy);
 }
 
 template <class ST>
@@ -222,47 +218,29 @@ __host__ __device__ __forceinline__ void prism_steps(const double4* pb, const do
 	double C01[4], C02[4], C12[4];
 	// ---- tet A = (b0 b1 b2 t2): local 0 1 2 3.  Final afterwards: everything of b2, C22
 	tet_eval(pb[0], pb[1], pb[2], pt[2], ub[0], ub[1], ub[2], ut[2], a0, P, o);
-	// what tet A makes final is kept in registers until the gate after tet B: the summing warps then have two thirds of
-	// a prism's time to finish with the previous layer
-	double fin[17];
+	// staged as soon as it is final: the gate (the kernel waits there until the summing warps have released this staging
+	// buffer) comes after the element math of tet A -- with two staging buffers it is open long before
+	st.gate();
 	#pragma unroll
-	for (int i = 0; i < 3; ++i) fin[i] = bot.D[6 + i] + o.D[6 + i];                        // D(b2)
+	for (int i = 0; i < 3; ++i) st.put(6 + i, bot.D[6 + i] + o.D[6 + i]);                  // D(b2)
+	put_blk(st, 13, 1, bot.E[4] + o.E[4], bot.E[5] + o.E[5], bot.E[6] + o.E[6], bot.E[7] + o.E[7]);           // (0,2) -> E(b0b2)
+	put_blk(st, 17, 2, bot.E[8] + o.E[12], bot.E[9] + o.E[13], bot.E[10] + o.E[14], bot.E[11] + o.E[15]);     // (1,2) -> E(b1b2)
+	put_blk(st, 47, 8, o.E[20], o.E[21], o.E[22], o.E[23]);                                                   // (2,3) -> C22
+	st.put(25, bot.F[4] + o.F[4]); st.put(26, bot.F[5] + o.F[5]);                          // F(b2)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		fin[3 + i] = bot.E[4 + i] + o.E[4 + i];                                            // (0,2) -> E(b0b2)
-		fin[7 + i] = bot.E[8 + i] + o.E[12 + i];                                           // (1,2) -> E(b1b2)
-		fin[11 + i] = o.E[20 + i];                                                         // (2,3) -> C22
 		bot.E[i] += o.E[i];                                                                // (0,1) -> E(b0b1)
 		C02[i] = o.E[8 + i];                                                               // (0,3) -> C02
 		C12[i] = o.E[16 + i];                                                              // (1,3) -> C12
 	}
-	fin[15] = bot.F[4] + o.F[4]; fin[16] = bot.F[5] + o.F[5];                              // F(b2)
 	#pragma unroll
 	for (int i = 0; i < 6; ++i) bot.D[i] += o.D[i];                                        // D(b0) D(b1)
 	#pragma unroll
 	for (int i = 0; i < 4; ++i) bot.F[i] += o.F[i];
 	top.D[6] = o.D[9]; top.D[7] = o.D[10]; top.D[8] = o.D[11];                             // D(t2)
 	top.F[4] = o.F[6]; top.F[5] = o.F[7];
-#ifndef TILE_GATE_B
-	st.gate();
-	#pragma unroll
-	for (int i = 0; i < 3; ++i) st.put(6 + i, fin[i]);
-	put_blk(st, 13, 1, fin[3], fin[4], fin[5], fin[6]);
-	put_blk(st, 17, 2, fin[7], fin[8], fin[9], fin[10]);
-	put_blk(st, 47, 8, fin[11], fin[12], fin[13], fin[14]);
-	st.put(25, fin[15]); st.put(26, fin[16]);
-#endif
 	// ---- tet B = (b0 b1 t1 t2).  Final afterwards: everything of b1, C11, C12
 	tet_eval(pb[0], pb[1], pt[1], pt[2], ub[0], ub[1], ut[1], ut[2], a1, P, o);
-#ifdef TILE_GATE_B
-	st.gate();
-	#pragma unroll
-	for (int i = 0; i < 3; ++i) st.put(6 + i, fin[i]);
-	put_blk(st, 13, 1, fin[3], fin[4], fin[5], fin[6]);
-	put_blk(st, 17, 2, fin[7], fin[8], fin[9], fin[10]);
-	put_blk(st, 47, 8, fin[11], fin[12], fin[13], fin[14]);
-	st.put(25, fin[15]); st.put(26, fin[16]);
-#endif
 	#pragma unroll
 	for (int i = 0; i < 3; ++i) st.put(3 + i, bot.D[3 + i] + o.D[3 + i]);                 // D(b1)
 	put_blk(st, 9, 0, bot.E[0] + o.E[0], bot.E[1] + o.E[1], bot.E[2] + o.E[2], bot.E[3] + o.E[3]);            // (0,1) -> E(b0b1)
@@ -350,17 +328,21 @@ __host__ __device__ __noinline__ double4 entry_total(const double* stage, const 
 }
 
 // ------------------------------------------------------------------------------------------------
-// the kernel: 8 compute warps (one thread per prism column) + 4 summing warps, registers re-balanced with
-// setmaxnreg (TILE_REG_C / TILE_REG_S: the CTA's register pool is conserved), hand-over through two named barriers:
-//   FULL   compute warps arrive after staging layer k, summing warps wait
-//   EMPTY  summing warps arrive after reading layer k, compute warps wait before they stage layer k + 1
-// so the sums of layer k overlap the element math of layer k + 1.  The vertex data of the next layer arrives by
-// cp.async (LDGSTS) into a per-thread shared-memory slot while the current prism is computed; the tile's table of
-// (thread, slot) contributions is copied to shared memory once per CTA.
-#define BAR_FULL  1
-#define BAR_EMPTY 2
-#define BAR_SUM   3
-#define BAR_VDATA 4
+// the kernel: 8 compute warps (one thread per prism column) + 8 summing warps, registers re-balanced with setmaxnreg
+// (TILE_REG_C / TILE_REG_S: the CTA's register pool is conserved), hand-over through named barriers:
+//   FULL[b]   compute warps arrive after staging a layer into buffer b, summing warps wait
+//   EMPTY[b]  summing warps arrive after reading buffer b, compute warps wait before they stage into it again
+//   VDATA     summing warps arrive when the vertex package of the next prism has landed, compute warps wait
+//   VREAD     compute warps arrive when they hold a package in registers, summing warps wait before they refill the buffer
+// so the sums of layer k overlap the element math of layer k + 1 (TILE_NBUF = 2: all of it).  The vertex data of the next
+// layer arrives by cp.async (LDGSTS) into a per-thread shared-memory slot while the current prism is computed -- no global
+// loads inside the march; the tile's table of (thread, slot) contributions is copied to shared memory once per CTA.
+#define BAR_FULL  1            // + buffer
+#define BAR_EMPTY 3            // + buffer
+#define BAR_SUM   5
+#define BAR_VDATA 6
+#define BAR_VREAD 7
+#define TILE_NTHR (TILE_TW + TILE_S)
 __device__ __forceinline__ void bar_sync(const int id, const int n)   { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(const int id, const int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
@@ -396,43 +378,35 @@ __device__ __forceinline__ double4 entry_total_dev(const double* stage, const ui
 }
 
 struct DevStage {
-	double* sb; bool wait; uint32_t flags;
-#ifdef TILE_GATE_END
-	// (experiment, -DTILE_GATE_END: 5 % faster, but 190 more bytes of spills per thread: +16 % DRAM traffic)
-	// everything a prism stages is held back (registers, what does not fit: local memory) until the whole prism is
-	// computed: the summing warps then have a full prism's time for the previous layer
-	double v[TILE_NSLOT];
-	__device__ __forceinline__ void gate() {}
-	__device__ __forceinline__ void put(const int slot, const double x) { v[slot] = x; }
-	__device__ __forceinline__ void flush(const int n) {
-		if (wait) bar_sync(BAR_EMPTY, TILE_T + TILE_S);
-		#pragma unroll
-		for (int i = 0; i < TILE_NSLOT; ++i) if (i < n) sb[i * TILE_T] = v[i];
-	}
-#else
-	__device__ __forceinline__ void gate() { if (wait) bar_sync(BAR_EMPTY, TILE_T + TILE_S); }
+	double* sb; bool wait; int bar; uint32_t flags;
+	__device__ __forceinline__ void gate() { if (wait) bar_sync(bar, TILE_NTHR); }
 	__device__ __forceinline__ void put(const int slot, const double v) { sb[slot * TILE_T] = v; }
-	__device__ __forceinline__ void flush(const int) {}
-#endif
+	__device__ __forceinline__ void put_off(const int slot, const int d, const double v) { sb[slot * TILE_T + d * TILE_T] = v; }
 };
 
-__global__ void __launch_bounds__(TILE_T + TILE_S, TILE_CTAS)
+#define TILE_STAGE_BYTES ((size_t)TILE_NSLOT * TILE_T * 8)
+#define TILE_VBUF_BYTES  ((size_t)8 * TILE_T * 16)
+
+__global__ void __launch_bounds__(TILE_NTHR, TILE_CTAS)
 k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
        const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const uint8_t* __restrict__ einfo, const uint16_t* __restrict__ tflag,
        const int32_t* __restrict__ out, const int32_t* __restrict__ out2, const int64_t n_ent,
        const double4* __restrict__ geo, const double2* __restrict__ zS, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	double* stage = (double*)smem_raw;                                              // [TILE_NSLOT][TILE_T]
-	double2* vbuf = (double2*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8);         // [2][8][TILE_T]: per prism {z, S}, {u_x, u_y} of the three top vertices, ainv of the three tets
-	uint16_t* stab = (uint16_t*)(smem_raw + (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 8 * TILE_T * 16);   // [entries][W]
+	double* stage = (double*)smem_raw;                                              // [TILE_NBUF][TILE_NSLOT][TILE_T]
+	double2* vbuf = (double2*)(smem_raw + TILE_NBUF * TILE_STAGE_BYTES);            // [8][TILE_T]: per prism {z, S}, {u_x, u_y} of the three top vertices, ainv of the three tets
+	uint16_t* stab = (uint16_t*)(smem_raw + TILE_NBUF * TILE_STAGE_BYTES + TILE_VBUF_BYTES);   // [entries][W]
 	uint8_t* sinfo = (uint8_t*)(stab + TILE_TABW);                                  // [entries]
 	const int tile = tile0 + blockIdx.x;
 	const int NZ = NL - 1;
-	if (threadIdx.x < TILE_T) {
+	if (threadIdx.x < TILE_TW) {
 		// ================================================================= compute warps: no global loads inside the march
 		asm volatile("setmaxnreg.inc.sync.aligned.u32 " TILE_REG_C ";");
-		const int t = threadIdx.x;
+		const int lane = threadIdx.x & 31;
+		// lanes beyond TILE_LANES shadow lane 0 of their warp: same inputs, same arithmetic, the same values stored to the same
+		// addresses -- harmless, and no predicate in the march
+		const int t = (threadIdx.x >> 5) * TILE_LANES + (lane < TILE_LANES ? lane : 0);
 		const uint32_t tflags = tflag[(size_t)tile * TILE_T + t];
 		double4 pb[3], pt[3];
 		double2 ub[3], ut[3];
@@ -445,8 +419,8 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }        // layer 0: straight into registers
 		}
 		for (int k = 0; k < NZ; ++k) {
-			bar_sync(BAR_VDATA, TILE_T + TILE_S);               // the summing warps have brought in this prism's package
-			const double2* vb = vbuf + (size_t)(k & 1) * 8 * TILE_T + t;
+			bar_sync(BAR_VDATA, TILE_NTHR);                     // the summing warps have brought in this prism's package
+			const double2* vb = vbuf + t;
 			#pragma unroll
 			for (int i = 0; i < 3; ++i) {
 				const double2 q0 = vb[(2 * i) * TILE_T];
@@ -454,31 +428,32 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 				ut[i] = vb[(2 * i + 1) * TILE_T];
 			}
 			const double2 a01 = vb[6 * TILE_T], a2x = vb[7 * TILE_T];
-			DevStage st = { stage + t, k > 0, tflags };
+			if (k + 1 < NZ) bar_arrive(BAR_VREAD, TILE_NTHR);   // the package is in registers: its buffer may be refilled
+			const int b = (TILE_NBUF == 2) ? (k & 1) : 0;
+			DevStage st = { stage + (size_t)b * TILE_NSLOT * TILE_T + t, k >= TILE_NBUF, BAR_EMPTY + b, tflags };
 			prism_steps(pb, ub, pt, ut, a01.x, a01.y, a2x.x, P, bot, top, st);
-			st.flush(TILE_NSLOT);
 			asm volatile("fence.acq_rel.cta;" ::: "memory");
-			bar_arrive(BAR_FULL, TILE_T + TILE_S);
+			bar_arrive(BAR_FULL + b, TILE_NTHR);
 			bot = top;
 			#pragma unroll
 			for (int i = 0; i < 3; ++i) { pb[i] = pt[i]; ub[i] = ut[i]; }
 		}
-		DevStage st = { stage + t, NZ > 0, tflags };
+		const int b = (TILE_NBUF == 2) ? (NZ & 1) : 0;
+		DevStage st = { stage + (size_t)b * TILE_NSLOT * TILE_T + t, NZ >= TILE_NBUF, BAR_EMPTY + b, tflags };
 		iface_stage(bot, st);
-		st.flush(27);
 		asm volatile("fence.acq_rel.cta;" ::: "memory");
-		bar_arrive(BAR_FULL, TILE_T + TILE_S);
+		bar_arrive(BAR_FULL + b, TILE_NTHR);
 	} else {
 		// ================================================================= summing warps (and feeders of the compute warps)
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 " TILE_REG_S ";");
-		const int sidx = threadIdx.x - TILE_T;
+		const int sidx = threadIdx.x - TILE_TW;
 		const int e_lo = ent0[tile], ne = ent0[tile + 1] - e_lo;
 		// package of prism j for compute thread c: {z, S} and u of the three vertices of layer j + 1, ainv of the three tets
 		auto feed = [&](const int j) {
 			for (int c = sidx; c < TILE_T; c += TILE_S) {
 				const int32_t* tv = tvert + ((size_t)tile * NL + j + 1) * 3 * TILE_T + c;
 				const int32_t* tn = tnode + ((size_t)tile * NL + j + 1) * 3 * TILE_T + c;
-				double2* vb = vbuf + (size_t)(j & 1) * 8 * TILE_T + c;
+				double2* vb = vbuf + c;
 				#pragma unroll
 				for (int i = 0; i < 3; ++i) { cp_async16(vb + (2 * i) * TILE_T, &zS[tv[i * TILE_T]]); cp_async16(vb + (2 * i + 1) * TILE_T, &u[tn[i * TILE_T]]); }
 				const double* ta = tainv + (((size_t)tile * NZ + j) * TILE_T + c) * 4;
@@ -486,8 +461,12 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			}
 			asm volatile("cp.async.commit_group;" ::: "memory");
 		};
+		auto release = [&]() {                                  // the package requested last is complete: hand it to the compute warps
+			asm volatile("cp.async.wait_group 0;" ::: "memory");
+			asm volatile("fence.acq_rel.cta;" ::: "memory");
+			bar_arrive(BAR_VDATA, TILE_NTHR);
+		};
 		if (NZ >= 1) feed(0);
-		if (NZ >= 2) feed(1);
 		{	// the tile's table -> shared memory (16-byte pieces)
 			const uint4* src = (const uint4*)(tab + (size_t)e_lo * W);
 			uint4* dst = (uint4*)stab;
@@ -496,31 +475,28 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			for (int i = sidx; i < ne; i += TILE_S) sinfo[i] = einfo[e_lo + i];
 		}
 		bar_sync(BAR_SUM, TILE_S);
-		if (NZ >= 1) {
-			if (NZ >= 2) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-			asm volatile("fence.acq_rel.cta;" ::: "memory");
-			bar_arrive(BAR_VDATA, TILE_T + TILE_S);             // package 0 is in
-		}
+		if (NZ >= 1) release();                                 // package 0
+		if (NZ >= 2) { bar_sync(BAR_VREAD, TILE_NTHR); feed(1); release(); }      // package 1, as soon as package 0 is in registers
 		for (int k = 0; k <= NZ; ++k) {
 			int o[TILE_EPT], o2[TILE_EPT];
 			const int32_t* ok = out + (size_t)k * n_ent + e_lo;
 			const int32_t* ok2 = out2 + (size_t)k * n_ent + e_lo;
 			#pragma unroll
 			for (int i = 0; i < TILE_EPT; ++i) { const int e = sidx + i * TILE_S; o[i] = (e < ne) ? ok[e] : -1; o2[i] = (e < ne) ? ok2[e] : -1; }
-			bar_sync(BAR_FULL, TILE_T + TILE_S);
-			// the compute warps are done with prism k (they read its package at the start): release package k + 1, which
-			// was requested one prism ago, and request package k + 2 into the buffer that just became free
-			if (k + 1 < NZ) {
-				asm volatile("cp.async.wait_group 0;" ::: "memory");
-				asm volatile("fence.acq_rel.cta;" ::: "memory");
-				bar_arrive(BAR_VDATA, TILE_T + TILE_S);
-			}
-			if (k + 2 < NZ) feed(k + 2);
+			const int b = (TILE_NBUF == 2) ? (k & 1) : 0;
+			const double* stg = stage + (size_t)b * TILE_NSLOT * TILE_T;
+			bar_sync(BAR_FULL + b, TILE_NTHR);
+			// layer k is staged, so the compute warps are starting prism k + 1 and take its package into registers: after the
+			// first entry request package k + 2 into the same buffer; it lands while the other entries are summed and is
+			// handed over before the last one
+			const bool feeding = k + 2 < NZ;
 			#pragma unroll
 			for (int i = 0; i < TILE_EPT; ++i) {
+				if (i == 1 && feeding) { bar_sync(BAR_VREAD, TILE_NTHR); feed(k + 2); }
+				if (i == TILE_EPT - 1 && feeding) release();
 				if (o[i] == -1) continue;
 				const int e = sidx + i * TILE_S;
-				const double4 acc = entry_total_dev(stage, stab + (size_t)e * W, sinfo[e], W);
+				const double4 acc = entry_total_dev(stg, stab + (size_t)e * W, sinfo[e], W);
 				const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
 				if (o[i] >= 0) {
 					double2* dst = (double2*)val + 2 * (size_t)o[i];
@@ -535,7 +511,7 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 					*(double2*)(F + 2 * (size_t)(-o[i] - 2)) = make_double2(a0, a1);
 				}
 			}
-			if (k < NZ) bar_arrive(BAR_EMPTY, TILE_T + TILE_S);
+			if (k + TILE_NBUF <= NZ) bar_arrive(BAR_EMPTY + b, TILE_NTHR);
 		}
 	}
 }
@@ -569,7 +545,7 @@ bool bp_tiles_serve(const bp_ctx* c, int what)
 	return c->env.asm_tiled != 0;
 }
 
-static size_t tile_smem_bytes() { return (size_t)TILE_NSLOT * TILE_T * 8 + (size_t)2 * 8 * TILE_T * 16 + (size_t)TILE_TABW * 2 + TILE_MAXE; }
+static size_t tile_smem_bytes() { return TILE_NBUF * TILE_STAGE_BYTES + TILE_VBUF_BYTES + (size_t)TILE_TABW * 2 + TILE_MAXE; }
 
 static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile, cudaStream_t stream = nullptr)
 {
@@ -583,7 +559,7 @@ static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile, cudaSt
 		T->attr_set = true;
 	}
 	if (ntile <= 0) return;
-	k_tile<<<ntile, TILE_T + TILE_S, sm, stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_einfo, T->d_tflag, T->d_out, T->d_out2,
+	k_tile<<<ntile, TILE_NTHR, sm, stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_einfo, T->d_tflag, T->d_out, T->d_out2,
 	                                                   T->n_ent, c->d_geo, c->d_zS, (const double2*)c->d_u, c->d_F, c->d_val, P);
 	c->launches++;
 }
@@ -1207,6 +1183,7 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 		double* sb; uint32_t flags;
 		void gate() {}
 		void put(int slot, double v) { sb[(size_t)slot * TILE_T] = v; }
+		void put_off(int slot, int d, double v) { sb[(size_t)(slot + d) * TILE_T] = v; }
 	};
 	const int W = T->W;
 	#pragma omp parallel
