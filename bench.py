@@ -388,7 +388,8 @@ def run_ours(args):
 		newton = {"solve_s": t_dev, "converged": st['converged'], "newton_iterations": st['iterations'],
 		          "krylov_iterations": st['krylov_iterations'], "assemble_ms": st['t_assemble_ms'], "krylov_ms": st['t_krylov_ms'],
 		          "preconditioner": ctx.pc_label(), "rtol": 1e-9, "krylov_rtol": 1e-5,
-		          "gpu_launches": st['gpu_launches'],
+		          "gpu_launches": st['gpu_launches'], "host_launches": st.get('host_launches'),
+		          "host_launches_per_krylov_iteration": (st['host_launches'] / max(st['krylov_iterations'], 1)) if st.get('host_launches') is not None else None,
 		          "mixed_precision": "the multigrid smoother reads an FP32 copy of the level matrices; CG, its SpMV, the residual and all vectors are FP64"}
 		if not multi:
 			uh = np.full(nd, 3e-16)

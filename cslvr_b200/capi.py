@@ -58,7 +58,8 @@ class bp_stats(C.Structure):
 	            ('t_assemble_ms', C.c_double), ('t_krylov_ms', C.c_double),
 	            ('t_total_ms', C.c_double), ('n_assemblies', C.c_int32),
 	            ('gpu_launches', C.c_int32), ('residual_history', C.c_double * 64),
-	            ('krylov_unconverged', C.c_int32), ('krylov_last_relres', C.c_double)]
+	            ('krylov_unconverged', C.c_int32), ('krylov_last_relres', C.c_double),
+	            ('host_launches', C.c_int32)]
 
 	def as_dict(self):
 		n = min(self.newton_iterations + 1, 64)
@@ -69,7 +70,8 @@ class bp_stats(C.Structure):
 		            t_assemble_ms=self.t_assemble_ms, t_krylov_ms=self.t_krylov_ms,
 		            t_total_ms=self.t_total_ms, n_assemblies=int(self.n_assemblies),
 		            gpu_launches=int(self.gpu_launches),
-		            krylov_unconverged=int(self.krylov_unconverged), krylov_last_relres=self.krylov_last_relres)
+		            krylov_unconverged=int(self.krylov_unconverged), krylov_last_relres=self.krylov_last_relres,
+		            host_launches=int(self.host_launches))
 
 
 # every symbol include/cslvr_b200.h declares (tests check the library exports them all)

@@ -37,6 +37,7 @@ void bp_env_read(bp_env* e)
 	e->mg_repl = geti("BP_MG_REPL", 32768);
 	e->asm_tiled = geti("BP_ASM_TILED", -1);
 	e->cg_graph = geti("BP_CG_GRAPH", 1) != 0;
+	e->p2p = geti("BP_P2P", 1) != 0;
 }
 
 // ------------------------------------------------------------------ helpers
@@ -204,24 +205,84 @@ static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 	if ((rc = bp_comm_allreduce(cs, n, SC_T0, 3))) return rc;
 	for (int r = 0; r < n; ++r) bp_launch_pcg_p(cs[r], 1, 0);
 	const int maxit = cs[0]->prm.krylov_maxit > 0 ? cs[0]->prm.krylov_maxit : 10000;
+	// one CG iteration; par = parity of the iteration (the device-resident scalars alternate between two sets)
+	auto iterate = [&](const int par) -> int {
+		int rc_;
+		if ((rc_ = bp_comm_halo(cs, n, 1))) return rc_;
+		for (int r = 0; r < n; ++r) bp_launch_spmv(cs[r], cs[r]->d_p, cs[r]->d_Ap, 1);
+		if ((rc_ = bp_comm_allreduce(cs, n, SC_PAP, 1))) return rc_;
+		if (fused) {
+			for (int r = 0; r < n; ++r) bp_launch_pcg_update(cs[r], par);
+		} else {
+			for (int r = 0; r < n; ++r) bp_launch_pcg_update2(cs[r], par);
+			if ((rc_ = group_pc_apply(cs, n))) return rc_;
+			for (int r = 0; r < n; ++r) bp_launch_dots3(cs[r], par ? SC_T0 : SC_T1, 1);
+		}
+		if ((rc_ = bp_comm_allreduce(cs, n, par ? SC_T0 : SC_T1, 3))) return rc_;
+		for (int r = 0; r < n; ++r) bp_launch_pcg_p(cs[r], 0, par);
+		return BP_OK;
+	};
+	// The iteration is a fixed launch sequence (every scalar, the convergence flag and the Chebyshev bounds live on the
+	// device; a converged solve turns the remaining kernels of a batch into no-ops), so two iterations (both parities) are
+	// captured ONCE as a CUDA graph -- the V-cycle graph becomes a child node, the peer-memory / NCCL exchanges are captured
+	// with it -- and the host issues one graph launch per two iterations instead of ~12 launches + 1 graph.  The first two
+	// iterations of a solve run directly when the graph does not exist yet: the multigrid captures its own graph there.
+	bp_ctx* c0 = cs[0];
+	struct Key { const void* inner; const void* stream; double lmax, ratio, alpha; int pc, deg, smoother, n, f32, maxit_even; } key;
+	memset(&key, 0, sizeof(key));
+	const void* inner = nullptr;
+	const bool settled = (c0->prm.pc != BP_PC_MG) || bp_mg_settled(cs, n, &inner);
+	key.inner = inner; key.stream = (const void*)c0->stream; key.lmax = (c0->prm.pc == BP_PC_CHEBYSHEV) ? c0->cheb_lmax : 0.0;
+	key.ratio = c0->prm.pc_eig_ratio; key.alpha = c0->prm.mg_coarse_scale; key.pc = c0->prm.pc; key.deg = c0->prm.pc_degree;
+	key.smoother = c0->prm.mg_smoother; key.n = n; key.f32 = c0->env.mg_fp32 ? 1 : 0;
+	if (c0->cg_graph && memcmp(&key, c0->cg_key, sizeof(key)) != 0) { cudaGraphExecDestroy(c0->cg_graph); c0->cg_graph = nullptr; }
+	static_assert(sizeof(Key) <= sizeof(c0->cg_key), "bp_ctx::cg_key too small");
 	int k = 0;
 	bool done = false;
 	while (k < maxit && !done) {
 		const int batch = std::min(fused ? 32 : 8, maxit - k);
-		for (int i = 0; i < batch; ++i) {
-			if ((rc = bp_comm_halo(cs, n, 1))) return rc;
-			for (int r = 0; r < n; ++r) bp_launch_spmv(cs[r], cs[r]->d_p, cs[r]->d_Ap, 1);
-			if ((rc = bp_comm_allreduce(cs, n, SC_PAP, 1))) return rc;
-			const int par = (k + i) & 1;
-			if (fused) {
-				for (int r = 0; r < n; ++r) bp_launch_pcg_update(cs[r], par);
-			} else {
-				for (int r = 0; r < n; ++r) bp_launch_pcg_update2(cs[r], par);
-				if ((rc = group_pc_apply(cs, n))) return rc;
-				for (int r = 0; r < n; ++r) bp_launch_dots3(cs[r], par ? SC_T0 : SC_T1, 1);
+		int i = 0;
+		while (i < batch) {
+			const bool pair_ok = c0->env.cg_graph && !c0->cg_no_graph && ((k + i) & 1) == 0 && i + 2 <= batch;
+			if (pair_ok && !c0->cg_graph && (k + i >= 2 || settled)) {
+				// the preconditioner's own graph may have been (re)built by the direct iterations: look again
+				const void* in2 = nullptr;
+				if (c0->prm.pc != BP_PC_MG || bp_mg_settled(cs, n, &in2)) {
+					key.inner = in2;
+					std::vector<int64_t> l0(n);
+					for (int r = 0; r < n; ++r) l0[r] = cs[r]->launches;
+					cudaGraph_t g = nullptr;
+					cudaError_t eb = cudaStreamBeginCapture(c0->stream, cudaStreamCaptureModeThreadLocal);
+					if (eb == cudaSuccess) {
+						rc = iterate(0);
+						if (!rc) rc = iterate(1);
+						eb = cudaStreamEndCapture(c0->stream, &g);
+						if (rc == BP_OK && eb == cudaSuccess) eb = cudaGraphInstantiate(&c0->cg_graph, g, 0);
+						if (g) cudaGraphDestroy(g);
+						if (rc != BP_OK || eb != cudaSuccess) c0->cg_graph = nullptr;
+					}
+					if (!c0->cg_graph) { cudaGetLastError(); c0->cg_no_graph = true; rc = BP_OK; }    // not capturable here: keep launching directly
+					else {
+						c0->cg_launches = 0;
+						for (int r = 0; r < n; ++r) c0->cg_launches += cs[r]->launches - l0[r];
+						memcpy(c0->cg_key, &key, sizeof(key));
+					}
+					for (int r = 0; r < n; ++r) cs[r]->launches = l0[r];
+				}
 			}
-			if ((rc = bp_comm_allreduce(cs, n, par ? SC_T0 : SC_T1, 3))) return rc;
-			for (int r = 0; r < n; ++r) bp_launch_pcg_p(cs[r], 0, par);
+			if (pair_ok && c0->cg_graph) {
+				BP_CUDA(c0, cudaGraphLaunch(c0->cg_graph, c0->stream));
+				c0->launches += c0->cg_launches;
+				c0->host_launches++;
+				i += 2;
+			} else {
+				int64_t l0 = 0, l1 = 0;
+				for (int r = 0; r < n; ++r) l0 += cs[r]->launches;
+				if ((rc = iterate((k + i) & 1))) return rc;
+				for (int r = 0; r < n; ++r) l1 += cs[r]->launches;
+				c0->host_launches += l1 - l0;      // (a V-cycle graph inside counts with all its kernels: an upper bound)
+				++i;
+			}
 		}
 		k += batch;
 		if ((rc = read_scalars(cs[0]))) return rc;
@@ -252,6 +313,7 @@ static int group_newton(bp_ctx** cs, int n, bp_stats* st)
 	int rc;
 	int64_t l0 = 0;
 	const int unconv0 = c0->krylov_unconverged;
+	const int64_t hl0 = c0->host_launches;
 	for (int r = 0; r < n; ++r) { if ((rc = ready(cs[r]))) { if (r) c0->err = cs[r]->err; return rc; } l0 += cs[r]->launches; }
 	cudaEvent_t eA, eB, eT0, eT1;
 	cudaEventCreate(&eA); cudaEventCreate(&eB); cudaEventCreate(&eT0); cudaEventCreate(&eT1);
@@ -304,6 +366,7 @@ out:
 	int64_t l1 = 0;
 	for (int r = 0; r < n; ++r) l1 += cs[r]->launches;
 	s.gpu_launches = (int32_t)(l1 - l0);
+	s.host_launches = (int32_t)(c0->host_launches - hl0);
 	s.krylov_unconverged = c0->krylov_unconverged - unconv0;
 	s.krylov_last_relres = c0->krylov_last_relres;
 	if (st) *st = s;

@@ -45,6 +45,7 @@ struct bp_env {
 	double mg_lmax_scale = 1.0;     // BP_MG_LMAX_SCALE: factor on the Gershgorin bound of lmax(D^-1 A) the multigrid smoothers use (experiments)
 	int    asm_tiled = -1;          // BP_ASM_TILED: 1 / 0 force / forbid the tiled cell kernel (-1 = automatic)
 	bool   cg_graph = true;         // BP_CG_GRAPH=0: launch the CG iteration directly instead of replaying its graph
+	bool   p2p = true;              // BP_P2P=0: halo exchanges and scalar all-reduces through NCCL instead of peer memory
 };
 void bp_env_read(bp_env* e);
 
@@ -59,6 +60,7 @@ struct AsmParams {
 struct bp_tiles;        // tiled cell assembly (bp_tiles.cu)
 
 struct bp_comm_state;   // NCCL binding (bp_comm.cu)
+struct bp_p2p_halo;     // peer-memory exchange of one partitioned context (bp_comm.cu)
 struct bp_mg;           // multigrid hierarchy (bp_mg.cu)
 
 struct bp_ctx {
@@ -153,6 +155,8 @@ struct bp_ctx {
 	double*  d_sendbuf = nullptr;
 	int64_t  n_send = 0;
 	bp_comm_state* comm = nullptr;
+	bp_p2p_halo* p2p = nullptr;          // peer-memory exchange (nullptr: NCCL send / recv)
+	bool     p2p_tried = false;          // bp_comm_p2p_attach ran for this context (it is collective: once)
 	bp_mg*   mg = nullptr;
 	bp_tiles* tiles = nullptr;           // tiled cell assembly: nullptr when the mesh is not an extruded prism mesh (k_rows serves it)
 	std::string tiles_why;               // why not
@@ -162,6 +166,11 @@ struct bp_ctx {
 
 	bool have_S = false, have_A = false, have_beta = false, have_J = false, have_B = false;
 	int64_t launches = 0;
+	int64_t host_launches = 0;           // graph launches of the CG loop (each replays two iterations)
+	cudaGraphExec_t cg_graph = nullptr;  // two CG iterations (both parities), captured once (bp_api.cu::group_pcg)
+	unsigned char cg_key[96] = { 0 };    // what that graph was captured for
+	int64_t cg_launches = 0;             // kernels inside it
+	bool    cg_no_graph = false;         // the stream cannot be captured: launch directly
 	int     krylov_unconverged = 0;      // linear solves that stopped at krylov_maxit (bp_stats)
 	double  krylov_last_relres = 0.0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -253,4 +262,7 @@ int  bp_comm_allreduce_buf(bp_ctx** ctxs, int n, double** bufs, size_t count, in
 int  bp_comm_rank(const bp_ctx* c);      // rank / number of ranks of the context's communicator (0 / 1 without one)
 int  bp_comm_size(const bp_ctx* c);
 void bp_comm_free(bp_ctx* c);
+bool bp_mg_settled(bp_ctx** cs, int n, const void** id);   // the V-cycle's launch sequence is final: an enclosing stream capture is safe
+int  bp_comm_p2p_attach(bp_ctx* c);   // collective: landing buffer of a partitioned context in the peer-mapped arena
+void bp_comm_p2p_detach(bp_ctx* c);
 double* bp_vec(bp_ctx* c, int which);

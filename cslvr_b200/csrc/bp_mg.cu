@@ -599,7 +599,9 @@ static int mgc_attach_halo(bp_ctx* c, bp_mg_level& L)
 	M->comm = c->comm;                       // shared, owned by the fine context
 	UPM(M->d_send_nodes, L.h_send_nodes.data(), L.h_send_nodes.size());
 	UPM(M->d_sendbuf, (const double*)nullptr, (size_t)2 * std::max<int64_t>(M->n_send, 1));
-	return BP_OK;
+	M->device = c->device;
+	M->env = c->env;
+	return bp_comm_p2p_attach(M);            // collective: every rank attaches its levels in the same order
 }
 
 // ---- replicated tail (see bp_mg::R): the pattern of the last coupled level is gathered from all ranks (every rank adds its
@@ -1264,6 +1266,17 @@ bool bp_mg_use_coupled(bp_ctx** cs, int n)
 	for (int r = 0; r < n; ++r) if (cs[r]->n_cols <= 0) return false;
 	return true;
 }
+// The V-cycle's launch sequence is final -- its graph exists, or it is launched directly for good -- so a stream capture
+// around it (the CG iteration graph) will not run into a capture of its own.  id changes when the graph is rebuilt.
+bool bp_mg_settled(bp_ctx** cs, int n, const void** id)
+{
+	(void)n;
+	bp_mg* mg = cs[0]->mg;
+	if (!mg) return false;
+	*id = (const void*)mg->graph;
+	if (mg->coupled) return mg->graph != nullptr || mg->no_graph || !cs[0]->env.mg_coupled_graph;
+	return mg->graph != nullptr || mg->no_graph;
+}
 int bp_mg_prepare_group(bp_ctx** cs, int n) { return mgc_prepare(cs, n); }
 int bp_mg_apply_group(bp_ctx** cs, int n) { return mgc_apply(cs, n); }
 
@@ -1504,6 +1517,7 @@ int bp_mg_apply(bp_ctx* c)
 
 void bp_mg_free(bp_ctx* c)
 {
+	if (c->cg_graph) { cudaGraphExecDestroy(c->cg_graph); c->cg_graph = nullptr; }      // it replays this hierarchy's buffers
 	if (!c->mg) return;
 	for (size_t l = 0; l < c->mg->lv.size(); ++l) {
 		bp_mg_level& L = c->mg->lv[l];
@@ -1511,6 +1525,7 @@ void bp_mg_free(bp_ctx* c)
 		for (void* p : t) if (p) cudaFree(p);
 		if (l > 0 && L.M) {
 			bp_ctx* M = L.M;
+			bp_comm_p2p_detach(M);
 			void* ptrs[] = { M->d_send_nodes, M->d_sendbuf, M->d_sell_ptr, M->d_col, M->d_diag, M->d_val, M->d_valf, M->d_dinv, M->d_F, M->d_z, M->d_z2, M->d_cd, M->d_io, M->d_sc, M->d_part, M->d_counter };
 			for (void* p : ptrs) if (p) cudaFree(p);
 			if (M->h_sc) cudaFreeHost(M->h_sc);

@@ -337,6 +337,8 @@ __host__ __device__ __noinline__ double4 entry_total(const double* stage, const 
 // so the sums of layer k overlap the element math of layer k + 1 (TILE_NBUF = 2: all of it).  The vertex data of the next
 // layer arrives by cp.async (LDGSTS) into a per-thread shared-memory slot while the current prism is computed -- no global
 // loads inside the march; the tile's table of (thread, slot) contributions is copied to shared memory once per CTA.
+// No fence in front of the arrivals: bar.arrive / bar.sync order the shared-memory accesses of the threads that take part
+// (the producer / consumer pattern of the PTX manual).
 #define BAR_FULL  1            // + buffer
 #define BAR_EMPTY 3            // + buffer
 #define BAR_SUM   5
@@ -432,7 +434,6 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			const int b = (TILE_NBUF == 2) ? (k & 1) : 0;
 			DevStage st = { stage + (size_t)b * TILE_NSLOT * TILE_T + t, k >= TILE_NBUF, BAR_EMPTY + b, tflags };
 			prism_steps(pb, ub, pt, ut, a01.x, a01.y, a2x.x, P, bot, top, st);
-			asm volatile("fence.acq_rel.cta;" ::: "memory");
 			bar_arrive(BAR_FULL + b, TILE_NTHR);
 			bot = top;
 			#pragma unroll
@@ -441,7 +442,6 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		const int b = (TILE_NBUF == 2) ? (NZ & 1) : 0;
 		DevStage st = { stage + (size_t)b * TILE_NSLOT * TILE_T + t, NZ >= TILE_NBUF, BAR_EMPTY + b, tflags };
 		iface_stage(bot, st);
-		asm volatile("fence.acq_rel.cta;" ::: "memory");
 		bar_arrive(BAR_FULL + b, TILE_NTHR);
 	} else {
 		// ================================================================= summing warps (and feeders of the compute warps)
@@ -463,7 +463,6 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		};
 		auto release = [&]() {                                  // the package requested last is complete: hand it to the compute warps
 			asm volatile("cp.async.wait_group 0;" ::: "memory");
-			asm volatile("fence.acq_rel.cta;" ::: "memory");
 			bar_arrive(BAR_VDATA, TILE_NTHR);
 		};
 		if (NZ >= 1) feed(0);

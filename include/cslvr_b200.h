@@ -183,6 +183,7 @@ typedef struct {
 	double  residual_history[64];
 	int32_t krylov_unconverged;      /* linear solves that stopped at krylov_maxit            */
 	double  krylov_last_relres;      /* relative residual of the last linear solve            */
+	int32_t host_launches;           /* launches the host issued for them (a graph replay of two CG iterations counts once) */
 } bp_stats;
 
 /* ---- life cycle ---------------------------------------------------------- */
