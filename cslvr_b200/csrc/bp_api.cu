@@ -254,14 +254,19 @@ static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 					cudaGraph_t g = nullptr;
 					cudaError_t eb = cudaStreamBeginCapture(c0->stream, cudaStreamCaptureModeThreadLocal);
 					if (eb == cudaSuccess) {
+						for (int r = 0; r < n; ++r) cs[r]->outer_capture = true;
 						rc = iterate(0);
 						if (!rc) rc = iterate(1);
+						for (int r = 0; r < n; ++r) cs[r]->outer_capture = false;
 						eb = cudaStreamEndCapture(c0->stream, &g);
 						if (rc == BP_OK && eb == cudaSuccess) eb = cudaGraphInstantiate(&c0->cg_graph, g, 0);
 						if (g) cudaGraphDestroy(g);
 						if (rc != BP_OK || eb != cudaSuccess) c0->cg_graph = nullptr;
 					}
-					if (!c0->cg_graph) { cudaGetLastError(); c0->cg_no_graph = true; rc = BP_OK; }    // not capturable here: keep launching directly
+					if (!c0->cg_graph) {    // not capturable here: keep launching directly
+						if (c0->prm.verbose) fprintf(stderr, "[cslvr_b200] CG iteration graph: capture failed (rc %d, %s); launching directly\n", rc, cudaGetErrorString(eb));
+						cudaGetLastError(); c0->cg_no_graph = true; rc = BP_OK;
+					}
 					else {
 						c0->cg_launches = 0;
 						for (int r = 0; r < n; ++r) c0->cg_launches += cs[r]->launches - l0[r];

@@ -171,6 +171,7 @@ struct bp_ctx {
 	unsigned char cg_key[96] = { 0 };    // what that graph was captured for
 	int64_t cg_launches = 0;             // kernels inside it
 	bool    cg_no_graph = false;         // the stream cannot be captured: launch directly
+	bool    outer_capture = false;       // group_pcg is capturing: the V-cycle joins that capture instead of replaying its own graph
 	int     krylov_unconverged = 0;      // linear solves that stopped at krylov_maxit (bp_stats)
 	double  krylov_last_relres = 0.0;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;

@@ -1137,6 +1137,7 @@ static int mgc_vcycle(bp_ctx** cs, int n, int l, double** rhs, int deg, double r
 			bp_ctx* R = mg->R;
 			const int64_t nloc = mg->lv[l].n, l0 = R->launches;
 			R->stream = cs[r]->stream;
+			R->outer_capture = cs[0]->outer_capture;
 			for (size_t q = 1; q < R->mg->lv.size(); ++q) R->mg->lv[q].M->stream = cs[r]->stream;
 			if ((rc = bp_mg_apply(R))) { cs[0]->err = R->err; return rc; }
 			cs[r]->launches += R->launches - l0;
@@ -1220,6 +1221,7 @@ static int mgc_apply(bp_ctx** cs, int n)
 	bp_mg* mg = cs[0]->mg;                  // the graph of an in-process group lives in its first context
 	const int deg = std::max(cs[0]->prm.pc_degree, 1);
 	const double ratio = std::max(cs[0]->prm.pc_eig_ratio, 1.5);
+	if (cs[0]->outer_capture) return mgc_apply_direct(cs, n, deg, ratio);      // into the caller's capture, kernel by kernel
 	const bool want_graph = cs[0]->env.mg_coupled_graph && !mg->no_graph;
 	if (mg->graph && (mg->g_r != cs[0]->d_r || mg->g_z != cs[0]->d_z || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_alpha != cs[0]->prm.mg_coarse_scale || mg->g_f32 != mg->f32)) {
 		cudaGraphExecDestroy(mg->graph);
@@ -1483,6 +1485,14 @@ int bp_mg_apply(bp_ctx* c)
 	if (mg->graph && (mg->g_r != c->d_r || mg->g_z != c->d_z || mg->g_z2 != c->d_z2 || mg->g_deg != deg || mg->g_ratio != ratio || mg->g_smoother != c->prm.mg_smoother || mg->g_alpha != c->prm.mg_coarse_scale || mg->g_f32 != mg->f32)) {
 		cudaGraphExecDestroy(mg->graph);
 		mg->graph = nullptr;
+	}
+	if (c->outer_capture) {
+		// the caller is capturing a graph of its own (the CG iteration): the V-cycle goes into it kernel by kernel
+		for (size_t l = 1; l < mg->lv.size(); ++l) { mg->lv[l].M->launches = 0; mg->lv[l].M->stream = c->stream; }
+		double* out = vcycle(c, mg, 0, c->d_r, deg, ratio);
+		if (out != c->d_z) BP_CUDA(c, cudaMemcpyAsync(c->d_z, out, (size_t)2 * c->nn_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+		for (size_t l = 1; l < mg->lv.size(); ++l) c->launches += mg->lv[l].M->launches;
+		return BP_OK;
 	}
 	if (!mg->graph) {
 		int64_t l0 = c->launches;
