@@ -514,6 +514,17 @@ class BPContext(object):
 	def launch_count(self):
 		return int(self.lib.bp_launch_count(self.h))
 
+	def assembly_kernel_name(self):
+		"""the cell kernel a fused F + J pass runs with the current parameters (bench lines / profiles)."""
+		mode = int(self._last_params.assembly) if self._last_params is not None else 0
+		if mode == 1:
+			return "k_cell<F,J>"
+		self.lib.bp_debug_tiles_why.argtypes = [C.c_void_p]
+		self.lib.bp_debug_tiles_why.restype = C.c_char_p
+		tiled = mode in (0, 3) and self.lib.bp_debug_tiles_why(self.h) == b"" and os.environ.get('BP_ASM_TILED', '') != '0' \
+			and not int(self._last_params.reduced_stokes if self._last_params is not None else 0)
+		return "k_tile" if tiled else "k_rows<F,J>"
+
 	def comm_init(self, unique_id, rank, n_ranks):
 		self._check(self.lib.bp_comm_init(self.h, nccl_library_path().encode(), unique_id, rank, n_ranks))
 

@@ -352,12 +352,22 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc)
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
 
+// a 2x2 block = one 32-byte sector of the SELL-32 Jacobian: ONE 256-bit store (STG.E.256, sm_100) instead of two 16-byte
+// halves -- half the store instructions and tag look-ups in the LSU the staging traffic shares, no partial sectors
+__device__ __forceinline__ void st_block(double* p, const double a, const double b, const double c, const double d)
+{
+	asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // the summing warps' version of entry_total for entries of one type: the eight table words of an entry arrive with one
 // 16-byte load, two contributions are in flight at a time (eight independent loads), additions in table order
 __device__ __forceinline__ double4 entry_total_dev(const double* stage, const uint16_t* w, const uint32_t info, const int W)
 {
-	if (info & 32) return entry_total(stage, w, info);
-	const int cnt = info & 31, kind = info >> 6;
+#ifdef TILE_EXP_NODATA
+	const int cnt = (info & 31) ? 1 : 0, kind = info >> 6;
+#else
+	const int cnt = info & 31, kind = info >> 6;                    // (entries of mixed types, info & 32, do not come here)
+#endif
 	const int s2 = (kind == 0) ? 2 * TILE_T : TILE_T, s3 = (kind == 0) ? 3 * TILE_T : (kind == 1 ? 2 * TILE_T : TILE_T);
 	double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 	for (int c0 = 0; c0 < cnt; c0 += 8) {
@@ -385,6 +395,15 @@ struct DevStage {
 	__device__ __forceinline__ void put(const int slot, const double v) { sb[slot * TILE_T] = v; }
 	__device__ __forceinline__ void put_off(const int slot, const int d, const double v) { sb[slot * TILE_T + d * TILE_T] = v; }
 };
+
+// -DTILE_TIMING (experiments): clock64 phase timers in one compute and one summing warp of every 400th tile, printed by the kernel
+#ifdef TILE_TIMING
+#define TILE_CLOCK_BEGIN(n) long long tm[n] = { 0 }, t_q = clock64(), t_start = t_q;
+#define TICK(j) { const long long t_ = clock64(); tm[j] += t_ - t_q; t_q = t_; }
+#else
+#define TILE_CLOCK_BEGIN(n)
+#define TICK(j)
+#endif
 
 #define TILE_STAGE_BYTES ((size_t)TILE_NSLOT * TILE_T * 8)
 #define TILE_VBUF_BYTES  ((size_t)8 * TILE_T * 16)
@@ -420,8 +439,11 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			#pragma unroll
 			for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }        // layer 0: straight into registers
 		}
+		TILE_CLOCK_BEGIN(4)
 		for (int k = 0; k < NZ; ++k) {
+			TICK(3)
 			bar_sync(BAR_VDATA, TILE_NTHR);                     // the summing warps have brought in this prism's package
+			TICK(0)
 			const double2* vb = vbuf + t;
 			#pragma unroll
 			for (int i = 0; i < 3; ++i) {
@@ -433,7 +455,9 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			if (k + 1 < NZ) bar_arrive(BAR_VREAD, TILE_NTHR);   // the package is in registers: its buffer may be refilled
 			const int b = (TILE_NBUF == 2) ? (k & 1) : 0;
 			DevStage st = { stage + (size_t)b * TILE_NSLOT * TILE_T + t, k >= TILE_NBUF, BAR_EMPTY + b, tflags };
+			TICK(1)
 			prism_steps(pb, ub, pt, ut, a01.x, a01.y, a2x.x, P, bot, top, st);
+			TICK(2)
 			bar_arrive(BAR_FULL + b, TILE_NTHR);
 			bot = top;
 			#pragma unroll
@@ -443,6 +467,10 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		DevStage st = { stage + (size_t)b * TILE_NSLOT * TILE_T + t, NZ >= TILE_NBUF, BAR_EMPTY + b, tflags };
 		iface_stage(bot, st);
 		bar_arrive(BAR_FULL + b, TILE_NTHR);
+#ifdef TILE_TIMING
+		if (threadIdx.x == 0 && (blockIdx.x % 400) == 7)
+			printf("tile %d compute warp: total %lld | wait VDATA %lld  package read %lld  prism (incl. gate) %lld  loop tail %lld\n", (int)blockIdx.x, clock64() - t_start, tm[0], tm[1], tm[2], tm[3]);
+#endif
 	} else {
 		// ================================================================= summing warps (and feeders of the compute warps)
 		asm volatile("setmaxnreg.dec.sync.aligned.u32 " TILE_REG_S ";");
@@ -476,6 +504,7 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 		bar_sync(BAR_SUM, TILE_S);
 		if (NZ >= 1) release();                                 // package 0
 		if (NZ >= 2) { bar_sync(BAR_VREAD, TILE_NTHR); feed(1); release(); }      // package 1, as soon as package 0 is in registers
+		TILE_CLOCK_BEGIN(8)
 		for (int k = 0; k <= NZ; ++k) {
 			int o[TILE_EPT], o2[TILE_EPT];
 			const int32_t* ok = out + (size_t)k * n_ent + e_lo;
@@ -484,34 +513,60 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			for (int i = 0; i < TILE_EPT; ++i) { const int e = sidx + i * TILE_S; o[i] = (e < ne) ? ok[e] : -1; o2[i] = (e < ne) ? ok2[e] : -1; }
 			const int b = (TILE_NBUF == 2) ? (k & 1) : 0;
 			const double* stg = stage + (size_t)b * TILE_NSLOT * TILE_T;
+			TICK(0)
 			bar_sync(BAR_FULL + b, TILE_NTHR);
+			TICK(1)
 			// layer k is staged, so the compute warps are starting prism k + 1 and take its package into registers: after the
 			// first entry request package k + 2 into the same buffer; it lands while the other entries are summed and is
 			// handed over before the last one
 			const bool feeding = k + 2 < NZ;
+			auto emit = [&](const int oo, const int oo2, const double4 acc) {
+#ifdef TILE_EXP_NOSTORE
+				if (acc.x == 1.2345e301) F[0] = acc.y + acc.z + acc.w + oo2;
+				return;
+#endif
+				if (oo >= 0) {
+					st_block(val + 4 * (size_t)oo, acc.x, acc.y, acc.z, acc.w);
+					if (oo2 >= 0) st_block(val + 4 * (size_t)oo2, acc.x, acc.z, acc.y, acc.w);      // J is symmetric: the transposed block of the partner row, same sum
+				} else {
+					*(double2*)(F + 2 * (size_t)(-oo - 2)) = make_double2(acc.x, acc.y);
+				}
+			};
+			uint32_t mixed = 0;
 			#pragma unroll
 			for (int i = 0; i < TILE_EPT; ++i) {
-				if (i == 1 && feeding) { bar_sync(BAR_VREAD, TILE_NTHR); feed(k + 2); }
-				if (i == TILE_EPT - 1 && feeding) release();
+				if (i == 1) TICK(2)
+				if (i == 1 && feeding) { bar_sync(BAR_VREAD, TILE_NTHR); TICK(3) feed(k + 2); TICK(4) }
+				if (i == TILE_EPT - 1) TICK(5)
+				if (i == TILE_EPT - 1 && feeding) { release(); TICK(6) }
 				if (o[i] == -1) continue;
 				const int e = sidx + i * TILE_S;
-				const double4 acc = entry_total_dev(stg, stab + (size_t)e * W, sinfo[e], W);
-				const double a0 = acc.x, a1 = acc.y, a2 = acc.z, a3 = acc.w;
-				if (o[i] >= 0) {
-					double2* dst = (double2*)val + 2 * (size_t)o[i];
-					dst[0] = make_double2(a0, a1);
-					dst[1] = make_double2(a2, a3);
-					if (o2[i] >= 0) {                      // J is symmetric: the transposed block of the partner row, same sum
-						double2* dt = (double2*)val + 2 * (size_t)o2[i];
-						dt[0] = make_double2(a0, a2);
-						dt[1] = make_double2(a1, a3);
-					}
-				} else {
-					*(double2*)(F + 2 * (size_t)(-o[i] - 2)) = make_double2(a0, a1);
+				const uint32_t info = sinfo[e];
+				if (info & 32) { mixed |= 1u << i; continue; }
+				emit(o[i], o2[i], entry_total_dev(stg, stab + (size_t)e * W, info, W));
+			}
+			// rare (columns that meet themselves on tiny periodic meshes): entries whose contributions have different
+			// types -- the generic sum, one copy of it, no call in the loop above (a call there spills the summing warps)
+			if (mixed) {
+				#pragma unroll 1
+				for (int i = 0; i < TILE_EPT; ++i) {
+					if (!((mixed >> i) & 1u)) continue;
+					const int e = sidx + i * TILE_S;
+					const uint16_t* w = stab + (size_t)e * W;
+					const int cnt = sinfo[e] & 31;
+					double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+					for (int c = 0; c < cnt; ++c) entry_add(stg, w[c], a0, a1, a2, a3);
+					emit(ok[e], ok2[e], make_double4(a0, a1, a2, a3));
 				}
 			}
 			if (k + TILE_NBUF <= NZ) bar_arrive(BAR_EMPTY + b, TILE_NTHR);
+			TICK(7)
 		}
+#ifdef TILE_TIMING
+		if (sidx == 0 && (blockIdx.x % 400) == 7)
+			printf("tile %d summing warp: total %lld | top (index loads) %lld  wait FULL %lld  entry 0 %lld  wait VREAD %lld  feed %lld  entries 1.. %lld  release %lld  last entry + arrive %lld\n",
+			       (int)blockIdx.x, clock64() - t_start, tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7]);
+#endif
 	}
 }
 
