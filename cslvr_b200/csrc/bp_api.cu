@@ -333,8 +333,11 @@ static int group_newton(bp_ctx** cs, int n, bp_stats* st)
 		return BP_OK;
 	};
 	double rn = 0.0;
+	// Dirichlet rows (bp_set_dirichlet): b_i = u_i - g_i before the norm, symmetric elimination before the linear solve
+	auto bc_rows = [&]() { for (int r = 0; r < n; ++r) if (cs[r]->have_bc) bp_launch_bc_rows(cs[r], 1.0); };
+	auto bc_eliminate = [&]() { for (int r = 0; r < n; ++r) if (cs[r]->have_bc) bp_launch_bc_eliminate(cs[r]); };
 	rc = timed_assemble(BP_ASSEMBLE_F | BP_ASSEMBLE_J);
-	if (!rc) rc = group_norm_F(cs, n, &rn);
+	if (!rc) { bc_rows(); rc = group_norm_F(cs, n, &rn); }
 	if (rc) goto out;
 	s.residual_norm0 = rn;
 	s.residual_history[0] = rn;
@@ -342,6 +345,7 @@ static int group_newton(bp_ctx** cs, int n, bp_stats* st)
 	s.converged = (rn < P.newton_atol);
 	while (!s.converged && s.newton_iterations < P.newton_maxit) {
 		int kit = 0;
+		bc_eliminate();
 		cudaEventRecord(eA, c0->stream);
 		rc = group_pcg(cs, n, &kit, nullptr);
 		cudaEventRecord(eB, c0->stream);
@@ -351,6 +355,7 @@ static int group_newton(bp_ctx** cs, int n, bp_stats* st)
 		for (int r = 0; r < n; ++r) bp_launch_axpy(cs[r], -P.newton_relax, cs[r]->d_dx, cs[r]->d_u);
 		s.newton_iterations++;
 		if ((rc = timed_assemble(BP_ASSEMBLE_F | BP_ASSEMBLE_J))) goto out;
+		bc_rows();
 		if ((rc = group_norm_F(cs, n, &rn))) goto out;
 		if (s.newton_iterations < 64) s.residual_history[s.newton_iterations] = rn;
 		if (P.verbose)
@@ -420,7 +425,7 @@ void bp_destroy(bp_ctx* c)
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_zS, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_mirror, c->d_val, c->d_valf, c->d_csr_src, c->d_csr_out, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
-		c->d_io, c->d_io2, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
+		c->d_io, c->d_io2, c->d_bcmask, c->d_bcval, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
 	if (c->ev0) cudaEventDestroy(c->ev0);
@@ -668,6 +673,28 @@ int bp_spmv(bp_ctx* c, const double* x, double* y, int on_device)
 	return BP_OK;
 }
 
+int bp_set_dirichlet(bp_ctx* c, int64_t n, const int32_t* dofs, const double* values)
+{
+	if (!c || n < 0 || (n > 0 && (!dofs || !values))) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	if (n == 0) { c->have_bc = false; return BP_OK; }
+	if (c->prm.reduced_stokes) return bp_fail(c, BP_ERR_ARG, "bp_set_dirichlet: not available for the reduced-Stokes solve");
+	std::vector<double> m((size_t)c->nd_ext, 0.0), g((size_t)c->nd_ext, 0.0);
+	for (int64_t k = 0; k < n; ++k) {
+		if (dofs[k] < 0 || dofs[k] >= c->nd_ext) return bp_fail(c, BP_ERR_ARG, "bp_set_dirichlet: dof %d outside [0, %lld)", dofs[k], (long long)c->nd_ext);
+		m[dofs[k]] = 1.0; g[dofs[k]] = values[k];
+	}
+	const size_t nb = (size_t)2 * c->nn * sizeof(double);
+	if (!c->d_bcmask) { BP_CUDA(c, cudaMalloc((void**)&c->d_bcmask, nb)); BP_CUDA(c, cudaMalloc((void**)&c->d_bcval, nb)); }
+	BP_CUDA(c, cudaMemcpyAsync(c->d_io, m.data(), m.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	bp_launch_gather_in(c, c->d_io, c->d_bcmask);
+	BP_CUDA(c, cudaMemcpyAsync(c->d_io2, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	bp_launch_gather_in(c, c->d_io2, c->d_bcval);
+	BP_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->have_bc = true;
+	return BP_OK;
+}
+
 int bp_krylov_solve(bp_ctx* c, const double* b, double* dx, int on_device, int32_t* iterations, double* rel_residual)
 {
 	if (!c || !b || !dx) return BP_ERR_ARG;
@@ -743,6 +770,7 @@ int bp_linear_solve(bp_ctx* c, const double* u_lin, double* u_out, int on_device
 	if ((rc = vec_in(c, u_lin, on_device, c->d_u))) return rc;
 	bp_ctx* cs[1] = { c };
 	if ((rc = group_assemble(cs, 1, BP_ASSEMBLE_F | BP_ASSEMBLE_J | 16))) return rc;     // K(u_lin), f
+	if (c->have_bc) { bp_launch_bc_rows(c, 0.0); bp_launch_bc_eliminate(c); }             // the solve returns -u: d = -g
 	int it = 0;
 	if ((rc = group_pcg(cs, 1, &it, nullptr))) return rc;                                  // dx = K^-1 f
 	if (iterations) *iterations = it;

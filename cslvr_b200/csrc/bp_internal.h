@@ -154,6 +154,9 @@ struct bp_ctx {
 	std::vector<int32_t> h_send_nodes;
 	double*  d_sendbuf = nullptr;
 	int64_t  n_send = 0;
+	// Dirichlet rows of the momentum solve (bp_set_dirichlet): 1.0 / 0.0 and the prescribed value per internal dof
+	double  *d_bcmask = nullptr, *d_bcval = nullptr;
+	bool     have_bc = false;
 	bp_comm_state* comm = nullptr;
 	bp_p2p_halo* p2p = nullptr;          // peer-memory exchange (nullptr: NCCL send / recv)
 	bool     p2p_tried = false;          // bp_comm_p2p_attach ran for this context (it is collective: once)
@@ -206,6 +209,8 @@ void bp_launch_csr_export(bp_ctx* c, double* out);
 void bp_launch_pc_setup(bp_ctx* c);
 void bp_launch_set_S(bp_ctx* c, const double* S_dev);
 void bp_launch_pack_halo(bp_ctx* c, const double* vec);
+void bp_launch_bc_rows(bp_ctx* c, double sign);   // constrained rows of d_F <- sign * u - g (d in d_io for bp_launch_bc_eliminate)
+void bp_launch_bc_eliminate(bp_ctx* c);           // free rows lifted by J d, rows / columns of the constrained dofs -> identity
 void bp_launch_dot_owned(bp_ctx* c, const double* a, const double* b, int sc_slot);
 void bp_launch_axpy(bp_ctx* c, double alpha, const double* x, double* y);   // y += alpha x
 void bp_launch_pcg_init(bp_ctx* c);

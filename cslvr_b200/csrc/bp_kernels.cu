@@ -1133,6 +1133,64 @@ void bp_launch_spmv(bp_ctx* c, const double* x, double* y, int with_dot)
 	c->launches++;
 }
 
+// ---------------------------------------------------------------- Dirichlet rows (momentumbp.py:101-112)
+// dolfin's NewtonSolver applies a DirichletBC to the update (SURVEY A-N): on a constrained dof b_i = u_i - g_i and the
+// row of J is an identity row, so the Newton step carries u_i to g_i.  The constrained dofs are eliminated
+// symmetrically here (columns too, the free rows lifted by J d) -- the same solution, and CG keeps an SPD matrix.
+// d = what the solve must return on the constrained dofs: u - g (Newton: sign = 1) or -g (linear=True: the solve
+// returns -u, sign = 0); zero elsewhere.  All local dofs, ghosts included (their columns are eliminated as well).
+__global__ void k_bc_d(int n2, const double* __restrict__ mask, const double* __restrict__ g, const double* __restrict__ u, double sign, double* __restrict__ d)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+		d[i] = mask[i] != 0.0 ? sign * u[i] - g[i] : 0.0;
+}
+// constrained rows of the right-hand side (owned dofs)
+__global__ void k_bc_rows(int n2, const double* __restrict__ mask, const double* __restrict__ d, double* __restrict__ F)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+		if (mask[i] != 0.0) F[i] = d[i];
+}
+// free rows: F -= J d (Jd computed with the unconstrained J)
+__global__ void k_bc_lift(int n2, const double* __restrict__ mask, const double* __restrict__ Jd, double* __restrict__ F)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x)
+		if (mask[i] == 0.0) F[i] -= Jd[i];
+}
+// rows and columns of the constrained dofs -> identity (one thread per owned block row)
+__global__ void k_bc_matrix(int n, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowlen, const int32_t* __restrict__ col,
+                            const double* __restrict__ mask, double* __restrict__ val)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const bool r0 = mask[2 * i] != 0.0, r1 = mask[2 * i + 1] != 0.0;
+		const int base = sell_ptr[i >> 5] + (i & 31);
+		for (int k = 0; k < rowlen[i]; ++k) {
+			const int s = base + 32 * k, j = col[s];
+			const bool c0 = mask[2 * j] != 0.0, c1 = mask[2 * j + 1] != 0.0;
+			if (!(r0 | r1 | c0 | c1)) continue;
+			double* v = val + 4 * (size_t)s;
+			if (r0 | c0) v[0] = (j == i && r0) ? 1.0 : 0.0;
+			if (r0 | c1) v[1] = 0.0;
+			if (r1 | c0) v[2] = 0.0;
+			if (r1 | c1) v[3] = (j == i && r1) ? 1.0 : 0.0;
+		}
+	}
+}
+void bp_launch_bc_rows(bp_ctx* c, double sign)
+{
+	const int n2a = (int)(2 * c->nn), n2o = (int)(2 * c->nn_owned);
+	k_bc_d<<<red_blocks(n2a, 256), 256, 0, c->stream>>>(n2a, c->d_bcmask, c->d_bcval, c->d_u, sign, c->d_io);
+	k_bc_rows<<<red_blocks(n2o, 256), 256, 0, c->stream>>>(n2o, c->d_bcmask, c->d_io, c->d_F);
+	c->launches += 2;
+}
+void bp_launch_bc_eliminate(bp_ctx* c)
+{
+	const int n2o = (int)(2 * c->nn_owned), no = (int)c->nn_owned;
+	bp_launch_spmv(c, c->d_io, c->d_io2, 0);                 // J d with the unconstrained J (d: bp_launch_bc_rows)
+	k_bc_lift<<<red_blocks(n2o, 256), 256, 0, c->stream>>>(n2o, c->d_bcmask, c->d_io2, c->d_F);
+	k_bc_matrix<<<red_blocks(no, 128), 128, 0, c->stream>>>(no, c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_bcmask, c->d_val);
+	c->launches += 2;
+}
+
 // ---------------------------------------------------------------- vector glue
 __global__ void k_gather_in(int n2, const int32_t* __restrict__ ext_dof, const double* __restrict__ ext, double* __restrict__ in)
 {

@@ -209,6 +209,9 @@ class D3Model(object):
 		self.T      = Function(self.Q, 'T')             # cslvr/model.py:2544-2551
 		self.Tp     = Function(self.Q, 'Tp')
 		self.W      = Function(self.Q, 'W')
+		self.u_x_lat = Function(self.Q, 'u_x_lat')      # cslvr/model.py:2531-2533: velocity on the basin divides
+		self.u_y_lat = Function(self.Q, 'u_y_lat')
+		self.u_z_lat = Function(self.Q, 'u_z_lat')
 		self.E.values[:] = 1.0
 		self.ff = None
 
@@ -242,6 +245,30 @@ class D3Model(object):
 	def init_B(self, B):
 		print_text("::: initializng basal topography :::", cls=self)
 		self.assign_variable(self.B, B)
+
+	def init_u_lat(self, u_lat):
+		"""x-component of the lateral (basin divide) velocity, cslvr/model.py:976-985 (which assigns to a
+		``self.u_lat`` that does not exist; ``u_x_lat`` is the Function momentumbp.py:106 reads)."""
+		print_text("::: initializing u lateral b.c. :::", cls=self)
+		self.assign_variable(self.u_x_lat, u_lat)
+
+	def init_u_y_lat(self, u_y_lat):
+		print_text("::: initializing v lateral b.c. :::", cls=self)                   # cslvr/model.py:987-996
+		self.assign_variable(self.u_y_lat, u_y_lat)
+
+	def init_u_z_lat(self, u_z_lat):
+		print_text("::: initializing w lateral b.c. :::", cls=self)                   # cslvr/model.py:998-1007
+		self.assign_variable(self.u_z_lat, u_z_lat)
+
+	def divide_nodes(self):
+		"""nodes of the facets marked GAMMA_L_DVD: where DirichletBC(Q, g, ff, GAMMA_L_DVD) constrains."""
+		sel = np.flatnonzero(self.ff == self.GAMMA_L_DVD)
+		if sel.size == 0:
+			return np.zeros(0, dtype=np.int64)
+		cv = self.mesh.cells()[self.facet_cell[sel]]
+		keep = np.ones(cv.shape, dtype=bool)
+		keep[np.arange(sel.size), self.facet_local[sel]] = False                     # facet i is opposite local vertex i
+		return np.unique(np.asarray(self.vertex_to_node)[cv[keep]])
 
 	def init_beta(self, beta):
 		print_text("::: initializing basal traction coefficient :::", cls=self)

@@ -35,16 +35,21 @@ class MomentumBPBase(Momentum):
 			sys.exit(1)
 		if model.ff is None:
 			raise RuntimeError("model.calculate_boundaries() must be called before a momentum object is created")
-		if use_lat_bcs:
-			# cslvr/momentumbp.py:495 calls quasi_stress_tensor with three arguments (it
-			# takes two, :150): the reference raises here as well
-			raise TypeError("quasi_stress_tensor() takes 3 positional arguments but 4 were given "
-			                "(use_lat_bcs=True is broken in cslvr/momentumbp.py:495 too)")
 		self.Q = model.QM2
 		self.device = device
 		self.set_unknown(Function(self.Q, name='u_h'))
 		self.u_z = Function(model.Q, name='u_z')
-		self.set_boundary_conditions([])          # cslvr/momentumbp.py:101-112: none without mark_divide
+		# cslvr/momentumbp.py:101-112: DirichletBC(Q.sub(0), u_x_lat, ff, GAMMA_L_DVD), DirichletBC(Q.sub(1), u_y_lat, ...):
+		# kept as (dofs, Function, component) so that the values are read at solve time, as dolfin does
+		mom_bcs = []
+		self.lateral_u_z_bc = False
+		if not model.use_periodic and model.mark_divide and use_lat_bcs:
+			print_text("    - using Dirichlet lateral boundary conditions -", cls=self)
+			nodes = model.divide_nodes()
+			mom_bcs.append((2 * nodes, model.u_x_lat, nodes))
+			mom_bcs.append((2 * nodes + 1, model.u_y_lat, nodes))
+			self.lateral_u_z_bc = nodes.size > 0      # u_z_bcs gets DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD) as well
+		self.set_boundary_conditions(mom_bcs)
 		self._ctx = None
 		self._ctx_key = None
 		super(MomentumBPBase, self).__init__(model=model, solve_params=solve_params, linear=linear,
@@ -168,8 +173,19 @@ class MomentumBPBase(Momentum):
 		overrides, as ``parameters['form_compiler']['quadrature_degree']`` does in the reference."""
 		return self.solve_params.get('quadrature_degree', 9 if self.model.energy_dependent_rate_factor else 5)
 
+	def _apply_boundary_conditions(self, c):
+		"""hand the DirichletBCs (cslvr/momentumbp.py:101-112) to the library: bp_set_dirichlet."""
+		bcs = self.get_boundary_conditions() or []
+		if bcs:
+			dofs = np.concatenate([b[0] for b in bcs])
+			vals = np.concatenate([b[1].values[b[2]] for b in bcs])
+			c.set_dirichlet(dofs, vals)
+		else:
+			c.set_dirichlet(np.zeros(0, dtype=np.int32), np.zeros(0))
+
 	def _newton_solve(self, ns):
 		c = self._context()
+		self._apply_boundary_conditions(c)
 		c.set_params(**self._solver_kwargs(ns))
 		u = self.get_unknown()
 		stats = c.newton_solve(u.values)
@@ -187,6 +203,7 @@ class MomentumBPBase(Momentum):
 		c.set_params(krylov_rtol=ks.get('relative_tolerance', 1e-5), krylov_atol=ks.get('absolute_tolerance', 1e-50),
 		             krylov_maxit=ks.get('maximum_iterations', 10000), preconditioner=self._PC_MAP.get(pc, 'mg'),
 		             quadrature_degree=self._quadrature_degree())
+		self._apply_boundary_conditions(c)
 		ul = np.empty(self.Q.dim())
 		ul[0::2], ul[1::2] = self.model.u.values[0::3], self.model.u.values[1::3]
 		self.get_unknown().values[:] = c.linear_solve(ul)
@@ -226,6 +243,9 @@ class MomentumBPBase(Momentum):
 		# project the basal kinematic condition, assemble the continuity system, apply the
 		# basal Dirichlet rows and solve (cslvr/momentumbp.py:231-253) -- all on the device
 		m = self.model
+		if getattr(self, 'lateral_u_z_bc', False):
+			raise NotImplementedError("solve_vert_velocity with DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD) (cslvr/momentumbp.py:110-111) "
+			                          "is not served by the device solve yet: set solve_params['solve_vert_velocity'] = False")
 		c = self._context()
 		c.set_field(capi.FIELD_B, m.vertex_field(m.B))
 		if getattr(m, 'B_ring', None) is not None:
@@ -267,4 +287,9 @@ class MomentumDukowiczBP(MomentumBPBase):
 		print_text("::: INITIALIZING DUKOWICZ BP VELOCITY PHYSICS :::", cls=self)
 		if (not model.use_periodic and use_pressure_bc):
 			print_text("    - using water pressure lateral boundary condition -", cls=self)
+		if use_lat_bcs:
+			# cslvr/momentumbp.py:495 calls quasi_stress_tensor with three arguments (it takes two, :150): the
+			# reference raises here as well; MomentumBP (whose stress term is commented out, :384-393) does not
+			raise TypeError("quasi_stress_tensor() takes 3 positional arguments but 4 were given "
+			                "(use_lat_bcs=True is broken in cslvr/momentumbp.py:495 too; use MomentumBP)")
 		self.set_residual('bp-dukowicz')

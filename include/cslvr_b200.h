@@ -203,6 +203,16 @@ int  bp_set_stream(bp_ctx* ctx, void* cuda_stream); /* run on the caller's strea
  * cslvr/model.py:486-497, 691-733 -> assign_variable model.py:2166-2221           */
 int  bp_set_field(bp_ctx* ctx, int field, const double* values, int64_t n, int on_device);
 
+/* Dirichlet conditions of the momentum solve: DirichletBC(Q.sub(0), u_x_lat, ff, GAMMA_L_DVD) and its
+ * u_y twin, cslvr/momentumbp.py:101-112 (MomentumBP with use_lat_bcs on a mesh with mark_divide).  dofs
+ * are in the caller's numbering (ghost dofs of a partitioned mesh included), values the prescribed
+ * velocities.  bp_newton_solve / bp_linear_solve then treat those rows as dolfin's NewtonSolver does
+ * (b_i = u_i - g_i, identity rows: the update carries u_i to g_i; columns eliminated as well so that CG
+ * keeps a symmetric matrix).  bp_assemble keeps returning the unconstrained F and J, as assemble() does.
+ * n = 0 removes the conditions.                                                                         */
+int  bp_set_dirichlet(bp_ctx* ctx, int64_t n, const int32_t* dofs, const double* values);
+
+
 /* sizes after the mesh has been digested */
 int  bp_get_sizes(const bp_ctx* ctx, int64_t* n_nodes, int64_t* n_dofs, int64_t* nnz_csr,
                   int64_t* nnz_blocks, int64_t* n_cells, int64_t* n_basal_facets);

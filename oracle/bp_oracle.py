@@ -590,22 +590,41 @@ class BPProblem(object):
 
 	# ---- Newton (dolfin NewtonSolver semantics, SURVEY A-N) ----------------
 	def newton(self, u0=None, rtol=1e-9, atol=1e-10, maxit=25, relax=1.0,
-	           linear_solver='direct', krylov_rtol=1e-5, verbose=False):
-		"""physics.py:664-678 -> dolfin.solve(F == 0, u, J=J).
+	           linear_solver='direct', krylov_rtol=1e-5, verbose=False, bcs=None):
+		"""physics.py:664-678 -> dolfin.solve(F == 0, u, J=J, bcs=bcs).
 
 		Cold start from DOLFIN_EPS (momentumbp.py:265-266).  ``linear_solver``:
 		'direct' (sparse LU, the parity setting) or 'cg' (Jacobi-PCG with a
 		PETSc-like relative tolerance on the preconditioned residual).
+		``bcs = (dofs, values)``: the DirichletBCs of momentumbp.py:101-112 the way dolfin's
+		NewtonSolver applies them (SURVEY A-N): b_i = u_i - g_i on the constrained rows, those
+		rows of J replaced by identity rows -- so the update carries u_i to g_i.
 		"""
 		u = np.full(self.n_dofs, DOLFIN_EPS) if u0 is None else np.array(u0, dtype=np.float64)
-		b = self.residual(u)
+		if bcs is not None:
+			bd, bg = np.asarray(bcs[0], dtype=np.int64), np.asarray(bcs[1], dtype=np.float64)
+			free = np.ones(self.n_dofs); free[bd] = 0.0
+			_res, _jac = self.residual, self.jacobian_matrix
+
+			def residual(v):
+				r = _res(v); r[bd] = v[bd] - bg
+				return r
+
+			def jacobian_matrix(v):
+				Jm = sp.diags(free) @ _jac(v).tocsr()                 # bc.apply(A): the rows only
+				return (Jm + sp.diags(1.0 - free)).tocsr()
+			return self._newton_core(u, residual, jacobian_matrix, rtol, atol, maxit, relax, linear_solver, krylov_rtol, verbose)
+		return self._newton_core(u, self.residual, self.jacobian_matrix, rtol, atol, maxit, relax, linear_solver, krylov_rtol, verbose)
+
+	def _newton_core(self, u, residual, jacobian_matrix, rtol, atol, maxit, relax, linear_solver, krylov_rtol, verbose):
+		b = residual(u)
 		r0 = np.linalg.norm(b)
 		hist = [r0]
 		it = 0
 		kits = 0
 		conv = (r0 < atol)
 		while not conv and it < maxit:
-			Jm = self.jacobian_matrix(u)
+			Jm = jacobian_matrix(u)
 			if linear_solver == 'direct':
 				dx = spla.splu(Jm.tocsc()).solve(b)
 			else:
@@ -616,7 +635,7 @@ class BPProblem(object):
 				                   callback=lambda xk: cnt.__setitem__(0, cnt[0] + 1))
 				kits += cnt[0]
 			u = u - relax * dx
-			b = self.residual(u)
+			b = residual(u)
 			r = np.linalg.norm(b)
 			hist.append(r)
 			it += 1

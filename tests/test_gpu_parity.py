@@ -684,3 +684,47 @@ def test_reduced_stokes_with_the_energy_dependent_rate_factor():
 	F, J = c.assemble(u, want_F=True, want_J=True)
 	assert relerr(F, P.residual(u)) < TOL_ASM and relerr(J, P.jacobian(u)) < TOL_ASM
 	c.close()
+
+
+def test_newton_with_lateral_dirichlet_conditions_matches_oracle():
+	"""MomentumBP(use_lat_bcs=True) on a mesh with basin divides (cslvr/momentumbp.py:101-112, d3model.py:441-448): the
+	Newton solve with DirichletBCs on GAMMA_L_DVD -- dolfin applies them to the update (SURVEY A-N) -- against the
+	oracle's constrained Newton (identity rows, sparse LU): same iteration count, velocity to 1e-8, constrained dofs
+	exact; the linear=True solve obeys the conditions as well."""
+	from cslvr_b200 import MomentumBP
+	m = marine_model(n=(10, 8, 4))
+	X = m.mesh.coordinates()
+	L = X[:, 0].max()
+	contour = np.column_stack([np.full(400, L), np.linspace(X[:, 1].min(), X[:, 1].max(), 400)])
+	m.calculate_boundaries(mask=m.mask_callable, mark_divide=True, contour=contour)
+	m.init_u_lat(lambda x, y, z: 40.0 + 10.0 * np.sin(3 * y / L))
+	m.init_u_y_lat(lambda x, y, z: 5.0 * np.cos(2 * x / L))
+	mom = MomentumBP(m, use_lat_bcs=True)
+	ns = mom.solve_params['solver']['newton_solver']
+	ns.update(relative_tolerance=1e-11, maximum_iterations=60, relaxation_parameter=0.7)
+	ns['krylov_solver'] = {'relative_tolerance': 1e-13, 'monitor_convergence': False}
+	mom.solve_params['solve_vert_velocity'] = False
+	mom.solve_params['solve_pressure'] = False
+	mom.solve()
+	u = mom.get_unknown().values.copy()
+	bcs = mom.get_boundary_conditions()
+	dofs = np.concatenate([b[0] for b in bcs])
+	vals = np.concatenate([b[1].values[b[2]] for b in bcs])
+	assert dofs.size > 0
+	P = oracle_problem(m)
+	uo, io = P.newton(rtol=1e-11, maxit=60, relax=0.7, bcs=(dofs, vals))
+	assert io['converged'] and abs(io['iterations'] - mom.stats['iterations']) <= 1
+	assert relerr(u, uo) < 1e-8
+	assert np.abs(u[dofs] - vals).max() < 1e-9 * np.abs(vals).max()
+	# without the conditions the solution is a different one (the test has teeth)
+	un, _ = P.newton(rtol=1e-11, maxit=60, relax=0.7)
+	assert relerr(un, uo) > 1e-3
+	# linear=True: K(u_lin) u = f with the same rows constrained
+	m.u.values[0::3], m.u.values[1::3] = u[0::2], u[1::2]
+	lin = MomentumBP(m, use_lat_bcs=True, linear=True)
+	lin.solve_params['solve_vert_velocity'] = False
+	lin.solve_params['solve_pressure'] = False
+	lin.solve_params['solver']['krylov_solver'] = {'relative_tolerance': 1e-13}      # the rows are only as exact as the Krylov solve
+	lin.solve()
+	ul = lin.get_unknown().values
+	assert np.abs(ul[dofs] - vals).max() < 1e-9 * np.abs(vals).max()

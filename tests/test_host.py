@@ -179,3 +179,28 @@ def test_basin_divide_markers():
 	       {(int(c), int(l)): int(k) for c, l, k in zip(fc, fl, ff)}
 	with pytest.raises(SystemExit):
 		m.calculate_boundaries(mark_divide=True)
+
+
+def test_lateral_dirichlet_conditions_of_momentum_bp():
+	"""cslvr/momentumbp.py:101-112: with mark_divide and use_lat_bcs MomentumBP constrains (u_x, u_y) on the nodes of
+	the GAMMA_L_DVD facets to (u_x_lat, u_y_lat); MomentumDukowiczBP raises there (momentumbp.py:495), as upstream."""
+	from cslvr_b200 import MomentumBP, MomentumDukowiczBP
+	m = marine_model()
+	X = m.mesh.coordinates()
+	L = X[:, 0].max()
+	contour = np.column_stack([np.full(200, L), np.linspace(X[:, 1].min(), X[:, 1].max(), 200)])
+	m.calculate_boundaries(mask=m.mask_callable, mark_divide=True, contour=contour)
+	nodes = m.divide_nodes()
+	# the divide is every lateral side but x = L: its nodes are the mesh vertices on x = 0, y = 0 or y = max (all layers)
+	xf = m.flat_coordinates
+	on = (np.abs(xf[:, 0]) < 1e-9) | (np.abs(xf[:, 1]) < 1e-9) | (np.abs(xf[:, 1] - xf[:, 1].max()) < 1e-9)
+	assert np.array_equal(nodes, np.flatnonzero(on))
+	m.init_u_lat(lambda x, y, z: 3.0 + 0.0 * x)
+	m.init_u_y_lat(-1.5)
+	mom = MomentumBP(m, use_lat_bcs=True)
+	bcs = mom.get_boundary_conditions()
+	assert len(bcs) == 2 and np.array_equal(bcs[0][0], 2 * nodes) and np.array_equal(bcs[1][0], 2 * nodes + 1)
+	assert np.allclose(bcs[0][1].values[bcs[0][2]], 3.0) and np.allclose(bcs[1][1].values[bcs[1][2]], -1.5)
+	assert MomentumBP(m).get_boundary_conditions() == []              # not without use_lat_bcs
+	with pytest.raises(TypeError):
+		MomentumDukowiczBP(m, use_lat_bcs=True)

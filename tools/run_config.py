@@ -1,9 +1,13 @@
 #!/usr/bin/env python
-"""Solve one BASELINE.json configuration at a chosen size on one GPU and print the solver
-statistics (not a bench line: set-up is numpy, the solve is the library).
+"""Solve one BASELINE.json configuration at a chosen size and print the solver statistics as one JSON line
+(not a bench line: set-up is numpy, the solve is the library).  One GPU, or one rank per GPU under torchrun:
+every rank builds the synthetic model, keeps its slab of ice columns (cslvr_b200.partition) and the ranks
+solve together (peer-memory / NCCL halo exchange, coupled multigrid).
 
-    python tools/run_config.py eismint 577 577 5        # config 3, 9.99 M tets
-    python tools/run_config.py greenland 260 520 5
+    python tools/run_config.py eismint 577 577 5                      # config 3, 9.99 M tets
+    python tools/run_config.py greenland 816 816 5                    # config 4, 19.98 M tets
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 \\
+        tools/run_config.py greenland 816 816 5
 """
 import json
 import os
@@ -20,26 +24,66 @@ os.environ.setdefault('CSLVR_B200_QUIET', '1')
 
 def main():
 	from cases import eismint_dome_model, greenland_like_model, product_context
+	from cslvr_b200 import capi
 	name = sys.argv[1]
 	n = tuple(int(a) for a in sys.argv[2:5])
+	world = int(os.environ.get('WORLD_SIZE', '1'))
+	rank = int(os.environ.get('RANK', '0'))
+	local = int(os.environ.get('LOCAL_RANK', '0'))
+	kw = dict(use_pressure_bc=(name != 'eismint'), relative_tolerance=1e-9, relaxation_parameter=0.7,
+	          maximum_iterations=60, krylov_rtol=1e-5)
 	t0 = time.time()
 	m = eismint_dome_model(n=n) if name == 'eismint' else greenland_like_model(n=n)
 	t_model = time.time() - t0
 	t0 = time.time()
-	c = product_context(m, use_pressure_bc=(name != 'eismint'), relative_tolerance=1e-9, relaxation_parameter=0.7,
-	                    maximum_iterations=60, krylov_rtol=1e-5)
+	if world == 1:
+		c = product_context(m, **kw)
+		nd, own = 2 * m.n_nodes, slice(None)
+		allmax = lambda *v: list(v)
+		allsum = allmax
+	else:
+		import torch
+		import torch.distributed as dist
+		from cslvr_b200.partition import partition_model, rank_context
+		torch.cuda.set_device(local)
+		dev = torch.device('cuda', local)
+		dist.init_process_group('nccl', device_id=dev)
+		rm = partition_model(m, world, rank)
+		c = rank_context(m, rm, device=local, **kw)
+		ids = [capi.comm_unique_id() if rank == 0 else None]
+		dist.broadcast_object_list(ids, src=0, device=dev)
+		c.comm_init(ids[0], rank, world)
+		nd, own = 2 * rm.n_nodes, slice(0, 2 * rm.n_owned)
+
+		def allmax(*v):
+			t = torch.tensor(list(v), device=dev, dtype=torch.float64)
+			dist.all_reduce(t, op=dist.ReduceOp.MAX)
+			return t.tolist()
+
+		def allsum(*v):
+			t = torch.tensor(list(v), device=dev, dtype=torch.float64)
+			dist.all_reduce(t, op=dist.ReduceOp.SUM)
+			return t.tolist()
 	t_ctx = time.time() - t0
-	u = np.full(2 * m.n_nodes, 3e-16)
+	u = np.full(nd, 3e-16)
+	allmax(0.0)                                          # every rank is ready
 	t0 = time.time()
 	st = c.newton_solve(u)
-	t_solve = time.time() - t0
-	ms = c.time_assemble(3, repeats=10, flush_l2=True)
-	out = dict(config=name, mesh=n, n_tets=m.num_cells, n_dofs=2 * m.n_nodes, host_model_s=t_model, context_setup_s=t_ctx,
-	           newton_solve_s=t_solve, converged=st['converged'], newton_iterations=st['iterations'],
-	           krylov_iterations=st['krylov_iterations'], assemble_ms_in_solve=st['t_assemble_ms'], krylov_ms=st['t_krylov_ms'],
-	           assembly_pass_ms=ms, assembly_mtets_s=m.num_cells / ms / 1e3, preconditioner=c.pc_label(),
-	           u_max=float(np.abs(u).max()), residual0=st['residual_norm0'], residual=st['residual_norm'])
-	print(json.dumps(out))
+	t_solve, = allmax(time.time() - t0)
+	ms, = allmax(c.time_assemble(3, repeats=10, flush_l2=True))
+	umax, = allmax(float(np.abs(u[own]).max()))
+	if rank == 0:
+		out = dict(config=name, mesh=n, n_gpus=world, n_tets=m.num_cells, n_dofs=2 * m.n_nodes, host_model_s=t_model, context_setup_s=t_ctx,
+		           newton_solve_s=t_solve, converged=st['converged'], newton_iterations=st['iterations'],
+		           krylov_iterations=st['krylov_iterations'], assemble_ms_in_solve=st['t_assemble_ms'], krylov_ms=st['t_krylov_ms'],
+		           assembly_pass_ms=ms, assembly_mtets_s=m.num_cells / ms / 1e3, preconditioner=c.pc_label(),
+		           gpu_launches=st['gpu_launches'], host_launches=st.get('host_launches'),
+		           u_max=umax, residual0=st['residual_norm0'], residual=st['residual_norm'])
+		print(json.dumps(out), flush=True)
+	c.close()
+	if world > 1:
+		dist.barrier()
+		dist.destroy_process_group()
 
 
 if __name__ == '__main__':
