@@ -183,6 +183,21 @@ def relerr_entrywise(a, b, floor=1e-10):
 	return float((np.abs(a - b)[m] / np.abs(b)[m]).max()) if m.any() else 0.0
 
 
+def bind_to_gpu_numa_node(index):
+	"""run this rank on the CPU cores next to its GPU (NVML's ideal affinity): the pinned host buffers of the end-to-end
+	arm are then allocated on the NUMA node the GPU's PCIe root hangs off, instead of crossing the socket link.  What a
+	launcher like `numactl` / `torchrun --numa-binding` does; BENCH_NO_BIND=1 leaves the affinity alone."""
+	if os.environ.get('BENCH_NO_BIND'):
+		return False
+	try:
+		import pynvml
+		pynvml.nvmlInit()
+		pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+		return True
+	except Exception:
+		return False
+
+
 def host_threads():
 	try:
 		return len(os.sched_getaffinity(0))
@@ -317,6 +332,9 @@ def run_ours(args):
 	torch.cuda.set_device(local)
 	dev = torch.device('cuda', local)
 	multi = world > 1
+	n_host_threads = host_threads()                 # before the binding below narrows the affinity mask
+	affinity0 = os.sched_getaffinity(0) if hasattr(os, 'sched_getaffinity') else None
+	bound = bind_to_gpu_numa_node(local)
 	dist = None
 	if multi:
 		import torch.distributed as dist
@@ -453,7 +471,9 @@ def run_ours(args):
 	# ---- parity at full size (untimed): the oracle's C twin on this rank's arrays ----------------
 	parity, cpu_base = None, None
 	if not args.no_parity:
-		co = oracle_for_slab(s, max(1, host_threads() // world))
+		if affinity0 is not None:
+			os.sched_setaffinity(0, affinity0)                            # the CPU checker / baseline gets every core back
+		co = oracle_for_slab(s, max(1, n_host_threads // world))
 		Fo, Jo, t_cpu = co.assemble(u_host)
 		own = slice(0, 2 * s.n_owned)
 		Fp = ctx.assemble(u_host, want_F=True, want_J=True, J=False)[0]
@@ -510,7 +530,8 @@ def run_ours(args):
 		        "config": {"workload": workload_name(world), "n_tets": nt_global, "tets_per_rank_incl_halo": nt_local, "n_dofs_rank0": 2 * no, "nnz_rank0": ctx.nnz,
 		                   "partition": "x-slabs of ice columns, 1 ghost node layer, halo of u by grouped ncclSend/ncclRecv before every assembly" if multi else "one GPU",
 		                   "l2": "per-rank working set (J values %d MB) larger than L2; roofline launches flush L2" % (8 * ctx.nnz >> 20),
-		                   "state": "synthetic sheared sliding flow, a function of the global node id"},
+		                   "state": "synthetic sheared sliding flow, a function of the global node id",
+		                   "host_binding": "rank bound to its GPU's NUMA node (NVML ideal affinity)" if bound else "none"},
 		        "e2e": {"value": nt_global / s_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": 8 * u_host.size * world, "d2h_bytes_per_step": 8 * u_host.size * world},
 		        "gpu_launches": int(launches),
 		        "roofline": {"kernel": kname + (" (rank 0)" if multi else ""), "bound": "hbm", "achieved": b_cell / (t_cell * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -529,7 +550,7 @@ def run_ours(args):
 		if cpu_base and not args.no_cpu:
 			line["cpu_baseline"] = cpu_base
 		if not multi and not args.no_cpu and not args.no_newton:
-			line["cpu_baseline_newton"] = cpu_newton_baseline(host_threads(), nxy=int(os.environ.get('BENCH_NEWTON_NXY', '130')))
+			line["cpu_baseline_newton"] = cpu_newton_baseline(n_host_threads, nxy=int(os.environ.get('BENCH_NEWTON_NXY', '130')))
 		emit(json.dumps(line))
 	if clocks: clocks.close()
 	ctx.close()
