@@ -524,6 +524,8 @@ def run_ours(args):
 		b_spmv = 9 * ctx.nnz + 40 * no
 		kname = ctx.assembly_kernel_name() if hasattr(ctx, 'assembly_kernel_name') else "k_rows<F,J>"
 		traffic, tsrc = measured_traffic(kname, nt_local)
+		if kname == "k_tile":
+			b_cell = b_full          # the tiled kernel also integrates the basal facets (folded into its first layer): the whole B_asm of SURVEY.md §8d
 		line = {"metric": METRIC, "value": nt_global / s_dev / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
 		        "ms_per_step": s_dev * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
 		        "data": "synthetic",

@@ -161,6 +161,7 @@ struct bp_ctx {
 	bp_p2p_halo* p2p = nullptr;          // peer-memory exchange (nullptr: NCCL send / recv)
 	bool     p2p_tried = false;          // bp_comm_p2p_attach ran for this context (it is collective: once)
 	bp_mg*   mg = nullptr;
+	std::vector<int32_t> h_fcell, h_finfo;   // integrating facets on the host (the tiled kernel folds the basal ones into its first layer)
 	bp_tiles* tiles = nullptr;           // tiled cell assembly: nullptr when the mesh is not an extruded prism mesh (k_rows serves it)
 	std::string tiles_why;               // why not
 	bool     host_only = false;          // debug contexts without a device (index-table emulation in the CPU test suite)
@@ -242,7 +243,8 @@ AsmParams bp_asm_params(const bp_ctx* c);
 
 // tiled cell assembly (bp_tiles.cu)
 int  bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n);
-bool bp_tiles_serve(const bp_ctx* c, int what);           // the tiled kernel serves this assembly request
+bool bp_tiles_serve(const bp_ctx* c, int what);
+bool bp_tiles_facet_lists(const bp_ctx* c, int64_t* n_fnodes, const int32_t** fn_node, const int32_t** fn_ptr, const int32_t** fn_inc);   // facets left for the facet kernel when the tiled kernel folds the basal ones in           // the tiled kernel serves this assembly request
 void bp_launch_tiles(bp_ctx* c, int what);                // d_u -> d_F / d_val (cell integrals)
 void bp_tiles_update_ainv(bp_ctx* c);                     // d_ainv -> tile order (after k_tet_ainv)
 void bp_tiles_free(bp_ctx* c);

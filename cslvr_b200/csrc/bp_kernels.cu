@@ -911,10 +911,14 @@ void bp_launch_facets(bp_ctx* c, int what)
 	AsmParams P = make_params(c);
 	const bool wf = what & BP_ASSEMBLE_F, wj = what & BP_ASSEMBLE_J;
 	const int gf = (int)((c->nf + TPB - 1) / TPB);
-	const int gfr = (int)((c->n_fnodes + TPB - 1) / TPB);
-	const bool use_fr = c->n_fnodes > 0 && !c->env.facet_atomic;
+	int64_t nfn = c->n_fnodes;
+	const int32_t *fnn = c->d_fn_node, *fnp = c->d_fn_ptr, *fni = c->d_fn_inc;
+	const bool folded = bp_tiles_serve(c, what) && bp_tiles_facet_lists(c, &nfn, &fnn, &fnp, &fni);   // the tiled kernel did the basal facets
+	if (folded && nfn == 0) return;
+	const int gfr = (int)((nfn + TPB - 1) / TPB);
+	const bool use_fr = nfn > 0 && (folded || !c->env.facet_atomic);
 	const double2* u2 = (const double2*)c->d_u;
-	#define FACETC(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)c->n_fnodes, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
+	#define FACETC(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)nfn, fnn, fnp, fni, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
 		else k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring); } while (0)
 	if (wf && wj) FACETC(true, true);
 	else if (wf)  FACETC(true, false);
@@ -947,13 +951,16 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		return;
 	}
 	const int gf = (int)((c->nf + TPB - 1) / TPB);
-	const int gfr = (int)((c->n_fnodes + TPB - 1) / TPB);
+	int64_t nfn = c->n_fnodes;
+	const int32_t *fnn = c->d_fn_node, *fnp = c->d_fn_ptr, *fni = c->d_fn_inc;
+	const bool folded = bp_tiles_serve(c, what) && bp_tiles_facet_lists(c, &nfn, &fnn, &fnp, &fni);   // the tiled kernel does the basal facets
+	const int gfr = (int)((nfn + TPB - 1) / TPB);
 	const double2* u2 = (const double2*)c->d_u;
 	const size_t row_smem = (size_t)4 * std::max(c->max_row - 1, 1) * RTPB * sizeof(double);   // the diagonal block lives in registers
 	const bool gather = c->prm.assembly == BP_ASM_GATHER || (c->prm.assembly == BP_ASM_AUTO && row_smem <= 200 * 1024);
 	// default: the atomic-free facet kernel (bitwise reproducible F and J); BP_FACET_ATOMIC=1 gives the atomic one back
-	const bool use_fr = (gather || bp_tiles_serve(c, what)) && c->n_fnodes > 0 && !c->env.facet_atomic;
-	#define FACET(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)c->n_fnodes, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
+	const bool use_fr = folded || ((gather || bp_tiles_serve(c, what)) && nfn > 0 && !c->env.facet_atomic);
+	#define FACET(WF, WJ) do { if (use_fr) k_facet_rows<WF, WJ><<<gfr, TPB, 0, c->stream>>>((int)nfn, fnn, fnp, fni, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, c->d_F, c->d_val, P, c->d_Bring); \
 		else k_facet<WF, WJ><<<gf, TPB, 0, c->stream>>>((int)c->nf, (int)c->nt, c->d_fac_cell, c->d_fac_info, c->d_tets, c->d_geo, c->d_v2n, u2, c->d_beta, c->d_tet_blk, (int)c->nn_owned, c->d_F, c->d_val, P, c->d_Bring); } while (0)
 	const bool tiled = bp_tiles_serve(c, what);
 	if (tiled) {
@@ -983,12 +990,13 @@ void bp_launch_assemble(bp_ctx* c, int what)
 		else if (wf)  CELL(true, false);
 		else if (wj)  CELL(false, true);
 	}
-	if (c->nf) {
+	const bool run_facets = c->nf && !(folded && nfn == 0);
+	if (run_facets) {
 		if (wf && wj) FACET(true, true);
 		else if (wf)  FACET(true, false);
 		else if (wj)  FACET(false, true);
 	}
-	c->launches += 1 + (c->nf ? 1 : 0);
+	c->launches += 1 + (run_facets ? 1 : 0);
 	if (wj) c->have_J = true;
 }
 

@@ -328,6 +328,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		finfo.push_back(lf | (basal << 8) | (press << 9) | ((mk == 3) << 10));   // bit 10: dGamma_bg (grounded bed), the reduced-Stokes sliding set
 	}
 	c->nf = (int64_t)fcell.size();
+	c->h_fcell = fcell; c->h_finfo = finfo;
 	{	// facet row gather: every owned node touched by an integrating facet, with its (facet, local vertex) pairs
 		static const int LOCG[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
 		std::vector<int32_t> cntn(no, 0);

@@ -80,6 +80,15 @@ struct bp_tiles {
 	int32_t *d_vert = nullptr, *d_node = nullptr, *d_tet = nullptr, *d_nthr = nullptr, *d_ent0 = nullptr, *d_out = nullptr, *d_out2 = nullptr;
 	uint16_t *d_tab = nullptr;                // [n_ent][W]
 	uint16_t *d_tflag = nullptr;              // [n_tiles][TILE_T] which staged blocks a compute thread writes transposed
+	// basal facets folded into the march: the bottom triangle of a prism column IS its basal facet, so the sliding and
+	// water-pressure integrals of dGamma_b / dGamma_bw start the bottom-interface accumulators instead of being added by a
+	// second kernel through read-modify-write of the finished rows.  Bit 0: sliding (markers 3, 5), bit 1: water pressure (5).
+	uint8_t  *d_tfacet = nullptr;             // [n_tiles][TILE_T]
+	std::vector<uint8_t> h_tfacet;
+	bool      folded = false;                 // ... and the facet kernel only sees the facets that are left (the lateral ones)
+	int32_t  *d_fn_node = nullptr, *d_fn_ptr = nullptr, *d_fn_inc = nullptr;   // their row-gather lists (as bp_ctx::d_fn_*)
+	int64_t   n_fnodes = 0;
+	std::vector<uint8_t> h_facet_node;        // owned nodes they add to (pipelined host-buffer path)
 	uint8_t  *d_einfo = nullptr;              // [n_ent] contributions (bits 0-4) | mixed types (bit 5) | kind (bits 6-7: 0 block, 1 diagonal, 2 F)
 	double  *d_ainv = nullptr;
 	bool     attr_set = false;
@@ -290,6 +299,55 @@ __host__ __device__ __forceinline__ void iface_stage(const Iface& bot, ST& st)  
 	for (int i = 0; i < 6; ++i) st.put(21 + i, bot.F[i]);
 }
 
+// The basal facet of a prism column (its bottom triangle b0 b1 b2) into the accumulators of the bottom interface:
+// sliding  1/2 beta u.u dGamma_b  and water pressure  -f_w u.n_h dGamma_bw  (cslvr/momentumbp.py:473-486), exact P1 mass
+// integrals -- the expressions of k_facet_rows (bp_kernels.cu).  The outward normal points away from t2, which sits
+// straight above b2: n_z < 0.
+__host__ __device__ __forceinline__ void facet_fold(const double4* pb, const double2* ub, const double bt0, const double bt1, const double bt2,
+                                                     const uint32_t fl, const AsmParams& P, Iface& bot)
+{
+	const double ax = pb[1].x - pb[0].x, ay = pb[1].y - pb[0].y, az = pb[1].z - pb[0].z;
+	const double bx = pb[2].x - pb[0].x, by = pb[2].y - pb[0].y, bz = pb[2].z - pb[0].z;
+	double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
+	const double nrm = sqrt(nx * nx + ny * ny + nz * nz);
+	const double area = 0.5 * nrm;
+	const double sgn = (nz > 0.0 ? -1.0 : 1.0) / nrm;
+	nx *= sgn; ny *= sgn;
+	const double bt[3] = { bt0, bt1, bt2 };
+	if (fl & 1u) {
+		// K[a][b] = |f| sum_d beta_d int(l_a l_b l_d),  int = {1/10, 1/30, 1/60}
+		const double bs = bt[0] + bt[1] + bt[2];
+		#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			const double Kaa = area * (bt[a] * (1.0 / 10.0) + (bs - bt[a]) * (1.0 / 30.0));
+			bot.D[3 * a] += Kaa; bot.D[3 * a + 2] += Kaa;
+			if (!P.picard) { bot.F[2 * a] += Kaa * ub[a].x; bot.F[2 * a + 1] += Kaa * ub[a].y; }
+			#pragma unroll
+			for (int b = a + 1; b < 3; ++b) {
+				const double Kab = area * ((bt[a] + bt[b]) * (1.0 / 30.0) + (bs - bt[a] - bt[b]) * (1.0 / 60.0));
+				const int pr = (a == 0) ? (b - 1) : 2;
+				bot.E[4 * pr] += Kab; bot.E[4 * pr + 3] += Kab;
+				if (!P.picard) {
+					bot.F[2 * a] += Kab * ub[b].x; bot.F[2 * a + 1] += Kab * ub[b].y;
+					bot.F[2 * b] += Kab * ub[a].x; bot.F[2 * b + 1] += Kab * ub[a].y;
+				}
+			}
+		}
+	}
+	if (fl & 2u) {
+		// f_w = rho g (S - z) - rho_sw g D,  D = -min(0, z)   (momentumbp.py:477, d3model.py:858-861)
+		double fw[3];
+		#pragma unroll
+		for (int a = 0; a < 3; ++a) fw[a] = P.rho_g * (pb[a].w - pb[a].z) - P.rho_sw_g * (-fmin(0.0, pb[a].z));
+		const double fs = fw[0] + fw[1] + fw[2];
+		#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			const double m = area * (fs + fw[a]) * (1.0 / 12.0);
+			bot.F[2 * a] -= nx * m; bot.F[2 * a + 1] -= ny * m;
+		}
+	}
+}
+
 // add one contribution (a table word) from the staged buffer st[slot][TILE_T]
 __host__ __device__ __forceinline__ void entry_add(const double* st, const uint32_t x, double& a0, double& a1, double& a2, double& a3)
 {
@@ -412,6 +470,7 @@ __global__ void __launch_bounds__(TILE_NTHR, TILE_CTAS)
 k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ tvert, const int32_t* __restrict__ tnode, const double* __restrict__ tainv,
        const int32_t* __restrict__ ent0, const uint16_t* __restrict__ tab, const uint8_t* __restrict__ einfo, const uint16_t* __restrict__ tflag,
        const int32_t* __restrict__ out, const int32_t* __restrict__ out2, const int64_t n_ent,
+       const uint8_t* __restrict__ tfacet, const double* __restrict__ beta,
        const double4* __restrict__ geo, const double2* __restrict__ zS, const double2* __restrict__ u, double* __restrict__ F, double* __restrict__ val, const AsmParams P)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -438,6 +497,8 @@ k_tile(const int tile0, const int NL, const int W, const int32_t* __restrict__ t
 			const int32_t* tn = tnode + (size_t)tile * NL * 3 * TILE_T + t;
 			#pragma unroll
 			for (int i = 0; i < 3; ++i) { pb[i] = geo[tv[i * TILE_T]]; ub[i] = u[tn[i * TILE_T]]; }        // layer 0: straight into registers
+			const uint32_t ffl = tfacet ? tfacet[(size_t)tile * TILE_T + t] : 0u;
+			if (ffl) facet_fold(pb, ub, beta[tv[0]], beta[tv[TILE_T]], beta[tv[2 * TILE_T]], ffl, P, bot);          // the basal facet starts the bottom interface
 		}
 		TILE_CLOCK_BEGIN(4)
 		for (int k = 0; k < NZ; ++k) {
@@ -591,6 +652,14 @@ void bp_tiles_update_ainv(bp_ctx* c)
 	c->launches++;
 }
 
+// the facet lists the facet kernel runs with when the tiled kernel serves the assembly (the basal facets are folded in)
+bool bp_tiles_facet_lists(const bp_ctx* c, int64_t* n_fnodes, const int32_t** fn_node, const int32_t** fn_ptr, const int32_t** fn_inc)
+{
+	if (!c->tiles || !c->tiles->folded) return false;
+	*n_fnodes = c->tiles->n_fnodes; *fn_node = c->tiles->d_fn_node; *fn_ptr = c->tiles->d_fn_ptr; *fn_inc = c->tiles->d_fn_inc;
+	return true;
+}
+
 bool bp_tiles_serve(const bp_ctx* c, int what)
 {
 	if (!c->tiles || c->prm.reduced_stokes) return false;
@@ -614,7 +683,7 @@ static void launch_tiles_range(bp_ctx* c, int what, int tile0, int ntile, cudaSt
 	}
 	if (ntile <= 0) return;
 	k_tile<<<ntile, TILE_NTHR, sm, stream>>>(tile0, T->NL, T->W, T->d_vert, T->d_node, T->d_ainv, T->d_ent0, T->d_tab, T->d_einfo, T->d_tflag, T->d_out, T->d_out2,
-	                                                   T->n_ent, c->d_geo, c->d_zS, (const double2*)c->d_u, c->d_F, c->d_val, P);
+	                                                   T->n_ent, T->folded ? T->d_tfacet : nullptr, c->d_beta, c->d_geo, c->d_zS, (const double2*)c->d_u, c->d_F, c->d_val, P);
 	c->launches++;
 }
 
@@ -686,7 +755,7 @@ void bp_tiles_free(bp_ctx* c)
 {
 	if (!c->tiles) return;
 	bp_tiles* T = c->tiles;
-	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_out2, T->d_tab, T->d_tflag, T->d_einfo, T->d_ainv };
+	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_out2, T->d_tab, T->d_tflag, T->d_einfo, T->d_ainv, T->d_tfacet, T->d_fn_node, T->d_fn_ptr, T->d_fn_inc };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	delete T;
 	c->tiles = nullptr;
@@ -833,6 +902,23 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (bad) return no_tiles(c, "prisms are not split into three tets the same way along a column");
 	{ std::vector<Rec>().swap(rec); }
 
+	// ---- 3b. basal facets = bottom triangles of prism columns: folded into the march (see bp_tiles::d_tfacet) ----
+	// facet (cell, local facet) is the bottom of column r iff the cell is r's tet A of layer 0 and the vertex opposite the
+	// facet is its t2 (layer 1).  Everything else (the lateral water-pressure facets) stays with the facet kernel.
+	std::vector<uint8_t> colflag(ntri, 0), facet_folded(c->h_fcell.size(), 0);
+	const bool fold = !c->env.facet_atomic && !c->prm.reduced_stokes;
+	if (fold) {
+		std::vector<int32_t> tetA_col(nt, -1);
+		for (int64_t r = 0; r < ntri; ++r) tetA_col[tri_tet[(size_t)r * NZ * 3]] = (int32_t)r;
+		for (size_t f = 0; f < c->h_fcell.size(); ++f) {
+			const int32_t cell = c->h_fcell[f], info = c->h_finfo[f], lf = info & 0xff;
+			const int32_t r = tetA_col[cell];
+			if (r < 0 || vlay[m->cells[(int64_t)cell * 4 + lf]] != 1) continue;
+			colflag[r] |= (uint8_t)(((info >> 8) & 1) | (((info >> 9) & 1) << 1));
+			facet_folded[f] = 1;
+		}
+	}
+
 	// ---- 4. tiles of owned ice columns: compact footprint patches, at most TILE_T prism columns touch one ----
 	std::vector<int64_t> ctp(n_ncol + 1, 0);                   // node column -> prism columns touching it
 	for (int64_t r = 0; r < ntri; ++r) {
@@ -942,6 +1028,8 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	T->h_node.assign((size_t)n_tiles * NL * 3 * TILE_T, 0);
 	T->h_tet.assign((size_t)n_tiles * NZ * 3 * TILE_T, -1);
 	T->h_nthr.assign(n_tiles, 0);
+	T->h_tfacet.assign((size_t)n_tiles * TILE_T, 0);
+	T->folded = fold;
 	T->h_ent0.assign(n_tiles + 1, 0);
 	struct Con { int8_t kind; int64_t delta; int32_t p, q; int16_t t; uint8_t code; };
 	struct Ent { int8_t kind, mirror; int32_t p, q; };       // mirror: -1 none, 0 / 2 the transposed block is the partner's same-layer / below block
@@ -985,6 +1073,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 			cons.clear();
 			for (size_t t = 0; t < tris.size(); ++t) {
 				const int32_t r = tris[t];
+				T->h_tfacet[(size_t)tl * TILE_T + t] = colflag[r];
 				int32_t nc[3];
 				for (int i = 0; i < 3; ++i) {
 					const int32_t vc = tri_col[3 * r + i];
@@ -1133,6 +1222,29 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	}
 	if (miss) { delete T; return no_tiles(c, "internal: the tile tables do not cover every Jacobian block exactly once"); }
 
+	// ---- the facets that are left for the facet kernel: row-gather lists as in bp_setup.cu, without the folded ones
+	std::vector<int32_t> fn_node, fn_ptr(1, 0), fn_inc;
+	T->h_facet_node.assign((size_t)std::max<int64_t>(no, 1), 0);
+	if (fold) {
+		static const int LOCG[4][3] = { { 1, 2, 3 }, { 0, 2, 3 }, { 0, 1, 3 }, { 0, 1, 2 } };
+		std::vector<int32_t> cntn(no, 0), slot_of_node(no, -1);
+		auto node_of = [&](size_t f, int k) { return v2n[m->cells[(int64_t)c->h_fcell[f] * 4 + LOCG[c->h_finfo[f] & 0xff][k]]]; };
+		for (size_t f = 0; f < c->h_fcell.size(); ++f) if (!facet_folded[f])
+			for (int k = 0; k < 3; ++k) { const int32_t nd_ = node_of(f, k); if (nd_ < no) cntn[nd_]++; }
+		for (int64_t i = 0; i < no; ++i) if (cntn[i]) { slot_of_node[i] = (int32_t)fn_node.size(); fn_node.push_back((int32_t)i); fn_ptr.push_back(fn_ptr.back() + cntn[i]); T->h_facet_node[i] = 1; }
+		fn_inc.assign((size_t)std::max<int32_t>(fn_ptr.back(), 1), 0);
+		std::vector<int32_t> fillf(fn_node.size(), 0);
+		for (size_t f = 0; f < c->h_fcell.size(); ++f) if (!facet_folded[f])
+			for (int k = 0; k < 3; ++k) {
+				const int32_t nd_ = node_of(f, k);
+				if (nd_ >= no) continue;
+				const int32_t r = slot_of_node[nd_];
+				fn_inc[fn_ptr[r] + fillf[r]++] = (int32_t)(f * 4 + k);
+			}
+		T->n_fnodes = (int64_t)fn_node.size();
+	}
+	const std::vector<uint8_t>& facet_node = fold ? T->h_facet_node : c->h_facet_node;
+
 	// ---- groups of tiles for the pipelined host-buffer path
 	if (!c->host_only && c->identity_dofs && nn == no) {
 		const int K = std::max(1, std::min(c->env.pipe_k, std::min(8, n_tiles / 148)));
@@ -1173,7 +1285,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 				if (!mark[i]) { ++i; continue; }
 				int64_t j = i;
 				bool facet = false;
-				while (j < nn && mark[j]) { facet |= (!c->h_facet_node.empty() && c->h_facet_node[j]); ++j; }
+				while (j < nn && mark[j]) { facet |= (j < (int64_t)facet_node.size() && facet_node[j]); ++j; }
 				(facet ? ch.out_facet : ch.out_plain).push_back({ (int32_t)i, (int32_t)j });
 				i = j;
 			}
@@ -1203,6 +1315,8 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (!rc) rc = up(c, &T->d_tab, T->h_tab);
 	if (!rc) rc = up(c, &T->d_tflag, T->h_tflag);
 	if (!rc) rc = up(c, &T->d_einfo, T->h_einfo);
+	if (!rc) rc = up(c, &T->d_tfacet, T->h_tfacet);
+	if (!rc && fold) { rc = up(c, &T->d_fn_node, fn_node); if (!rc) rc = up(c, &T->d_fn_ptr, fn_ptr); if (!rc) rc = up(c, &T->d_fn_inc, fn_inc); }
 	if (!rc && !c->host_only) {
 		cudaError_t e = cudaMalloc((void**)&T->d_ainv, (size_t)n_tiles * NZ * 4 * TILE_T * sizeof(double));
 		if (e != cudaSuccess) rc = bp_fail(c, BP_ERR_CUDA, "cudaMalloc(tile ainv) failed: %s", cudaGetErrorString(e));
