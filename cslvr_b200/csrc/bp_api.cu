@@ -21,7 +21,7 @@ void bp_env_read(bp_env* e)
 {
 	auto geti = [](const char* k, int d) { const char* v = getenv(k); return v ? atoi(v) : d; };
 	auto getd = [](const char* k, double d) { const char* v = getenv(k); return v ? atof(v) : d; };
-	e->pipe_k = geti("BP_PIPE_K", 4);
+	e->pipe_k = geti("BP_PIPE_K", 8);
 	e->no_pipeline = getenv("BP_NO_PIPELINE") != nullptr;
 	e->facet_atomic = geti("BP_FACET_ATOMIC", 0) != 0;
 	e->has_horizontal_first = getenv("BP_MG_HORIZONTAL_FIRST") != nullptr;
@@ -38,6 +38,7 @@ void bp_env_read(bp_env* e)
 	e->asm_tiled = geti("BP_ASM_TILED", -1);
 	e->cg_graph = geti("BP_CG_GRAPH", 1) != 0;
 	e->p2p = geti("BP_P2P", 1) != 0;
+	e->pipe_graph = geti("BP_PIPE_GRAPH", 1) != 0;
 }
 
 // ------------------------------------------------------------------ helpers

@@ -30,7 +30,7 @@ enum {
 
 // run-time switches, read from the environment ONCE per context at bp_create -- never per launch
 struct bp_env {
-	int    pipe_k = 4;              // BP_PIPE_K
+	int    pipe_k = 8;              // BP_PIPE_K
 	bool   no_pipeline = false;     // BP_NO_PIPELINE
 	bool   facet_atomic = false;    // BP_FACET_ATOMIC=1: the atomic facet kernel (default: row gather, reproducible)
 	bool   has_horizontal_first = false;
@@ -45,6 +45,7 @@ struct bp_env {
 	double mg_lmax_scale = 1.0;     // BP_MG_LMAX_SCALE: factor on the Gershgorin bound of lmax(D^-1 A) the multigrid smoothers use (experiments)
 	int    asm_tiled = -1;          // BP_ASM_TILED: 1 / 0 force / forbid the tiled cell kernel (-1 = automatic)
 	bool   cg_graph = true;         // BP_CG_GRAPH=0: launch the CG iteration directly instead of replaying its graph
+	bool   pipe_graph = true;       // BP_PIPE_GRAPH=0: issue the pipelined host-buffer bp_assemble stream by stream instead of replaying its graph
 	bool   p2p = true;              // BP_P2P=0: halo exchanges and scalar all-reduces through NCCL instead of peer memory
 };
 void bp_env_read(bp_env* e);

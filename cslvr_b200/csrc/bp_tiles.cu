@@ -85,6 +85,9 @@ struct bp_tiles {
 	// second kernel through read-modify-write of the finished rows.  Bit 0: sliding (markers 3, 5), bit 1: water pressure (5).
 	uint8_t  *d_tfacet = nullptr;             // [n_tiles][TILE_T]
 	std::vector<uint8_t> h_tfacet;
+	// the pipelined host-buffer call as one graph (bp_tiles_assemble_pipelined)
+	cudaGraphExec_t pipe_graph = nullptr;
+	const void *pg_u = nullptr, *pg_F = nullptr; int pg_what = 0; cudaStream_t pg_stream = nullptr; int64_t pg_launches = 0; bool pipe_no_graph = false;
 	bool      folded = false;                 // ... and the facet kernel only sees the facets that are left (the lateral ones)
 	int32_t  *d_fn_node = nullptr, *d_fn_ptr = nullptr, *d_fn_inc = nullptr;   // their row-gather lists (as bp_ctx::d_fn_*)
 	int64_t   n_fnodes = 0;
@@ -699,30 +702,48 @@ bool bp_tiles_pipeline_ready(const bp_ctx* c, int what)
 	       c->nn == c->nn_owned && c->nd_ext == 2 * c->nn && !c->env.no_pipeline;
 }
 
-int bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
+// copy node ranges [first, second) of a dof vector (2 doubles per node) between host and device.  On a layer-major
+// numbering the ranges of a group of tiles are one range per layer -- equal length, equal stride: ONE strided (2-D) copy
+// instead of six small ones (each small copy costs the copy engine ~5 us of set-up: 25 of them made 16 MB take 0.46 ms
+// instead of 0.31 ms).
+static cudaError_t copy_ranges(double* dst, const double* src, const std::vector<std::pair<int32_t, int32_t>>& rs, cudaMemcpyKind kind, cudaStream_t st)
+{
+	size_t i = 0;
+	while (i < rs.size()) {
+		const int64_t len = rs[i].second - rs[i].first;
+		size_t j = i + 1;
+		int64_t stride = 0;
+		if (j < rs.size() && rs[j].second - rs[j].first == len) {
+			stride = rs[j].first - rs[i].first;
+			while (j < rs.size() && rs[j].second - rs[j].first == len && rs[j].first - rs[j - 1].first == stride) ++j;
+		}
+		cudaError_t e;
+		if (j - i >= 2 && stride >= len)
+			e = cudaMemcpy2DAsync(dst + 2 * (size_t)rs[i].first, (size_t)stride * 16, src + 2 * (size_t)rs[i].first, (size_t)stride * 16, (size_t)len * 16, j - i, kind, st);
+		else { j = i + 1; e = cudaMemcpyAsync(dst + 2 * (size_t)rs[i].first, src + 2 * (size_t)rs[i].first, (size_t)len * 16, kind, st); }
+		if (e != cudaSuccess) return e;
+		i = j;
+	}
+	return cudaSuccess;
+}
+
+// issue the pipeline (copies in / group kernels / facet kernel / copies out) on the four streams.  join = true (graph
+// capture): the side streams are joined back into c->stream at the end instead of being synchronised by the host.
+static int pipeline_issue(bp_ctx* c, int what, const double* u, double* F, bool join)
 {
 	bp_tiles* T = c->tiles;
 	const int K = (int)T->chunks.size();
-	if (!c->s_h2d) {
-		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
-		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
-		c->pipe_ev.resize(2 * 8 + 2);
-		for (auto& e : c->pipe_ev) BP_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	}
 	cudaEvent_t* e_h = c->pipe_ev.data();
 	cudaEvent_t* e_c = c->pipe_ev.data() + 8;
-	cudaEvent_t e_f = c->pipe_ev[16], e_0 = c->pipe_ev[17];
-	bp_update_ainv(c);
+	cudaEvent_t e_f = c->pipe_ev[16], e_0 = c->pipe_ev[17], e_j0 = c->pipe_ev[18], e_j1 = c->pipe_ev[19], e_j2 = c->pipe_ev[20];
 	BP_CUDA(c, cudaEventRecord(e_0, c->stream));
 	BP_CUDA(c, cudaStreamWaitEvent(c->s_h2d, e_0, 0));
 	BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_0, 0));
 	for (int k = 0; k < K; ++k) {
-		for (const auto& r : T->chunks[k].in)
-			BP_CUDA(c, cudaMemcpyAsync(c->d_u + 2 * (size_t)r.first, u + 2 * (size_t)r.first, (size_t)(r.second - r.first) * 2 * sizeof(double), cudaMemcpyHostToDevice, c->s_h2d));
+		BP_CUDA(c, copy_ranges(c->d_u, u, T->chunks[k].in, cudaMemcpyHostToDevice, c->s_h2d));
 		BP_CUDA(c, cudaEventRecord(e_h[k], c->s_h2d));
 	}
 	// the groups' kernels alternate between two streams: the partial last wave of one overlaps the first wave of the next
-	if (!c->s_aux) BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
 	BP_CUDA(c, cudaStreamWaitEvent(c->s_aux, e_0, 0));
 	for (int k = 0; k < K; ++k) {
 		cudaStream_t sk = (k & 1) ? c->s_aux : c->stream;
@@ -733,19 +754,87 @@ int bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
 	for (int k = 1; k < K; k += 2) BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_c[k], 0));
 	bp_launch_facets(c, what);
 	BP_CUDA(c, cudaEventRecord(e_f, c->stream));
-	if (what & BP_ASSEMBLE_J) c->have_J = true;
 	if (F) {
 		for (int k = 0; k < K; ++k) {
 			BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_c[k], 0));
-			for (const auto& r : T->chunks[k].out_plain)
-				BP_CUDA(c, cudaMemcpyAsync(F + 2 * (size_t)r.first, c->d_F + 2 * (size_t)r.first, (size_t)(r.second - r.first) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
+			BP_CUDA(c, copy_ranges(F, c->d_F, T->chunks[k].out_plain, cudaMemcpyDeviceToHost, c->s_d2h));
 		}
 		BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_f, 0));
-		for (int k = 0; k < K; ++k)
-			for (const auto& r : T->chunks[k].out_facet)
-				BP_CUDA(c, cudaMemcpyAsync(F + 2 * (size_t)r.first, c->d_F + 2 * (size_t)r.first, (size_t)(r.second - r.first) * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->s_d2h));
-		BP_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+		for (int k = 0; k < K; ++k) BP_CUDA(c, copy_ranges(F, c->d_F, T->chunks[k].out_facet, cudaMemcpyDeviceToHost, c->s_d2h));
 	}
+	if (join) {
+		BP_CUDA(c, cudaEventRecord(e_j0, c->s_h2d)); BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_j0, 0));
+		BP_CUDA(c, cudaEventRecord(e_j1, c->s_d2h)); BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_j1, 0));
+		BP_CUDA(c, cudaEventRecord(e_j2, c->s_aux)); BP_CUDA(c, cudaStreamWaitEvent(c->stream, e_j2, 0));
+	}
+	return BP_OK;
+}
+
+static bool is_pinned_host(const void* p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeHost;
+}
+
+int bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
+{
+	bp_tiles* T = c->tiles;
+	if (!c->s_h2d) {
+		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
+		c->pipe_ev.resize(2 * 8 + 5);
+		for (auto& e : c->pipe_ev) BP_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	bp_update_ainv(c);
+	// The ~40 stream operations of one call cost the host ~0.1 ms -- a seventh of the call at 5 M tets.  With pinned
+	// caller buffers the whole pipeline is captured once per (u, F, what, stream) as a CUDA graph over the four streams
+	// and replayed with a single launch; pageable buffers (their copies cannot be captured) take the direct path.
+	const bool graphable = c->env.pipe_graph && !T->pipe_no_graph && is_pinned_host(u) && (!F || is_pinned_host(F));
+	if (graphable) {
+		if (T->pipe_graph && (T->pg_u != u || T->pg_F != F || T->pg_what != what || T->pg_stream != c->stream)) { cudaGraphExecDestroy(T->pipe_graph); T->pipe_graph = nullptr; }
+		if (!T->pipe_graph) {
+			const int64_t l0 = c->launches;
+			cudaGraph_t g = nullptr;
+			cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+			int rc = BP_OK;
+			if (e == cudaSuccess) {
+				rc = pipeline_issue(c, what, u, F, true);
+				e = cudaStreamEndCapture(c->stream, &g);
+				if (rc == BP_OK && e == cudaSuccess) e = cudaGraphInstantiate(&T->pipe_graph, g, 0);
+				if (g) cudaGraphDestroy(g);
+				if (rc != BP_OK || e != cudaSuccess) T->pipe_graph = nullptr;
+			}
+			if (!T->pipe_graph) { cudaGetLastError(); T->pipe_no_graph = true; c->launches = l0; }
+			else { T->pg_launches = c->launches - l0; c->launches = l0; T->pg_u = u; T->pg_F = F; T->pg_what = what; T->pg_stream = c->stream; }
+		}
+		if (T->pipe_graph) {
+			BP_CUDA(c, cudaGraphLaunch(T->pipe_graph, c->stream));
+			c->launches += T->pg_launches;
+			if (what & BP_ASSEMBLE_J) c->have_J = true;
+			BP_CUDA(c, cudaStreamSynchronize(c->stream));
+			BP_CUDA(c, cudaGetLastError());
+			return BP_OK;
+		}
+	}
+	// BP_PIPE_TRACE=1 (experiments, direct path): when each stream of the pipeline finished, relative to its start
+	static const bool trace = getenv("BP_PIPE_TRACE") != nullptr;
+	cudaEvent_t t0 = nullptr, t1 = nullptr, t2 = nullptr, t3 = nullptr;
+	if (trace) { cudaEventCreate(&t0); cudaEventCreate(&t1); cudaEventCreate(&t2); cudaEventCreate(&t3); cudaEventRecord(t0, c->stream); }
+	int rc = pipeline_issue(c, what, u, F, false);
+	if (rc) return rc;
+	if (trace) {
+		cudaEventRecord(t1, c->s_h2d); cudaEventRecord(t2, c->stream); cudaEventRecord(t3, c->s_d2h);
+		cudaEventSynchronize(t1); cudaEventSynchronize(t2); cudaEventSynchronize(t3);
+		float a = 0, b = 0, d = 0;
+		cudaEventElapsedTime(&a, t0, t1); cudaEventElapsedTime(&b, t0, t2); cudaEventElapsedTime(&d, t0, t3);
+		fprintf(stderr, "[cslvr_b200] pipeline trace: copies in done %.3f ms, kernels done %.3f ms, copies out done %.3f ms\n", a, b, d);
+		cudaEventDestroy(t0); cudaEventDestroy(t1); cudaEventDestroy(t2); cudaEventDestroy(t3);
+	}
+	if (what & BP_ASSEMBLE_J) c->have_J = true;
+	if (F) BP_CUDA(c, cudaStreamSynchronize(c->s_d2h));
+	BP_CUDA(c, cudaStreamSynchronize(c->s_aux));
 	BP_CUDA(c, cudaStreamSynchronize(c->stream));
 	BP_CUDA(c, cudaGetLastError());
 	return BP_OK;
@@ -757,6 +846,7 @@ void bp_tiles_free(bp_ctx* c)
 	bp_tiles* T = c->tiles;
 	void* ptrs[] = { T->d_vert, T->d_node, T->d_tet, T->d_nthr, T->d_ent0, T->d_out, T->d_out2, T->d_tab, T->d_tflag, T->d_einfo, T->d_ainv, T->d_tfacet, T->d_fn_node, T->d_fn_ptr, T->d_fn_inc };
 	for (void* p : ptrs) if (p) cudaFree(p);
+	if (T->pipe_graph) cudaGraphExecDestroy(T->pipe_graph);
 	delete T;
 	c->tiles = nullptr;
 }
@@ -1248,6 +1338,8 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	// ---- groups of tiles for the pipelined host-buffer path
 	if (!c->host_only && c->identity_dofs && nn == no) {
 		const int K = std::max(1, std::min(c->env.pipe_k, std::min(8, n_tiles / 148)));
+		int n_sm = 0;
+		{ int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); cudaGetLastError(); }
 		std::vector<uint8_t> have(nn, 0), mark(nn, 0);
 		const int GAP = 128;                                  // ranges closer than this are copied as one (the nodes between are needed later anyway)
 		// group boundaries sit where a strip of tiles ends (tiles are ordered strip by strip): the node ranges of a group are
@@ -1256,11 +1348,13 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		bound[K] = n_tiles;
 		for (int k = 1; k < K; ++k) {
 			int b = (int)((int64_t)k * n_tiles / K);
+			// whole waves: a group of tiles that ends just below a multiple of the SM count wastes no partial wave
+			if (n_sm > 0 && b >= n_sm) b = (int)std::lround((double)b / n_sm) * n_sm;
 			int lo_b = b, hi_b = b;
 			auto strip_of = [&](int tl) { return ybin[own_cols[tile_c0[tl]]]; };
 			while (lo_b > bound[k - 1] + 1 && strip_of(lo_b) == strip_of(lo_b - 1)) --lo_b;
 			while (hi_b < n_tiles && strip_of(hi_b) == strip_of(hi_b - 1)) ++hi_b;
-			b = (b - lo_b <= hi_b - b && lo_b > bound[k - 1]) ? lo_b : hi_b;
+			b = (lo_b > bound[k - 1] && (n_sm > 0 || b - lo_b <= hi_b - b)) ? lo_b : hi_b;      // at or just below the wave boundary
 			bound[k] = std::min(std::max(b, bound[k - 1]), n_tiles);
 		}
 		T->chunks.resize(K);
