@@ -429,6 +429,7 @@ void bp_destroy(bp_ctx* c)
 		c->d_io, c->d_io2, c->d_bcmask, c->d_bcval, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
+	if (c->h_halo_stage) cudaFreeHost(c->h_halo_stage);
 	if (c->ev0) cudaEventDestroy(c->ev0);
 	if (c->ev1) cudaEventDestroy(c->ev1);
 	if (c->s_h2d) cudaStreamDestroy(c->s_h2d);

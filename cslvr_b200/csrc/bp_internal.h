@@ -187,6 +187,7 @@ struct bp_ctx {
 	std::vector<uint8_t> h_facet_node;   // owned node gets a facet integral (its F row is final after the facet kernel only)
 	cudaStream_t s_h2d = nullptr, s_d2h = nullptr, s_aux = nullptr;
 	std::vector<cudaEvent_t> pipe_ev;
+	double* h_halo_stage = nullptr;      // pinned: boundary values of a host-side u for the neighbours (pipelined bp_assemble of a partitioned context)
 };
 
 // ---- helpers -------------------------------------------------------------

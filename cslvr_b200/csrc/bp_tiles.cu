@@ -698,8 +698,8 @@ void bp_launch_tiles(bp_ctx* c, int what) { launch_tiles_range(c, what, 0, c->ti
 // after the facet kernel.  Needs the caller's numbering to be the internal one (no ghosts, identity dof map).
 bool bp_tiles_pipeline_ready(const bp_ctx* c, int what)
 {
-	return bp_tiles_serve(c, what) && !(what & ~(BP_ASSEMBLE_F | BP_ASSEMBLE_J)) && !c->tiles->chunks.empty() && c->identity_dofs && !c->comm &&
-	       c->nn == c->nn_owned && c->nd_ext == 2 * c->nn && !c->env.no_pipeline;
+	return bp_tiles_serve(c, what) && !(what & ~(BP_ASSEMBLE_F | BP_ASSEMBLE_J)) && !c->tiles->chunks.empty() && c->identity_dofs &&
+	       (c->nn == c->nn_owned || (c->comm && c->n_nbr > 0)) && c->nd_ext == 2 * c->nn && !c->env.no_pipeline;
 }
 
 // copy node ranges [first, second) of a dof vector (2 doubles per node) between host and device.  On a layer-major
@@ -727,6 +727,11 @@ static cudaError_t copy_ranges(double* dst, const double* src, const std::vector
 	return cudaSuccess;
 }
 
+__global__ void k_scatter_nodes(int n, const int32_t* __restrict__ nodes, const double2* __restrict__ packed, double2* __restrict__ vec)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) vec[nodes[i]] = packed[i];
+}
+
 // issue the pipeline (copies in / group kernels / facet kernel / copies out) on the four streams.  join = true (graph
 // capture): the side streams are joined back into c->stream at the end instead of being synchronised by the host.
 static int pipeline_issue(bp_ctx* c, int what, const double* u, double* F, bool join)
@@ -739,12 +744,29 @@ static int pipeline_issue(bp_ctx* c, int what, const double* u, double* F, bool 
 	BP_CUDA(c, cudaEventRecord(e_0, c->stream));
 	BP_CUDA(c, cudaStreamWaitEvent(c->s_h2d, e_0, 0));
 	BP_CUDA(c, cudaStreamWaitEvent(c->s_d2h, e_0, 0));
+	const bool part = c->nn > c->nn_owned;
+	cudaEvent_t e_halo = c->pipe_ev[21];
+	if (part) {
+		// partitioned: the boundary values the neighbours need were gathered from the caller's vector on the host
+		// (bp_tiles_assemble_pipelined); they go ahead of everything else, the halo exchange runs while the bulk of u is
+		// still on its way, and every group of tiles waits for the ghost rows as well as for its own ranges
+		if (c->n_send) {
+			BP_CUDA(c, cudaMemcpyAsync(c->d_sendbuf, c->h_halo_stage, (size_t)2 * c->n_send * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+			k_scatter_nodes<<<(int)((c->n_send + 255) / 256), 256, 0, c->stream>>>((int)c->n_send, c->d_send_nodes, (const double2*)c->d_sendbuf, (double2*)c->d_u);
+			c->launches++;
+		}
+		bp_ctx* cs[1] = { c };
+		int rc_ = bp_comm_halo(cs, 1, 0);
+		if (rc_) return rc_;
+		BP_CUDA(c, cudaEventRecord(e_halo, c->stream));
+	}
 	for (int k = 0; k < K; ++k) {
 		BP_CUDA(c, copy_ranges(c->d_u, u, T->chunks[k].in, cudaMemcpyHostToDevice, c->s_h2d));
 		BP_CUDA(c, cudaEventRecord(e_h[k], c->s_h2d));
 	}
 	// the groups' kernels alternate between two streams: the partial last wave of one overlaps the first wave of the next
 	BP_CUDA(c, cudaStreamWaitEvent(c->s_aux, e_0, 0));
+	if (part) BP_CUDA(c, cudaStreamWaitEvent(c->s_aux, e_halo, 0));
 	for (int k = 0; k < K; ++k) {
 		cudaStream_t sk = (k & 1) ? c->s_aux : c->stream;
 		BP_CUDA(c, cudaStreamWaitEvent(sk, e_h[k], 0));
@@ -784,10 +806,17 @@ int bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
 		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
 		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
 		BP_CUDA(c, cudaStreamCreateWithFlags(&c->s_aux, cudaStreamNonBlocking));
-		c->pipe_ev.resize(2 * 8 + 5);
+		c->pipe_ev.resize(2 * 8 + 6);
 		for (auto& e : c->pipe_ev) BP_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	}
 	bp_update_ainv(c);
+	if (c->nn > c->nn_owned && c->n_send) {            // boundary values for the neighbours: a few thousand nodes, gathered here
+		if (!c->h_halo_stage) BP_CUDA(c, cudaMallocHost((void**)&c->h_halo_stage, (size_t)2 * c->n_send * sizeof(double)));
+		for (int64_t i = 0; i < c->n_send; ++i) {
+			const size_t nd_ = (size_t)c->h_send_nodes[i];
+			c->h_halo_stage[2 * i] = u[2 * nd_]; c->h_halo_stage[2 * i + 1] = u[2 * nd_ + 1];
+		}
+	}
 	// The ~40 stream operations of one call cost the host ~0.1 ms -- a seventh of the call at 5 M tets.  With pinned
 	// caller buffers the whole pipeline is captured once per (u, F, what, stream) as a CUDA graph over the four streams
 	// and replayed with a single launch; pageable buffers (their copies cannot be captured) take the direct path.
@@ -1336,11 +1365,13 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	const std::vector<uint8_t>& facet_node = fold ? T->h_facet_node : c->h_facet_node;
 
 	// ---- groups of tiles for the pipelined host-buffer path
-	if (!c->host_only && c->identity_dofs && nn == no) {
+	// (a partitioned context too: its ghost nodes -- the tail of the numbering -- come from the neighbours, not from the host)
+	if (!c->host_only && c->identity_dofs && (nn == no || c->n_nbr > 0)) {
 		const int K = std::max(1, std::min(c->env.pipe_k, std::min(8, n_tiles / 148)));
 		int n_sm = 0;
 		{ int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); cudaGetLastError(); }
 		std::vector<uint8_t> have(nn, 0), mark(nn, 0);
+		for (int64_t i = no; i < nn; ++i) have[i] = 1;
 		const int GAP = 128;                                  // ranges closer than this are copied as one (the nodes between are needed later anyway)
 		// group boundaries sit where a strip of tiles ends (tiles are ordered strip by strip): the node ranges of a group are
 		// then whole rows of columns per layer -- a handful of large copies instead of one per row of a cut strip
