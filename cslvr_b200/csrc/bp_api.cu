@@ -41,6 +41,17 @@ void bp_env_read(bp_env* e)
 	e->pipe_graph = geti("BP_PIPE_GRAPH", 1) != 0;
 }
 
+#include <chrono>
+static double wall_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+bp_stage_timer::bp_stage_timer(const char* w) : t0(wall_now()), on(getenv("BP_SETUP_TRACE") != nullptr), what(w) {}
+void bp_stage_timer::lap(const char* stage)
+{
+	if (!on) return;
+	const double t = wall_now();
+	fprintf(stderr, "[cslvr_b200] %s: %-28s %.3f s\n", what, stage, t - t0);
+	t0 = t;
+}
+
 // ------------------------------------------------------------------ helpers
 static int check_params(bp_ctx* c, const bp_params* p)
 {

@@ -50,6 +50,13 @@ struct bp_env {
 };
 void bp_env_read(bp_env* e);
 
+// BP_SETUP_TRACE=1: wall time of the host set-up stages on stderr
+struct bp_stage_timer {
+	double t0; bool on; const char* what;
+	bp_stage_timer(const char* w);
+	void lap(const char* stage);
+};
+
 // constants of the element kernels (built from bp_params per launch)
 struct AsmParams {
 	double n, eps_reg, rho_g, rho_sw_g;

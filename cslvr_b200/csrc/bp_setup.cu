@@ -47,6 +47,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		if (m->cells[i] < 0 || m->cells[i] >= nv)
 			return bp_fail(c, BP_ERR_ARG, "bp_mesh: cells[%lld] = %d out of range", (long long)i, m->cells[i]);
 
+	bp_stage_timer tm("setup");
 	// ---- nodes --------------------------------------------------------------
 	std::vector<int32_t> v2n(nv, -1);
 	if (m->cell_dofs) {
@@ -108,6 +109,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	if (c->nn_owned > nn) return bp_fail(c, BP_ERR_ARG, "bp_mesh: n_owned_nodes > number of nodes");
 	const int64_t no = c->nn_owned;
 
+	tm.lap("nodes");
 	// ---- node -> incident cells ------------------------------------------------
 	std::vector<int32_t> cn((size_t)nt * 4);
 	for (int64_t i = 0; i < nt * 4; ++i) cn[i] = v2n[m->cells[i]];
@@ -120,6 +122,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		for (int64_t t = 0; t < nt; ++t)
 			for (int a = 0; a < 4; ++a) ncell[fill[cn[t * 4 + a]]++] = (int32_t)t;
 	}
+	tm.lap("node->cells");
 	// ---- BSR pattern of the owned rows: row i = sorted unique nodes sharing a cell ---
 	c->h_rowptr.assign(no + 1, 0);
 	#pragma omp parallel
@@ -160,6 +163,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	for (int64_t i = 0; i < no; ++i)
 		if (diag[i] < 0 && nptr[i + 1] > nptr[i]) return bp_fail(c, BP_ERR_ARG, "internal: missing diagonal block");
 
+	tm.lap("BSR pattern");
 	// ---- SELL-32 slots of the resident Jacobian: block k of row i lives at
 	// sell_ptr[i/32] + 32 k + (i%32); padding slots keep value 0 and point at the row itself
 	const int64_t nsl_j = (no + 31) / 32;
@@ -188,6 +192,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		for (int32_t k = 0; k < w; ++k) sell_col[slot_of(i, k)] = 0;
 	}
 
+	tm.lap("SELL slots");
 	// ---- per-tet block slots [16][nt] ------------------------------------------
 	std::vector<int32_t> tet_blk((size_t)nt * 16);
 	#pragma omp parallel for schedule(static)
@@ -205,6 +210,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 			}
 		}
 
+	tm.lap("tet block slots");
 	// ---- row-gather incidences: for every owned node the (tet, local vertex) pairs that
 	// touch it, SELL-32 layout (slice of 32 rows, entry e of lane l at base + 32 e + l),
 	// with the block positions of the tet's four nodes inside the node's block row.
@@ -312,6 +318,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		c->n_inc_slots = (int64_t)nslot;
 	}
 
+	tm.lap("row-gather incidences");
 	// ---- facets that integrate something ----------------------------------------
 	// dGamma_b = {3,5}, dGamma_bw = {5}, dGamma_lt = {4,10}: cslvr/d3model.py:576-598
 	std::vector<int32_t> fcell, finfo;
@@ -365,6 +372,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		UP(c->d_bcnode, bc.data(), bc.size());
 	}
 
+	tm.lap("facets");
 	// ---- ice columns (vertical-line preconditioner): owned nodes with the same (x, y),
 	// ordered bottom to top; slots of the diagonal and of the up / down coupling blocks
 	{
@@ -435,6 +443,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		UP(c->d_tri_l, tri_l.data(), no);
 	}
 
+	tm.lap("ice columns");
 	// ---- halo -----------------------------------------------------------------
 	c->n_nbr = (m->n_owned_nodes >= 0) ? m->n_neighbors : 0;
 	if (c->n_nbr > 0) {
@@ -454,6 +463,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		return bp_fail(c, BP_ERR_ARG, "bp_mesh: ghost nodes without neighbours");
 	}
 
+	tm.lap("halo");
 	// ---- upload ---------------------------------------------------------------
 	{
 		std::vector<double4> geo(nv);
@@ -509,7 +519,8 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		BP_CUDA(c, cudaMemset(c->d_val, 0, (size_t)std::max<int64_t>(c->n_slots, 1) * 4 * sizeof(double)));
 	}
 	// tiled cell assembly for extruded prism meshes (bp_tiles.cu); other meshes are served by the row gather
-	return bp_setup_tiles(c, m, v2n);
+	tm.lap("upload");
+	{ const int rc_t = bp_setup_tiles(c, m, v2n); tm.lap("tiles"); return rc_t; }
 }
 
 // Scalar CSR in the caller's numbering: row = caller's dof, columns ascending,

@@ -908,6 +908,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	const int64_t nv = c->nv, nt = c->nt, nn = c->nn, no = c->nn_owned;
 	if (no == 0) return no_tiles(c, "no owned nodes");
 
+	bp_stage_timer tt("tiles");
 	// ---- 1. vertex columns: vertices with equal (x, y), bottom -> top --------------------------
 	double lo[2] = { 1e300, 1e300 }, hi[2] = { -1e300, -1e300 };
 	for (int64_t v = 0; v < nv; ++v) for (int d = 0; d < 2; ++d) { lo[d] = std::min(lo[d], m->coords[3 * v + d]); hi[d] = std::max(hi[d], m->coords[3 * v + d]); }
@@ -936,6 +937,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		}
 	if (nt % (3 * NZ)) return no_tiles(c, "cell count is not 3 x layers x triangles");
 
+	tt.lap("vertex columns");
 	// ---- 2. node columns (periodic images of a vertex column share one node column) -------------
 	std::vector<int32_t> ncol(nn, -1), nlay(nn, -1), ncol_of_vcol(nvc), colnode;
 	int32_t n_ncol = 0;
@@ -965,6 +967,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		col_owned[q] = ow;
 	}
 
+	tt.lap("node columns");
 	// ---- 3. prism columns: every tet lies in one (triangle of vertex columns, layer); 3 tets per prism -------
 	struct Rec { int32_t a, b, cc, k, t; };
 	std::vector<Rec> rec(nt);
@@ -1021,6 +1024,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	if (bad) return no_tiles(c, "prisms are not split into three tets the same way along a column");
 	{ std::vector<Rec>().swap(rec); }
 
+	tt.lap("prism columns");
 	// ---- 3b. basal facets = bottom triangles of prism columns: folded into the march (see bp_tiles::d_tfacet) ----
 	// facet (cell, local facet) is the bottom of column r iff the cell is r's tet A of layer 0 and the vertex opposite the
 	// facet is its t2 (layer 1).  Everything else (the lateral water-pressure facets) stays with the facet kernel.
@@ -1038,6 +1042,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		}
 	}
 
+	tt.lap("facet fold");
 	// ---- 4. tiles of owned ice columns: compact footprint patches, at most TILE_T prism columns touch one ----
 	std::vector<int64_t> ctp(n_ncol + 1, 0);                   // node column -> prism columns touching it
 	for (int64_t r = 0; r < ntri; ++r) {
@@ -1140,6 +1145,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	}
 	const int n_tiles = (int)tile_c0.size() - 1;
 
+	tt.lap("tiling");
 	// ---- 5 + 6. per tile: thread list (prism columns), vertex / node / tet tables, sum tables -----------------
 	bp_tiles* T = new bp_tiles();
 	T->n_tiles = n_tiles; T->NL = NL; T->n_prism_cols = ntri; T->W = W;
@@ -1341,6 +1347,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	}
 	if (miss) { delete T; return no_tiles(c, "internal: the tile tables do not cover every Jacobian block exactly once"); }
 
+	tt.lap("tables");
 	// ---- the facets that are left for the facet kernel: row-gather lists as in bp_setup.cu, without the folded ones
 	std::vector<int32_t> fn_node, fn_ptr(1, 0), fn_inc;
 	T->h_facet_node.assign((size_t)std::max<int64_t>(no, 1), 0);
@@ -1364,6 +1371,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	}
 	const std::vector<uint8_t>& facet_node = fold ? T->h_facet_node : c->h_facet_node;
 
+	tt.lap("facet lists");
 	// ---- groups of tiles for the pipelined host-buffer path
 	// (a partitioned context too: its ghost nodes -- the tail of the numbering -- come from the neighbours, not from the host)
 	if (!c->host_only && c->identity_dofs && (nn == no || c->n_nbr > 0)) {
@@ -1430,6 +1438,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		if (nr > 600) T->chunks.clear();                      // a numbering without locality: too many small copies, the plain path serves it
 	}
 
+	tt.lap("pipeline groups");
 	int rc = up(c, &T->d_vert, T->h_vert);
 	if (!rc) rc = up(c, &T->d_node, T->h_node);
 	if (!rc) rc = up(c, &T->d_tet, T->h_tet);
