@@ -477,7 +477,8 @@ def run_ours(args):
 		Fo, Jo, t_cpu = co.assemble(u_host)
 		own = slice(0, 2 * s.n_owned)
 		Fp = ctx.assemble(u_host, want_F=True, want_J=True, J=False)[0]
-		eF = max(relerr(Fp[own], Fo[own]), relerr(F_pin.numpy()[own], Fo[own]))          # ... and the F the timed end-to-end calls left in the pinned buffer
+		step_dev()
+		eF = max(relerr(Fp[own], Fo[own]), relerr(F_pin.numpy()[own], Fo[own]), relerr(F_dev.cpu().numpy()[own], Fo[own]))   # ... and the F of the timed calls: pinned host buffer (e2e) and device buffer (value)
 		x = np.sin(0.61 * np.repeat(s.node_global, 2) + np.tile([0.3, 1.1], s.n_nodes))      # a function of the global node id
 		import scipy.sparse as sp
 		Jx_o = sp.csr_matrix((Jo, co.indices, co.indptr), shape=(nd, nd)) @ x
