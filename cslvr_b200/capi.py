@@ -76,7 +76,7 @@ class bp_stats(C.Structure):
 
 # every symbol include/cslvr_b200.h declares (tests check the library exports them all)
 SYMBOLS = ['bp_create', 'bp_destroy', 'bp_last_error', 'bp_set_params', 'bp_set_stream',
-           'bp_set_field', 'bp_set_dirichlet', 'bp_get_sizes', 'bp_csr_pattern', 'bp_assemble', 'bp_spmv',
+           'bp_set_field', 'bp_set_dirichlet', 'bp_set_dirichlet_uz', 'bp_get_sizes', 'bp_csr_pattern', 'bp_assemble', 'bp_spmv',
            'bp_krylov_solve', 'bp_newton_solve', 'bp_time_assemble', 'bp_time_spmv',
            'bp_launch_count', 'bp_comm_unique_id', 'bp_comm_init',
            'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity', 'bp_linear_solve',
@@ -507,6 +507,13 @@ class BPContext(object):
 		g = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), d.shape))
 		self.lib.bp_set_dirichlet.argtypes = [C.c_void_p, C.c_int64, c_i32p, c_f64p]
 		self._check(self.lib.bp_set_dirichlet(self.h, d.size, d.ctypes.data_as(c_i32p), g.ctypes.data_as(c_f64p)))
+
+	def set_dirichlet_uz(self, vertices, values):
+		"""lateral Dirichlet values of the u_z solve (bp_set_dirichlet_uz), by mesh vertex."""
+		v = np.ascontiguousarray(vertices, dtype=np.int32)
+		g = np.ascontiguousarray(np.broadcast_to(np.asarray(values, dtype=np.float64), v.shape))
+		self.lib.bp_set_dirichlet_uz.argtypes = [C.c_void_p, C.c_int64, c_i32p, c_f64p]
+		self._check(self.lib.bp_set_dirichlet_uz(self.h, v.size, v.ctypes.data_as(c_i32p), g.ctypes.data_as(c_f64p)))
 
 	def time_assemble(self, what=ASSEMBLE_F | ASSEMBLE_J, repeats=20, flush_l2=True):
 		ms = C.c_double()

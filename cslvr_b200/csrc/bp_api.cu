@@ -437,7 +437,7 @@ void bp_destroy(bp_ctx* c)
 	bp_comm_free(c);
 	void* ptrs[] = { c->d_geo, c->d_A, c->d_beta, c->d_tets, c->d_v2n, c->d_tet_blk, c->d_inc_slice, c->d_inc_code, c->d_inc_pos, c->d_inc_v, c->d_soa, c->d_zS, c->d_uvert, c->d_fac_cell, c->d_fac_info, c->d_fn_node, c->d_fn_ptr, c->d_fn_inc, c->d_ext_dof,
 		c->d_sell_ptr, c->d_rowlen, c->d_col, c->d_diag, c->d_mirror, c->d_val, c->d_valf, c->d_csr_src, c->d_csr_out, c->d_u, c->d_F, c->d_dx, c->d_r, c->d_z, c->d_p, c->d_Ap,
-		c->d_io, c->d_io2, c->d_bcmask, c->d_bcval, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
+		c->d_io, c->d_io2, c->d_bcmask, c->d_bcval, c->d_uzbc_node, c->d_uzbc_val, c->d_z2, c->d_cd, c->d_aux, c->d_Bv, c->d_Bring, c->d_uz, c->d_uvert2, c->d_bcnode, c->d_Tp, c->d_W, c->d_E, c->d_ainv, c->d_colptr, c->d_colnode, c->d_tri_d, c->d_tri_u, c->d_tri_l, c->d_dinv, c->d_sc, c->d_part, c->d_counter, c->d_send_nodes, c->d_sendbuf };
 	for (void* p : ptrs) if (p) cudaFree(p);
 	if (c->h_sc) cudaFreeHost(c->h_sc);
 	if (c->h_halo_stage) cudaFreeHost(c->h_halo_stage);
@@ -721,6 +721,31 @@ int bp_set_dirichlet(bp_ctx* c, int64_t n, const int32_t* dofs, const double* va
 	return BP_OK;
 }
 
+int bp_set_dirichlet_uz(bp_ctx* c, int64_t n, const int32_t* vertices, const double* values)
+{
+	if (!c || n < 0 || (n > 0 && (!vertices || !values))) return BP_ERR_ARG;
+	BP_CUDA(c, cudaSetDevice(c->device));
+	std::vector<uint8_t> bc = c->h_bcnode;
+	std::vector<int32_t> nodes;
+	std::vector<double> vals;
+	for (int64_t k = 0; k < n; ++k) {
+		if (vertices[k] < 0 || vertices[k] >= c->nv) return bp_fail(c, BP_ERR_ARG, "bp_set_dirichlet_uz: vertex %d outside [0, %lld)", vertices[k], (long long)c->nv);
+		const int32_t nd_ = c->h_v2n.empty() ? vertices[k] : c->h_v2n[vertices[k]];
+		if (nd_ >= c->nn_owned) continue;                  // a ghost: its owner constrains it
+		if (!(bc[nd_] & 2)) { bc[nd_] |= 2; nodes.push_back(nd_); vals.push_back(values[k]); }
+	}
+	if (c->d_uzbc_node) { cudaFree(c->d_uzbc_node); cudaFree(c->d_uzbc_val); c->d_uzbc_node = nullptr; c->d_uzbc_val = nullptr; }
+	c->n_uzbc = (int64_t)nodes.size();
+	if (c->n_uzbc) {
+		BP_CUDA(c, cudaMalloc((void**)&c->d_uzbc_node, nodes.size() * sizeof(int32_t)));
+		BP_CUDA(c, cudaMalloc((void**)&c->d_uzbc_val, vals.size() * sizeof(double)));
+		BP_CUDA(c, cudaMemcpy(c->d_uzbc_node, nodes.data(), nodes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+		BP_CUDA(c, cudaMemcpy(c->d_uzbc_val, vals.data(), vals.size() * sizeof(double), cudaMemcpyHostToDevice));
+	}
+	if (!bc.empty()) BP_CUDA(c, cudaMemcpy(c->d_bcnode, bc.data(), bc.size(), cudaMemcpyHostToDevice));
+	return BP_OK;
+}
+
 int bp_krylov_solve(bp_ctx* c, const double* b, double* dx, int on_device, int32_t* iterations, double* rel_residual)
 {
 	if (!c || !b || !dx) return BP_ERR_ARG;
@@ -882,6 +907,7 @@ static int vert_velocity_core(bp_ctx* c, int32_t* iterations)
 	}
 	BP_CUDA(c, cudaMemcpyAsync(c->d_aux, c->d_dx, (size_t)2 * c->nn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
 	// 2. the continuity system with Dirichlet rows -> d_val (component 0 of the blocks), d_F
+	bp_launch_uz_lateral_values(c, c->d_aux);      // DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD): applied last, it wins on shared nodes
 	bp_launch_rows_aux(c, 2);
 	// 3. BiCGStab, right-preconditioned by the pivoted tridiagonal solve of every column
 	const size_t nb = (size_t)2 * c->nn * sizeof(double);

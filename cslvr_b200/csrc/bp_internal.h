@@ -89,6 +89,7 @@ struct bp_ctx {
 	int64_t n_basal = 0;
 	bool    identity_dofs = true;    // caller's dof == 2*node + c
 	bool    identity_v2n = true;
+	std::vector<int32_t> h_v2n;          // vertex -> internal node (kept on the host for bp_set_dirichlet_uz; empty = identity)
 
 	// host topology kept for the lazy CSR export
 	std::vector<int32_t> h_ext_dof;      // [2*nn] caller's dof of (node, c): [2*i+c]
@@ -107,7 +108,9 @@ struct bp_ctx {
 	double  *d_Bv = nullptr, *d_Bring = nullptr;   // bed height / basal melt per vertex (u_z solve only)
 	double*  d_uz = nullptr;             // frozen vertical velocity per vertex (reduced-Stokes model, BP_FIELD_UZ)
 	double*  d_uvert2 = nullptr;         // [2*nv] second per-vertex velocity (viscosity state of bp_rs_solve_pressure)
-	uint8_t* d_bcnode = nullptr;         // owned node lies on a basal facet (Dirichlet dof of the u_z system)
+	uint8_t* d_bcnode = nullptr;         // owned node lies on a basal facet (Dirichlet dof of the u_z system) or carries a lateral u_z condition
+	std::vector<uint8_t> h_bcnode;       // the basal ones (bp_set_dirichlet_uz adds to a copy of it)
+	int32_t* d_uzbc_node = nullptr; double* d_uzbc_val = nullptr; int64_t n_uzbc = 0;   // lateral Dirichlet nodes of the u_z solve and their values
 	double*  d_aux = nullptr;            // [2*nn] u_z_b per node
 	int4*    d_tets = nullptr;
 	int32_t* d_v2n = nullptr;            // nullptr when identity
@@ -219,6 +222,7 @@ void bp_launch_csr_export(bp_ctx* c, double* out);
 void bp_launch_pc_setup(bp_ctx* c);
 void bp_launch_set_S(bp_ctx* c, const double* S_dev);
 void bp_launch_pack_halo(bp_ctx* c, const double* vec);
+void bp_launch_uz_lateral_values(bp_ctx* c, double* node_vec);
 void bp_launch_bc_rows(bp_ctx* c, double sign);   // constrained rows of d_F <- sign * u - g (d in d_io for bp_launch_bc_eliminate)
 void bp_launch_bc_eliminate(bp_ctx* c);           // free rows lifted by J d, rows / columns of the constrained dofs -> identity
 void bp_launch_dot_owned(bp_ctx* c, const double* a, const double* b, int sc_slot);

@@ -847,6 +847,17 @@ void bp_launch_rows_aux(bp_ctx* c, int kind, const double2* u_eta_vertex, const 
 	if (kind == 0) AUX(0); else if (kind == 1) AUX(1); else AUX(2);
 	c->launches++;
 }
+__global__ void k_set_node_x(int n, const int32_t* __restrict__ nodes, const double* __restrict__ vals, double2* __restrict__ vec)
+{
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) vec[nodes[i]].x = vals[i];
+}
+// the lateral Dirichlet values of the u_z system replace the projected basal value on their nodes (bp_set_dirichlet_uz)
+void bp_launch_uz_lateral_values(bp_ctx* c, double* node_vec)
+{
+	if (!c->n_uzbc) return;
+	k_set_node_x<<<(int)((c->n_uzbc + 255) / 256), 256, 0, c->stream>>>((int)c->n_uzbc, c->d_uzbc_node, c->d_uzbc_val, (double2*)node_vec);
+	c->launches++;
+}
 void bp_launch_node_to_vertex(bp_ctx* c, const double* node_vec, int comp, double* vertex_out)
 {
 	k_node_to_vertex<<<red_blocks_fwd(c->nv, 256), 256, 0, c->stream>>>((int)c->nv, c->d_v2n, node_vec, comp, vertex_out);

@@ -369,6 +369,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 		std::vector<uint8_t> bc((size_t)std::max<int64_t>(no, 1), 0);
 		for (size_t f = 0; f < fcell.size(); ++f) if ((finfo[f] >> 8) & 1)
 			for (int k = 0; k < 3; ++k) { const int32_t nd_ = cn[(int64_t)fcell[f] * 4 + LOC[finfo[f] & 0xff][k]]; if (nd_ < no) bc[nd_] = 1; }
+		c->h_bcnode = bc;
 		UP(c->d_bcnode, bc.data(), bc.size());
 	}
 
@@ -491,6 +492,7 @@ int bp_setup_topology(bp_ctx* c, const bp_mesh* m)
 	if (!c->host_only) BP_CUDA(c, cudaMemset(c->d_uz, 0, (size_t)nv * sizeof(double)));
 	UP(c->d_uvert2, (const double*)nullptr, 2 * nv);
 	UP(c->d_tets, (const int4*)m->cells, nt);
+	if (!c->identity_v2n) c->h_v2n = v2n;
 	if (!c->identity_v2n) { UP(c->d_v2n, v2n.data(), nv); UP(c->d_uvert, (const double*)nullptr, (size_t)2 * nv); }
 	UP(c->d_tet_blk, tet_blk.data(), (size_t)nt * 16);
 	UP(c->d_fac_cell, fcell.data(), c->nf);

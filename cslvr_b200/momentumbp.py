@@ -243,10 +243,12 @@ class MomentumBPBase(Momentum):
 		# project the basal kinematic condition, assemble the continuity system, apply the
 		# basal Dirichlet rows and solve (cslvr/momentumbp.py:231-253) -- all on the device
 		m = self.model
-		if getattr(self, 'lateral_u_z_bc', False):
-			raise NotImplementedError("solve_vert_velocity with DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD) (cslvr/momentumbp.py:110-111) "
-			                          "is not served by the device solve yet: set solve_params['solve_vert_velocity'] = False")
 		c = self._context()
+		if getattr(self, 'lateral_u_z_bc', False):         # u_z_bcs also holds DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD), momentumbp.py:110-111
+			nodes = m.divide_nodes()
+			c.set_dirichlet_uz(np.asarray(m.node_vertex)[nodes], m.u_z_lat.values[nodes])
+		else:
+			c.set_dirichlet_uz(np.zeros(0, dtype=np.int32), np.zeros(0))
 		c.set_field(capi.FIELD_B, m.vertex_field(m.B))
 		if getattr(m, 'B_ring', None) is not None:
 			c.set_field(capi.FIELD_B_RING, m.vertex_field(m.B_ring))

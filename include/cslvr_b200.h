@@ -211,6 +211,9 @@ int  bp_set_field(bp_ctx* ctx, int field, const double* values, int64_t n, int o
  * keeps a symmetric matrix).  bp_assemble keeps returning the unconstrained F and J, as assemble() does.
  * n = 0 removes the conditions.                                                                         */
 int  bp_set_dirichlet(bp_ctx* ctx, int64_t n, const int32_t* dofs, const double* values);
+/* ... and of bp_solve_vert_velocity: DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD) (cslvr/momentumbp.py:110-111), by mesh vertex;
+ * applied after the basal conditions, so it wins on the nodes they share (bc.apply in list order).  n = 0 removes them. */
+int  bp_set_dirichlet_uz(bp_ctx* ctx, int64_t n, const int32_t* vertices, const double* values);
 
 
 /* sizes after the mesh has been digested */

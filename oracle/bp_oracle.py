@@ -507,7 +507,7 @@ class BPProblem(object):
 		return spla.spsolve(self.mass_matrix().tocsc(), rhs)
 
 	# ---- solve_vert_velocity, cslvr/momentumbp.py:60-85, 231-253 ----------------
-	def vert_velocity(self, u, B, B_ring=None):
+	def vert_velocity(self, u, B, B_ring=None, lateral_bc=None):
 		"""u_z from the continuity equation the way the reference does it:
 
 		1. u_z_b = project((-B_ring - u_x n_b0 - u_y n_b1) / n_b2, Q) with
@@ -548,6 +548,11 @@ class BPProblem(object):
 			A.rows[i] = [i]
 			A.data[i] = [1.0]
 		b[bn] = uzb[bn]
+		if lateral_bc is not None:                             # DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD), momentumbp.py:110-111: applied last
+			for i, g_ in zip(np.asarray(lateral_bc[0], dtype=np.int64), np.asarray(lateral_bc[1], dtype=np.float64)):
+				A.rows[i] = [i]
+				A.data[i] = [1.0]
+				b[i] = g_
 		return spla.spsolve(A.tocsc(), b), uzb
 
 	# ---- linear=True, cslvr/momentumbp.py:396 / 503, physics.py:655-661 ----------

@@ -719,6 +719,13 @@ def test_newton_with_lateral_dirichlet_conditions_matches_oracle():
 	# without the conditions the solution is a different one (the test has teeth)
 	un, _ = P.newton(rtol=1e-11, maxit=60, relax=0.7)
 	assert relerr(un, uo) > 1e-3
+	# u_z with its lateral condition DirichletBC(Q, u_z_lat, ff, GAMMA_L_DVD) on top of the basal ones (momentumbp.py:110-111)
+	m.init_u_z_lat(lambda x, y, z: -0.3 + 1e-5 * x)
+	mom.solve_vert_velocity()
+	nodes = m.divide_nodes()
+	uz_o, _ = P.vert_velocity(u, m.vertex_field(m.B), lateral_bc=(nodes, m.u_z_lat.values[nodes]))
+	assert relerr(mom.u_z.values, uz_o) < 1e-7
+	assert np.abs(mom.u_z.values[nodes] - m.u_z_lat.values[nodes]).max() < 1e-9
 	# linear=True: K(u_lin) u = f with the same rows constrained
 	m.u.values[0::3], m.u.values[1::3] = u[0::2], u[1::2]
 	lin = MomentumBP(m, use_lat_bcs=True, linear=True)
