@@ -81,7 +81,7 @@ SYMBOLS = ['bp_create', 'bp_destroy', 'bp_last_error', 'bp_set_params', 'bp_set_
            'bp_launch_count', 'bp_comm_unique_id', 'bp_comm_init',
            'bp_newton_solve_group', 'bp_assemble_group', 'bp_solve_pressure', 'bp_solve_vert_velocity', 'bp_linear_solve',
            'bp_rs_newton_solve', 'bp_rs_solve_pressure',
-           'bp_debug_create_host', 'bp_debug_bsr_pattern', 'bp_debug_tiles_emulate', 'bp_debug_tiles_info', 'bp_debug_tiles_why']
+           'bp_debug_create_host', 'bp_debug_bsr_pattern', 'bp_debug_tiles_emulate', 'bp_debug_tiles_emulate_facets', 'bp_debug_tiles_info', 'bp_debug_tiles_why']
 
 _lib = None
 
@@ -627,16 +627,23 @@ class HostTileContext(object):
 		col = np.ctypeslib.as_array(ci, shape=(max(int(rowptr[-1]), 1),))[:rowptr[-1]].copy()
 		return rowptr, col
 
-	def emulate(self, S_vertex, u_nodes, ainv_cells, picard=False):
-		"""(F[2*n_owned], J blocks [nnzb, 2, 2] in BSR row order) of the CELL integrals at ``u_nodes`` ([2*node + c])."""
+	def emulate(self, S_vertex, u_nodes, ainv_cells, picard=False, beta_vertex=None):
+		"""(F[2*n_owned], J blocks [nnzb, 2, 2] in BSR row order) of the CELL integrals at ``u_nodes`` ([2*node + c]);
+		with ``beta_vertex`` also the basal facet integrals the kernel folds into its first layer."""
 		xyzS = np.ascontiguousarray(np.column_stack([self.coords, np.asarray(S_vertex, dtype=np.float64)]))
 		u = np.ascontiguousarray(u_nodes, dtype=np.float64)
 		a = np.ascontiguousarray(ainv_cells, dtype=np.float64)
 		rowptr, col = self.bsr_pattern()
 		F = np.zeros(2 * (rowptr.size - 1))
 		J = np.zeros(4 * int(rowptr[-1]))
-		rc = self.lib.bp_debug_tiles_emulate(self.h, xyzS.ctypes.data_as(c_f64p), u.ctypes.data_as(c_f64p), a.ctypes.data_as(c_f64p),
-		                                     int(bool(picard)), F.ctypes.data_as(c_f64p), J.ctypes.data_as(c_f64p))
+		if beta_vertex is not None:
+			b = np.ascontiguousarray(beta_vertex, dtype=np.float64)
+			self.lib.bp_debug_tiles_emulate_facets.argtypes = [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p, C.c_int, c_f64p, c_f64p]
+			rc = self.lib.bp_debug_tiles_emulate_facets(self.h, xyzS.ctypes.data_as(c_f64p), u.ctypes.data_as(c_f64p), a.ctypes.data_as(c_f64p),
+			                                            b.ctypes.data_as(c_f64p), int(bool(picard)), F.ctypes.data_as(c_f64p), J.ctypes.data_as(c_f64p))
+		else:
+			rc = self.lib.bp_debug_tiles_emulate(self.h, xyzS.ctypes.data_as(c_f64p), u.ctypes.data_as(c_f64p), a.ctypes.data_as(c_f64p),
+			                                     int(bool(picard)), F.ctypes.data_as(c_f64p), J.ctypes.data_as(c_f64p))
 		if rc != BP_OK:
 			raise BPError(rc, self.lib.bp_last_error(self.h).decode())
 		return F, J.reshape(-1, 2, 2), rowptr, col

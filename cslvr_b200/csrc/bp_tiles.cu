@@ -1469,8 +1469,8 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 
 // ------------------------------------------------------------------------------------------------
 // host emulation of k_tile: same tables, same element math, same order of additions.  Debug / CPU tests only.
-extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const double* u, const double* ainv, int picard,
-                                      double* F, double* Jblocks)
+static int tiles_emulate(bp_ctx* c, const double* vert_xyzS, const double* u, const double* ainv, const double* beta, int picard,
+                         double* F, double* Jblocks)
 {
 	if (!c || !c->tiles) return bp_fail(c, BP_ERR_STATE, "no tile tables: %s", c ? c->tiles_why.c_str() : "");
 	bp_tiles* T = c->tiles;
@@ -1506,6 +1506,11 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 							pt[i] = geo[T->h_vert[(((size_t)tile * NL + k + 1) * 3 + i) * TILE_T + t]];
 							ut[i] = u2[T->h_node[(((size_t)tile * NL + k + 1) * 3 + i) * TILE_T + t]];
 						}
+						if (k == 0 && beta && T->folded) {           // the basal facet starts the bottom interface, as in the kernel
+							const uint32_t ffl = T->h_tfacet[(size_t)tile * TILE_T + t];
+							const int32_t* tv = T->h_vert.data() + (size_t)tile * NL * 3 * TILE_T + t;
+							if (ffl) facet_fold(pb, ub, beta[tv[0]], beta[tv[TILE_T]], beta[tv[2 * TILE_T]], ffl, P, bot[t]);
+						}
 						double a[3];
 						for (int j = 0; j < 3; ++j) { const int32_t tt = T->h_tet[(((size_t)tile * NZ + k) * 3 + j) * TILE_T + t]; a[j] = tt >= 0 ? ainv[tt] : 0.0; }
 						prism_steps(pb, ub, pt, ut, a[0], a[1], a[2], P, bot[t], top[t], st);
@@ -1530,6 +1535,20 @@ extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const 
 		for (int32_t k = 0; k < c->h_rowptr[i + 1] - c->h_rowptr[i]; ++k)
 			memcpy(Jblocks + 4 * ((size_t)c->h_rowptr[i] + k), val.data() + 4 * ((size_t)c->h_sell_ptr[i >> 5] + 32 * k + (i & 31)), 4 * sizeof(double));
 	return BP_OK;
+}
+
+extern "C" int bp_debug_tiles_emulate(bp_ctx* c, const double* vert_xyzS, const double* u, const double* ainv, int picard,
+                                      double* F, double* Jblocks)
+{
+	return tiles_emulate(c, vert_xyzS, u, ainv, nullptr, picard, F, Jblocks);
+}
+
+// ... with the basal facets the kernel folds into its first layer (beta: per vertex): cells + dGamma_b / dGamma_bw
+extern "C" int bp_debug_tiles_emulate_facets(bp_ctx* c, const double* vert_xyzS, const double* u, const double* ainv, const double* beta,
+                                             int picard, double* F, double* Jblocks)
+{
+	if (!beta) return BP_ERR_ARG;
+	return tiles_emulate(c, vert_xyzS, u, ainv, beta, picard, F, Jblocks);
 }
 
 extern "C" int bp_debug_tiles_info(const bp_ctx* c, int64_t* n_tiles, int64_t* n_prism_cols, int64_t* n_threads_used, int64_t* n_entries, int64_t* n_contrib)

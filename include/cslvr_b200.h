@@ -305,6 +305,9 @@ int  bp_debug_create_host(bp_ctx** out, const bp_mesh* mesh, const bp_params* pa
 int  bp_debug_bsr_pattern(const bp_ctx* ctx, int64_t* n_rows, const int32_t** rowptr, const int32_t** col);
 int  bp_debug_tiles_emulate(bp_ctx* ctx, const double* vert_xyzS, const double* u, const double* ainv,
                             int picard, double* F, double* J_blocks);
+/* ... plus the basal facets (markers 3, 5) the kernel folds into its first layer; beta: [n_vertices] */
+int  bp_debug_tiles_emulate_facets(bp_ctx* ctx, const double* vert_xyzS, const double* u, const double* ainv, const double* beta,
+                                   int picard, double* F, double* J_blocks);
 int  bp_debug_tiles_info(const bp_ctx* ctx, int64_t* n_tiles, int64_t* n_prism_columns,
                          int64_t* n_threads_used, int64_t* n_entries, int64_t* n_contributions);
 const char* bp_debug_tiles_why(const bp_ctx* ctx);   /* why the mesh is not served by the tiled kernel ("" if it is) */

@@ -71,6 +71,17 @@ def test_tile_tables_and_element_math_match_the_oracle(name):
 	assert relerr(Fp, P0.residual(np.zeros_like(u))) < 1e-12                       # F(0) is exactly the gravity term
 	Jps = _blocks_to_csr(Jp, rowptr, col, P.n_dofs)
 	assert abs(Jps - Jps.T).max() < 1e-12 * abs(Jps).max()
+	# the kernel folds the basal facets (dGamma_b: sliding, dGamma_bw: water pressure) into its first layer -- the bottom
+	# triangle of a prism column is its basal facet: cells + those facets against the oracle with exactly them
+	basal = np.isin(m.ff, (3, 5))
+	assert basal.any()
+	Pb = bo.BPProblem(P.coords, P.cells, P.cell_dofs, P.n_dofs, m.facet_cell[basal], m.facet_local[basal], m.ff[basal], P.S, P.A, P.beta,
+	                  periodic=P.periodic, use_pressure_bc=True, consts=P.c)
+	Ff, Jf, _, _ = h.emulate(m.vertex_field(m.S), u, _ainv(m.vertex_field(m.A), m.mesh.cells()), beta_vertex=m.vertex_field(m.beta))
+	Jbo = sp.csr_matrix((Pb.jacobian(u), ix, ip), shape=(P.n_dofs, P.n_dofs))
+	assert relerr(Ff, Pb.residual(u)) < 1e-12
+	assert abs(_blocks_to_csr(Jf, rowptr, col, P.n_dofs) - Jbo).max() < 1e-12 * abs(Jbo).max()
+	assert relerr(Ff, F) > 1e-6                                          # the facets do contribute
 	h.close()
 
 
