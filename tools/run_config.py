@@ -72,13 +72,48 @@ def main():
 	t_solve, = allmax(time.time() - t0)
 	ms, = allmax(c.time_assemble(3, repeats=10, flush_l2=True))
 	umax, = allmax(float(np.abs(u[own]).max()))
+	# parity at full size (untimed): F and J x of the CUDA path at the converged velocity against the oracle's C twin on
+	# this rank's arrays (owned rows are complete locally), and the oracle's own residual there
+	parity = None
+	if '--no-parity' not in sys.argv:
+		import scipy.sparse as sp
+		from oracle import bp_oracle as bo
+		from oracle.bp_oracle_cwrap import COracle
+		if world == 1:
+			coords, cells, v2n, nn = m.mesh.coordinates(), m.mesh.cells(), np.asarray(m.vertex_to_node), m.n_nodes
+			facets = (m.facet_cell, m.facet_local, m.ff)
+			fS, fA, fb = m.vertex_field(m.S), m.vertex_field(m.A), m.vertex_field(m.beta)
+			gid = np.arange(nn)
+		else:
+			coords, cells, v2n, nn = rm.coords, rm.cells, rm.vertex_to_node, rm.n_nodes
+			facets, fS, fA, fb, gid = rm.facets, rm.fields['S'], rm.fields['A'], rm.fields['beta'], rm.node_global
+		n2 = 2 * np.asarray(v2n)[cells]
+		cd = np.concatenate([n2, n2 + 1], axis=1).astype(np.int32)
+		P = bo.BPProblem(coords, cells, cd, 2 * nn, facets[0], facets[1], facets[2], fS, fA, fb, periodic=m.use_periodic,
+		                 use_pressure_bc=kw['use_pressure_bc'], consts=dict(n=m.n, eps_reg=m.eps_reg, rho_i=m.rho_i, rhosw=m.rhosw, g=m.g))
+		co = COracle(P, threads=max(1, (os.cpu_count() or 1) // world))
+		# (F itself is ~1e-9 of its terms at the solution: it is compared at a perturbed state, the residual at the solution separately)
+		up = u * (1.0 + 1e-2 * np.sin(0.37 * np.repeat(gid, 2) + np.tile([0.0, 0.7], nn)))
+		r_sol = co.assemble(u, want_J=False)[0]
+		Fo, Jo, _ = co.assemble(up)
+		Fp, _ = c.assemble(up, want_F=True, want_J=True, J=False)
+		x = np.sin(0.61 * np.repeat(gid, 2) + np.tile([0.3, 1.1], nn))
+		Jx_o = sp.csr_matrix((Jo, co.indices, co.indptr), shape=(2 * nn, 2 * nn)) @ x
+		Jx_p = c.spmv(x)
+		scale = lambda a: max(float(np.abs(a).max()), 1e-300)
+		eF, eJ = allmax(float(np.abs(Fp[own] - Fo[own]).max()), float(np.abs(Jx_p[own] - Jx_o[own]).max()))
+		sF, sJ = allmax(scale(Fo[own]), scale(Jx_o[own]))
+		a, = allsum(float(r_sol[own] @ r_sol[own]))
+		parity = dict(F_rel=eF / sF, Jx_rel=eJ / sJ, oracle_residual_at_solution=float(np.sqrt(a)), oracle_residual_rel=float(np.sqrt(a)) / st['residual_norm0'],
+		              checked="F and J x at the converged velocity perturbed by 1 % vs oracle/bp_oracle_c.c on every rank's arrays (owned rows); the oracle's residual at the converged velocity", tolerance=1e-12)
+		parity['ok'] = bool(parity['F_rel'] < 1e-12 and parity['Jx_rel'] < 1e-12)
 	if rank == 0:
 		out = dict(config=name, mesh=n, n_gpus=world, n_tets=m.num_cells, n_dofs=2 * m.n_nodes, host_model_s=t_model, context_setup_s=t_ctx,
 		           newton_solve_s=t_solve, converged=st['converged'], newton_iterations=st['iterations'],
 		           krylov_iterations=st['krylov_iterations'], assemble_ms_in_solve=st['t_assemble_ms'], krylov_ms=st['t_krylov_ms'],
 		           assembly_pass_ms=ms, assembly_mtets_s=m.num_cells / ms / 1e3, preconditioner=c.pc_label(),
 		           gpu_launches=st['gpu_launches'], host_launches=st.get('host_launches'),
-		           u_max=umax, residual0=st['residual_norm0'], residual=st['residual_norm'])
+		           u_max=umax, residual0=st['residual_norm0'], residual=st['residual_norm'], parity=parity)
 		print(json.dumps(out), flush=True)
 	c.close()
 	if world > 1:
