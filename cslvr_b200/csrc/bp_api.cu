@@ -240,7 +240,7 @@ static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 	// with it -- and the host issues one graph launch per two iterations instead of ~12 launches + 1 graph.  The first two
 	// iterations of a solve run directly when the graph does not exist yet: the multigrid captures its own graph there.
 	bp_ctx* c0 = cs[0];
-	struct Key { const void* inner; const void* stream; double lmax, ratio, alpha; int pc, deg, smoother, n, f32, maxit_even; } key;
+	struct Key { const void* inner; const void* stream; double lmax, ratio, alpha; int pc, deg, smoother, n, f32; } key;
 	memset(&key, 0, sizeof(key));
 	const void* inner = nullptr;
 	const bool settled = (c0->prm.pc != BP_PC_MG) || bp_mg_settled(cs, n, &inner);

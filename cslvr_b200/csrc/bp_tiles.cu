@@ -16,13 +16,16 @@
 //     registers; per layer the thread stages 51 doubles in shared memory ([slot][thread]: bank =
 //     thread, conflict-free): the interface blocks 3 x D (symmetric 2x2), 3 x E, 3 x F and the six
 //     blocks between the two layers;
-//   * after one barrier the CTA's threads turn to the block rows of the tile's own columns: a
-//     table (layer-independent) lists for every Jacobian block the (thread, staged slot) pairs to
-//     add -- fixed order, no atomics, bitwise reproducible -- and the SELL-32 slot it goes to.
-//     Rows are complete inside the tile: prism columns that touch a tile column but belong to a
-//     neighbouring tile are recomputed (halo factor ~1.2).
-// Staging is double-buffered, so summing layer k overlaps computing layer k + 1 with ONE barrier
-// per layer.  Every J block and F entry is written exactly once (checked at set-up).
+//   * 8 summing warps of the same CTA (warp-specialised, registers re-balanced with setmaxnreg) turn the staged values
+//     into the block rows of the tile's own columns: a table (layer-independent) lists for every Jacobian block the
+//     (thread, staged slot) pairs to add -- fixed order, no atomics, bitwise reproducible -- and the SELL-32 slot it goes
+//     to (one 256-bit store per block; J is symmetric: the transposed block of the partner row from the same sum).
+//     Rows are complete inside the tile: prism columns that touch a tile column but belong to a neighbouring tile are
+//     recomputed (halo factor ~1.2).  The same warps feed the compute warps (cp.async vertex packages);
+//   * the basal facet of a prism column is its bottom triangle: sliding and water-pressure integrals start the bottom
+//     interface of the march, so the facet kernel only runs for lateral facets.
+// Staging is double-buffered (224 prism columns per tile), hand-over by named barriers: summing layer k overlaps
+// computing layer k + 1.  Every J block and F entry is written exactly once (checked at set-up).
 //
 // The index tables are also run by a host emulator (bp_debug_tiles_emulate): the CPU test suite
 // checks tables + element math against the oracle without a GPU.  It is not reachable from
