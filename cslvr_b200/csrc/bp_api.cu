@@ -240,13 +240,14 @@ static int group_pcg(bp_ctx** cs, int n, int* iters, double* relres)
 	// with it -- and the host issues one graph launch per two iterations instead of ~12 launches + 1 graph.  The first two
 	// iterations of a solve run directly when the graph does not exist yet: the multigrid captures its own graph there.
 	bp_ctx* c0 = cs[0];
-	struct Key { const void* inner; const void* stream; double lmax, ratio, alpha; int pc, deg, smoother, n, f32; } key;
+	struct Key { const void* inner; const void* stream; double lmax, ratio, alpha, rtol, atol; int pc, deg, smoother, n, f32, norm_pc; } key;   // everything a captured kernel argument depends on
 	memset(&key, 0, sizeof(key));
 	const void* inner = nullptr;
 	const bool settled = (c0->prm.pc != BP_PC_MG) || bp_mg_settled(cs, n, &inner);
 	key.inner = inner; key.stream = (const void*)c0->stream; key.lmax = (c0->prm.pc == BP_PC_CHEBYSHEV) ? c0->cheb_lmax : 0.0;
 	key.ratio = c0->prm.pc_eig_ratio; key.alpha = c0->prm.mg_coarse_scale; key.pc = c0->prm.pc; key.deg = c0->prm.pc_degree;
 	key.smoother = c0->prm.mg_smoother; key.n = n; key.f32 = c0->env.mg_fp32 ? 1 : 0;
+	key.rtol = c0->prm.krylov_rtol; key.atol = c0->prm.krylov_atol; key.norm_pc = c0->prm.krylov_norm_preconditioned;      // arguments of k_pcg_p
 	if (c0->cg_graph && memcmp(&key, c0->cg_key, sizeof(key)) != 0) { cudaGraphExecDestroy(c0->cg_graph); c0->cg_graph = nullptr; }
 	static_assert(sizeof(Key) <= sizeof(c0->cg_key), "bp_ctx::cg_key too small");
 	int k = 0;

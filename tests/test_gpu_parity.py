@@ -735,3 +735,19 @@ def test_newton_with_lateral_dirichlet_conditions_matches_oracle():
 	lin.solve()
 	ul = lin.get_unknown().values
 	assert np.abs(ul[dofs] - vals).max() < 1e-9 * np.abs(vals).max()
+
+
+def test_krylov_tolerance_change_is_honoured_by_the_iteration_graph():
+	"""the CG iteration replays as a CUDA graph whose kernels carry the tolerances as arguments: a changed krylov_rtol on
+	the same context must rebuild it (PETSc reads the tolerances at every KSPSolve)."""
+	m = ismip_model('A', n=(16, 16, 4))
+	c = product_context(m, krylov_rtol=1e-3, preconditioner='mg')
+	u = state(2 * m.n_nodes, 5)
+	F, _ = c.assemble(u, want_F=True, want_J=True, J=False)
+	_, it1, rr1 = c.krylov_solve(F)
+	_, it1b, rr1b = c.krylov_solve(F)                    # second solve: the graph exists now
+	c.set_params(krylov_rtol=1e-11, preconditioner='mg')
+	_, it2, rr2 = c.krylov_solve(F)
+	assert rr1 < 1e-3 and rr1b < 1e-3 and it1b == it1
+	assert rr2 < 1e-11 and it2 > it1
+	c.close()
