@@ -492,6 +492,7 @@ int bp_set_params(bp_ctx* c, const bp_params* p)
 	store_params(c, p);
 	c->ainv_dirty = true;
 	cudaSetDevice(c->device);
+	bp_tiles_params_changed(c);
 	bp_upload_quadrature(c);
 	return BP_OK;
 }

@@ -261,6 +261,7 @@ bool bp_tiles_facet_lists(const bp_ctx* c, int64_t* n_fnodes, const int32_t** fn
 void bp_launch_tiles(bp_ctx* c, int what);                // d_u -> d_F / d_val (cell integrals)
 void bp_tiles_update_ainv(bp_ctx* c);                     // d_ainv -> tile order (after k_tet_ainv)
 void bp_tiles_free(bp_ctx* c);
+void bp_tiles_params_changed(bp_ctx* c);                  // drop the captured host-buffer pipeline (its kernels carry the constants)
 bool bp_tiles_pipeline_ready(const bp_ctx* c, int what);  // host-buffer bp_assemble can run the tiled kernel pipelined
 int  bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F);
 

@@ -872,6 +872,12 @@ int bp_tiles_assemble_pipelined(bp_ctx* c, int what, const double* u, double* F)
 	return BP_OK;
 }
 
+// bp_set_params: the captured pipeline carries the physical constants as kernel arguments
+void bp_tiles_params_changed(bp_ctx* c)
+{
+	if (c->tiles && c->tiles->pipe_graph) { cudaGraphExecDestroy(c->tiles->pipe_graph); c->tiles->pipe_graph = nullptr; }
+}
+
 void bp_tiles_free(bp_ctx* c)
 {
 	if (!c->tiles) return;
