@@ -32,6 +32,7 @@
 // bp_assemble.
 #include "bp_internal.h"
 #include <algorithm>
+#include <parallel/algorithm>     // __gnu_parallel::sort for the million-element sorts of the set-up (OpenMP)
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -927,7 +928,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		key[v] = ((int64_t)std::llround((m->coords[3 * v] - lo[0]) * sx_) << 22) | (int64_t)std::llround((m->coords[3 * v + 1] - lo[1]) * sy_);
 	std::vector<int32_t> ord(nv);
 	std::iota(ord.begin(), ord.end(), 0);
-	std::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return key[a] != key[b] ? key[a] < key[b] : (m->coords[3 * a + 2] != m->coords[3 * b + 2] ? m->coords[3 * a + 2] < m->coords[3 * b + 2] : a < b); });
+	__gnu_parallel::sort(ord.begin(), ord.end(), [&](int32_t a, int32_t b) { return key[a] != key[b] ? key[a] < key[b] : (m->coords[3 * a + 2] != m->coords[3 * b + 2] ? m->coords[3 * a + 2] < m->coords[3 * b + 2] : a < b); });
 	int NL = 1;
 	while (NL < nv && key[ord[NL]] == key[ord[0]]) ++NL;
 	if (NL < 2 || nv % NL) return no_tiles(c, "vertices do not form columns of equal length");
@@ -993,7 +994,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 		rec[t] = { uq[0], uq[1], uq[2], kmin, (int32_t)t };
 	}
 	if (bad) return no_tiles(c, "a cell does not span three vertex columns and two adjacent layers");
-	std::sort(rec.begin(), rec.end(), [](const Rec& x, const Rec& y) {
+	__gnu_parallel::sort(rec.begin(), rec.end(), [](const Rec& x, const Rec& y) {
 		if (x.a != y.a) return x.a < y.a; if (x.b != y.b) return x.b < y.b; if (x.cc != y.cc) return x.cc < y.cc; if (x.k != y.k) return x.k < y.k; return x.t < y.t; });
 	const int64_t ntri = nt / (3 * NZ);
 	std::vector<int32_t> tri_col(3 * ntri), tri_tet((size_t)ntri * NZ * 3);       // canonical vertex columns; tets (A, B, C) per layer
@@ -1088,7 +1089,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 				}
 			}
 		}
-		std::sort(pk.begin(), pk.end(), [](const PK& a, const PK& b) { if (a.p != b.p) return a.p < b.p; if (a.kind != b.kind) return a.kind < b.kind; return a.q < b.q; });
+		__gnu_parallel::sort(pk.begin(), pk.end(), [](const PK& a, const PK& b) { if (a.p != b.p) return a.p < b.p; if (a.kind != b.kind) return a.kind < b.kind; return a.q < b.q; });
 		pk.erase(std::unique(pk.begin(), pk.end(), [](const PK& a, const PK& b) { return a.p == b.p && a.kind == b.kind && a.q == b.q; }), pk.end());
 		for (const PK& e : pk) pkp[e.p + 1]++;
 		for (int32_t q = 0; q < n_ncol; ++q) pkp[q + 1] += pkp[q];
@@ -1114,7 +1115,7 @@ int bp_setup_tiles(bp_ctx* c, const bp_mesh* m, const std::vector<int32_t>& v2n)
 	const double strip_h = 7.0 / std::sqrt(rho);                  // ~7 rows of columns per strip: (7 + 1) x (15 + 1) x 2 = 256 prism columns (x 8 for 128)
 	std::vector<int64_t> ybin(n_ncol, 0);
 	for (int32_t q : own_cols) ybin[q] = (int64_t)std::floor((cy[q] - olo[1]) / strip_h + 1e-9);
-	std::sort(own_cols.begin(), own_cols.end(), [&](int32_t a, int32_t b) {
+	__gnu_parallel::sort(own_cols.begin(), own_cols.end(), [&](int32_t a, int32_t b) {
 		if (ybin[a] != ybin[b]) return ybin[a] < ybin[b]; if (cx[a] != cx[b]) return cx[a] < cx[b]; if (cy[a] != cy[b]) return cy[a] < cy[b]; return a < b; });
 	std::vector<int32_t> tile_c0(1, 0);                            // tile -> range of own_cols
 	{
