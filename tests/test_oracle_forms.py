@@ -252,3 +252,37 @@ def test_reduced_stokes_golden_vectors_reproduce(name):
 	un, info = P.newton_rs()
 	assert info['iterations'] == int(g['newton_iterations']) and relerr(un, g['u_newton']) < 1e-9
 	assert relerr(P.uz, g['uz_newton']) < 1e-8
+
+
+def test_symmetric_elimination_of_dirichlet_rows_equals_dolfins_row_replacement():
+	"""dolfin's NewtonSolver replaces the constrained rows of J by identity rows and sets b_i = u_i - g_i (SURVEY A-N:
+	bc.apply, non-symmetric).  The library eliminates the constrained dofs symmetrically instead -- free rows lifted by
+	J d, rows AND columns replaced -- so that CG keeps an SPD matrix (bp_set_dirichlet): the same Newton
+	update, and the eliminated matrix is symmetric positive definite."""
+	import scipy.sparse as sp
+	import scipy.sparse.linalg as spl
+	from cases import marine_model, oracle_problem
+	m = marine_model()
+	P = oracle_problem(m)
+	rng = np.random.default_rng(11)
+	u = rng.normal(size=P.n_dofs) * 20.0
+	J = P.jacobian_matrix(u).tocsr()
+	F = P.residual(u)
+	bd = np.sort(rng.choice(P.n_dofs, size=P.n_dofs // 9, replace=False))
+	g = rng.normal(size=bd.size) * 5.0
+	free = np.ones(P.n_dofs); free[bd] = 0.0
+	d = np.zeros(P.n_dofs); d[bd] = u[bd] - g
+	# dolfin: rows only
+	Jn = (sp.diags(free) @ J + sp.diags(1.0 - free)).tocsc()
+	bn = F.copy(); bn[bd] = d[bd]
+	dx_n = spl.spsolve(Jn, bn)
+	# the library: b_free -= J d, rows and columns -> identity
+	bs = F - J @ d; bs[bd] = d[bd]
+	Js = (sp.diags(free) @ J @ sp.diags(free) + sp.diags(1.0 - free)).tocsc()
+	dx_s = spl.spsolve(Js, bs)
+	# (J is badly scaled at a random state: the two LU solutions agree to its conditioning, the residual of dolfin's system is exact)
+	assert np.abs(Jn @ dx_s - bn).max() < 1e-9 * np.abs(bn).max()
+	assert np.abs(dx_s - dx_n).max() < 1e-4 * np.abs(dx_n).max()
+	assert np.allclose(dx_s[bd], u[bd] - g)
+	assert abs(Js - Js.T).max() < 1e-12 * abs(Js).max()
+	assert spl.eigsh(Js, k=1, which='SA', return_eigenvectors=False, tol=1e-6)[0] > 0.0
