@@ -22,7 +22,10 @@ roofline    the dominant kernel (cell assembly) timed alone with CUDA events on 
 newton      the whole dolfin.solve(F == 0, u, J=J) call from the cold start, reference defaults.
 parity      untimed, at FULL size: F, the CSR pattern and every entry of J against the oracle's C twin
             (N = 1), F and J x on every rank's rows (N > 1), and the oracle's own residual at the
-            product's converged velocity.
+            product's converged velocity.  F_rel also covers the F that the TIMED calls left behind: the
+            device buffer of the `value` loop and the pinned host buffer of the `e2e` loop.
+config.host_binding   every rank runs on the CPU cores next to its GPU (NVML's ideal affinity), as a launcher
+            with NUMA binding would arrange; the CPU checker / baseline legs get the full affinity mask back.
 cpu_baseline / cpu_baseline_newton / --impl reference
             the oracle's C/OpenMP restatement of the reference's CPU path ("port": the reference is
             Python on an un-vendored FEniCS stack and cannot run here) on all host cores.
